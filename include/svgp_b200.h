@@ -1,0 +1,175 @@
+/*
+ * svgp_b200.h -- C ABI of libsvgp_b200.so: the sm_100a kernels behind the SVGP hot path
+ * of ratschlab/SVGP-VAE (the Hensman-style SVGP object in SVGPVAE_model.py).
+ *
+ * The reference has no FFI: its boundary is a duck-typed Python object (mainSVGP /
+ * mnistSVGP / spritesSVGP / SVGP) whose methods expand into stock TensorFlow ops.  Every
+ * entry point below replaces one such op chain; the "replaces" line cites it
+ * (file:line in the reference tree).  svgp_vae_b200/_lib.py binds exactly these symbols
+ * with ctypes; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; matrices are row-major with
+ *     an explicit leading dimension (in elements); batches use an element stride
+ *   - the caller (PyTorch) allocates all outputs and workspaces; the library never
+ *     allocates or frees device memory and keeps no mutable global state except the
+ *     thread-local last-error string
+ *   - `stream` is a cudaStream_t passed as void*; calls on distinct streams are independent
+ *   - return 0 on success; SVGP_ERR_ARG (-1) bad argument; SVGP_ERR_CUDA (-2) CUDA runtime
+ *     error (text via svgp_last_error()); SVGP_ERR_UNSUPPORTED (-4) shape not handled by
+ *     the requested implementation.  A non-positive-definite pivot in svgp_chol_f64 is
+ *     reported on the device: status[b] = 1 + (failing column), never as NaN-propagation only.
+ *   - there is no CPU fallback anywhere behind this header.
+ */
+#ifndef SVGP_B200_H_
+#define SVGP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVGP_OK 0
+#define SVGP_ERR_ARG (-1)
+#define SVGP_ERR_CUDA (-2)
+#define SVGP_ERR_UNSUPPORTED (-4)
+
+/* factor kernels of the two-block product kernel  k(x,z) = kA(xA,zA) * kB(xB,zB)            */
+#define SVGP_K_NONE 0   /* factor == 1                                                        */
+#define SVGP_K_SE 1     /* tfk.ExponentiatedQuadratic: s^2 exp(-|x-z|^2 / (2 l^2))             */
+#define SVGP_K_EXPSIN 2 /* tfk.ExpSinSquared, period 2*pi: s^2 exp(-2 sum sin^2((x-z)/2)/l^2)  */
+#define SVGP_K_LINEAR 3 /* tfk.Linear(): x . z                                                */
+#define SVGP_K_COSINE 4 /* Linear divided by |x||z|  (K_obj_normalize)                        */
+
+/* implementation selector for the GEMM-class entry points */
+#define SVGP_IMPL_AUTO 0
+#define SVGP_IMPL_SIMT 1 /* fp32 CUDA-core tiles, any shape                                   */
+#define SVGP_IMPL_TC 2   /* tcgen05 / TMEM / TMA, 3xTF32 split operands                       */
+
+int svgp_version(void);
+const char* svgp_last_error(void); /* host string, thread-local */
+int svgp_device_ok(void);          /* 1 if the current device is compute capability 10.x      */
+
+/* ---------------------------------------------------------------------------------------
+ * K1  kernel-matrix builder
+ * replaces: mnistSVGP.kernel_matrix SVGPVAE_model.py:427-476, spritesSVGP.kernel_matrix
+ *           :550-600, ball kernel.matrix :81-86/:152-157 and the tfp.math.psd_kernels
+ *           .matrix/.apply calls under them.
+ * Fx (N x d) / Fz (M x d) are dense fp32 feature rows [block A | block B], d = dim_a+dim_b.
+ * hyp = device float[4] = {amplitude_a, length_a, amplitude_b, length_b} (unused entries 1).
+ * Outputs (any may be NULL): K (N x M), Kt (M x N, the transpose).  When K_lo / Kt_lo are
+ * non-NULL the value is written as a TF32 pair: K = rna_tf32(k), K_lo = rna_tf32(k - K).
+ * ------------------------------------------------------------------------------------- */
+int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M,
+                    int type_a, int dim_a, int type_b, int dim_b, const float* hyp,
+                    float* K, float* K_lo, int64_t ldk, float* Kt, float* Kt_lo, int64_t ldkt,
+                    void* stream);
+
+/* adjoint of svgp_kernel_fwd.  G (N x M) is dObjective/dK.  dFx (N x d) is overwritten;
+ * dFz (M x d, double) and dhyp (double[4]) are ACCUMULATED into (caller zeroes them).
+ * replaces: tf.gradients through kernel_matrix (MNIST_experiment.py:202-208).                */
+int svgp_kernel_bwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M,
+                    int type_a, int dim_a, int type_b, int dim_b, const float* hyp,
+                    const float* G, int64_t ldg, float* dFx, double* dFz, double* dhyp, void* stream);
+
+/* element-wise kernel .apply: kd[i] = k(Fx[i], Fy[i])  (diag_only=True, :458-467/:572-583)   */
+int svgp_kernel_diag_fwd(const float* Fx, int64_t ldx, const float* Fy, int64_t ldy, int64_t N,
+                         int type_a, int dim_a, int type_b, int dim_b, const float* hyp, float* kd,
+                         void* stream);
+int svgp_kernel_diag_bwd(const float* Fx, int64_t ldx, const float* Fy, int64_t ldy, int64_t N,
+                         int type_a, int dim_a, int type_b, int dim_b, const float* hyp,
+                         const float* g, float* dFx, float* dFy, double* dhyp, void* stream);
+
+/* embedding gather / scatter-add (tf.gather :451,455,565,570 and its IndexedSlices gradient)
+ * out[i, :] = table[ids[i], :];  dtable[ids[i], :] += g[i, :]  (dtable double, caller zeroes) */
+int svgp_gather_rows(const float* table, int64_t ldt, int64_t rows, const int64_t* ids, int64_t N,
+                     int64_t d, float* out, int64_t ldo, void* stream);
+int svgp_scatter_add_rows(const float* g, int64_t ldg, const int64_t* ids, int64_t N, int64_t d,
+                          int64_t rows, double* dtable, int64_t ldt, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * The operand "Kop" of the GEMM-class calls is K_nm (N x M).  SIMT: pass K (fp32) and NULL
+ * for the other planes.  TC: pass the four TF32 planes written by svgp_kernel_fwd.
+ * ------------------------------------------------------------------------------------- */
+typedef struct svgp_kop {
+  const float* K;     /* N x M, ld = ldk   (TC: hi plane)            */
+  const float* K_lo;  /* N x M             (TC only, else NULL)      */
+  const float* Kt;    /* M x N, ld = ldkt  (TC only: hi plane)       */
+  const float* Kt_lo; /* M x N             (TC only)                 */
+  int64_t N, M, ldk, ldkt;
+} svgp_kop;
+
+/* K2  batched weighted SYRK   A[l] = sum_i W[i,l] k_i k_i^T   (L x M x M, double, ACCUMULATED:
+ * caller zeroes; both triangles written).  W is N x L fp32 (any sign); the TC path reads the
+ * channel-major copy Wt (L x N, ld = ldwt, 16-byte aligned rows) instead, the SIMT path ignores it.
+ * replaces: K_mn (K_nm * 1/sigma^2) SVGPVAE_model.py:328-330 (:160 for the ball) and, as the
+ * adjoint of svgp_rowquad, the (b,m,m) trace pattern :286-294.                               */
+int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, const float* Wt, int64_t ldwt, int64_t L,
+              double* A, int impl, int64_t chunk_rows, void* stream);
+
+/* V[l, :] += sum_i X[i,l] k_i          (L x M double, accumulated)  -- K_mn (p*y), :333-334   */
+int svgp_gemm_tn(const svgp_kop* kop, const float* X, int64_t ldx, int64_t L, double* V, void* stream);
+
+/* out[i,l] = k_i . Wm[l,:]             (N x L fp32)   -- K_xm (S K_mn p y), :332-334; :264-265 */
+int svgp_gemm_nn(const svgp_kop* kop, const float* Wm, int64_t ldwm, int64_t L, float* out,
+                 int64_t ldo, void* stream);
+
+/* K4  row-wise quadratic forms  q[i,l] = k_i^T S_l k_i  (N x L fp32).
+ * S (L x M x M, symmetric) is given as fp32 planes S_hi (+ S_lo for TC; NULL for SIMT).
+ * If `tri` != 0 the planes hold a lower-triangular factor Rinv_l instead and
+ * q[i,l] = |Rinv_l k_i|^2 (half the work).  L may be 1 with N x 1 output (h_i = k^T Kinv k).
+ * replaces: diag_part(K_xm Sigma_l^-1 K_mx), diag_part(K_xm K_mm^-1 K_mx) :336-337, :284.    */
+int svgp_rowquad(const svgp_kop* kop, const float* S_hi, const float* S_lo, int64_t L, int tri,
+                 float* q, int64_t ldq, int impl, void* stream);
+
+/* out[i, :] (+)= sum_l W[i,l] * (G_l k_i)     (N x M fp32), G (L x M x M symmetric) as planes.
+ * accumulate != 0 adds to `out`.  This is dObjective/dK_nm through svgp_syrk (W=p, G=dA+dA^T)
+ * and through svgp_rowquad (W=2*dq, G=S).  replaces: tf.gradients through :328-337.          */
+int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const float* G_hi,
+                     const float* G_lo, int64_t L, float* out, int64_t ldo, int accumulate, int impl,
+                     void* stream);
+
+/* out (N x M) (+)= W (N x L) @ V (L x M), all fp32 -- rank-L part of dK_nm (p_m, mean terms)  */
+int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t lda, const float* B,
+                  int64_t ldb, float* C, int64_t ldc, int accumulate, void* stream);
+
+/* split a double array into a TF32 pair: hi = rna_tf32(x), lo = rna_tf32(x - hi)              */
+int svgp_split_tf32(const double* x, float* hi, float* lo, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K3  batched float64 factorisations over the latent channels
+ * replaces: tf.linalg.cholesky :270-274 / :129-130, tf.linalg.inv :239,319,331 / :83,154,161
+ * ------------------------------------------------------------------------------------- */
+/* in-place lower Cholesky of `batch` SPD matrices (M x M, ld, stride); the strict upper
+ * triangle is zeroed.  status[b] = 0 ok, 1 + column of the first non-positive pivot.
+ * ws: double[batch * 32 * 32] scratch.                                                        */
+int svgp_chol_f64(double* A, int64_t M, int64_t ld, int64_t stride, int64_t batch, int* status,
+                  double* ws, void* stream);
+/* Linv = inverse of the lower-triangular factor (strict upper triangle of Linv zeroed)        */
+int svgp_trinv_f64(const double* Lf, double* Linv, int64_t M, int64_t ld, int64_t stride,
+                   int64_t batch, double* ws, void* stream);
+/* C[b] = alpha op(A[b]) op(B[b]) + beta C[b]; row-major, trans flags 0/1, stride 0 broadcasts */
+int svgp_gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, double alpha,
+                  const double* A, int64_t lda, int64_t strideA, const double* B, int64_t ldb,
+                  int64_t strideB, double beta, double* C, int64_t ldc, int64_t strideC, int64_t batch,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------
+ * K4  fused row terms
+ * ------------------------------------------------------------------------------------- */
+/* p = reciprocal_no_nan(noise), py = p*y and the per-channel sums
+ * sums[0,l] = sum_i p kappa_i, sums[1,l] = sum_i p y^2, sums[2,l] = sum_i log noise
+ * (double[3*L], accumulated).   replaces :282, :297-299 (row sums), utils.py:498-502          */
+int svgp_rowstats_fwd(const float* y, const float* noise, const float* kappa, int64_t N, int64_t L,
+                      float* p, float* py, double* sums, void* stream);
+/* p_v = kappa - h + q1 (optionally clipped to [lo,hi], SVGPVAE_model.py:891-892) written
+ * over q1; clipsum[l] += sum_i p_il (p_v_clipped - p_v_raw).                                  */
+int svgp_predictive_fwd(const float* kappa, const float* h, float* q1_pv, const float* p, int64_t N,
+                        int64_t L, int clip, float clip_lo, float clip_hi, double* clipsum,
+                        unsigned char* clipmask, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVGP_B200_H_ */

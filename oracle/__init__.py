@@ -1,0 +1,30 @@
+"""CPU oracle for the SVGP hot path of ratschlab/SVGP-VAE -- TEST INFRASTRUCTURE ONLY.
+
+This package is a float64 CPU restatement (torch-CPU, so reverse-mode gradients come
+from torch autograd) of the reference's Hensman-style sparse variational GP:
+
+  * ``tfp_kernels``       -- tensorflow-probability 0.8.0 ``psd_kernels`` (third-party,
+                             un-vendored; requirements.txt:9) restated from its public
+                             definition: ExponentiatedQuadratic, ExpSinSquared, Linear.
+  * ``svgp_literal``      -- op-for-op restatement of SVGPVAE_model.py:13-635 (SVGP,
+                             mainSVGP, mnistSVGP, spritesSVGP), utils.py:483-504
+                             (gauss_cross_entropy) and the two call sites
+                             SVGPVAE_model.py:865-898 / :674-697.  Keeps the (b,m,m)
+                             lambda_mat tensor, the explicit inverses and every quirk.
+  * ``svgp_streamlined``  -- the same mathematics in the jitter-exact collapsed form the
+                             CUDA path computes; must agree with the
+                             literal form to ~1e-12 (tests/test_oracle.py).
+
+PARITY UNPINNED: the reference ships no tests, golden vectors or known-answer
+fixtures for this path and TensorFlow 1.15 + TFP 0.8 cannot be
+installed in this image (python 3.12, no wheel, no network), so the oracle cannot be
+checked against the reference's own outputs.  It is pinned instead by (i) line-by-line
+correspondence with the cited ranges, (ii) literal == streamlined, (iii) an independent
+implementation of the kernel formulas (scikit-learn), (iv) the exact-GP limit
+(m = b, Z = X) against the independent formulation in GPVAE_Pearce_model.py:49-84 and
+(v) the survey-session numbers of SURVEY App. B.
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl
+reference`` legs of ``bench.py`` may import this package.  The product package
+``svgp_vae_b200`` never does: it fails loudly when its CUDA library is missing.
+"""

@@ -1,0 +1,329 @@
+"""Tensor-level wrappers around the C ABI (one method per entry point of include/svgp_b200.h).
+
+``CudaBackend`` is the only backend the product ships: PyTorch supplies device memory and the
+current stream, every FLOP runs in libsvgp_b200.so.  The host logic in ops.py / step.py talks to
+``get_backend()`` so that the CPU test-suite can exercise that logic against a float64 oracle
+backend (tests/oracle_backend.py, injected with ``set_backend_for_tests``) -- the package itself
+never imports the oracle and never falls back to it.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, KopStruct
+
+
+class Kop:
+    """K_nm (N x M) in the storage the GEMM-class kernels read.
+
+    SIMT: one fp32 matrix.  TC: TF32 (hi, lo) planes of K_nm and of its transpose (see
+    tc_engine.cu); ``value()`` reassembles hi + lo when a plain matrix is asked for.
+    """
+
+    def __init__(self, K, K_lo=None, Kt=None, Kt_lo=None, N=None, M=None):
+        self.K, self.K_lo, self.Kt, self.Kt_lo = K, K_lo, Kt, Kt_lo
+        self.N = K.shape[0] if N is None else N
+        self.M = K.shape[1] if M is None else M
+
+    @property
+    def tc(self):
+        return self.K_lo is not None
+
+    def value(self):
+        K = self.K[: self.N, : self.M]
+        return K if self.K_lo is None else K + self.K_lo[: self.N, : self.M]
+
+    def struct(self):
+        s = KopStruct()
+        s.K = self.K.data_ptr()
+        s.K_lo = self.K_lo.data_ptr() if self.K_lo is not None else None
+        s.Kt = self.Kt.data_ptr() if self.Kt is not None else None
+        s.Kt_lo = self.Kt_lo.data_ptr() if self.Kt_lo is not None else None
+        s.N, s.M = self.N, self.M
+        s.ldk = self.K.stride(0)
+        s.ldkt = self.Kt.stride(0) if self.Kt is not None else 0
+        return s
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t):
+    assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous(), (t.dtype, t.shape, t.is_contiguous())
+    return t
+
+
+def _f64c(t):
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), (t.dtype, t.shape)
+    return t
+
+
+def _pad(n, m):
+    return (n + m - 1) // m * m
+
+
+class CudaBackend:
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.SvgpLibraryError("svgp_vae_b200 needs a CUDA device (no CPU fallback)")
+        if not _lib.load().svgp_device_ok():
+            raise _lib.SvgpLibraryError("svgp_vae_b200 kernels are built for sm_100a only (B200)")
+        self.launches = 0          # kernels launched through this backend (bench reports it)
+        self.tc_min_rows = int(os.environ.get("SVGP_TC_MIN_ROWS", "2048"))
+
+    # ---- K1 --------------------------------------------------------------------------------
+    def want_tc(self, N, M):
+        return N >= self.tc_min_rows and M >= 128
+
+    def kernel_fwd(self, spec, Fx, Fz, hyp, tc=False):
+        Fx, Fz, hyp = _f32c(Fx), _f32c(Fz), _f32c(hyp)
+        N, M = Fx.shape[0], Fz.shape[0]
+        ta, da, tb, db = spec
+        if tc:
+            ldk, ldkt = _pad(M, 4), _pad(N, 4)
+            K = torch.empty((N, ldk), device=Fx.device, dtype=torch.float32)
+            K_lo = torch.empty_like(K)
+            Kt = torch.empty((M, ldkt), device=Fx.device, dtype=torch.float32)
+            Kt_lo = torch.empty_like(Kt)
+            if ldk != M:
+                K.zero_(); K_lo.zero_()
+            if ldkt != N:
+                Kt.zero_(); Kt_lo.zero_()
+            kop = Kop(K, K_lo, Kt, Kt_lo, N, M)
+        else:
+            K = torch.empty((N, M), device=Fx.device, dtype=torch.float32)
+            kop = Kop(K)
+        _lib.call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+                  _ptr(kop.K), _ptr(kop.K_lo), kop.K.stride(0), _ptr(kop.Kt), _ptr(kop.Kt_lo),
+                  kop.Kt.stride(0) if kop.Kt is not None else 0, _stream())
+        self.launches += 1
+        return kop
+
+    def kernel_bwd(self, spec, Fx, Fz, hyp, G, need_x=True, need_z=True):
+        Fx, Fz, hyp, G = _f32c(Fx), _f32c(Fz), _f32c(hyp), _f32c(G)
+        N, M, d = Fx.shape[0], Fz.shape[0], Fx.shape[1]
+        ta, da, tb, db = spec
+        dFx = torch.empty((N, d), device=Fx.device, dtype=torch.float32) if need_x else None
+        dFz = torch.zeros((M, d), device=Fx.device, dtype=torch.float64) if need_z else None
+        dhyp = torch.zeros(4, device=Fx.device, dtype=torch.float64)
+        _lib.call("svgp_kernel_bwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+                  _ptr(G), G.stride(0), _ptr(dFx), _ptr(dFz), _ptr(dhyp), _stream())
+        self.launches += int(need_x) + int(need_z)
+        return dFx, dFz, dhyp
+
+    def kernel_diag_fwd(self, spec, Fx, Fy, hyp):
+        Fx, Fy, hyp = _f32c(Fx), _f32c(Fy), _f32c(hyp)
+        ta, da, tb, db = spec
+        kd = torch.empty(Fx.shape[0], device=Fx.device, dtype=torch.float32)
+        _lib.call("svgp_kernel_diag_fwd", _ptr(Fx), Fx.stride(0), _ptr(Fy), Fy.stride(0), Fx.shape[0], ta, da, tb, db,
+                  _ptr(hyp), _ptr(kd), _stream())
+        self.launches += 1
+        return kd
+
+    def kernel_diag_bwd(self, spec, Fx, Fy, hyp, g):
+        Fx, Fy, hyp, g = _f32c(Fx), _f32c(Fy), _f32c(hyp), _f32c(g)
+        ta, da, tb, db = spec
+        dFx, dFy = torch.empty_like(Fx), torch.empty_like(Fy)
+        dhyp = torch.zeros(4, device=Fx.device, dtype=torch.float64)
+        _lib.call("svgp_kernel_diag_bwd", _ptr(Fx), Fx.stride(0), _ptr(Fy), Fy.stride(0), Fx.shape[0], ta, da, tb, db,
+                  _ptr(hyp), _ptr(g), _ptr(dFx), _ptr(dFy), _ptr(dhyp), _stream())
+        self.launches += 1
+        return dFx, dFy, dhyp
+
+    def gather_rows(self, table, ids):
+        table = _f32c(table)
+        assert ids.dtype == torch.int64 and ids.is_contiguous()
+        out = torch.empty((ids.shape[0], table.shape[1]), device=table.device, dtype=torch.float32)
+        _lib.call("svgp_gather_rows", _ptr(table), table.stride(0), table.shape[0], _ptr(ids), ids.shape[0],
+                  table.shape[1], _ptr(out), out.stride(0), _stream())
+        self.launches += 1
+        return out
+
+    def scatter_add_rows(self, g, ids, rows):
+        g = _f32c(g)
+        dt = torch.zeros((rows, g.shape[1]), device=g.device, dtype=torch.float64)
+        _lib.call("svgp_scatter_add_rows", _ptr(g), g.stride(0), _ptr(ids), ids.shape[0], g.shape[1], rows, _ptr(dt),
+                  dt.stride(0), _stream())
+        self.launches += 1
+        return dt
+
+    # ---- GEMM class ------------------------------------------------------------------------
+    def _planes(self, S64, tc):
+        """(L, M, M) float64 -> fp32 plane(s) the kernels read."""
+        S64 = _f64c(S64)
+        if not tc:
+            return S64.to(torch.float32), None
+        hi = torch.empty(S64.shape, device=S64.device, dtype=torch.float32)
+        lo = torch.empty_like(hi)
+        _lib.call("svgp_split_tf32", _ptr(S64), _ptr(hi), _ptr(lo), S64.numel(), _stream())
+        self.launches += 1
+        return hi, lo
+
+    def syrk(self, kop, W, impl=IMPL_AUTO, chunk_rows=0):
+        W = _f32c(W)
+        L = W.shape[1]
+        A = torch.zeros((L, kop.M, kop.M), device=W.device, dtype=torch.float64)
+        Wt = None
+        use_tc = kop.tc and impl != IMPL_SIMT
+        if use_tc:
+            ldwt = _pad(kop.N, 4)
+            Wt = torch.zeros((L, ldwt), device=W.device, dtype=torch.float32)
+            Wt[:, : kop.N] = W.t()
+        s = kop.struct()
+        _lib.call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(Wt), Wt.stride(0) if Wt is not None else 0, L,
+                  _ptr(A), IMPL_TC if use_tc else IMPL_SIMT, chunk_rows, _stream())
+        self.launches += 1
+        return A
+
+    def _plane_structs(self, kop):
+        """gemm_tn / gemm_nn read one fp32 plane; a TC operand is the exact sum hi + lo of two planes, so the
+        (linear) product is run once per plane and summed."""
+        s = kop.struct()
+        if not kop.tc:
+            return [s]
+        s_lo = kop.struct()
+        s_lo.K = kop.K_lo.data_ptr()
+        return [s, s_lo]
+
+    def gemm_tn(self, kop, X):
+        X = _f32c(X)
+        L = X.shape[1]
+        V = torch.zeros((L, kop.M), device=X.device, dtype=torch.float64)
+        for s in self._plane_structs(kop):
+            _lib.call("svgp_gemm_tn", ctypes.byref(s), _ptr(X), X.stride(0), L, _ptr(V), _stream())
+            self.launches += 1
+        return V
+
+    def gemm_nn(self, kop, Wm):
+        Wm = _f32c(Wm)
+        L = Wm.shape[0]
+        outs = []
+        for s in self._plane_structs(kop):
+            out = torch.empty((kop.N, L), device=Wm.device, dtype=torch.float32)
+            _lib.call("svgp_gemm_nn", ctypes.byref(s), _ptr(Wm), Wm.stride(0), L, _ptr(out), out.stride(0), _stream())
+            self.launches += 1
+            outs.append(out)
+        return outs[0] if len(outs) == 1 else outs[0].add_(outs[1])
+
+    def rowquad(self, kop, S64, tri=False, impl=IMPL_AUTO):
+        L = S64.shape[0]
+        use_tc = kop.tc and impl != IMPL_SIMT
+        hi, lo = self._planes(S64, use_tc)
+        q = torch.empty((kop.N, L), device=S64.device, dtype=torch.float32)
+        s = kop.struct()
+        _lib.call("svgp_rowquad", ctypes.byref(s), _ptr(hi), _ptr(lo), L, int(bool(tri)), _ptr(q), q.stride(0),
+                  IMPL_TC if use_tc else IMPL_SIMT, _stream())
+        self.launches += 1
+        return q
+
+    def scaled_gemm(self, kop, W, G64, out=None, impl=IMPL_AUTO):
+        W = _f32c(W)
+        L = W.shape[1]
+        use_tc = kop.tc and impl != IMPL_SIMT
+        hi, lo = self._planes(G64, use_tc)
+        accumulate = out is not None
+        if out is None:
+            out = torch.empty((kop.N, kop.M), device=W.device, dtype=torch.float32)
+        s = kop.struct()
+        _lib.call("svgp_scaled_gemm", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(hi), _ptr(lo), L, _ptr(out),
+                  out.stride(0), int(accumulate), IMPL_TC if use_tc else IMPL_SIMT, _stream())
+        self.launches += 1
+        return out
+
+    def gemm_f32(self, A, B, out=None):
+        A, B = _f32c(A), _f32c(B)
+        accumulate = out is not None
+        if out is None:
+            out = torch.empty((A.shape[0], B.shape[1]), device=A.device, dtype=torch.float32)
+        _lib.call("svgp_gemm_f32", A.shape[0], B.shape[1], A.shape[1], _ptr(A), A.stride(0), _ptr(B), B.stride(0),
+                  _ptr(out), out.stride(0), int(accumulate), _stream())
+        self.launches += 1
+        return out
+
+    # ---- K3 --------------------------------------------------------------------------------
+    def chol(self, X):
+        """Lower Cholesky factors of a (B, M, M) float64 batch; returns (Lf, status int32[B])."""
+        X = _f64c(X)
+        B, M, _ = X.shape
+        Lf = X.clone()
+        status = torch.zeros(B, device=X.device, dtype=torch.int32)
+        ws = torch.empty(B * 32 * 32, device=X.device, dtype=torch.float64)
+        _lib.call("svgp_chol_f64", _ptr(Lf), M, M, M * M, B, _ptr(status), _ptr(ws), _stream())
+        self.launches += 3 * ((M + 31) // 32)
+        return Lf, status
+
+    def trinv(self, Lf):
+        Lf = _f64c(Lf)
+        B, M, _ = Lf.shape
+        nblk = (M + 31) // 32
+        Linv = torch.empty_like(Lf)
+        ws = torch.empty(B * nblk * 32 * 32 + B * 32 * M, device=Lf.device, dtype=torch.float64)
+        _lib.call("svgp_trinv_f64", _ptr(Lf), _ptr(Linv), M, M, M * M, B, _ptr(ws), _stream())
+        self.launches += 2 * nblk + 2
+        return Linv
+
+    def bmm64(self, A, B, transA=False, transB=False):
+        """C[b] = op(A[b]) op(B[b]); a leading batch of 1 broadcasts against the other operand."""
+        A, B = _f64c(A), _f64c(B)
+        nb = max(A.shape[0], B.shape[0])
+        Mr = A.shape[2] if transA else A.shape[1]
+        Kd = A.shape[1] if transA else A.shape[2]
+        Nc = B.shape[1] if transB else B.shape[2]
+        assert Kd == (B.shape[2] if transB else B.shape[1]), (A.shape, B.shape, transA, transB)
+        C = torch.empty((nb, Mr, Nc), device=A.device, dtype=torch.float64)
+        sA = 0 if (A.shape[0] == 1 and nb > 1) else A.shape[1] * A.shape[2]
+        sB = 0 if (B.shape[0] == 1 and nb > 1) else B.shape[1] * B.shape[2]
+        _lib.call("svgp_gemm_f64", int(transA), int(transB), Mr, Nc, Kd, 1.0, _ptr(A), A.shape[2], sA, _ptr(B),
+                  B.shape[2], sB, 0.0, _ptr(C), Nc, Mr * Nc, nb, _stream())
+        self.launches += 1
+        return C
+
+    # ---- K4 row terms ----------------------------------------------------------------------
+    def rowstats(self, y, noise, kappa):
+        y, noise, kappa = _f32c(y), _f32c(noise), _f32c(kappa)
+        N, L = y.shape
+        p, py = torch.empty_like(y), torch.empty_like(y)
+        sums = torch.zeros((3, L), device=y.device, dtype=torch.float64)
+        _lib.call("svgp_rowstats_fwd", _ptr(y), _ptr(noise), _ptr(kappa), N, L, _ptr(p), _ptr(py), _ptr(sums), _stream())
+        self.launches += 1
+        return p, py, sums
+
+    def predictive(self, kappa, h, q1, p, clip=None):
+        kappa, h, q1 = _f32c(kappa), _f32c(h), _f32c(q1)
+        N, L = q1.shape
+        pv = q1.clone()
+        clipsum = torch.zeros(L, device=q1.device, dtype=torch.float64)
+        mask = torch.zeros((N, L), device=q1.device, dtype=torch.uint8) if clip else None
+        lo, hi = clip if clip else (0.0, 0.0)
+        _lib.call("svgp_predictive_fwd", _ptr(kappa), _ptr(h), _ptr(pv), _ptr(_f32c(p)) if clip else None, N, L,
+                  int(bool(clip)), lo, hi, _ptr(clipsum), _ptr(mask), _stream())
+        self.launches += 1
+        return pv, clipsum, mask
+
+
+_BACKEND = None
+
+
+def get_backend():
+    global _BACKEND
+    if _BACKEND is None:
+        _BACKEND = CudaBackend()          # raises if the library / device is missing: no fallback
+    return _BACKEND
+
+
+def set_backend_for_tests(backend):
+    """Test hook (tests/ only): run the host logic against a float64 CPU oracle backend."""
+    global _BACKEND
+    old = _BACKEND
+    _BACKEND = backend
+    return old

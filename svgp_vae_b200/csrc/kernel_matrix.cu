@@ -1,0 +1,582 @@
+// K1: kernel-matrix builder, its adjoint, the element-wise (diag) form and the embedding
+// gather / scatter.  Replaces mnistSVGP.kernel_matrix (SVGPVAE_model.py:427-476),
+// spritesSVGP.kernel_matrix (:550-600), the ball's kernel.matrix calls (:81-86, :152-157)
+// and the tfp.math.psd_kernels arithmetic under them (formulas: oracle/tfp_kernels.py).
+//
+// k(x, z) = kA(xA, zA) * kB(xB, zB), each factor one of NONE / SE / EXPSIN / LINEAR / COSINE.
+// The builder is HBM-bound: every output element is written once (coalesced, through a
+// padded shared-memory tile so that both K (N x M) and its transpose Kt (M x N) leave the SM
+// as full 256-byte row segments), optionally as a TF32 hi/lo pair for the tcgen05 consumers.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace svgp {
+
+// ------------------------------------------------------------------------------------------
+// error plumbing (shared by every translation unit)
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    return SVGP_ERR_CUDA;
+  }
+  return SVGP_OK;
+}
+const char* last_error() { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// factor arithmetic
+// ------------------------------------------------------------------------------------------
+struct Spec {
+  int ta, da, tb, db;
+};
+
+struct Hyp {
+  float amp_a, len_a, amp_b, len_b;
+};
+
+__device__ __forceinline__ Hyp load_hyp(const float* hyp) {
+  Hyp h;
+  h.amp_a = hyp[0]; h.len_a = hyp[1]; h.amp_b = hyp[2]; h.len_b = hyp[3];
+  return h;
+}
+
+// value of one factor.  nx / nz are the Euclidean norms of the feature blocks (COSINE only).
+__device__ __forceinline__ float factor_value(int type, const float* x, const float* z, int d, float amp,
+                                              float len, float nx, float nz) {
+  if (type == SVGP_K_NONE) return 1.0f;
+  if (type == SVGP_K_SE) {
+    float r2 = 0.f;
+    for (int f = 0; f < d; ++f) { float t = x[f] - z[f]; r2 = fmaf(t, t, r2); }
+    return amp * amp * expf(-0.5f * r2 / (len * len));
+  }
+  if (type == SVGP_K_EXPSIN) {
+    float u = 0.f;
+    for (int f = 0; f < d; ++f) { float s = sinf(0.5f * fabsf(x[f] - z[f])); u = fmaf(s, s, u); }
+    return amp * amp * expf(-2.0f * u / (len * len));
+  }
+  float dot = 0.f;
+  for (int f = 0; f < d; ++f) dot = fmaf(x[f], z[f], dot);
+  if (type == SVGP_K_COSINE) dot = dot / (nx * nz);
+  return dot;
+}
+
+// adjoint coefficients of one factor for one (row, col) pair, given gk = g * (other factor):
+//   d/dz_f = c1 * x_f + c2z * z_f (+ e for EXPSIN on its single feature, sign + for z, - for x)
+//   d/dx_f = c1 * z_f + c2x * x_f
+//   d/d amp, d/d len returned through damp / dlen
+struct FactorAdj {
+  float c1, c2z, c2x, e, damp, dlen;
+};
+__device__ __forceinline__ FactorAdj factor_adjoint(int type, const float* x, const float* z, int d, float amp,
+                                                    float len, float nx, float nz, float kval, float gk) {
+  FactorAdj a = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (type == SVGP_K_SE) {
+    float r2 = 0.f;
+    for (int f = 0; f < d; ++f) { float t = x[f] - z[f]; r2 = fmaf(t, t, r2); }
+    float il2 = 1.0f / (len * len);
+    a.c1 = gk * kval * il2;      // dk/dz_f = k (x_f - z_f)/l^2
+    a.c2z = -a.c1;
+    a.c2x = -a.c1;               // dk/dx_f = k (z_f - x_f)/l^2
+    a.damp = gk * 2.0f * kval / amp;
+    a.dlen = gk * kval * r2 * il2 / len;
+  } else if (type == SVGP_K_EXPSIN) {
+    float dd = x[0] - z[0];
+    float s = sinf(0.5f * dd);
+    float il2 = 1.0f / (len * len);
+    a.e = gk * kval * sinf(dd) * il2;          // dk/dz = k sin(x - z)/l^2 ; dk/dx = -that
+    a.damp = gk * 2.0f * kval / amp;
+    a.dlen = gk * kval * 4.0f * s * s * il2 / len;
+  } else if (type == SVGP_K_LINEAR) {
+    a.c1 = gk;
+  } else if (type == SVGP_K_COSINE) {
+    a.c1 = gk / (nx * nz);
+    a.c2z = -gk * kval / (nz * nz);
+    a.c2x = -gk * kval / (nx * nx);
+  }
+  return a;
+}
+
+constexpr int TILE = 64;        // rows and columns per shared tile
+constexpr int THREADS = 256;
+constexpr int MAXD = 32;        // max total feature count
+
+__device__ __forceinline__ float block_norm(const float* v, int d) {
+  float s = 0.f;
+  for (int f = 0; f < d; ++f) s = fmaf(v[f], v[f], s);
+  return sqrtf(s);
+}
+
+// load `rows` feature rows (d floats, leading dim ld) starting at row r0 into sm[TILE][dp],
+// plus the two block norms; rows beyond `total` are zero-filled
+__device__ __forceinline__ void load_features(const float* F, int64_t ld, int64_t r0, int64_t total, int d, int dp,
+                                              Spec sp, float* sm, float* na, float* nb) {
+  for (int idx = threadIdx.x; idx < TILE * d; idx += THREADS) {
+    int r = idx / d, f = idx - r * d;
+    int64_t gr = r0 + r;
+    sm[r * dp + f] = (gr < total) ? F[gr * ld + f] : 0.f;
+  }
+  __syncthreads();
+  if (threadIdx.x < TILE) {
+    int r = threadIdx.x;
+    bool valid = (r0 + r) < total;    // padding rows get norm 1 so that 0/0 never appears
+    na[r] = (valid && sp.ta == SVGP_K_COSINE) ? block_norm(sm + r * dp, sp.da) : 1.f;
+    nb[r] = (valid && sp.tb == SVGP_K_COSINE) ? block_norm(sm + r * dp + sp.da, sp.db) : 1.f;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
+    const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz, int64_t M,
+    Spec sp, const float* __restrict__ hyp, float* __restrict__ K, float* __restrict__ K_lo, int64_t ldk,
+    float* __restrict__ Kt, float* __restrict__ Kt_lo, int64_t ldkt) {
+  extern __shared__ float smem[];
+  const int d = sp.da + sp.db, dp = d | 1;
+  float* xs = smem;                    // [TILE][dp]
+  float* zs = xs + TILE * dp;          // [TILE][dp]
+  float* tile = zs + TILE * dp;        // [TILE][TILE+1]
+  float* nxa = tile + TILE * (TILE + 1);
+  float* nxb = nxa + TILE;
+  float* nza = nxb + TILE;
+  float* nzb = nza + TILE;
+  const Hyp h = load_hyp(hyp);
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int64_t ntiles_r = (N + TILE - 1) / TILE;
+
+  load_features(Fz, ldz, col0, M, d, dp, sp, zs, nza, nzb);
+  const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;   // 4 row groups
+  for (int64_t rt = blockIdx.y; rt < ntiles_r; rt += gridDim.y) {
+    const int64_t row0 = rt * TILE;
+    load_features(Fx, ldx, row0, N, d, dp, sp, xs, nxa, nxb);
+#pragma unroll 4
+    for (int j = 0; j < TILE / 4; ++j) {
+      int r = rg + 4 * j;
+      float ka = factor_value(sp.ta, xs + r * dp, zs + c * dp, sp.da, h.amp_a, h.len_a, nxa[r], nza[c]);
+      float kb = factor_value(sp.tb, xs + r * dp + sp.da, zs + c * dp + sp.da, sp.db, h.amp_b, h.len_b, nxb[r], nzb[c]);
+      tile[r * (TILE + 1) + c] = ka * kb;
+    }
+    __syncthreads();
+    if (K) {
+#pragma unroll 4
+      for (int j = 0; j < TILE / 4; ++j) {
+        int r = rg + 4 * j;
+        int64_t gr = row0 + r, gc = col0 + c;
+        if (gr < N && gc < M) {
+          float v = tile[r * (TILE + 1) + c];
+          if (K_lo) {
+            float hi = to_tf32(v);
+            K[gr * ldk + gc] = hi;
+            K_lo[gr * ldk + gc] = to_tf32(v - hi);
+          } else {
+            K[gr * ldk + gc] = v;
+          }
+        }
+      }
+    }
+    if (Kt) {
+      // transposed write: consecutive threads walk consecutive datapoints of one inducing column
+      const int r = threadIdx.x % TILE, cg = threadIdx.x / TILE;
+#pragma unroll 4
+      for (int j = 0; j < TILE / 4; ++j) {
+        int cc = cg + 4 * j;
+        int64_t gr = row0 + r, gc = col0 + cc;
+        if (gr < N && gc < M) {
+          float v = tile[r * (TILE + 1) + cc];
+          if (Kt_lo) {
+            float hi = to_tf32(v);
+            Kt[gc * ldkt + gr] = hi;
+            Kt_lo[gc * ldkt + gr] = to_tf32(v - hi);
+          } else {
+            Kt[gc * ldkt + gr] = v;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward.  Two passes over the same tiles so that neither needs float atomics on N-sized data:
+//   pass X: one block per row tile walks every column tile      -> dFx rows (plain stores)
+//   pass Z: one block per (column tile, row slab) walks its rows -> dFz, dhyp (double atomics,
+//           one flush per block)
+// ------------------------------------------------------------------------------------------
+template <bool PASS_X>
+__global__ void __launch_bounds__(THREADS) kernel_bwd_kernel(
+    const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz, int64_t M,
+    Spec sp, const float* __restrict__ hyp, const float* __restrict__ G, int64_t ldg, float* __restrict__ dFx,
+    double* __restrict__ dFz, double* __restrict__ dhyp) {
+  extern __shared__ float smem[];
+  const int d = sp.da + sp.db, dp = d | 1;
+  float* xs = smem;
+  float* zs = xs + TILE * dp;
+  float* c1a = zs + TILE * dp;                  // [TILE][TILE+1] coefficient on the other side's features (block A)
+  float* c1b = c1a + TILE * (TILE + 1);         // same, block B
+  float* nxa = c1b + TILE * (TILE + 1);
+  float* nxb = nxa + TILE;
+  float* nza = nxb + TILE;
+  float* nzb = nza + TILE;
+  float* own = nzb + TILE;                      // [TILE][4]: scalar coefficients on own features {c2 A, c2 B, e A, e B}
+  float* hred = own + TILE * 4;                 // [4] hyper partials (float atomics in smem)
+  const Hyp h = load_hyp(hyp);
+  const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;
+  const int64_t ntr = (N + TILE - 1) / TILE, ntc = (M + TILE - 1) / TILE;
+
+  // outer = the tile whose gradient this block owns, inner = the tiles it walks
+  const int64_t n_outer = PASS_X ? ntr : ntc;
+  const int64_t n_inner = PASS_X ? ntc : ntr;
+  for (int64_t ot = blockIdx.x; ot < n_outer; ot += gridDim.x) {
+    // accumulators for (own row/col = threadIdx%TILE, features fg, fg+4, ...)
+    float acc[MAXD / 4];
+#pragma unroll
+    for (int q = 0; q < MAXD / 4; ++q) acc[q] = 0.f;
+    float own_acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float hy[4] = {0.f, 0.f, 0.f, 0.f};
+    if (threadIdx.x < 4) hred[threadIdx.x] = 0.f;
+    if (PASS_X) load_features(Fx, ldx, ot * TILE, N, d, dp, sp, xs, nxa, nxb);
+    else        load_features(Fz, ldz, ot * TILE, M, d, dp, sp, zs, nza, nzb);
+
+    for (int64_t it = (PASS_X ? 0 : blockIdx.y); it < n_inner; it += (PASS_X ? 1 : gridDim.y)) {
+      const int64_t row0 = (PASS_X ? ot : it) * TILE, col0 = (PASS_X ? it : ot) * TILE;
+      if (PASS_X) load_features(Fz, ldz, col0, M, d, dp, sp, zs, nza, nzb);
+      else        load_features(Fx, ldx, row0, N, d, dp, sp, xs, nxa, nxb);
+      for (int idx = threadIdx.x; idx < TILE * 4; idx += THREADS) own[idx] = 0.f;
+      __syncthreads();
+      // phase 1: coefficients for the 64x64 tile (thread: fixed column c, rows rg + 4j)
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;   // PASS_Z: sums over rows for column c
+      for (int j = 0; j < TILE / 4; ++j) {
+        int r = rg + 4 * j;
+        int64_t gr = row0 + r, gc = col0 + c;
+        float g = (gr < N && gc < M) ? G[gr * ldg + gc] : 0.f;
+        const float* xa = xs + r * dp;
+        const float* za = zs + c * dp;
+        float ka = factor_value(sp.ta, xa, za, sp.da, h.amp_a, h.len_a, nxa[r], nza[c]);
+        float kb = factor_value(sp.tb, xa + sp.da, za + sp.da, sp.db, h.amp_b, h.len_b, nxb[r], nzb[c]);
+        FactorAdj A = factor_adjoint(sp.ta, xa, za, sp.da, h.amp_a, h.len_a, nxa[r], nza[c], ka, g * kb);
+        FactorAdj B = factor_adjoint(sp.tb, xa + sp.da, za + sp.da, sp.db, h.amp_b, h.len_b, nxb[r], nzb[c], kb, g * ka);
+        c1a[r * (TILE + 1) + c] = A.c1;
+        c1b[r * (TILE + 1) + c] = B.c1;
+        if (PASS_X) {
+          // sums over columns for row r: reduce across the 32 lanes of this warp (same row)
+          float s0 = warp_sum(A.c2x), s1 = warp_sum(B.c2x), s2 = warp_sum(-A.e), s3 = warp_sum(-B.e);
+          if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&own[r * 4 + 0], s0); atomicAdd(&own[r * 4 + 1], s1);
+            atomicAdd(&own[r * 4 + 2], s2); atomicAdd(&own[r * 4 + 3], s3);
+          }
+        } else {
+          o0 += A.c2z; o1 += B.c2z; o2 += A.e; o3 += B.e;
+          hy[0] += A.damp; hy[1] += A.dlen; hy[2] += B.damp; hy[3] += B.dlen;
+        }
+      }
+      if (!PASS_X) {
+        atomicAdd(&own[c * 4 + 0], o0); atomicAdd(&own[c * 4 + 1], o1);
+        atomicAdd(&own[c * 4 + 2], o2); atomicAdd(&own[c * 4 + 3], o3);
+      }
+      __syncthreads();
+      // phase 2: own-side gradient. thread: own index o = threadIdx%TILE, features fg + 4q
+      {
+        const int o = threadIdx.x % TILE, fg = threadIdx.x / TILE;
+#pragma unroll
+        for (int q = 0; q < MAXD / 4; ++q) {
+          const int f = fg + 4 * q;
+          if (f < d) {
+            const float* cmat = (f < sp.da) ? c1a : c1b;
+            float s = 0.f;
+            if (PASS_X) {
+              for (int k = 0; k < TILE; ++k) s = fmaf(cmat[o * (TILE + 1) + k], zs[k * dp + f], s);
+            } else {
+              for (int k = 0; k < TILE; ++k) s = fmaf(cmat[k * (TILE + 1) + o], xs[k * dp + f], s);
+            }
+            acc[q] += s;
+          }
+        }
+        if (fg == 0) {
+          own_acc[0] += own[o * 4 + 0]; own_acc[1] += own[o * 4 + 1];
+          own_acc[2] += own[o * 4 + 2]; own_acc[3] += own[o * 4 + 3];
+        }
+      }
+      __syncthreads();
+    }
+    // flush
+    {
+      const int o = threadIdx.x % TILE, fg = threadIdx.x / TILE;
+      const int64_t go = ot * TILE + o;
+      const float* self = (PASS_X ? xs : zs) + o * dp;
+      // broadcast the per-own-index scalars from the fg == 0 thread through shared memory
+      if (fg == 0) { own[o * 4 + 0] = own_acc[0]; own[o * 4 + 1] = own_acc[1]; own[o * 4 + 2] = own_acc[2]; own[o * 4 + 3] = own_acc[3]; }
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < MAXD / 4; ++q) {
+        const int f = fg + 4 * q;
+        if (f >= d) continue;
+        bool inA = f < sp.da;
+        float v = acc[q] + own[o * 4 + (inA ? 0 : 1)] * self[f];
+        // EXPSIN contributes only through its single feature (the first of its block)
+        if (inA && f == 0 && sp.ta == SVGP_K_EXPSIN) v += own[o * 4 + 2];
+        if (!inA && f == sp.da && sp.tb == SVGP_K_EXPSIN) v += own[o * 4 + 3];
+        if (PASS_X) {
+          if (go < N) dFx[go * d + f] = v;
+        } else {
+          if (go < M) atomicAdd(&dFz[go * d + f], (double)v);
+        }
+      }
+      if (!PASS_X) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float s = warp_sum(hy[k]);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&hred[k], s);
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) atomicAdd(&dhyp[threadIdx.x], (double)hred[threadIdx.x]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise apply (diag_only=True)
+// ------------------------------------------------------------------------------------------
+__global__ void kernel_diag_fwd_kernel(const float* __restrict__ Fx, int64_t ldx, const float* __restrict__ Fy,
+                                       int64_t ldy, int64_t N, Spec sp, const float* __restrict__ hyp,
+                                       float* __restrict__ kd) {
+  const Hyp h = load_hyp(hyp);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[MAXD], y[MAXD];
+    const int d = sp.da + sp.db;
+    for (int f = 0; f < d; ++f) { x[f] = Fx[i * ldx + f]; y[f] = Fy[i * ldy + f]; }
+    float nxa = 1.f, nya = 1.f, nxb = 1.f, nyb = 1.f;
+    if (sp.ta == SVGP_K_COSINE) { nxa = block_norm(x, sp.da); nya = block_norm(y, sp.da); }
+    if (sp.tb == SVGP_K_COSINE) { nxb = block_norm(x + sp.da, sp.db); nyb = block_norm(y + sp.da, sp.db); }
+    float ka = factor_value(sp.ta, x, y, sp.da, h.amp_a, h.len_a, nxa, nya);
+    float kb = factor_value(sp.tb, x + sp.da, y + sp.da, sp.db, h.amp_b, h.len_b, nxb, nyb);
+    kd[i] = ka * kb;
+  }
+}
+
+__global__ void kernel_diag_bwd_kernel(const float* __restrict__ Fx, int64_t ldx, const float* __restrict__ Fy,
+                                       int64_t ldy, int64_t N, Spec sp, const float* __restrict__ hyp,
+                                       const float* __restrict__ g, float* __restrict__ dFx, float* __restrict__ dFy,
+                                       double* __restrict__ dhyp) {
+  const Hyp h = load_hyp(hyp);
+  float hy[4] = {0.f, 0.f, 0.f, 0.f};
+  const int d = sp.da + sp.db;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+    float x[MAXD], y[MAXD];
+    for (int f = 0; f < d; ++f) { x[f] = Fx[i * ldx + f]; y[f] = Fy[i * ldy + f]; }
+    float nxa = 1.f, nya = 1.f, nxb = 1.f, nyb = 1.f;
+    if (sp.ta == SVGP_K_COSINE) { nxa = block_norm(x, sp.da); nya = block_norm(y, sp.da); }
+    if (sp.tb == SVGP_K_COSINE) { nxb = block_norm(x + sp.da, sp.db); nyb = block_norm(y + sp.da, sp.db); }
+    float ka = factor_value(sp.ta, x, y, sp.da, h.amp_a, h.len_a, nxa, nya);
+    float kb = factor_value(sp.tb, x + sp.da, y + sp.da, sp.db, h.amp_b, h.len_b, nxb, nyb);
+    float gi = g[i];
+    FactorAdj A = factor_adjoint(sp.ta, x, y, sp.da, h.amp_a, h.len_a, nxa, nya, ka, gi * kb);
+    FactorAdj B = factor_adjoint(sp.tb, x + sp.da, y + sp.da, sp.db, h.amp_b, h.len_b, nxb, nyb, kb, gi * ka);
+    for (int f = 0; f < d; ++f) {
+      const FactorAdj& T = (f < sp.da) ? A : B;
+      int type = (f < sp.da) ? sp.ta : sp.tb;
+      bool first = (f == 0) || (f == sp.da);
+      float ex = (type == SVGP_K_EXPSIN && first) ? T.e : 0.f;
+      dFx[i * d + f] = T.c1 * y[f] + T.c2x * x[f] - ex;
+      dFy[i * d + f] = T.c1 * x[f] + T.c2z * y[f] + ex;
+    }
+    hy[0] += A.damp; hy[1] += A.dlen; hy[2] += B.damp; hy[3] += B.dlen;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float s = warp_sum(hy[k]);
+    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(&dhyp[k], (double)s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// gather / scatter-add
+// ------------------------------------------------------------------------------------------
+__global__ void gather_rows_kernel(const float* __restrict__ table, int64_t ldt, int64_t rows,
+                                   const int64_t* __restrict__ ids, int64_t N, int64_t d, float* __restrict__ out,
+                                   int64_t ldo) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < N * d; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t i = idx / d, f = idx - i * d;
+    int64_t r = ids[i];
+    out[i * ldo + f] = (r >= 0 && r < rows) ? table[r * ldt + f] : 0.f;
+  }
+}
+
+// Rows arrive grouped by id in practice (16 frames per MNIST digit, 72 action ids for 500 SPRITES rows), so each
+// warp first folds runs of equal ids inside its 32 consecutive rows (shuffle segmented sum) and only the run
+// heads issue a double atomic: the duplicate factor of the data becomes the atomic-traffic reduction factor.
+__global__ void scatter_add_rows_kernel(const float* __restrict__ g, int64_t ldg, const int64_t* __restrict__ ids,
+                                        int64_t N, int64_t d, int64_t rows, double* __restrict__ dtable, int64_t ldt) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = warp * 32; base < N; base += nwarps * 32) {
+    int64_t i = base + lane;
+    int64_t id = (i < N) ? ids[i] : -1;
+    int64_t prev = __shfl_up_sync(0xffffffffu, id, 1);
+    bool head = (lane == 0) || (prev != id);
+    unsigned heads = __ballot_sync(0xffffffffu, head);
+    // length of the run starting at this lane
+    unsigned after = heads & ~((2u << lane) - 1u);     // heads strictly above this lane
+    int next = after ? (__ffs(after) - 1) : 32;
+    for (int64_t f = 0; f < d; ++f) {
+      float v = (i < N) ? g[i * ldg + f] : 0.f;
+      // segmented inclusive suffix-sum within runs: fold from the right
+      float s = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        float t = __shfl_down_sync(0xffffffffu, s, o);
+        if (lane + o < next) s += t;
+      }
+      if (head && id >= 0 && id < rows) atomicAdd(&dtable[id * ldt + f], (double)s);
+    }
+  }
+}
+
+static size_t fwd_smem(int d) {
+  int dp = d | 1;
+  return sizeof(float) * (2 * TILE * dp + TILE * (TILE + 1) + 4 * TILE);
+}
+static size_t bwd_smem(int d) {
+  int dp = d | 1;
+  return sizeof(float) * (2 * TILE * dp + 2 * TILE * (TILE + 1) + 4 * TILE + 4 * TILE + 4);
+}
+
+static int check_spec(int ta, int da, int tb, int db) {
+  auto ok = [](int t, int d) {
+    if (t < 0 || t > 4 || d < 0) return false;
+    if (t == SVGP_K_NONE) return d == 0;
+    if (t == SVGP_K_EXPSIN) return d == 1;
+    return d >= 1;
+  };
+  return ok(ta, da) && ok(tb, db) && (da + db) >= 1 && (da + db) <= MAXD;
+}
+
+}  // namespace svgp
+
+using namespace svgp;
+
+extern "C" {
+
+int svgp_version(void) { return 100; }
+const char* svgp_last_error(void) { return svgp::last_error(); }
+int svgp_device_ok(void) {
+  int dev = 0;
+  cudaDeviceProp p;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&p, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return p.major == 10 ? 1 : 0;
+}
+
+int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a,
+                    int dim_a, int type_b, int dim_b, const float* hyp, float* K, float* K_lo, int64_t ldk,
+                    float* Kt, float* Kt_lo, int64_t ldkt, void* stream) {
+  SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
+  SVGP_REQUIRE(Fx && Fz && hyp && N >= 0 && M >= 0, "null input");
+  SVGP_REQUIRE((K || Kt), "no output requested");
+  SVGP_REQUIRE(!(K_lo && !K) && !(Kt_lo && !Kt), "lo plane without hi plane");
+  if (N == 0 || M == 0) return SVGP_OK;
+  Spec sp{type_a, dim_a, type_b, dim_b};
+  int64_t ntc = ceil_div(M, TILE), ntr = ceil_div(N, TILE);
+  // grid.y strides over row tiles; keep >= ~8 CTAs per SM in flight without exceeding the 65535 limit
+  int64_t gy = ntr;
+  int64_t cap = (148 * 16 + ntc - 1) / ntc;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  dim3 grid((unsigned)ntc, (unsigned)gy);
+  kernel_fwd_kernel<<<grid, THREADS, fwd_smem(dim_a + dim_b), (cudaStream_t)stream>>>(
+      Fx, ldx, N, Fz, ldz, M, sp, hyp, K, K_lo, ldk, Kt, Kt_lo, ldkt);
+  return check_launch("svgp_kernel_fwd");
+}
+
+int svgp_kernel_bwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a,
+                    int dim_a, int type_b, int dim_b, const float* hyp, const float* G, int64_t ldg, float* dFx,
+                    double* dFz, double* dhyp, void* stream) {
+  SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
+  SVGP_REQUIRE(Fx && Fz && hyp && G && N >= 0 && M >= 0, "null input");
+  if (N == 0 || M == 0) return SVGP_OK;
+  Spec sp{type_a, dim_a, type_b, dim_b};
+  size_t sm = bwd_smem(dim_a + dim_b);
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t ntc = ceil_div(M, TILE), ntr = ceil_div(N, TILE);
+  if (dFx) {
+    int64_t gx = ntr < 148 * 8 ? ntr : 148 * 8;
+    kernel_bwd_kernel<true><<<(unsigned)gx, THREADS, sm, st>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, G, ldg, dFx, nullptr, nullptr);
+    int rc = check_launch("svgp_kernel_bwd(x)");
+    if (rc) return rc;
+  }
+  if (dFz) {
+    SVGP_REQUIRE(dhyp != nullptr, "dhyp required with dFz");
+    int64_t gy = (148 * 8 + ntc - 1) / ntc;
+    if (gy > ntr) gy = ntr;
+    if (gy < 1) gy = 1;
+    dim3 grid((unsigned)(ntc < 65535 ? ntc : 65535), (unsigned)gy);
+    kernel_bwd_kernel<false><<<grid, THREADS, sm, st>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, G, ldg, nullptr, dFz, dhyp);
+    int rc = check_launch("svgp_kernel_bwd(z)");
+    if (rc) return rc;
+  }
+  return SVGP_OK;
+}
+
+int svgp_kernel_diag_fwd(const float* Fx, int64_t ldx, const float* Fy, int64_t ldy, int64_t N, int type_a, int dim_a,
+                         int type_b, int dim_b, const float* hyp, float* kd, void* stream) {
+  SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
+  SVGP_REQUIRE(Fx && Fy && hyp && kd && N >= 0, "null input");
+  if (N == 0) return SVGP_OK;
+  Spec sp{type_a, dim_a, type_b, dim_b};
+  int64_t blocks = ceil_div(N, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  kernel_diag_fwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Fx, ldx, Fy, ldy, N, sp, hyp, kd);
+  return check_launch("svgp_kernel_diag_fwd");
+}
+
+int svgp_kernel_diag_bwd(const float* Fx, int64_t ldx, const float* Fy, int64_t ldy, int64_t N, int type_a, int dim_a,
+                         int type_b, int dim_b, const float* hyp, const float* g, float* dFx, float* dFy, double* dhyp,
+                         void* stream) {
+  SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
+  SVGP_REQUIRE(Fx && Fy && hyp && g && dFx && dFy && dhyp && N >= 0, "null input");
+  if (N == 0) return SVGP_OK;
+  Spec sp{type_a, dim_a, type_b, dim_b};
+  int64_t blocks = ceil_div(N, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  kernel_diag_bwd_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Fx, ldx, Fy, ldy, N, sp, hyp, g, dFx, dFy, dhyp);
+  return check_launch("svgp_kernel_diag_bwd");
+}
+
+int svgp_gather_rows(const float* table, int64_t ldt, int64_t rows, const int64_t* ids, int64_t N, int64_t d, float* out,
+                     int64_t ldo, void* stream) {
+  SVGP_REQUIRE(table && ids && out && N >= 0 && d >= 1 && rows >= 1, "bad argument");
+  if (N == 0) return SVGP_OK;
+  int64_t blocks = ceil_div(N * d, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  gather_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(table, ldt, rows, ids, N, d, out, ldo);
+  return check_launch("svgp_gather_rows");
+}
+
+int svgp_scatter_add_rows(const float* g, int64_t ldg, const int64_t* ids, int64_t N, int64_t d, int64_t rows,
+                          double* dtable, int64_t ldt, void* stream) {
+  SVGP_REQUIRE(g && ids && dtable && N >= 0 && d >= 1 && rows >= 1, "bad argument");
+  if (N == 0) return SVGP_OK;
+  int64_t blocks = ceil_div(N, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  scatter_add_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, ldg, ids, N, d, rows, dtable, ldt);
+  return check_launch("svgp_scatter_add_rows");
+}
+
+}  // extern "C"

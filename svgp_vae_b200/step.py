@@ -1,0 +1,239 @@
+"""The batched SVGP step: all L latent channels of one (sharded) mini-batch in one call.
+
+Replaces the per-channel Python loop of forward_pass_SVGPVAE (SVGPVAE_model.py:865-898) and the
+two methods it calls per channel (approximate_posterior_params :303-343, variational_loss
+:220-301, gauss_cross_entropy utils.py:483-504).  Same mathematics, reorganised:
+
+  pass A   K1 builds K_nm (TF32 planes when large), K_mm, kappa; row stats; the only reductions
+           over datapoints: A_l = sum_i p_il k_i k_i^T (K2, tcgen05 SYRK) and v_l = sum_i p_il y_il k_i
+           -> all-reduce over the N-shards -> replicated float64 M x M stage (K3)
+  pass B   per-row predictive moments p_m = K_nm w_l, p_v = kappa - h + |R_l^-1 k_i|^2 (K4)
+  [decoder / caller]
+  pass C   adjoints of p_m, p_v: weighted SYRK + skinny GEMM -> all-reduce -> adjoint of the
+           M x M stage (torch autograd over ops.bmm64 / spd_inverse_logdet / spd_logdet)
+  pass D   dK_nm = sum_l diag(w_l) K_nm G_l (one tcgen05 GEMM over 2L+1 stacked channels), the
+           row-dots k_i^T dA_l k_i, and K1's adjoint into features / inducing points / hypers.
+
+Every sum over datapoints inside L3 and the cross entropy is taken against A_l / v_l (e.g.
+sum_i p_il k_i^T W_l k_i = <W_l, A_l>), so the (b, m, m) tensor of :286-294 never exists and the
+catastrophic cancellation between sum L3 and ce_term happens in float64.
+"""
+import math
+
+import torch
+
+from . import ops
+from .backend import get_backend
+
+LOG_2PI = 1.8378770664093453      # utils.py:498
+LOG_2PI_RT = math.log(2.0 * math.pi)
+
+
+def _allreduce(t, group):
+    if group is not None:
+        torch.distributed.all_reduce(t, group=group)
+    return t
+
+
+def _world(group):
+    return 1 if group is None else torch.distributed.get_world_size(group)
+
+
+def mm_stage(A, V, sums, K, jitter, c, b_total):
+    """Replicated float64 M x M stage (SVGPVAE_model.py:318-319, 328-331, 339-341, 264-279).
+
+    A (L,M,M), V (L,M), sums (3,L) = [sum p kappa, sum p y^2, sum log noise], K (M,M).
+    Differentiable w.r.t. all four.  The jitter placement is the reference's: Sigma is built from the
+    un-jittered K and jittered before inversion; mu_hat / A_hat use the un-jittered K; Kinv is the
+    inverse of K + jI.
+    """
+    L, M, _ = A.shape
+    eye = torch.eye(M, dtype=A.dtype, device=A.device)
+    Kb = K.unsqueeze(0)
+    Kinv_b, ldK, _ = ops.spd_inverse_logdet(Kb + jitter * eye)
+    Sigma = Kb + c * A + jitter * eye
+    S, _, Linv = ops.spd_inverse_logdet(Sigma)
+    w = c * ops.bmv64(S, V)                                   # p_m = K_nm w
+    mu_hat = ops.bmm64(w.unsqueeze(0), Kb).squeeze(0)         # K w   (K symmetric)
+    a = ops.bmm64(mu_hat.unsqueeze(0), Kinv_b).squeeze(0)     # Kinv mu_hat
+    KS = ops.bmm64(Kb, S)
+    A_hat = ops.bmm64(KS, Kb)
+    ld_Ahat = ops.spd_logdet(A_hat + jitter * eye)
+    tr_KinvAhat = (Kinv_b * A_hat).sum((-1, -2))
+    kl = 0.5 * (ldK - ld_Ahat - M + tr_KinvAhat + (mu_hat * a).sum(-1))
+    Wm = ops.bmm64(ops.bmm64(Kinv_b, A_hat), Kinv_b)          # Kinv A_hat Kinv
+    s_pk, s_pyy, s_log = sums[0], sums[1], sums[2]
+    s_ph = (Kinv_b * A).sum((-1, -2))
+    s_t = (Wm * A).sum((-1, -2))
+    Aa = ops.bmv64(A, a)
+    recon = -0.5 * (s_pk - s_ph + s_t + s_log + b_total * LOG_2PI_RT + s_pyy - 2.0 * (a * V).sum(-1)
+                    + (a * Aa).sum(-1))
+    Aw = ops.bmv64(A, w)
+    s_ppv = s_pk - s_ph + (S * A).sum((-1, -2))
+    ce = -0.5 * (b_total * LOG_2PI + s_log + s_ppv + (w * Aw).sum(-1) - 2.0 * (w * V).sum(-1) + s_pyy)
+    return dict(S=S, w=w, Kinv=Kinv_b, Linv=Linv, recon=recon, kl=kl, ce=ce, mu_hat=mu_hat, A_hat=A_hat)
+
+
+class _SVGPStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, Fx, Fz, hyp, y, noise, cfg):
+        be = get_backend()
+        spec, jitter, N_train = cfg["spec"], cfg["jitter"], cfg["N_train"]
+        group, clip = cfg.get("group"), cfg.get("clip_pv")
+        Fx32, Fz32, hyp32 = Fx.float().contiguous(), Fz.float().contiguous(), hyp.float().contiguous()
+        y32, n32 = y.float().contiguous(), noise.float().contiguous()
+        N, L = y32.shape
+        M = Fz32.shape[0]
+        tc = cfg.get("tc")
+        if tc is None:
+            tc = be.want_tc(N, M)
+
+        # pass A
+        kop = be.kernel_fwd(spec, Fx32, Fz32, hyp32, tc=tc)
+        Kmm = be.kernel_fwd(spec, Fz32, Fz32, hyp32, tc=False).K
+        kappa = be.kernel_diag_fwd(spec, Fx32, Fx32, hyp32)
+        p, py, sums = be.rowstats(y32, n32, kappa)
+        A = be.syrk(kop, p, chunk_rows=cfg.get("chunk_rows", 0))
+        V = be.gemm_tn(kop, py)
+        count = torch.tensor([float(N)], dtype=torch.float64, device=y32.device)
+        for t in (A, V, sums, count):
+            _allreduce(t, group)
+        b_total = float(count.item()) if group is not None else float(N)
+        c = N_train / b_total
+
+        with torch.enable_grad():
+            leaves = [t.detach().requires_grad_(True) for t in (A, V, sums, Kmm.double())]
+            mm = mm_stage(leaves[0], leaves[1], leaves[2], leaves[3], jitter, c, b_total)
+
+        # pass B
+        S, w, Kinv, Linv = mm["S"].detach(), mm["w"].detach(), mm["Kinv"].detach(), mm["Linv"]
+        h = be.rowquad(kop, Kinv).squeeze(1)
+        q1 = be.rowquad(kop, Linv, tri=True) if cfg.get("tri", True) else be.rowquad(kop, S)
+        pm = be.gemm_nn(kop, w.float().contiguous())
+        pv, clipsum, mask = be.predictive(kappa, h, q1, p, clip)
+        ce = mm["ce"].detach().clone()
+        if clip:
+            _allreduce(clipsum, group)
+            ce = ce - 0.5 * clipsum
+
+        ctx.cfg, ctx.kop, ctx.mm, ctx.leaves = cfg, kop, mm, leaves
+        ctx.b_total, ctx.c = b_total, c
+        ctx.save_for_backward(Fx32, Fz32, hyp32, y32, n32, p, kappa, h, pv, q1 if clip else pv, mask if clip else pv, S, w, Kinv)
+        ctx.in_dtypes = (Fx.dtype, Fz.dtype, hyp.dtype, y.dtype, noise.dtype)
+        out_dt = y.dtype
+        mu_hat, A_hat = mm["mu_hat"].detach(), mm["A_hat"].detach()
+        ctx.mark_non_differentiable(mu_hat, A_hat)
+        return pm.to(out_dt), pv.to(out_dt), mm["recon"].detach().clone(), mm["kl"].detach().clone(), ce, mu_hat, A_hat
+
+    @staticmethod
+    def backward(ctx, g_pm, g_pv, g_recon, g_kl, g_ce, _g_mu, _g_Ahat):
+        be = get_backend()
+        cfg, kop, mm = ctx.cfg, ctx.kop, ctx.mm
+        spec, group, clip = cfg["spec"], cfg.get("group"), cfg.get("clip_pv")
+        Fx, Fz, hyp, y, noise, p, kappa, h, pv, q1raw, mask, S, w, Kinv = ctx.saved_tensors
+        N, L = y.shape
+        M = Fz.shape[0]
+        dev = y.device
+        zeros_L = torch.zeros(L, dtype=torch.float64, device=dev)
+        g_recon = zeros_L if g_recon is None else g_recon.double()
+        g_kl = zeros_L if g_kl is None else g_kl.double()
+        g_ce = zeros_L if g_ce is None else g_ce.double()
+        g_pm = torch.zeros_like(y) if g_pm is None else g_pm.float().contiguous()
+        g_pv = torch.zeros_like(y) if g_pv is None else g_pv.float()
+        # scalar adjoints are per-rank shares of the same global scalars: total = sum over ranks
+        sc = torch.stack([g_recon, g_kl, g_ce])
+        _allreduce(sc, group)
+        g_recon, g_kl, g_ce = sc[0], sc[1], sc[2]
+
+        # ---- pass C: row-local adjoints of the predictive moments --------------------------------
+        gce32 = g_ce.float()
+        if clip:
+            m = mask.bool()
+            pv_raw = kappa[:, None] - h[:, None] + q1raw
+            # d/d pv_raw: unclipped rows pass g_pv; clipped rows only see the clip correction of the collapsed CE sum
+            G_q1 = torch.where(m, 0.5 * gce32[None, :] * p, g_pv)
+            G_p_clip = -0.5 * gce32[None, :] * (pv - pv_raw)
+        else:
+            G_q1 = g_pv
+            G_p_clip = None
+        G_q1 = G_q1.contiguous()
+        G_kappa = G_q1.sum(1)                                    # d/d kappa_i  (and -d/d h_i)
+        G_S = be.syrk(kop, G_q1, chunk_rows=cfg.get("chunk_rows", 0))
+        G_w = be.gemm_tn(kop, g_pm)
+        G_Kinv = be.syrk(kop, (-G_kappa)[:, None].contiguous())
+        for t in (G_S, G_w, G_Kinv):
+            _allreduce(t, group)
+
+        # ---- adjoint of the replicated M x M stage -----------------------------------------------
+        A_, V_, sums_, K_ = ctx.leaves
+        gA, gV, gsums, gK = torch.autograd.grad(
+            [mm["S"], mm["w"], mm["Kinv"], mm["recon"], mm["kl"], mm["ce"]], [A_, V_, sums_, K_],
+            grad_outputs=[G_S, G_w, G_Kinv, g_recon, g_kl, g_ce], allow_unused=True)
+        gsums = torch.zeros_like(sums_) if gsums is None else gsums
+
+        # ---- pass D: back to the rows ------------------------------------------------------------
+        # dK_nm: one stacked GEMM over [p | 2 dq1 | 2 dh] x [dA + dA^T ; S ; Kinv]
+        Wstack = torch.cat([p, 2.0 * G_q1, (-2.0 * G_kappa)[:, None]], dim=1).contiguous()
+        Gstack = torch.cat([gA + gA.transpose(-1, -2), S, Kinv], dim=0).contiguous()
+        G_K = be.scaled_gemm(kop, Wstack, Gstack)
+        del Wstack, Gstack
+        py = p * y
+        be.gemm_f32(py.contiguous(), gV.float().contiguous(), out=G_K)          # via v_l
+        be.gemm_f32(g_pm, w.float().contiguous(), out=G_K)                       # via p_m
+        # dp, dy, dnoise
+        G_p = be.rowquad(kop, ops._sym(gA).contiguous())                         # k^T dA k
+        G_py = be.gemm_nn(kop, gV.float().contiguous())
+        gs = gsums.float()
+        G_p = G_p + y * G_py + kappa[:, None] * gs[0][None, :] + (y * y) * gs[1][None, :]
+        if G_p_clip is not None:
+            G_p = G_p + G_p_clip
+        G_y = p * G_py + 2.0 * py * gs[1][None, :]
+        nz = noise != 0
+        safe = torch.where(nz, noise, torch.ones_like(noise))
+        G_noise = torch.where(nz, -p * p * G_p, torch.zeros_like(p)) + gs[2][None, :] / safe
+        G_kappa = G_kappa + (p * gs[0][None, :]).sum(1)
+
+        # ---- K1 adjoint ----------------------------------------------------------------------------
+        need_x = ctx.needs_input_grad[0]
+        Gk = G_K if G_K.shape[1] == M else G_K[:, :M].contiguous()
+        dFx, dFz, dhyp = be.kernel_bwd(spec, Fx, Fz, hyp, Gk, need_x=need_x, need_z=True)
+        dkx, dky, dhyp_d = be.kernel_diag_bwd(spec, Fx, Fx, hyp, G_kappa.contiguous())
+        dhyp = dhyp + dhyp_d
+        if need_x:
+            dFx = dFx + dkx + dky
+        # replicated K_mm: every rank holds the full adjoint -> give each rank a 1/world share so that the
+        # caller's sum over ranks (parameters are replicated) counts it once
+        share = 1.0 / _world(group)
+        gKf = (share * gK).float().contiguous()
+        dZa, dZb, dhyp_m = be.kernel_bwd(spec, Fz, Fz, hyp, gKf, need_x=True, need_z=True)
+        dFz = dFz + dZa.double() + dZb
+        dhyp = dhyp + dhyp_m
+        ctx.mm = ctx.leaves = None
+        dx, dz, dh, dy, dn = ctx.in_dtypes
+        return (dFx.to(dx) if need_x else None, dFz.to(dz), dhyp.to(dh), G_y.to(dy), G_noise.to(dn), None)
+
+
+def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, group=None, tc=None, tri=True,
+              chunk_rows=0):
+    """All-channel SVGP step on one shard of datapoints.
+
+    Fx (N, d) data features, Fz (M, d) inducing features, hyp (4,) kernel hypers, y / noise (N, L)
+    encoder means / variances.  ``group``: torch.distributed group over which the datapoints are
+    sharded (None = single process); A_l, v_l and the scalar sums are all-reduced over it.
+
+    Returns dict(p_m, p_v (N, L); recon_l, kl_l, ce_l (L,) float64 -- GLOBAL sums, identical on all
+    ranks; mu_hat (L, M), A_hat (L, M, M) float64, detached).
+    Gradient convention when sharded: make each rank's loss ``local terms + global terms / world``;
+    gradients of replicated parameters then come out as per-rank partial sums (sum them).
+    """
+    cfg = dict(spec=spec, N_train=float(N_train), jitter=float(jitter), clip_pv=clip_pv, group=group, tc=tc, tri=tri,
+               chunk_rows=chunk_rows)
+    pm, pv, recon, kl, ce, mu_hat, A_hat = _SVGPStep.apply(Fx, Fz, hyp, y, noise, cfg)
+    return dict(p_m=pm, p_v=pv, recon_l=recon, kl_l=kl, ce_l=ce, mu_hat=mu_hat, A_hat=A_hat)
+
+
+def elbo_terms(res, b, N_train):
+    """SVGPVAE_model.py:880-898 on the per-channel sums: inside_elbo, ce_term, KL_term (Hensman branch)."""
+    recon, kl, ce = res["recon_l"].sum(), res["kl_l"].sum(), res["ce_l"].sum()
+    inside = recon - (b / N_train) * kl
+    return dict(inside_elbo_recon=recon, inside_elbo_kl=kl, inside_elbo=inside, ce_term=ce, KL_term=-ce + inside)
