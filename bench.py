@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""Benchmark of the SVGP ELBO + gradient step (BASELINE.json metric) on N GPUs of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+    python bench.py --impl reference [--steps K] [--warmup W]      # CPU restatement of the reference path
+
+One step = forward (p_m, p_v, inside_elbo_recon/kl, ce_term) + backward of
+J = KL_term + <g_m, p_m> + <g_v, p_v> to y, noise, inducing points and kernel hypers, on the SWEEP
+workload of SURVEY 8(d): N = 1e6 datapoints per GPU (weak scaling), M = 1024, L = 64, product-SE kernel
+d = 4 + 4, jitter 1e-2.  Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e`
+includes the pinned-host -> device copy of (aux, y, noise) and the device -> host read of p_m, p_v, dy,
+dnoise and the scalars every step.  roofline: tensor-core bound, F_alg = 9 L M^2 per datapoint, e = 3
+TF32 MMAs per algorithmic MAC (3xTF32); peak = TF32 cuBLAS GEMM measured in this run.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU, M_IND, L_CH = 1_000_000, 1024, 64
+METRIC = "SVGP ELBO+grad datapoints/s at M=1024,L=64"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="datapoints per GPU (default: the named workload)")
+    ap.add_argument("--m", type=int, default=M_IND)
+    ap.add_argument("--l", type=int, default=L_CH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=1024)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.samples, self.stop = index, [], threading.Event()
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append(f)
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop.wait(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU restatement (the "reference arm" and the cpu_baseline leg): oracle/ is only touched here
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(n_sample, M, L, threads=None):
+    """fwd + bwd of the streamlined float64 restatement on `n_sample` rows; returns (t_rows, t_mm) seconds:
+    the part proportional to the number of rows and the row-independent M x M part."""
+    from oracle import svgp_streamlined as st
+    from oracle import tfp_kernels as tfk
+    from svgp_vae_b200 import configs
+    cfg = configs.sweep_inputs(n_sample, M, L, device="cpu", N_train=n_sample)
+    X, y, nz = cfg["aux"].double(), cfg["y"].double().requires_grad_(True), cfg["noise"].double().requires_grad_(True)
+    Z = torch.as_tensor(cfg["ctor"]["initial_inducing_points"]).double().requires_grad_(True)
+    one = torch.ones((), dtype=torch.float64)
+    kern = lambda a, b: tfk.ExponentiatedQuadratic(one, one).matrix(a[:, :4], b[:, :4]) * tfk.ExponentiatedQuadratic(one, one).matrix(a[:, 4:], b[:, 4:])
+    g = torch.Generator().manual_seed(0)
+    gm, gv = torch.randn(n_sample, L, generator=g, dtype=torch.float64), torch.randn(n_sample, L, generator=g, dtype=torch.float64)
+
+    def full(rows):
+        t0 = time.perf_counter()
+        K_nm, K_mm = kern(X[:rows], Z), kern(Z, Z)
+        kappa = torch.ones(rows, dtype=torch.float64)
+        t = st.streamlined_terms(K_nm, K_mm, kappa, y[:rows], nz[:rows], float(rows), 1e-2)
+        gl = st.glue_from_terms(t, float(rows), float(rows))
+        J = gl["KL_term"] + (gm[:rows] * t["p_m"]).sum() + (gv[:rows] * t["p_v"]).sum()
+        torch.autograd.grad(J, [y, nz, Z])
+        return time.perf_counter() - t0
+
+    t_full = full(n_sample)
+    t_half = full(n_sample // 2)
+    t_rows = max(2.0 * (t_full - t_half), 1e-9)          # seconds for n_sample rows, row-proportional part
+    t_mm = max(t_full - t_rows, 0.0)
+    return t_rows, t_mm, t_full
+
+
+def cpu_baseline(args, n_total):
+    threads = torch.get_num_threads()     # (torch.set_num_threads breaks MKL's batched LU in this image: leave the default)
+    t_rows, t_mm, t_full = cpu_reference_step(args.cpu_sample, args.m, args.l)
+    t_total = t_rows * (n_total / args.cpu_sample) + t_mm
+    return {"value": n_total / t_total, "unit": "datapoints/s", "cores": threads, "kind": "port",
+            "sample": "streamlined float64 restatement (oracle/svgp_streamlined.py, torch-CPU/MKL; TensorFlow 1.15 is not installable) "
+                      "fwd+bwd on %d and %d rows of the same workload (M=%d, L=%d): row-proportional part %.2f s per %d rows, "
+                      "M x M part %.2f s; extrapolated linearly in rows to N=%d" % (args.cpu_sample, args.cpu_sample // 2, args.m, args.l,
+                                                                                   t_rows, args.cpu_sample, t_mm, n_total),
+            "seconds_measured": t_full}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = torch.get_num_threads()
+    n_total = args.n * args.gpus
+    vals = []
+    for i in range(args.warmup + args.steps):
+        t_rows, t_mm, t_full = cpu_reference_step(args.cpu_sample, args.m, args.l)
+        if i >= args.warmup:
+            vals.append((t_rows, t_mm, t_full))
+        if i == 0 and t_full * (args.warmup + args.steps) > 240:      # keep the whole run within minutes
+            vals.append((t_rows, t_mm, t_full))
+            break
+    t_rows = sorted(v[0] for v in vals)[len(vals) // 2]
+    t_mm = sorted(v[1] for v in vals)[len(vals) // 2]
+    t_total = t_rows * (n_total / args.cpu_sample) + t_mm
+    value = n_total / t_total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "datapoints/s", "n_gpus": args.gpus, "steps": len(vals),
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "SWEEP N=%d x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2" % (args.n, args.gpus, args.m, args.l)},
+            "cpu_baseline": {"value": value, "unit": "datapoints/s", "cores": threads, "kind": "port",
+                             "sample": "each step = fwd+bwd of the streamlined float64 restatement on %d (+%d) rows, extrapolated linearly in rows "
+                                       "to N=%d; TensorFlow 1.15 / TFP 0.8 cannot be installed here" % (args.cpu_sample, args.cpu_sample // 2, n_total)},
+            "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+def measure_tf32_peak(dev):
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    n = 8192
+    a = torch.randn(n, n, device=dev)
+    b = torch.randn(n, n, device=dev)
+    for _ in range(3):
+        a @ b
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(5):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        a @ b
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    torch.backends.cuda.matmul.allow_tf32 = old
+    del a, b
+    return best
+
+
+def run_gpu(args):
+    import torch.distributed as dist
+    import svgp_vae_b200 as pkg
+    from svgp_vae_b200 import backend, configs
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    be = backend.get_backend()
+    N, M, L = args.n, args.m, args.l
+    n_total = N * world
+
+    cfg = configs.sweep_inputs(N, M, L, device=dev, rank=rank, N_train=n_total)
+    svgp = pkg.productSVGP(**cfg["ctor"]).to(dev)
+    aux, y, noise = cfg["aux"], cfg["y"], cfg["noise"]
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    gm = torch.randn(N, L, generator=g, device=dev)
+    gv = torch.randn(N, L, generator=g, device=dev)
+    params = [p for p in svgp.parameters()]
+
+    def step(aux_d, y_d, nz_d):
+        y_d.requires_grad_(True); nz_d.requires_grad_(True)
+        for p in params:
+            p.grad = None
+        res = svgp.elbo_step(aux_d, y_d, nz_d, group=group)
+        # per-rank loss = local decoder stand-in + this rank's share of the replicated global scalar
+        J = (gm * res["p_m"]).sum().double() + (gv * res["p_v"]).sum().double() + res["KL_term"] / world
+        J.backward()
+        if group is not None:                                    # replicated parameters: sum the per-rank partial gradients
+            flat = torch.cat([p.grad.reshape(-1).double() for p in params])
+            dist.all_reduce(flat, group=group)
+        return res, y_d.grad, nz_d.grad
+
+    def timed(fn, steps):
+        if group is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if group is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if group is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    dev_step = lambda: step(aux, y.detach(), noise.detach())
+    for _ in range(args.warmup):
+        dev_step()
+    l0 = be.launches
+    with ClockSampler(local) as clocks:
+        ms = timed(dev_step, args.steps)
+    launches = (be.launches - l0) // max(args.steps, 1)
+
+    # per-kernel device times of one more step (CUDA events on the launch stream)
+    be.start_profile()
+    dev_step()
+    prof = be.stop_profile()
+
+    # e2e: pinned host buffers in, results out, every step
+    h_aux, h_y, h_nz = (t.detach().cpu().pin_memory() for t in (aux, y, noise))
+    h_out = [torch.empty((N, L), dtype=torch.float32).pin_memory() for _ in range(4)]
+
+    def e2e_step():
+        a = h_aux.to(dev, non_blocking=True); yy = h_y.to(dev, non_blocking=True); nn = h_nz.to(dev, non_blocking=True)
+        res, gy, gn = step(a, yy, nn)
+        for dst, src in zip(h_out, (res["p_m"], res["p_v"], gy, gn)):
+            dst.copy_(src.detach(), non_blocking=True)
+        float(res["KL_term"])                                     # scalar read-back (syncs)
+    e2e_step()
+    ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
+    h2d = sum(t.numel() * t.element_size() for t in (h_aux, h_y, h_nz))
+    d2h = sum(t.numel() * t.element_size() for t in h_out) + 8
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        tf32_peak = measure_tf32_peak(dev)
+        f_alg = 9.0 * L * M * M * N                     # per GPU per step
+        t_s = ms * 1e-3
+        # dominant kernel of the step
+        top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("", {"ms": float("nan"), "calls": 0})
+        kern_alg = {"svgp_scaled_gemm": 2.0 * N * M * M * (2 * L + 1), "svgp_syrk": 1.0 * N * M * M * L,
+                    "svgp_rowquad": None}
+        top_name, top_ms = top[0], top[1]["ms"] / max(top[1]["calls"], 1)
+        if top_name == "svgp_scaled_gemm":
+            top_flops = kern_alg["svgp_scaled_gemm"]
+        elif top_name == "svgp_syrk":
+            top_flops = kern_alg["svgp_syrk"]
+        else:
+            top_flops = float("nan")
+        achieved = 3.0 * top_flops / (top_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": n_total / t_s, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tcgen05, fp32 TMEM accumulate) + f64 MxM stage", "data": "synthetic",
+            "config": {"workload": "SWEEP N=%d per GPU x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3])" % (N, world, M, L),
+                       "l2": "inputs_exceed_l2 (K_nm TF32 planes = %.1f GB per GPU)" % (4 * N * M * 4 / 1e9),
+                       "parallelism": "N-sharded x%d, all-reduce of A_l/v_l and their adjoints" % world},
+            "roofline": {"bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf32_peak if tf32_peak else None, "traffic": None,
+                         "note": "achieved = 3 x algorithmic FLOPs of one launch (3xTF32: e = 3 MMAs per algorithmic MAC) / its CUDA-event duration; "
+                                 "peak = cuBLAS TF32 8192^3 GEMM measured in this run (MEASURED_PEAKS.json has bf16 only: %s burst / %s sustained)"
+                                 % (peaks.get("bf16_tflops"), peaks.get("bf16_tflops_sustained")),
+                         "step_algorithmic_tflops": f_alg / t_s / 1e12, "step_issued_tflops": 3 * f_alg / t_s / 1e12,
+                         "step_frac_of_tf32_peak": 3 * f_alg / t_s / 1e12 / tf32_peak if tf32_peak else None, "e": 3},
+            "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+            "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "datapoints/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, n_total)
+        print(json.dumps(line), flush=True)
+    if group is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -47,6 +47,21 @@ class Kop:
         return s
 
 
+_PROFILE = None
+
+
+def _call(name, *args):
+    """_lib.call, optionally bracketed by CUDA events on the launch stream (bench.py's per-kernel times)."""
+    if _PROFILE is None:
+        return _lib.call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = _lib.call(name, *args)
+    e1.record()
+    _PROFILE.append((name, e0, e1))
+    return rc
+
+
 def _ptr(t):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -81,6 +96,22 @@ class CudaBackend:
         self.launches = 0          # kernels launched through this backend (bench reports it)
         self.tc_min_rows = int(os.environ.get("SVGP_TC_MIN_ROWS", "2048"))
 
+    def start_profile(self):
+        global _PROFILE
+        _PROFILE = []
+
+    def stop_profile(self):
+        """-> {entry point: {"ms": total device time, "calls": n}} since start_profile()."""
+        global _PROFILE
+        torch.cuda.synchronize()
+        out = {}
+        for name, e0, e1 in _PROFILE or []:
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["calls"] += 1
+        _PROFILE = None
+        return out
+
     # ---- K1 --------------------------------------------------------------------------------
     def want_tc(self, N, M):
         return N >= self.tc_min_rows and M >= 128
@@ -103,7 +134,7 @@ class CudaBackend:
         else:
             K = torch.empty((N, M), device=Fx.device, dtype=torch.float32)
             kop = Kop(K)
-        _lib.call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+        _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
                   _ptr(kop.K), _ptr(kop.K_lo), kop.K.stride(0), _ptr(kop.Kt), _ptr(kop.Kt_lo),
                   kop.Kt.stride(0) if kop.Kt is not None else 0, _stream())
         self.launches += 1
@@ -116,7 +147,7 @@ class CudaBackend:
         dFx = torch.empty((N, d), device=Fx.device, dtype=torch.float32) if need_x else None
         dFz = torch.zeros((M, d), device=Fx.device, dtype=torch.float64) if need_z else None
         dhyp = torch.zeros(4, device=Fx.device, dtype=torch.float64)
-        _lib.call("svgp_kernel_bwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+        _call("svgp_kernel_bwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
                   _ptr(G), G.stride(0), _ptr(dFx), _ptr(dFz), _ptr(dhyp), _stream())
         self.launches += int(need_x) + int(need_z)
         return dFx, dFz, dhyp
@@ -125,7 +156,7 @@ class CudaBackend:
         Fx, Fy, hyp = _f32c(Fx), _f32c(Fy), _f32c(hyp)
         ta, da, tb, db = spec
         kd = torch.empty(Fx.shape[0], device=Fx.device, dtype=torch.float32)
-        _lib.call("svgp_kernel_diag_fwd", _ptr(Fx), Fx.stride(0), _ptr(Fy), Fy.stride(0), Fx.shape[0], ta, da, tb, db,
+        _call("svgp_kernel_diag_fwd", _ptr(Fx), Fx.stride(0), _ptr(Fy), Fy.stride(0), Fx.shape[0], ta, da, tb, db,
                   _ptr(hyp), _ptr(kd), _stream())
         self.launches += 1
         return kd
@@ -135,7 +166,7 @@ class CudaBackend:
         ta, da, tb, db = spec
         dFx, dFy = torch.empty_like(Fx), torch.empty_like(Fy)
         dhyp = torch.zeros(4, device=Fx.device, dtype=torch.float64)
-        _lib.call("svgp_kernel_diag_bwd", _ptr(Fx), Fx.stride(0), _ptr(Fy), Fy.stride(0), Fx.shape[0], ta, da, tb, db,
+        _call("svgp_kernel_diag_bwd", _ptr(Fx), Fx.stride(0), _ptr(Fy), Fy.stride(0), Fx.shape[0], ta, da, tb, db,
                   _ptr(hyp), _ptr(g), _ptr(dFx), _ptr(dFy), _ptr(dhyp), _stream())
         self.launches += 1
         return dFx, dFy, dhyp
@@ -144,7 +175,7 @@ class CudaBackend:
         table = _f32c(table)
         assert ids.dtype == torch.int64 and ids.is_contiguous()
         out = torch.empty((ids.shape[0], table.shape[1]), device=table.device, dtype=torch.float32)
-        _lib.call("svgp_gather_rows", _ptr(table), table.stride(0), table.shape[0], _ptr(ids), ids.shape[0],
+        _call("svgp_gather_rows", _ptr(table), table.stride(0), table.shape[0], _ptr(ids), ids.shape[0],
                   table.shape[1], _ptr(out), out.stride(0), _stream())
         self.launches += 1
         return out
@@ -152,7 +183,7 @@ class CudaBackend:
     def scatter_add_rows(self, g, ids, rows):
         g = _f32c(g)
         dt = torch.zeros((rows, g.shape[1]), device=g.device, dtype=torch.float64)
-        _lib.call("svgp_scatter_add_rows", _ptr(g), g.stride(0), _ptr(ids), ids.shape[0], g.shape[1], rows, _ptr(dt),
+        _call("svgp_scatter_add_rows", _ptr(g), g.stride(0), _ptr(ids), ids.shape[0], g.shape[1], rows, _ptr(dt),
                   dt.stride(0), _stream())
         self.launches += 1
         return dt
@@ -165,7 +196,7 @@ class CudaBackend:
             return S64.to(torch.float32), None
         hi = torch.empty(S64.shape, device=S64.device, dtype=torch.float32)
         lo = torch.empty_like(hi)
-        _lib.call("svgp_split_tf32", _ptr(S64), _ptr(hi), _ptr(lo), S64.numel(), _stream())
+        _call("svgp_split_tf32", _ptr(S64), _ptr(hi), _ptr(lo), S64.numel(), _stream())
         self.launches += 1
         return hi, lo
 
@@ -180,7 +211,7 @@ class CudaBackend:
             Wt = torch.zeros((L, ldwt), device=W.device, dtype=torch.float32)
             Wt[:, : kop.N] = W.t()
         s = kop.struct()
-        _lib.call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(Wt), Wt.stride(0) if Wt is not None else 0, L,
+        _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(Wt), Wt.stride(0) if Wt is not None else 0, L,
                   _ptr(A), IMPL_TC if use_tc else IMPL_SIMT, chunk_rows, _stream())
         self.launches += 1
         return A
@@ -200,7 +231,7 @@ class CudaBackend:
         L = X.shape[1]
         V = torch.zeros((L, kop.M), device=X.device, dtype=torch.float64)
         for s in self._plane_structs(kop):
-            _lib.call("svgp_gemm_tn", ctypes.byref(s), _ptr(X), X.stride(0), L, _ptr(V), _stream())
+            _call("svgp_gemm_tn", ctypes.byref(s), _ptr(X), X.stride(0), L, _ptr(V), _stream())
             self.launches += 1
         return V
 
@@ -210,7 +241,7 @@ class CudaBackend:
         outs = []
         for s in self._plane_structs(kop):
             out = torch.empty((kop.N, L), device=Wm.device, dtype=torch.float32)
-            _lib.call("svgp_gemm_nn", ctypes.byref(s), _ptr(Wm), Wm.stride(0), L, _ptr(out), out.stride(0), _stream())
+            _call("svgp_gemm_nn", ctypes.byref(s), _ptr(Wm), Wm.stride(0), L, _ptr(out), out.stride(0), _stream())
             self.launches += 1
             outs.append(out)
         return outs[0] if len(outs) == 1 else outs[0].add_(outs[1])
@@ -221,7 +252,7 @@ class CudaBackend:
         hi, lo = self._planes(S64, use_tc)
         q = torch.empty((kop.N, L), device=S64.device, dtype=torch.float32)
         s = kop.struct()
-        _lib.call("svgp_rowquad", ctypes.byref(s), _ptr(hi), _ptr(lo), L, int(bool(tri)), _ptr(q), q.stride(0),
+        _call("svgp_rowquad", ctypes.byref(s), _ptr(hi), _ptr(lo), L, int(bool(tri)), _ptr(q), q.stride(0),
                   IMPL_TC if use_tc else IMPL_SIMT, _stream())
         self.launches += 1
         return q
@@ -235,7 +266,7 @@ class CudaBackend:
         if out is None:
             out = torch.empty((kop.N, kop.M), device=W.device, dtype=torch.float32)
         s = kop.struct()
-        _lib.call("svgp_scaled_gemm", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(hi), _ptr(lo), L, _ptr(out),
+        _call("svgp_scaled_gemm", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(hi), _ptr(lo), L, _ptr(out),
                   out.stride(0), int(accumulate), IMPL_TC if use_tc else IMPL_SIMT, _stream())
         self.launches += 1
         return out
@@ -245,7 +276,7 @@ class CudaBackend:
         accumulate = out is not None
         if out is None:
             out = torch.empty((A.shape[0], B.shape[1]), device=A.device, dtype=torch.float32)
-        _lib.call("svgp_gemm_f32", A.shape[0], B.shape[1], A.shape[1], _ptr(A), A.stride(0), _ptr(B), B.stride(0),
+        _call("svgp_gemm_f32", A.shape[0], B.shape[1], A.shape[1], _ptr(A), A.stride(0), _ptr(B), B.stride(0),
                   _ptr(out), out.stride(0), int(accumulate), _stream())
         self.launches += 1
         return out
@@ -258,7 +289,7 @@ class CudaBackend:
         Lf = X.clone()
         status = torch.zeros(B, device=X.device, dtype=torch.int32)
         ws = torch.empty(B * 32 * 32, device=X.device, dtype=torch.float64)
-        _lib.call("svgp_chol_f64", _ptr(Lf), M, M, M * M, B, _ptr(status), _ptr(ws), _stream())
+        _call("svgp_chol_f64", _ptr(Lf), M, M, M * M, B, _ptr(status), _ptr(ws), _stream())
         self.launches += 3 * ((M + 31) // 32)
         return Lf, status
 
@@ -268,7 +299,7 @@ class CudaBackend:
         nblk = (M + 31) // 32
         Linv = torch.empty_like(Lf)
         ws = torch.empty(B * nblk * 32 * 32 + B * 32 * M, device=Lf.device, dtype=torch.float64)
-        _lib.call("svgp_trinv_f64", _ptr(Lf), _ptr(Linv), M, M, M * M, B, _ptr(ws), _stream())
+        _call("svgp_trinv_f64", _ptr(Lf), _ptr(Linv), M, M, M * M, B, _ptr(ws), _stream())
         self.launches += 2 * nblk + 2
         return Linv
 
@@ -283,7 +314,7 @@ class CudaBackend:
         C = torch.empty((nb, Mr, Nc), device=A.device, dtype=torch.float64)
         sA = 0 if (A.shape[0] == 1 and nb > 1) else A.shape[1] * A.shape[2]
         sB = 0 if (B.shape[0] == 1 and nb > 1) else B.shape[1] * B.shape[2]
-        _lib.call("svgp_gemm_f64", int(transA), int(transB), Mr, Nc, Kd, 1.0, _ptr(A), A.shape[2], sA, _ptr(B),
+        _call("svgp_gemm_f64", int(transA), int(transB), Mr, Nc, Kd, 1.0, _ptr(A), A.shape[2], sA, _ptr(B),
                   B.shape[2], sB, 0.0, _ptr(C), Nc, Mr * Nc, nb, _stream())
         self.launches += 1
         return C
@@ -294,7 +325,7 @@ class CudaBackend:
         N, L = y.shape
         p, py = torch.empty_like(y), torch.empty_like(y)
         sums = torch.zeros((3, L), device=y.device, dtype=torch.float64)
-        _lib.call("svgp_rowstats_fwd", _ptr(y), _ptr(noise), _ptr(kappa), N, L, _ptr(p), _ptr(py), _ptr(sums), _stream())
+        _call("svgp_rowstats_fwd", _ptr(y), _ptr(noise), _ptr(kappa), N, L, _ptr(p), _ptr(py), _ptr(sums), _stream())
         self.launches += 1
         return p, py, sums
 
@@ -305,7 +336,7 @@ class CudaBackend:
         clipsum = torch.zeros(L, device=q1.device, dtype=torch.float64)
         mask = torch.zeros((N, L), device=q1.device, dtype=torch.uint8) if clip else None
         lo, hi = clip if clip else (0.0, 0.0)
-        _lib.call("svgp_predictive_fwd", _ptr(kappa), _ptr(h), _ptr(pv), _ptr(_f32c(p)) if clip else None, N, L,
+        _call("svgp_predictive_fwd", _ptr(kappa), _ptr(h), _ptr(pv), _ptr(_f32c(p)) if clip else None, N, L,
                   int(bool(clip)), lo, hi, _ptr(clipsum), _ptr(mask), _stream())
         self.launches += 1
         return pv, clipsum, mask

@@ -9,8 +9,8 @@
 //   svgp_scaled_gemm out  = sum_l diag(W[:,l]) K_nm G_l               (adjoint of the two above)
 //   svgp_gemm_f32    plain C (+)= A B
 // and a sibling kernel does the row-wise quadratic forms svgp_rowquad (:336-337, :284).
-// fp32 products are accumulated in fp32 inside one reduction chunk and in fp64 across chunks
-// (double atomics), so that sums over ~1e6 datapoints keep fp32-level relative accuracy.
+// Operands are fp32, every product and accumulation is fp64 (the S_l / Kinv operands have large
+// cancelling entries), reductions over datapoints are folded across chunks with double atomics.
 #include "common.cuh"
 
 namespace svgp {
@@ -25,11 +25,11 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   int64_t k0, k1;
   op.krange(blockIdx.z, k0, k1);
-  float acc[4][4];
+  double acc[4][4];      // fp32 products, fp64 accumulation: S_l / Kinv have large cancelling entries (cond ~1e3..1e5)
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
   for (int64_t kb = k0; kb < k1; kb += BK) {
     // A tile: BK x BM, B tile: BK x BN; each thread loads 4 + 4 elements
@@ -49,15 +49,15 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+      double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = (double)As[kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = (double)Bs[kk][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
@@ -80,8 +80,8 @@ struct SyrkOp {     // z = l * nchunk + chunk
   }
   __device__ float a(int z, int64_t m, int64_t k) const { return K[k * ldk + m]; }
   __device__ float b(int z, int64_t k, int64_t n) const { return W[k * ldw + z / nchunk] * K[k * ldk + n]; }
-  __device__ void store(int z, int64_t m, int64_t n, float v) const {
-    atomicAdd(&A[((int64_t)(z / nchunk) * M + m) * M + n], (double)v);
+  __device__ void store(int z, int64_t m, int64_t n, double v) const {
+    atomicAdd(&A[((int64_t)(z / nchunk) * M + m) * M + n], v);
   }
 };
 struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
@@ -91,7 +91,7 @@ struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
   __device__ void krange(int z, int64_t& k0, int64_t& k1) const { k0 = (int64_t)z * chunk; k1 = min(N, k0 + chunk); }
   __device__ float a(int z, int64_t m, int64_t k) const { return X[k * ldx + m]; }
   __device__ float b(int z, int64_t k, int64_t n) const { return K[k * ldk + n]; }
-  __device__ void store(int z, int64_t m, int64_t n, float v) const { atomicAdd(&V[m * M + n], (double)v); }
+  __device__ void store(int z, int64_t m, int64_t n, double v) const { atomicAdd(&V[m * M + n], v); }
 };
 struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
@@ -100,7 +100,7 @@ struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
   __device__ void krange(int z, int64_t& k0, int64_t& k1) const { k0 = 0; k1 = M; }
   __device__ float a(int z, int64_t m, int64_t k) const { return K[m * ldk + k]; }
   __device__ float b(int z, int64_t k, int64_t n) const { return Wm[n * ldwm + k]; }
-  __device__ void store(int z, int64_t m, int64_t n, float v) const { out[m * ldo + n] = v; }
+  __device__ void store(int z, int64_t m, int64_t n, double v) const { out[m * ldo + n] = (float)v; }
 };
 struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
@@ -113,9 +113,9 @@ struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
     return W[m * ldw + l] * K[m * ldk + aa];
   }
   __device__ float b(int z, int64_t k, int64_t n) const { return G[k * M + n]; }   // (l*M + a)*M + c
-  __device__ void store(int z, int64_t m, int64_t n, float v) const {
+  __device__ void store(int z, int64_t m, int64_t n, double v) const {
     float* o = out + m * ldo + n;
-    *o = accumulate ? (*o + v) : v;
+    *o = accumulate ? (float)((double)*o + v) : (float)v;
   }
 };
 struct PlainOp {
@@ -125,9 +125,9 @@ struct PlainOp {
   __device__ void krange(int z, int64_t& k0, int64_t& k1) const { k0 = 0; k1 = Kd; }
   __device__ float a(int z, int64_t m, int64_t k) const { return A[m * lda + k]; }
   __device__ float b(int z, int64_t k, int64_t n) const { return B[k * ldb + n]; }
-  __device__ void store(int z, int64_t m, int64_t n, float v) const {
+  __device__ void store(int z, int64_t m, int64_t n, double v) const {
     float* o = C + m * ldc + n;
-    *o = accumulate ? (*o + v) : v;
+    *o = accumulate ? (float)((double)*o + v) : (float)v;
   }
 };
 
@@ -143,13 +143,13 @@ __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restric
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int l = blockIdx.y;
   const float* Sl = S + (int64_t)l * M * M;
-  float qacc[4] = {0.f, 0.f, 0.f, 0.f};
+  double qacc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int64_t n0 = 0; n0 < M; n0 += BN) {
-    float acc[4][4];
+    double acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
     const int64_t kend = tri ? min(M, n0 + BN) : M;     // Rinv[c][a] == 0 for a > c
     for (int64_t kb = 0; kb < kend; kb += BK) {
 #pragma unroll
@@ -167,15 +167,15 @@ __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restric
       __syncthreads();
 #pragma unroll
       for (int kk = 0; kk < BK; ++kk) {
-        float a[4], b[4];
+        double a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+        for (int i = 0; i < 4; ++i) a[i] = (double)As[kk][ty * 4 + i];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+        for (int j = 0; j < 4; ++j) b[j] = (double)Bs[kk][tx * 4 + j];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
       }
       __syncthreads();
     }
@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restric
       for (int j = 0; j < 4; ++j) {
         int64_t gn = n0 + tx * 4 + j;
         if (gm < N && gn < M) {
-          float other = tri ? acc[i][j] : K[gm * ldk + gn];
-          qacc[i] = fmaf(acc[i][j], other, qacc[i]);
+          double other = tri ? acc[i][j] : (double)K[gm * ldk + gn];
+          qacc[i] = fma(acc[i][j], other, qacc[i]);
         }
       }
     }
@@ -195,11 +195,11 @@ __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restric
   // the 16 threads tx = 0..15 of one ty hold partial sums of the same 4 rows (lanes [0,16) / [16,32) of a warp)
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float v = qacc[i];
+    double v = qacc[i];
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     int64_t gm = m0 + ty * 4 + i;
-    if (tx == 0 && gm < N) q[gm * ldq + l] = v;
+    if (tx == 0 && gm < N) q[gm * ldq + l] = (float)v;
   }
 }
 

@@ -145,6 +145,7 @@ struct TcParams {
   float* out;
   int64_t ldo;
   int accumulate;
+  int lflush;             // channels per TMEM accumulation chain
   int64_t n_items;
 };
 
@@ -220,16 +221,26 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   const uint32_t tmem_base = *tmem_ptr;
 
   // ---- work decomposition -------------------------------------------------------------------
-  // every role walks the same item sequence: item -> (sub-tiles, k-blocks per sub-tile)
+  // Every role walks the same sequence: item -> sub-tiles -> k-blocks.  One TMEM accumulator buffer
+  // holds one sub-tile; its MMA chain is kept short on purpose: the tensor core accumulates with
+  // truncation, so a chain of n MMAs carries a bias of up to ~n * 2^-24.  Long reductions (SYRK over
+  // N datapoints, SCALED over L * M) are therefore cut into sub-tiles that the epilogue folds into a
+  // CTA-owned global tile (double for SYRK, float for SCALED) with ordinary round-to-nearest adds.
+  //   SYRK    item = (tile pair, channel)      sub = chunk of `chunk_rows` datapoints
+  //   ROWQUAD item = (row tile, channel)       sub = column tile of B_l
+  //   SCALED  item = (row tile, column tile)   sub = group of `lflush` channels
   const int64_t M = P.M;
-  const int nct = (int)((M + BN - 1) / BN);                  // column tiles (ROWQUAD)
-  const int kb_full = (int)((M + BLOCK_K - 1) / BLOCK_K);    // k-blocks over the inducing dimension
+  const int nct = (int)((M + BN - 1) / BN);
+  const int kb_full = (int)((M + BLOCK_K - 1) / BLOCK_K);
 
-  auto item_subtiles = [&]() -> int { return MODE == MODE_ROWQUAD ? nct : 1; };
-  auto subtile_kblocks = [&](int64_t item, int sub) -> int {
+  auto item_subtiles = [&]() -> int {
+    if (MODE == MODE_SYRK) return (int)P.nchunk;
+    if (MODE == MODE_ROWQUAD) return nct;
+    return (int)((P.L + P.lflush - 1) / P.lflush);
+  };
+  auto subtile_kblocks = [&](int sub) -> int {
     if (MODE == MODE_SYRK) {
-      int64_t chunk = item / ((int64_t)P.ntile * P.L);
-      int64_t n0 = chunk * P.chunk_rows;
+      int64_t n0 = (int64_t)sub * P.chunk_rows;
       int64_t n1 = n0 + P.chunk_rows < P.N ? n0 + P.chunk_rows : P.N;
       return (int)((n1 - n0 + BLOCK_K - 1) / BLOCK_K);
     } else if (MODE == MODE_ROWQUAD) {
@@ -237,8 +248,31 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       int64_t kend = (int64_t)(sub + 1) * BN < M ? (int64_t)(sub + 1) * BN : M;
       return (int)((kend + BLOCK_K - 1) / BLOCK_K);
     } else {
-      return (int)(P.L * kb_full);
+      int64_t l0 = (int64_t)sub * P.lflush;
+      int64_t nl = l0 + P.lflush < P.L ? P.lflush : P.L - l0;
+      return (int)(nl * kb_full);
     }
+  };
+  // item -> coordinates
+  struct Item { int64_t l, itile; int a_row0, b_row0; };
+  auto decode = [&](int64_t item) -> Item {
+    Item it{0, 0, 0, 0};
+    if (MODE == MODE_SYRK) {
+      it.l = item % P.L;
+      int ta, tb;
+      syrk_tile_decode((int)(item / P.L), M, BN, ta, tb);
+      it.a_row0 = ta * BLOCK_M; it.b_row0 = tb * BN;
+    } else if (MODE == MODE_ROWQUAD) {
+      int64_t ntile_r = (P.N + BLOCK_M - 1) / BLOCK_M;
+      int64_t per_group = ntile_r * P.lgroup;
+      int64_t g = item / per_group, rem = item % per_group;
+      it.itile = rem / P.lgroup; it.l = g * P.lgroup + rem % P.lgroup;
+      it.a_row0 = (int)(it.itile * BLOCK_M);
+    } else {
+      it.itile = item / nct;
+      it.a_row0 = (int)(it.itile * BLOCK_M); it.b_row0 = (int)((item % nct) * BN);
+    }
+    return it;
   };
 
   if (warp == 0) {
@@ -246,40 +280,21 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-        int32_t a_row0 = 0, b_row0 = 0, k_base = 0;
-        int64_t l = 0, itile = 0;
-        if (MODE == MODE_SYRK) {
-          l = item % P.L;
-          int tidx = (int)((item / P.L) % P.ntile);
-          int64_t chunk = item / ((int64_t)P.ntile * P.L);
-          int ta, tb;
-          syrk_tile_decode(tidx, M, BN, ta, tb);
-          a_row0 = ta * BLOCK_M; b_row0 = tb * BN; k_base = (int32_t)(chunk * P.chunk_rows);
-        } else if (MODE == MODE_ROWQUAD) {
-          // item -> (channel group, row tile, channel in group)
-          int64_t ntile_r = (P.N + BLOCK_M - 1) / BLOCK_M;
-          int64_t per_group = ntile_r * P.lgroup;
-          int64_t g = item / per_group, rem = item % per_group;
-          itile = rem / P.lgroup; l = g * P.lgroup + rem % P.lgroup;
-          a_row0 = (int32_t)(itile * BLOCK_M);
-        } else {
-          itile = item / nct;
-          a_row0 = (int32_t)(itile * BLOCK_M); b_row0 = (int32_t)((item % nct) * BN);
-        }
+        const Item it = decode(item);
         const int nsub = item_subtiles();
         for (int sub = 0; sub < nsub; ++sub) {
-          const int nkb = subtile_kblocks(item, sub);
+          const int nkb = subtile_kblocks(sub);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* st = smem + stage * SL::STAGE_BYTES;
             int32_t ak, ar, bk, br;
             if (MODE == MODE_SYRK) {
-              ak = k_base + kb * BLOCK_K; ar = a_row0; bk = ak; br = b_row0;
+              ak = (int32_t)((int64_t)sub * P.chunk_rows) + kb * BLOCK_K; ar = it.a_row0; bk = ak; br = it.b_row0;
             } else if (MODE == MODE_ROWQUAD) {
-              ak = kb * BLOCK_K; ar = a_row0; bk = ak; br = (int32_t)(l * M + (int64_t)sub * BN);
+              ak = kb * BLOCK_K; ar = it.a_row0; bk = ak; br = (int32_t)(it.l * M + (int64_t)sub * BN);
             } else {
-              int lc = kb / kb_full, kk = kb % kb_full;
-              ak = kk * BLOCK_K; ar = a_row0; bk = ak; br = (int32_t)((int64_t)lc * M + b_row0);
+              int lc = sub * P.lflush + kb / kb_full, kk = kb % kb_full;
+              ak = kk * BLOCK_K; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)lc * M + it.b_row0);
             }
             mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
             tma_load_2d(st, &mapA_hi, &full[stage], ak, ar);
@@ -298,7 +313,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const int nsub = item_subtiles();
       for (int sub = 0; sub < nsub; ++sub) {
-        const int nkb = subtile_kblocks(item, sub);
+        const int nkb = subtile_kblocks(sub);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -332,22 +347,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     const int row = qd * 32 + lane;                  // output row inside the tile
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      int64_t l = 0, itile = 0;
-      int a_row0 = 0, b_row0 = 0;
-      if (MODE == MODE_SYRK) {
-        l = item % P.L;
-        int tidx = (int)((item / P.L) % P.ntile);
-        int ta, tb;
-        syrk_tile_decode(tidx, M, BN, ta, tb);
-        a_row0 = ta * BLOCK_M; b_row0 = tb * BN;
-      } else if (MODE == MODE_ROWQUAD) {
-        int64_t ntile_r = (P.N + BLOCK_M - 1) / BLOCK_M;
-        int64_t per_group = ntile_r * P.lgroup;
-        int64_t g = item / per_group, rem = item % per_group;
-        itile = rem / P.lgroup; l = g * P.lgroup + rem % P.lgroup;
-      } else {
-        itile = item / nct; b_row0 = (int)((item % nct) * BN);
-      }
+      const Item it = decode(item);
       float qsum = 0.f;
       const int nsub = item_subtiles();
       for (int sub = 0; sub < nsub; ++sub) {
@@ -359,20 +359,17 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           float v[32];
           tmem_ld32(taddr + c0, v);
           if (MODE == MODE_SYRK) {
-            const int64_t a = a_row0 + row;
+            // CTA-owned tile of the double accumulator: plain read-modify-write, lower triangle only
+            const int64_t a = it.a_row0 + row;
             if (a < M) {
-              double* Al = P.A + l * M * M;
+              double* Arow = P.A + (it.l * M + a) * M + it.b_row0 + c0;
+              const int64_t bmax = a - (it.b_row0 + c0);          // columns j <= bmax are on/below the diagonal
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const int64_t b = b_row0 + c0 + j;
-                if (b <= a) {                                     // b < M follows from a < M
-                  atomicAdd(Al + a * M + b, (double)v[j]);
-                  if (b < a) atomicAdd(Al + b * M + a, (double)v[j]);
-                }
-              }
+              for (int j = 0; j < 32; ++j)
+                if (j <= bmax) Arow[j] += (double)v[j];
             }
           } else if (MODE == MODE_ROWQUAD) {
-            const int64_t i = itile * BLOCK_M + row;
+            const int64_t i = it.itile * BLOCK_M + row;
             const int64_t cbase = (int64_t)sub * BN + c0;
             if (P.tri) {
 #pragma unroll
@@ -386,13 +383,13 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 if (cbase + j < M) qsum = fmaf(v[j], kh[j] + kl[j], qsum);
             }
           } else {
-            const int64_t i = itile * BLOCK_M + row;
+            const int64_t i = it.itile * BLOCK_M + row;
             if (i < P.N) {
-              float* o = P.out + i * P.ldo + b_row0 + c0;
+              float* o = P.out + i * P.ldo + it.b_row0 + c0;
+              const bool add = (sub > 0) || P.accumulate;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if ((int64_t)b_row0 + c0 + j < M) o[j] = P.accumulate ? o[j] + v[j] : v[j];
-              }
+              for (int j = 0; j < 32; ++j)
+                if ((int64_t)it.b_row0 + c0 + j < M) o[j] = add ? o[j] + v[j] : v[j];
             }
           }
         }
@@ -402,8 +399,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
       }
       if (MODE == MODE_ROWQUAD) {
-        const int64_t i = itile * BLOCK_M + row;
-        if (i < P.N && l < P.L) P.q[i * P.ldq + l] = qsum;
+        const int64_t i = it.itile * BLOCK_M + row;
+        if (i < P.N && it.l < P.L) P.q[i * P.ldq + it.l] = qsum;
       }
     }
   } else if (HAS_XFORM) {
@@ -415,56 +412,52 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     const int pchunk = t & 7, rbase = t >> 3;
     const int lchunk = pchunk ^ (rbase & 7);
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      int64_t l = 0, itile = 0, k_base = 0;
-      if (MODE == MODE_SYRK) {
-        l = item % P.L;
-        int64_t chunk = item / ((int64_t)P.ntile * P.L);
-        k_base = chunk * P.chunk_rows;
-      } else {
-        itile = item / nct;
-      }
-      const int nkb = subtile_kblocks(item, 0);
+      const Item it = decode(item);
       float rs[8];                                    // SCALED: per-row weights of the current channel
       int cur_l = -1;
-      for (int kb = 0; kb < nkb; ++kb) {
-        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODE == MODE_SYRK) {
-          const int64_t n = k_base + (int64_t)kb * BLOCK_K + lchunk * 4;
-          const float* wp = P.Wt + l * P.ldwt + n;
-          if (n + 3 < P.N) wv = *reinterpret_cast<const float4*>(wp);
-          else { if (n < P.N) wv.x = wp[0]; if (n + 1 < P.N) wv.y = wp[1]; if (n + 2 < P.N) wv.z = wp[2]; }
-        } else {
-          int lc = kb / kb_full;
-          if (lc != cur_l) {
-            cur_l = lc;
+      const int nsub = item_subtiles();
+      for (int sub = 0; sub < nsub; ++sub) {
+        const int nkb = subtile_kblocks(sub);
+        for (int kb = 0; kb < nkb; ++kb) {
+          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (MODE == MODE_SYRK) {
+            const int64_t n = (int64_t)sub * P.chunk_rows + (int64_t)kb * BLOCK_K + lchunk * 4;
+            const float* wp = P.Wt + it.l * P.ldwt + n;
+            if (n + 3 < P.N) wv = *reinterpret_cast<const float4*>(wp);
+            else { if (n < P.N) wv.x = wp[0]; if (n + 1 < P.N) wv.y = wp[1]; if (n + 2 < P.N) wv.z = wp[2]; }
+          } else {
+            int lc = sub * P.lflush + kb / kb_full;
+            if (lc != cur_l) {
+              cur_l = lc;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              int64_t i = itile * BLOCK_M + rbase + 16 * it;
-              rs[it] = (i < P.N) ? P.W[i * P.ldw + lc] : 0.f;
+              for (int r = 0; r < 8; ++r) {
+                int64_t i = it.itile * BLOCK_M + rbase + 16 * r;
+                rs[r] = (i < P.N) ? P.W[i * P.ldw + lc] : 0.f;
+              }
             }
           }
-        }
-        mbar_wait(&full[stage], phase);
-        uint8_t* st = smem + stage * SL::STAGE_BYTES;
-        constexpr int ROWS = (MODE == MODE_SYRK) ? BN : BLOCK_M;
-        uint8_t* hi_p = st + ((MODE == MODE_SYRK) ? 2 * SL::A_BYTES : 0);
-        uint8_t* lo_p = hi_p + ((MODE == MODE_SYRK) ? SL::B_BYTES : SL::A_BYTES);
+          mbar_wait(&full[stage], phase);
+          uint8_t* st = smem + stage * SL::STAGE_BYTES;
+          constexpr int ROWS = (MODE == MODE_SYRK) ? BN : BLOCK_M;
+          uint8_t* hi_p = st + ((MODE == MODE_SYRK) ? 2 * SL::A_BYTES : 0);
+          uint8_t* lo_p = hi_p + ((MODE == MODE_SYRK) ? SL::B_BYTES : SL::A_BYTES);
 #pragma unroll
-        for (int it = 0; it < ROWS / 16; ++it) {
-          const int off = (rbase + 16 * it) * 128 + pchunk * 16;
-          float4 h = *reinterpret_cast<float4*>(hi_p + off);
-          float4 lo4 = *reinterpret_cast<float4*>(lo_p + off);
-          float4 s = (MODE == MODE_SYRK) ? wv : make_float4(rs[it & 7], rs[it & 7], rs[it & 7], rs[it & 7]);
-          float y0 = (h.x + lo4.x) * s.x, y1 = (h.y + lo4.y) * s.y, y2 = (h.z + lo4.z) * s.z, y3 = (h.w + lo4.w) * s.w;
-          float4 nh = make_float4(to_tf32(y0), to_tf32(y1), to_tf32(y2), to_tf32(y3));
-          float4 nl = make_float4(to_tf32(y0 - nh.x), to_tf32(y1 - nh.y), to_tf32(y2 - nh.z), to_tf32(y3 - nh.w));
-          *reinterpret_cast<float4*>(hi_p + off) = nh;
-          *reinterpret_cast<float4*>(lo_p + off) = nl;
+          for (int r = 0; r < ROWS / 16; ++r) {
+            const int off = (rbase + 16 * r) * 128 + pchunk * 16;
+            float4 h = *reinterpret_cast<float4*>(hi_p + off);
+            float4 lo4 = *reinterpret_cast<float4*>(lo_p + off);
+            float4 s = (MODE == MODE_SYRK) ? wv : make_float4(rs[r & 7], rs[r & 7], rs[r & 7], rs[r & 7]);
+            float y0 = (h.x + lo4.x) * s.x, y1 = (h.y + lo4.y) * s.y, y2 = (h.z + lo4.z) * s.z, y3 = (h.w + lo4.w) * s.w;
+            float4 nh = make_float4(to_tf32(y0), to_tf32(y1), to_tf32(y2), to_tf32(y3));
+            float4 nl = make_float4(to_tf32(y0 - nh.x), to_tf32(y1 - nh.y), to_tf32(y2 - nh.z), to_tf32(y3 - nh.w));
+            *reinterpret_cast<float4*>(hi_p + off) = nh;
+            *reinterpret_cast<float4*>(lo_p + off) = nl;
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ready[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ready[stage]);
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   }
@@ -474,6 +467,15 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// copy the lower triangle of every A_l onto its upper triangle (the SYRK kernel only writes b <= a)
+__global__ void mirror_lower_kernel(double* __restrict__ A, int64_t M, int64_t L) {
+  const int64_t total = L * M * M;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t l = idx / (M * M), rem = idx - l * M * M, r = rem / M, c = rem - r * M;
+    if (c > r) A[idx] = A[(l * M + c) * M + r];
   }
 }
 
@@ -574,12 +576,17 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, int64_t L, doubl
   TcParams P{};
   P.N = kop->N; P.M = kop->M; P.L = L;
   P.Wt = Wt; P.ldwt = ldwt; P.A = A;
-  int64_t chunk = chunk_rows > 0 ? chunk_rows : 8192;
+  int64_t chunk = chunk_rows > 0 ? chunk_rows : 1024;
   chunk = (chunk + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
   P.chunk_rows = chunk; P.nchunk = ceil_div(kop->N, chunk);
   P.ntile = syrk_tile_count(kop->M, BN);
-  P.n_items = (int64_t)P.ntile * L * P.nchunk;
-  return dispatch_tc<MODE_SYRK>(a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
+  P.n_items = (int64_t)P.ntile * L;
+  rc = dispatch_tc<MODE_SYRK>(a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
+  if (rc) return rc;
+  int64_t blocks = ceil_div(L * kop->M * kop->M, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  mirror_lower_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, kop->M, L);
+  return check_launch("svgp_syrk(mirror)");
 }
 
 int tc_rowquad(const svgp_kop* kop, const float* S_hi, const float* S_lo, int64_t L, int tri, float* q, int64_t ldq,
@@ -617,6 +624,16 @@ int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const float
   TcParams P{};
   P.N = kop->N; P.M = kop->M; P.L = L;
   P.W = W; P.ldw = ldw; P.out = out; P.ldo = ldo; P.accumulate = accumulate;
+  {
+    // keep one accumulation chain to ~768 MMAs (measured truncation bias ~2.7e-8 per MMA -> ~2e-5):
+    // lflush channels x (M/32) k-blocks x 12 MMAs
+    int64_t kb = ceil_div(kop->M, BLOCK_K);
+    int64_t lf = 64 / (kb > 0 ? kb : 1);
+    const char* e = getenv("SVGP_TC_LFLUSH");
+    if (e && atoi(e) > 0) lf = atoi(e);
+    if (lf < 1) lf = 1;
+    P.lflush = (int)lf;
+  }
   P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(kop->M, BN);
   return dispatch_tc<MODE_SCALED>(a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");
 }

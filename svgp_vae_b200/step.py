@@ -50,7 +50,7 @@ def mm_stage(A, V, sums, K, jitter, c, b_total):
     L, M, _ = A.shape
     eye = torch.eye(M, dtype=A.dtype, device=A.device)
     Kb = K.unsqueeze(0)
-    Kinv_b, ldK, _ = ops.spd_inverse_logdet(Kb + jitter * eye)
+    Kinv_b, ldK, LinvK = ops.spd_inverse_logdet(Kb + jitter * eye)
     Sigma = Kb + c * A + jitter * eye
     S, _, Linv = ops.spd_inverse_logdet(Sigma)
     w = c * ops.bmv64(S, V)                                   # p_m = K_nm w
@@ -71,7 +71,7 @@ def mm_stage(A, V, sums, K, jitter, c, b_total):
     Aw = ops.bmv64(A, w)
     s_ppv = s_pk - s_ph + (S * A).sum((-1, -2))
     ce = -0.5 * (b_total * LOG_2PI + s_log + s_ppv + (w * Aw).sum(-1) - 2.0 * (w * V).sum(-1) + s_pyy)
-    return dict(S=S, w=w, Kinv=Kinv_b, Linv=Linv, recon=recon, kl=kl, ce=ce, mu_hat=mu_hat, A_hat=A_hat)
+    return dict(S=S, w=w, Kinv=Kinv_b, Linv=Linv, LinvK=LinvK, recon=recon, kl=kl, ce=ce, mu_hat=mu_hat, A_hat=A_hat)
 
 
 class _SVGPStep(torch.autograd.Function):
@@ -107,8 +107,14 @@ class _SVGPStep(torch.autograd.Function):
 
         # pass B
         S, w, Kinv, Linv = mm["S"].detach(), mm["w"].detach(), mm["Kinv"].detach(), mm["Linv"]
-        h = be.rowquad(kop, Kinv).squeeze(1)
-        q1 = be.rowquad(kop, Linv, tri=True) if cfg.get("tri", True) else be.rowquad(kop, S)
+        # quadratic forms through the Cholesky factors: |R^-1 k|^2 is a sum of squares (half the MMA work and
+        # no cancellation between the large entries of S_l / Kinv)
+        if cfg.get("tri", True):
+            h = be.rowquad(kop, mm["LinvK"], tri=True).squeeze(1)
+            q1 = be.rowquad(kop, Linv, tri=True)
+        else:
+            h = be.rowquad(kop, Kinv).squeeze(1)
+            q1 = be.rowquad(kop, S)
         pm = be.gemm_nn(kop, w.float().contiguous())
         pv, clipsum, mask = be.predictive(kappa, h, q1, p, clip)
         ce = mm["ce"].detach().clone()

@@ -1,0 +1,56 @@
+"""tcgen05 engine (3xTF32) against float64 on the device and against the SIMT kernels."""
+import pytest
+import torch
+
+from conftest import rel_err
+from svgp_vae_b200.backend import IMPL_SIMT, Kop
+
+pytestmark = pytest.mark.gpu
+SPEC = (1, 4, 1, 4)
+
+
+def _setup(be, N, M, L, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    Fx = torch.randn(N, 8, generator=g, device="cuda")
+    Fz = torch.randn(M, 8, generator=g, device="cuda")
+    hyp = torch.ones(4, device="cuda")
+    kop = be.kernel_fwd(SPEC, Fx, Fz, hyp, tc=True)
+    K64 = kop.value().double()
+    W = torch.randn(N, L, generator=g, device="cuda")
+    return kop, K64, W, g
+
+
+@pytest.mark.parametrize("shape", [(4096, 256, 3), (3000, 200, 2), (8192, 384, 2), (2500, 1024, 1)])
+def test_tc_syrk(cuda_backend, shape):
+    be = cuda_backend
+    N, M, L = shape
+    kop, K64, W, g = _setup(be, N, M, L)
+    ref = torch.einsum('il,ia,ib->lab', W.double(), K64, K64)
+    # the tensor core accumulates with truncation: the bias grows ~2.7e-8 per MMA of a chain (measured,
+    # profiles/r01_accuracy.md), so short chains (chunk_rows=128 -> 48 MMAs) reach fp32-level accuracy and
+    # the default chain (1024 rows -> 384 MMAs) stays ~1e-5
+    assert rel_err(be.syrk(kop, W, chunk_rows=128), ref) < 3e-6
+    A = be.syrk(kop, W)
+    assert rel_err(A, ref) < 3e-5
+    assert rel_err(A, A.transpose(1, 2)) == 0.0
+    A2 = be.syrk(Kop(kop.value().contiguous()), W, impl=IMPL_SIMT)
+    assert rel_err(A2, ref) < 1e-6 and rel_err(A, A2) < 3e-5
+
+
+@pytest.mark.parametrize("shape", [(4096, 256, 3), (3000, 200, 2), (2304, 1024, 2)])
+def test_tc_rowquad_scaled(cuda_backend, shape):
+    be = cuda_backend
+    N, M, L = shape
+    kop, K64, W, g = _setup(be, N, M, L, seed=1)
+    S = torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64)
+    S = (S + S.transpose(1, 2)).contiguous()
+    Lt = torch.tril(torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64)).contiguous()
+    ref = torch.einsum('ia,lab,ib->il', K64, S, K64)
+    assert rel_err(be.rowquad(kop, S), ref) < 3e-5
+    T = torch.einsum('ia,lca->ilc', K64, Lt)
+    assert rel_err(be.rowquad(kop, Lt, tri=True), (T * T).sum(-1)) < 3e-5
+    ref = torch.einsum('il,ia,lac->ic', W.double(), K64, S)
+    out = be.scaled_gemm(kop, W, S)
+    assert rel_err(out, ref) < 3e-5
+    be.scaled_gemm(kop, W, S, out=out)
+    assert rel_err(out, 2 * ref) < 3e-5

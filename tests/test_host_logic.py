@@ -1,0 +1,151 @@
+"""Host logic of the product (ops.py / step.py / svgp.py) on the CPU against the literal oracle, with the
+float64 oracle backend standing in for the CUDA library (tests only -- the product has no CPU path)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import refs
+from conftest import GOLDEN, MNIST_FIXTURE, rel_err
+from oracle import svgp_literal as lit
+import svgp_vae_b200 as pkg
+from svgp_vae_b200 import configs, ops
+
+TOL = 2e-5          # the stand-in backend rounds K_nm, p, ... to fp32 exactly like the CUDA path
+
+
+def _check(kind, cfg, clip=False):
+    o, s, op, sp = refs.make_pair(kind, cfg, "cpu")
+    r0, J0, g0 = refs.oracle_objective(o, op, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=clip)
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=clip)
+    assert rel_err(r1["p_m"], r0["p_m"]) < TOL and rel_err(r1["p_v"], r0["p_v"]) < TOL
+    for k in ("inside_elbo_recon", "inside_elbo_kl", "ce_term", "KL_term"):
+        assert abs(float(r1[k]) - float(r0[k])) < TOL * abs(float(r0[k])), k
+    for a, b in zip(g0, g1):
+        if a is not None and a.abs().max() > 0:
+            assert rel_err(b, a) < TOL
+    return r1, g1
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_step_mnist(oracle_backend, normalize):
+    r1, g1 = _check("mnist", configs.mnist_inputs(MNIST_FIXTURE, L=4, normalize=normalize))
+    gold = np.load(os.path.join(GOLDEN, "golden_outputs.npz"))
+    key = "mnist_norm" if normalize else "mnist"
+    assert rel_err(r1["p_m"], torch.from_numpy(gold[key + "/p_m"])) < TOL
+    assert rel_err(g1[2], torch.from_numpy(gold[key + "/grad_Z"])) < TOL
+
+
+def test_step_mnist_ragged_last_batch(oracle_backend):
+    _check("mnist", configs.mnist_inputs(MNIST_FIXTURE, L=2, b=210, rows="train", batch_index=15))
+
+
+@pytest.mark.parametrize("normalize", [True, False])
+def test_step_sprites_with_clip(oracle_backend, normalize):
+    _check("sprites", configs.sprites_inputs(M=72, L=4, normalize=normalize), clip=True)
+
+
+def test_step_sweep_kernel(oracle_backend):
+    _check("sweep", configs.sweep_inputs(500, 48, 3))
+
+
+def test_per_channel_api_matches_reference_signature(oracle_backend):
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=2)
+    o, s, op, sp = refs.make_pair("mnist", cfg, "cpu")
+    aux, y, nz = cfg["aux"], cfg["y"], cfg["noise"]
+    for l in range(2):
+        m0, B0, mu0, A0 = o.approximate_posterior_params(aux, aux, y[:, l], nz[:, l])
+        m1, B1, mu1, A1 = s.approximate_posterior_params(aux, aux, y[:, l], nz[:, l])
+        assert m1.dtype == torch.float64 and B1.shape == (256,) and mu1.shape == (32,) and A1.shape == (32, 32)
+        for a, b in ((m1, m0), (B1, B0), (mu1, mu0), (A1, A0)):
+            assert rel_err(a, b) < TOL
+        l0, k0 = o.variational_loss(aux, y[:, l], mu0, A0, nz[:, l])
+        l1, k1 = s.variational_loss(aux, y[:, l], mu1, A1, nz[:, l])
+        assert abs(float(l1) - float(l0)) < TOL * abs(float(l0)) and abs(float(k1) - float(k0)) < TOL * abs(float(k0))
+    # separate test / train index points (the prediction path's calling pattern, :1048-1050)
+    m0, B0, _, _ = o.approximate_posterior_params(aux[:40], aux, y[:, 0], nz[:, 0])
+    m1, B1, _, _ = s.approximate_posterior_params(aux[:40], aux, y[:, 0], nz[:, 0])
+    assert rel_err(m1, m0) < TOL and rel_err(B1, B0) < TOL
+    assert rel_err(s.mean_vector_bias_analysis(aux, y[:, 0], nz[:, 0]), o.mean_vector_bias_analysis(aux, y[:, 0], nz[:, 0])) < TOL
+    assert rel_err(s.kernel_matrix(aux, aux, False, False, True), o.kernel_matrix(aux, aux, False, False, True)) < 1e-6
+    assert len(s.variable_summary()) == 4 and all("GP" in n for n, _ in s.named_parameters())
+
+
+def test_sprites_precomputed_params(oracle_backend):
+    cfg = configs.sprites_inputs(M=72, L=1)
+    o, s, _, _ = refs.make_pair("sprites", cfg, "cpu")
+    g = torch.Generator().manual_seed(3)
+    mean_term = torch.randn(72, generator=g, dtype=torch.float64)
+    sig = torch.randn(72, 72, generator=g, dtype=torch.float64)
+    sig = sig @ sig.T / 72
+    m0, B0 = o.approximate_posterior_params_precomputed_GP_posterior_params(cfg["aux"].double(), mean_term, sig)
+    m1, B1 = s.approximate_posterior_params_precomputed_GP_posterior_params(cfg["aux"], mean_term.float(), sig.float())
+    assert rel_err(m1, m0) < TOL and rel_err(B1, B0) < TOL
+
+
+def test_ball_object(oracle_backend):
+    cfg = configs.ball_inputs(batch=6, tmax=9)
+    cfg["ctor"].update(num_inducing_points=5)
+    x, y, nz = cfg["x"], cfg["y"], cfg["noise"]
+    gold_like = []
+    for ch in range(2):
+        o = lit.BallSVGP(name="o", **cfg["ctor"])
+        s = pkg.SVGP(name="s", **cfg["ctor"])
+        y64, n64 = y[:, :, ch].double().requires_grad_(True), nz[:, :, ch].double().requires_grad_(True)
+        m0, B0, mu0, A0 = o.approximate_posterior_params(x.double(), y64, n64)
+        l0, k0 = o.variational_loss(x.double(), y64, n64, mu0, A0)
+        g0 = torch.autograd.grad((l0 - k0).sum(), [y64, n64])
+        y1, n1 = y[:, :, ch].clone().requires_grad_(True), nz[:, :, ch].clone().requires_grad_(True)
+        m1, B1, mu1, A1 = s.approximate_posterior_params(x, y=y1, noise=n1)
+        l1, k1 = s.variational_loss(x, y1, n1, mu_hat=mu1, A_hat=A1)
+        g1 = torch.autograd.grad((l1 - k1).double().sum(), [y1, n1])
+        for a, b in ((m1, m0), (B1, B0), (mu1, mu0), (A1, A0), (l1, l0), (k1, k0), (g1[0], g0[0]), (g1[1], g0[1])):
+            assert rel_err(a, b) < 5e-5          # results are returned in the object's float32
+        gold_like.append(k1)
+    assert gold_like[0].shape == (6,)
+
+
+def test_primitive_adjoints_against_autograd(oracle_backend):
+    """ops.py backward formulas vs torch autograd of the plain einsum definitions (float64 backend)."""
+    g = torch.Generator().manual_seed(0)
+    N, M, L = 23, 7, 3
+    K = torch.randn(N, M, generator=g, dtype=torch.float64, requires_grad=True)
+    W = torch.randn(N, L, generator=g, dtype=torch.float64, requires_grad=True)
+    S = torch.randn(L, M, M, generator=g, dtype=torch.float64, requires_grad=True)
+    Wm = torch.randn(L, M, generator=g, dtype=torch.float64, requires_grad=True)
+    G1 = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    G2 = torch.randn(N, L, generator=g, dtype=torch.float64)
+    G3 = torch.randn(L, M, generator=g, dtype=torch.float64)
+    pairs = [
+        (lambda: ops.syrk(K, W), lambda: torch.einsum('il,ia,ib->lab', W, K, K), G1, (K, W)),
+        (lambda: ops.rowquad(K, S).double(), lambda: torch.einsum('ia,lab,ib->il', K, S, K), G2, (K, S)),
+        (lambda: ops.kt_matmul(K, W), lambda: W.t() @ K, G3, (K, W)),
+        (lambda: ops.k_matmul(K, Wm).double(), lambda: K @ Wm.t(), G2, (K, Wm)),
+    ]
+    for f, ref, G, leaves in pairs:
+        a = torch.autograd.grad((f() * G).sum(), leaves)
+        b = torch.autograd.grad((ref() * G).sum(), leaves)
+        for x, yv in zip(a, b):
+            assert rel_err(x, yv) < 1e-5
+    X = torch.randn(L, M, M + 2, generator=g, dtype=torch.float64)
+    X = (X @ X.transpose(1, 2) + torch.eye(M, dtype=torch.float64)).requires_grad_(True)
+    Gi = torch.randn(L, M, M, generator=g, dtype=torch.float64)
+    gl = torch.randn(L, generator=g, dtype=torch.float64)
+    inv, ld, _ = ops.spd_inverse_logdet(X)
+    a = torch.autograd.grad((inv * Gi).sum() + (ld * gl).sum() + (ops.spd_logdet(X) * gl).sum(), X)[0]
+    b = torch.autograd.grad((torch.linalg.inv(X) * Gi).sum() + 2 * (torch.logdet(X) * gl).sum(), X)[0]
+    assert rel_err(ops._sym(a), ops._sym(b)) < 1e-10
+    A = torch.randn(L, M, 5, generator=g, dtype=torch.float64, requires_grad=True)
+    Bm = torch.randn(1, 5, M, generator=g, dtype=torch.float64, requires_grad=True)
+    for tA, tB in ((False, False), (True, False), (False, True), (True, True)):
+        A_ = A.transpose(1, 2).contiguous().detach().requires_grad_(True) if tA else A
+        B_ = Bm.transpose(1, 2).contiguous().detach().requires_grad_(True) if tB else Bm
+        out = ops.bmm64(A_, B_, tA, tB)
+        refo = (A_.transpose(1, 2) if tA else A_) @ (B_.transpose(1, 2) if tB else B_)
+        Go = torch.randn(*refo.shape, generator=g, dtype=torch.float64)
+        ga = torch.autograd.grad((out * Go).sum(), (A_, B_))
+        gb = torch.autograd.grad((refo * Go).sum(), (A_, B_))
+        assert rel_err(ga[0], gb[0]) < 1e-12 and rel_err(ga[1], gb[1]) < 1e-12
+    with pytest.raises(ops.NotPositiveDefinite):
+        ops.spd_logdet(-torch.eye(3, dtype=torch.float64)[None])

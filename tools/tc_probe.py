@@ -1,0 +1,62 @@
+"""Time the three tcgen05 kernels and K1 in isolation (CUDA events) and report algorithmic TFLOP/s / GB/s.
+Usage: python tools/tc_probe.py [N M L]   -> JSON lines on stdout."""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from svgp_vae_b200 import backend  # noqa: E402
+
+
+def timeit(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    return sorted(ts)[len(ts) // 2]
+
+
+def main():
+    N, M, L = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (131072, 1024, 8)
+    be = backend.get_backend()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    Fx = torch.randn(N, 8, generator=g, device="cuda"); Fz = torch.randn(M, 8, generator=g, device="cuda")
+    hyp = torch.ones(4, device="cuda")
+    spec = (1, 4, 1, 4)
+    t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=True))
+    print(json.dumps(dict(op="kernel_fwd_planes", N=N, M=M, ms=t, GBs=4 * N * M * 4 / t / 1e6)), flush=True)
+    t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=False))
+    print(json.dumps(dict(op="kernel_fwd_f32", N=N, M=M, ms=t, GBs=N * M * 4 / t / 1e6)), flush=True)
+    kop = be.kernel_fwd(spec, Fx, Fz, hyp, tc=True)
+    W = torch.randn(N, L, generator=g, device="cuda")
+    S = torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64); S = (S + S.transpose(1, 2)).contiguous()
+    Lt = torch.tril(S).contiguous()
+    for chunk in (2048, 8192, 32768):
+        t = timeit(lambda: be.syrk(kop, W, chunk_rows=chunk))
+        print(json.dumps(dict(op="syrk_tc", chunk=chunk, N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
+    t = timeit(lambda: be.rowquad(kop, S))
+    print(json.dumps(dict(op="rowquad_tc_full", N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
+    t = timeit(lambda: be.rowquad(kop, Lt, tri=True))
+    print(json.dumps(dict(op="rowquad_tc_tri", N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
+    t = timeit(lambda: be.scaled_gemm(kop, W, S))
+    print(json.dumps(dict(op="scaled_gemm_tc", N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
+    G = torch.randn(N, M, generator=g, device="cuda")
+    t = timeit(lambda: be.kernel_bwd(spec, Fx, Fz, hyp, G))
+    print(json.dumps(dict(op="kernel_bwd", N=N, M=M, ms=t)), flush=True)
+    X = torch.randn(64, M, M, generator=g, device="cuda", dtype=torch.float64)
+    X = X @ X.transpose(1, 2) / M + torch.eye(M, device="cuda", dtype=torch.float64)
+    t = timeit(lambda: be.chol(X)); print(json.dumps(dict(op="chol64", M=M, batch=64, ms=t)), flush=True)
+    Lf, _ = be.chol(X)
+    t = timeit(lambda: be.trinv(Lf)); print(json.dumps(dict(op="trinv64", M=M, batch=64, ms=t)), flush=True)
+    t = timeit(lambda: be.bmm64(X, X)); print(json.dumps(dict(op="bmm64", M=M, batch=64, ms=t, TFLOPs=2 * 64 * M ** 3 / t / 1e9)), flush=True)
+    t = timeit(lambda: be.gemm_tn(kop, W)); print(json.dumps(dict(op="gemm_tn", ms=t)), flush=True)
+    t = timeit(lambda: be.gemm_nn(kop, torch.randn(L, M, device="cuda"))); print(json.dumps(dict(op="gemm_nn", ms=t)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
