@@ -3,7 +3,7 @@
 // lives in memory as a TF32 pair x = hi + lo (written by K1 / svgp_split_tf32) and each k-step issues
 //     D += A_lo * B_hi;   D += A_hi * B_lo;   D += A_hi * B_hi          (fp32 accumulators in TMEM)
 //
-//   MODE_SYRK    A_l[a,b]  += sum_n Kt[a,n] * (w[n,l] Kt[b,n])   K2, SVGPVAE_model.py:328-330 and the
+//   MODE_SYRK    A_l[a,b]  += sum_n (w[n,l] Kt[a,n]) * Kt[b,n]   K2, SVGPVAE_model.py:328-330 and the
 //                                                                adjoint of the row-wise quadratic forms
 //   MODE_ROWQUAD q[i,l]     = sum_c (sum_a K[i,a] B_l[c,a]) * X   K4, :336-337, :284   (X = same product when
 //                                                                B_l is a triangular factor, else K[i,c])
@@ -438,9 +438,11 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           }
           mbar_wait(&full[stage], phase);
           uint8_t* st = smem + stage * SL::STAGE_BYTES;
-          constexpr int ROWS = (MODE == MODE_SYRK) ? BN : BLOCK_M;
-          uint8_t* hi_p = st + ((MODE == MODE_SYRK) ? 2 * SL::A_BYTES : 0);
-          uint8_t* lo_p = hi_p + ((MODE == MODE_SYRK) ? SL::B_BYTES : SL::A_BYTES);
+          // both modes rescale the 128-row A operand (for the SYRK the weight may sit on either factor of
+          // k_a k_b; the A tile is half the size of the B tile, which halves the shared-memory traffic here)
+          constexpr int ROWS = BLOCK_M;
+          uint8_t* hi_p = st;
+          uint8_t* lo_p = st + SL::A_BYTES;
 #pragma unroll
           for (int r = 0; r < ROWS / 16; ++r) {
             const int off = (rbase + 16 * r) * 128 + pchunk * 16;

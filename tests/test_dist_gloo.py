@@ -1,0 +1,75 @@
+"""N-sharded SVGP step over 2 ranks (gloo, CPU, float64 stand-in backend) == the single-process step.
+
+Covers the host logic of SURVEY 8(e): all-reduce of A_l / v_l / row sums in the forward, of their
+adjoints in the backward, the global batch size in N_train / b, and the gradient convention
+(per-rank loss = local terms + global scalars / world; replicated parameters get per-rank partial
+gradients that sum to the single-process gradient)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import refs
+from svgp_vae_b200 import configs
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, kind, cfg, clip, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    from oracle_backend import OracleBackend
+    from svgp_vae_b200 import backend
+    backend.set_backend_for_tests(OracleBackend())
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, s, _, sp = refs.make_pair(kind, cfg, "cpu")
+    n = cfg["aux"].shape[0] // world
+    sl = slice(rank * n, (rank + 1) * n)
+    y = cfg["y"][sl].clone().requires_grad_(True)
+    nz = cfg["noise"][sl].clone().requires_grad_(True)
+    res = s.elbo_step(cfg["aux"][sl], y, nz, clip_pv=clip, group=dist.group.WORLD)
+    gm, gv = refs.upstream(tuple(cfg["y"].shape))
+    J = (gm[sl].to(res["p_m"].dtype) * res["p_m"]).sum().double() + (gv[sl].to(res["p_v"].dtype) * res["p_v"]).sum().double() \
+        + res["KL_term"] / world
+    grads = torch.autograd.grad(J, [y, nz] + list(sp))
+    pg = [g.double().clone() for g in grads[2:]]
+    for g in pg:
+        dist.all_reduce(g)
+    Jt = J.detach().clone()
+    dist.all_reduce(Jt)
+    out[rank] = dict(p_m=res["p_m"].detach(), p_v=res["p_v"].detach(), KL_term=float(res["KL_term"]), J=float(Jt),
+                     gy=grads[0], gn=grads[1], pg=pg)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,clip", [("mnist", False), ("sprites", True)])
+def test_sharded_step_matches_single_process(oracle_backend, kind, clip):
+    from conftest import MNIST_FIXTURE, rel_err
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=3) if kind == "mnist" else configs.sprites_inputs(M=72, L=3, normalize=False)
+    _, s, _, sp = refs.make_pair(kind, cfg, "cpu")
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=clip)
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), kind, cfg, clip, out), nprocs=world, join=True)
+    n = cfg["aux"].shape[0] // world
+    tol = 2e-6
+    for r in range(world):
+        sl = slice(r * n, (r + 1) * n)
+        o = out[r]
+        assert rel_err(o["p_m"], r1["p_m"][sl]) < tol and rel_err(o["p_v"], r1["p_v"][sl]) < tol
+        assert abs(o["KL_term"] - float(r1["KL_term"])) < tol * abs(float(r1["KL_term"]))
+        assert abs(o["J"] - float(J1)) < tol * abs(float(J1))
+        assert rel_err(o["gy"], g1[0][sl]) < 1e-5 and rel_err(o["gn"], g1[1][sl]) < 1e-5
+        for a, b in zip(o["pg"], g1[2:]):
+            if b.abs().max() > 0:
+                assert rel_err(a, b) < 1e-5
