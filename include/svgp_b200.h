@@ -45,7 +45,7 @@ extern "C" {
 /* implementation selector for the GEMM-class entry points */
 #define SVGP_IMPL_AUTO 0
 #define SVGP_IMPL_SIMT 1 /* fp32 CUDA-core tiles, any shape                                   */
-#define SVGP_IMPL_TC 2   /* tcgen05 / TMEM / TMA, 3xTF32 split operands                       */
+#define SVGP_IMPL_TC 2   /* tcgen05 / TMEM / TMA, fp32-emulating 3 x FP16 split operands          */
 
 int svgp_version(void);
 const char* svgp_last_error(void); /* host string, thread-local */
@@ -58,13 +58,18 @@ int svgp_device_ok(void);          /* 1 if the current device is compute capabil
  *           .matrix/.apply calls under them.
  * Fx (N x d) / Fz (M x d) are dense fp32 feature rows [block A | block B], d = dim_a+dim_b.
  * hyp = device float[4] = {amplitude_a, length_a, amplitude_b, length_b} (unused entries 1).
- * Outputs (any may be NULL): K (N x M), Kt (M x N, the transpose).  When K_lo / Kt_lo are
- * non-NULL the value is written as a TF32 pair: K = rna_tf32(k), K_lo = rna_tf32(k - K).
+ * Outputs (each group may be NULL):
+ *   K   (N x M fp32, ld = ldk)                         plain matrix for the SIMT consumers
+ *   Kh, Kl   (N x M fp16 planes, ld = ldkh elements)   operand planes of the tcgen05 consumers:
+ *   Kth, Ktl (M x N fp16 planes, ld = ldkt elements)   value * scale = fp16 hi + fp16 lo (22 bits),
+ *            with scale = the power of two that puts the kernel's upper bound (amplitudes, max
+ *            feature norms) just below 2^14; kscale (device float[8], required with the planes)
+ *            receives {scale, 1/scale, ...scratch}.  Rows/columns beyond N / M up to ld stay untouched.
  * ------------------------------------------------------------------------------------- */
 int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M,
                     int type_a, int dim_a, int type_b, int dim_b, const float* hyp,
-                    float* K, float* K_lo, int64_t ldk, float* Kt, float* Kt_lo, int64_t ldkt,
-                    void* stream);
+                    float* K, int64_t ldk, void* Kh, void* Kl, int64_t ldkh, void* Kth, void* Ktl,
+                    int64_t ldkt, float* kscale, void* stream);
 
 /* adjoint of svgp_kernel_fwd.  G (N x M) is dObjective/dK.  dFx (N x d) is overwritten;
  * dFz (M x d, double) and dhyp (double[4]) are ACCUMULATED into (caller zeroes them).
@@ -89,24 +94,36 @@ int svgp_scatter_add_rows(const float* g, int64_t ldg, const int64_t* ids, int64
                           int64_t rows, double* dtable, int64_t ldt, void* stream);
 
 /* ---------------------------------------------------------------------------------------
- * The operand "Kop" of the GEMM-class calls is K_nm (N x M).  SIMT: pass K (fp32) and NULL
- * for the other planes.  TC: pass the four TF32 planes written by svgp_kernel_fwd.
+ * The operand "Kop" of the GEMM-class calls is K_nm (N x M).  SIMT: K (fp32), the planes NULL.
+ * TC: the four fp16 planes and kscale written by svgp_kernel_fwd (K may be NULL).
  * ------------------------------------------------------------------------------------- */
 typedef struct svgp_kop {
-  const float* K;     /* N x M, ld = ldk   (TC: hi plane)            */
-  const float* K_lo;  /* N x M             (TC only, else NULL)      */
-  const float* Kt;    /* M x N, ld = ldkt  (TC only: hi plane)       */
-  const float* Kt_lo; /* M x N             (TC only)                 */
-  int64_t N, M, ldk, ldkt;
+  const float* K;      /* N x M fp32, ld = ldk (SIMT operand; may be NULL when the planes are given) */
+  const void* Kh;      /* N x M fp16 hi plane, ld = ldkh                                            */
+  const void* Kl;      /* N x M fp16 lo plane                                                       */
+  const void* Kth;     /* M x N fp16 hi plane of the transpose, ld = ldkt                           */
+  const void* Ktl;     /* M x N fp16 lo plane                                                       */
+  const float* kscale; /* device float[>=2]: {scale, 1/scale} of the planes                         */
+  int64_t N, M, ldk, ldkh, ldkt;
 } svgp_kop;
 
+/* per-matrix fp16 operand planes of a (nb x rows x cols) float64 batch:  x * s_b = hi + lo with
+ * s_b = 2^(14 - e_b), max|x_b| = m 2^e_b (m in [0.5,1));  inv_scale: device float[2*nb] =
+ * {1/s_b ..., scratch...}.  replaces nothing in the reference: it is the operand format of the
+ * tensor-core calls below (the 3 x FP16 split emulating fp32 products).                        */
+int svgp_split_f16(const double* x, int64_t nb, int64_t count, void* hi, void* lo, float* inv_scale,
+                   void* stream);
+
 /* K2  batched weighted SYRK   A[l] = sum_i W[i,l] k_i k_i^T   (L x M x M, double, ACCUMULATED:
- * caller zeroes; both triangles written).  W is N x L fp32 (any sign); the TC path reads the
- * channel-major copy Wt (L x N, ld = ldwt, 16-byte aligned rows) instead, the SIMT path ignores it.
+ * caller zeroes; both triangles written).  W is N x L fp32 (any sign).  The TC path needs the
+ * workspace ws (float[svgp_syrk_ws_floats(N, L)]): it holds the channel-major copy of W scaled
+ * per channel by a power of two (|w s_l| <= 1, so that w * k stays inside fp16 range) and 1/s_l.
+ * chunk_rows: datapoints per TMEM accumulation chain (0 = default 2048).
  * replaces: K_mn (K_nm * 1/sigma^2) SVGPVAE_model.py:328-330 (:160 for the ball) and, as the
  * adjoint of svgp_rowquad, the (b,m,m) trace pattern :286-294.                               */
-int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, const float* Wt, int64_t ldwt, int64_t L,
-              double* A, int impl, int64_t chunk_rows, void* stream);
+int64_t svgp_syrk_ws_floats(int64_t N, int64_t L);
+int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, int impl,
+              int64_t chunk_rows, float* ws, void* stream);
 
 /* V[l, :] += sum_i X[i,l] k_i          (L x M double, accumulated)  -- K_mn (p*y), :333-334   */
 int svgp_gemm_tn(const svgp_kop* kop, const float* X, int64_t ldx, int64_t L, double* V, void* stream);
@@ -116,26 +133,26 @@ int svgp_gemm_nn(const svgp_kop* kop, const float* Wm, int64_t ldwm, int64_t L, 
                  int64_t ldo, void* stream);
 
 /* K4  row-wise quadratic forms  q[i,l] = k_i^T S_l k_i  (N x L fp32).
- * S (L x M x M, symmetric) is given as fp32 planes S_hi (+ S_lo for TC; NULL for SIMT).
- * If `tri` != 0 the planes hold a lower-triangular factor Rinv_l instead and
- * q[i,l] = |Rinv_l k_i|^2 (half the work).  L may be 1 with N x 1 output (h_i = k^T Kinv k).
+ * S (L x M x M, symmetric): SIMT takes one fp32 plane S_hi (S_lo, S_inv NULL); TC takes the fp16
+ * planes + inv_scale of svgp_split_f16.  If `tri` != 0 the planes hold a lower-triangular factor
+ * Rinv_l instead and q[i,l] = |Rinv_l k_i|^2 (half the work, a sum of squares: no cancellation).
+ * L may be 1 with N x 1 output (h_i = k^T Kinv k).
  * replaces: diag_part(K_xm Sigma_l^-1 K_mx), diag_part(K_xm K_mm^-1 K_mx) :336-337, :284.    */
-int svgp_rowquad(const svgp_kop* kop, const float* S_hi, const float* S_lo, int64_t L, int tri,
-                 float* q, int64_t ldq, int impl, void* stream);
+int svgp_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L,
+                 int tri, float* q, int64_t ldq, int impl, void* stream);
 
-/* out[i, :] (+)= sum_l W[i,l] * (G_l k_i)     (N x M fp32), G (L x M x M symmetric) as planes.
- * accumulate != 0 adds to `out`.  This is dObjective/dK_nm through svgp_syrk (W=p, G=dA+dA^T)
- * and through svgp_rowquad (W=2*dq, G=S).  replaces: tf.gradients through :328-337.          */
-int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const float* G_hi,
-                     const float* G_lo, int64_t L, float* out, int64_t ldo, int accumulate, int impl,
-                     void* stream);
+/* out[i, :] (+)= sum_l W[i,l] * (G_l k_i)     (N x M fp32), G (L x M x M symmetric) as planes
+ * (same convention as svgp_rowquad).  accumulate != 0 adds to `out`.  If dots != NULL also
+ * dots[i,l] += k_i^T G_l k_i for l < ndot (N x ndot fp32, caller zeroes) from the same products.
+ * This is dObjective/dK_nm through svgp_syrk (W = p, G = dA+dA^T; the dots are dObjective/dp) and
+ * through svgp_rowquad (W = 2 dq, G = S).  replaces: tf.gradients through :328-337.           */
+int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo,
+                     const float* G_inv, int64_t L, float* out, int64_t ldo, int accumulate, float* dots,
+                     int64_t lddots, int64_t ndot, int impl, void* stream);
 
 /* out (N x M) (+)= W (N x L) @ V (L x M), all fp32 -- rank-L part of dK_nm (p_m, mean terms)  */
 int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t lda, const float* B,
                   int64_t ldb, float* C, int64_t ldc, int accumulate, void* stream);
-
-/* split a double array into a TF32 pair: hi = rna_tf32(x), lo = rna_tf32(x - hi)              */
-int svgp_split_tf32(const double* x, float* hi, float* lo, int64_t n, void* stream);
 
 /* ---------------------------------------------------------------------------------------
  * K3  batched float64 factorisations over the latent channels

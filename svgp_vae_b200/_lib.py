@@ -17,8 +17,9 @@ IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
 
 class KopStruct(ctypes.Structure):
     """struct svgp_kop (include/svgp_b200.h)."""
-    _fields_ = [("K", c_void_p), ("K_lo", c_void_p), ("Kt", c_void_p), ("Kt_lo", c_void_p),
-                ("N", c_int64), ("M", c_int64), ("ldk", c_int64), ("ldkt", c_int64)]
+    _fields_ = [("K", c_void_p), ("Kh", c_void_p), ("Kl", c_void_p), ("Kth", c_void_p), ("Ktl", c_void_p),
+                ("kscale", c_void_p), ("N", c_int64), ("M", c_int64), ("ldk", c_int64), ("ldkh", c_int64),
+                ("ldkt", c_int64)]
 
 
 class SvgpLibraryError(RuntimeError):
@@ -32,20 +33,22 @@ SIGNATURES = {
     "svgp_last_error": [],
     "svgp_device_ok": [],
     "svgp_kernel_fwd": [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P,
-                        _P, _P, c_int64, _P, _P, c_int64, _P],
+                        _P, c_int64, _P, _P, c_int64, _P, _P, c_int64, _P, _P],
     "svgp_kernel_bwd": [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P,
                         _P, c_int64, _P, _P, _P, _P],
     "svgp_kernel_diag_fwd": [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P],
     "svgp_kernel_diag_bwd": [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "svgp_gather_rows": [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, _P],
     "svgp_scatter_add_rows": [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, c_int64, _P],
-    "svgp_syrk": [POINTER(KopStruct), _P, c_int64, _P, c_int64, c_int64, _P, c_int, c_int64, _P],
+    "svgp_syrk_ws_floats": [c_int64, c_int64],
+    "svgp_syrk": [POINTER(KopStruct), _P, c_int64, c_int64, _P, c_int, c_int64, _P, _P],
     "svgp_gemm_tn": [POINTER(KopStruct), _P, c_int64, c_int64, _P, _P],
     "svgp_gemm_nn": [POINTER(KopStruct), _P, c_int64, c_int64, _P, c_int64, _P],
-    "svgp_rowquad": [POINTER(KopStruct), _P, _P, c_int64, c_int, _P, c_int64, c_int, _P],
-    "svgp_scaled_gemm": [POINTER(KopStruct), _P, c_int64, _P, _P, c_int64, _P, c_int64, c_int, c_int, _P],
+    "svgp_rowquad": [POINTER(KopStruct), _P, _P, _P, c_int64, c_int, _P, c_int64, c_int, _P],
+    "svgp_scaled_gemm": [POINTER(KopStruct), _P, c_int64, _P, _P, _P, c_int64, _P, c_int64, c_int, _P, c_int64, c_int64,
+                         c_int, _P],
     "svgp_gemm_f32": [c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _P],
-    "svgp_split_tf32": [_P, _P, _P, c_int64, _P],
+    "svgp_split_f16": [_P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_chol_f64": [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P],
     "svgp_trinv_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P],
     "svgp_gemm_f64": [c_int, c_int, c_int64, c_int64, c_int64, c_double, _P, c_int64, c_int64, _P, c_int64,
@@ -53,7 +56,7 @@ SIGNATURES = {
     "svgp_rowstats_fwd": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_predictive_fwd": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P],
 }
-_RESTYPE = {"svgp_last_error": c_char_p}
+_RESTYPE = {"svgp_last_error": c_char_p, "svgp_syrk_ws_floats": c_int64}
 
 _lib = None
 

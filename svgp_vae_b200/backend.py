@@ -18,33 +18,50 @@ from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, KopStruct
 class Kop:
     """K_nm (N x M) in the storage the GEMM-class kernels read.
 
-    SIMT: one fp32 matrix.  TC: TF32 (hi, lo) planes of K_nm and of its transpose (see
-    tc_engine.cu); ``value()`` reassembles hi + lo when a plain matrix is asked for.
+    SIMT: one fp32 matrix ``K``.  TC: scaled fp16 (hi, lo) planes of K_nm (``Kh``/``Kl``) and of its transpose
+    (``Kth``/``Ktl``) plus the device scale record ``kscale`` = {scale, 1/scale, ...} (see tc_engine.cu);
+    ``value()`` reassembles (hi + lo) / scale when a plain matrix is asked for.
     """
 
-    def __init__(self, K, K_lo=None, Kt=None, Kt_lo=None, N=None, M=None):
-        self.K, self.K_lo, self.Kt, self.Kt_lo = K, K_lo, Kt, Kt_lo
-        self.N = K.shape[0] if N is None else N
-        self.M = K.shape[1] if M is None else M
+    def __init__(self, K=None, Kh=None, Kl=None, Kth=None, Ktl=None, kscale=None, N=None, M=None):
+        self.K, self.Kh, self.Kl, self.Kth, self.Ktl, self.kscale = K, Kh, Kl, Kth, Ktl, kscale
+        ref = K if K is not None else Kh
+        self.N = ref.shape[0] if N is None else N
+        self.M = ref.shape[1] if M is None else M
 
     @property
     def tc(self):
-        return self.K_lo is not None
+        return self.Kh is not None
+
+    @property
+    def device(self):
+        return (self.K if self.K is not None else self.Kh).device
 
     def value(self):
-        K = self.K[: self.N, : self.M]
-        return K if self.K_lo is None else K + self.K_lo[: self.N, : self.M]
+        if self.K is not None:
+            return self.K[: self.N, : self.M]
+        return (self.Kh[: self.N, : self.M].float() + self.Kl[: self.N, : self.M].float()) * self.kscale[1]
 
     def struct(self):
         s = KopStruct()
-        s.K = self.K.data_ptr()
-        s.K_lo = self.K_lo.data_ptr() if self.K_lo is not None else None
-        s.Kt = self.Kt.data_ptr() if self.Kt is not None else None
-        s.Kt_lo = self.Kt_lo.data_ptr() if self.Kt_lo is not None else None
+        s.K = self.K.data_ptr() if self.K is not None else None
+        s.Kh = self.Kh.data_ptr() if self.Kh is not None else None
+        s.Kl = self.Kl.data_ptr() if self.Kl is not None else None
+        s.Kth = self.Kth.data_ptr() if self.Kth is not None else None
+        s.Ktl = self.Ktl.data_ptr() if self.Ktl is not None else None
+        s.kscale = self.kscale.data_ptr() if self.kscale is not None else None
         s.N, s.M = self.N, self.M
-        s.ldk = self.K.stride(0)
-        s.ldkt = self.Kt.stride(0) if self.Kt is not None else 0
+        s.ldk = self.K.stride(0) if self.K is not None else 0
+        s.ldkh = self.Kh.stride(0) if self.Kh is not None else 0
+        s.ldkt = self.Kth.stride(0) if self.Kth is not None else 0
         return s
+
+
+class Planes:
+    """fp16 (hi, lo) operand planes of a (B, M, M) float64 batch with per-matrix 1/scale (svgp_split_f16)."""
+
+    def __init__(self, hi, lo, inv):
+        self.hi, self.lo, self.inv = hi, lo, inv
 
 
 _PROFILE = None
@@ -101,14 +118,16 @@ class CudaBackend:
         _PROFILE = []
 
     def stop_profile(self):
-        """-> {entry point: {"ms": total device time, "calls": n}} since start_profile()."""
+        """-> {entry point: {"ms": total device time, "calls": n, "max_ms": longest call}} since start_profile()."""
         global _PROFILE
         torch.cuda.synchronize()
         out = {}
         for name, e0, e1 in _PROFILE or []:
-            d = out.setdefault(name, {"ms": 0.0, "calls": 0})
-            d["ms"] += e0.elapsed_time(e1)
+            d = out.setdefault(name, {"ms": 0.0, "calls": 0, "max_ms": 0.0})
+            t = e0.elapsed_time(e1)
+            d["ms"] += t
             d["calls"] += 1
+            d["max_ms"] = max(d["max_ms"], t)
         _PROFILE = None
         return out
 
@@ -120,23 +139,24 @@ class CudaBackend:
         Fx, Fz, hyp = _f32c(Fx), _f32c(Fz), _f32c(hyp)
         N, M = Fx.shape[0], Fz.shape[0]
         ta, da, tb, db = spec
+        dev = Fx.device
         if tc:
-            ldk, ldkt = _pad(M, 4), _pad(N, 4)
-            K = torch.empty((N, ldk), device=Fx.device, dtype=torch.float32)
-            K_lo = torch.empty_like(K)
-            Kt = torch.empty((M, ldkt), device=Fx.device, dtype=torch.float32)
-            Kt_lo = torch.empty_like(Kt)
-            if ldk != M:
-                K.zero_(); K_lo.zero_()
-            if ldkt != N:
-                Kt.zero_(); Kt_lo.zero_()
-            kop = Kop(K, K_lo, Kt, Kt_lo, N, M)
+            ldkh, ldkt = _pad(M, 8), _pad(N, 8)
+            alloc = torch.zeros if (ldkh != M) else torch.empty
+            Kh = alloc((N, ldkh), device=dev, dtype=torch.float16)
+            Kl = alloc((N, ldkh), device=dev, dtype=torch.float16)
+            alloc = torch.zeros if (ldkt != N) else torch.empty
+            Kth = alloc((M, ldkt), device=dev, dtype=torch.float16)
+            Ktl = alloc((M, ldkt), device=dev, dtype=torch.float16)
+            kscale = torch.empty(8, device=dev, dtype=torch.float32)
+            kop = Kop(None, Kh, Kl, Kth, Ktl, kscale, N, M)
+            _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+                  None, 0, _ptr(Kh), _ptr(Kl), ldkh, _ptr(Kth), _ptr(Ktl), ldkt, _ptr(kscale), _stream())
         else:
-            K = torch.empty((N, M), device=Fx.device, dtype=torch.float32)
+            K = torch.empty((N, M), device=dev, dtype=torch.float32)
             kop = Kop(K)
-        _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
-                  _ptr(kop.K), _ptr(kop.K_lo), kop.K.stride(0), _ptr(kop.Kt), _ptr(kop.Kt_lo),
-                  kop.Kt.stride(0) if kop.Kt is not None else 0, _stream())
+            _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+                  _ptr(K), K.stride(0), None, None, 0, None, None, 0, None, _stream())
         self.launches += 1
         return kop
 
@@ -189,87 +209,85 @@ class CudaBackend:
         return dt
 
     # ---- GEMM class ------------------------------------------------------------------------
-    def _planes(self, S64, tc):
-        """(L, M, M) float64 -> fp32 plane(s) the kernels read."""
+    def planes(self, S64):
+        """(B, M, M) float64 -> scaled fp16 (hi, lo) planes + per-matrix 1/scale (the TC operand format)."""
         S64 = _f64c(S64)
-        if not tc:
-            return S64.to(torch.float32), None
-        hi = torch.empty(S64.shape, device=S64.device, dtype=torch.float32)
+        nb = S64.shape[0]
+        hi = torch.empty(S64.shape, device=S64.device, dtype=torch.float16)
         lo = torch.empty_like(hi)
-        _call("svgp_split_tf32", _ptr(S64), _ptr(hi), _ptr(lo), S64.numel(), _stream())
-        self.launches += 1
-        return hi, lo
+        inv = torch.empty(2 * nb, device=S64.device, dtype=torch.float32)
+        _call("svgp_split_f16", _ptr(S64), nb, S64[0].numel(), _ptr(hi), _ptr(lo), _ptr(inv), _stream())
+        self.launches += 2
+        return Planes(hi, lo, inv)
 
     def syrk(self, kop, W, impl=IMPL_AUTO, chunk_rows=0):
         W = _f32c(W)
         L = W.shape[1]
         A = torch.zeros((L, kop.M, kop.M), device=W.device, dtype=torch.float64)
-        Wt = None
         use_tc = kop.tc and impl != IMPL_SIMT
+        ws = None
         if use_tc:
-            ldwt = _pad(kop.N, 4)
-            Wt = torch.zeros((L, ldwt), device=W.device, dtype=torch.float32)
-            Wt[:, : kop.N] = W.t()
+            ws = torch.empty(int(_lib.load().svgp_syrk_ws_floats(kop.N, L)), device=W.device, dtype=torch.float32)
         s = kop.struct()
-        _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(Wt), Wt.stride(0) if Wt is not None else 0, L,
-                  _ptr(A), IMPL_TC if use_tc else IMPL_SIMT, chunk_rows, _stream())
-        self.launches += 1
+        _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), L, _ptr(A), IMPL_TC if use_tc else IMPL_SIMT, chunk_rows,
+              _ptr(ws), _stream())
+        self.launches += 4 if use_tc else 1
         return A
-
-    def _plane_structs(self, kop):
-        """gemm_tn / gemm_nn read one fp32 plane; a TC operand is the exact sum hi + lo of two planes, so the
-        (linear) product is run once per plane and summed."""
-        s = kop.struct()
-        if not kop.tc:
-            return [s]
-        s_lo = kop.struct()
-        s_lo.K = kop.K_lo.data_ptr()
-        return [s, s_lo]
 
     def gemm_tn(self, kop, X):
         X = _f32c(X)
         L = X.shape[1]
         V = torch.zeros((L, kop.M), device=X.device, dtype=torch.float64)
-        for s in self._plane_structs(kop):
-            _call("svgp_gemm_tn", ctypes.byref(s), _ptr(X), X.stride(0), L, _ptr(V), _stream())
-            self.launches += 1
+        s = kop.struct()
+        _call("svgp_gemm_tn", ctypes.byref(s), _ptr(X), X.stride(0), L, _ptr(V), _stream())
+        self.launches += 1
         return V
 
     def gemm_nn(self, kop, Wm):
         Wm = _f32c(Wm)
         L = Wm.shape[0]
-        outs = []
-        for s in self._plane_structs(kop):
-            out = torch.empty((kop.N, L), device=Wm.device, dtype=torch.float32)
-            _call("svgp_gemm_nn", ctypes.byref(s), _ptr(Wm), Wm.stride(0), L, _ptr(out), out.stride(0), _stream())
-            self.launches += 1
-            outs.append(out)
-        return outs[0] if len(outs) == 1 else outs[0].add_(outs[1])
+        out = torch.empty((kop.N, L), device=Wm.device, dtype=torch.float32)
+        s = kop.struct()
+        _call("svgp_gemm_nn", ctypes.byref(s), _ptr(Wm), Wm.stride(0), L, _ptr(out), out.stride(0), _stream())
+        self.launches += 1
+        return out
+
+    def _operand(self, S64, use_tc):
+        """-> (hi ptr, lo ptr, inv ptr, keep-alive) of a float64 batch in the format the chosen implementation reads."""
+        if use_tc:
+            pl = S64 if isinstance(S64, Planes) else self.planes(S64)
+            return _ptr(pl.hi), _ptr(pl.lo), _ptr(pl.inv), pl
+        S32 = _f64c(S64).to(torch.float32)
+        return _ptr(S32), None, None, S32
 
     def rowquad(self, kop, S64, tri=False, impl=IMPL_AUTO):
-        L = S64.shape[0]
+        L = (S64.hi if isinstance(S64, Planes) else S64).shape[0]
         use_tc = kop.tc and impl != IMPL_SIMT
-        hi, lo = self._planes(S64, use_tc)
-        q = torch.empty((kop.N, L), device=S64.device, dtype=torch.float32)
+        hi, lo, inv, keep = self._operand(S64, use_tc)
+        q = torch.empty((kop.N, L), device=kop.device, dtype=torch.float32)
         s = kop.struct()
-        _call("svgp_rowquad", ctypes.byref(s), _ptr(hi), _ptr(lo), L, int(bool(tri)), _ptr(q), q.stride(0),
-                  IMPL_TC if use_tc else IMPL_SIMT, _stream())
+        _call("svgp_rowquad", ctypes.byref(s), hi, lo, inv, L, int(bool(tri)), _ptr(q), q.stride(0),
+              IMPL_TC if use_tc else IMPL_SIMT, _stream())
         self.launches += 1
+        del keep
         return q
 
-    def scaled_gemm(self, kop, W, G64, out=None, impl=IMPL_AUTO):
+    def scaled_gemm(self, kop, W, G64, out=None, ndot=0, impl=IMPL_AUTO):
+        """out (+)= sum_l diag(W[:, l]) K G_l; with ndot > 0 also returns dots[i, l] = k_i^T G_l k_i for l < ndot."""
         W = _f32c(W)
         L = W.shape[1]
         use_tc = kop.tc and impl != IMPL_SIMT
-        hi, lo = self._planes(G64, use_tc)
+        hi, lo, inv, keep = self._operand(G64, use_tc)
         accumulate = out is not None
         if out is None:
             out = torch.empty((kop.N, kop.M), device=W.device, dtype=torch.float32)
+        dots = torch.zeros((kop.N, ndot), device=W.device, dtype=torch.float32) if ndot else None
         s = kop.struct()
-        _call("svgp_scaled_gemm", ctypes.byref(s), _ptr(W), W.stride(0), _ptr(hi), _ptr(lo), L, _ptr(out),
-                  out.stride(0), int(accumulate), IMPL_TC if use_tc else IMPL_SIMT, _stream())
-        self.launches += 1
-        return out
+        _call("svgp_scaled_gemm", ctypes.byref(s), _ptr(W), W.stride(0), hi, lo, inv, L, _ptr(out), out.stride(0),
+              int(accumulate), _ptr(dots), ndot, ndot, IMPL_TC if use_tc else IMPL_SIMT, _stream())
+        self.launches += 1 + (0 if use_tc or not ndot else 1)
+        del keep
+        return (out, dots) if ndot else out
 
     def gemm_f32(self, A, B, out=None):
         A, B = _f32c(A), _f32c(B)

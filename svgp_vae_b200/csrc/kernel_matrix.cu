@@ -6,7 +6,8 @@
 // k(x, z) = kA(xA, zA) * kB(xB, zB), each factor one of NONE / SE / EXPSIN / LINEAR / COSINE.
 // The builder is HBM-bound: every output element is written once (coalesced, through a
 // padded shared-memory tile so that both K (N x M) and its transpose Kt (M x N) leave the SM
-// as full 256-byte row segments), optionally as a TF32 hi/lo pair for the tcgen05 consumers.
+// as full row segments), optionally as a scaled fp16 hi/lo pair for the tcgen05 consumers.
+#include <cuda_fp16.h>
 #include <stdarg.h>
 
 #include "common.cuh"
@@ -138,10 +139,50 @@ __device__ __forceinline__ void load_features(const float* F, int64_t ld, int64_
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+// Power-of-two scale of the fp16 planes: the kernel's upper bound (amplitude^2 for the stationary factors,
+// max|x| max|z| for LINEAR, 1 for COSINE) is brought just below 2^14, so that value * scale = hi + lo keeps
+// 22 significand bits for every entry larger than 2^-17 of the bound and never overflows fp16.
+__device__ __forceinline__ float factor_bound(int type, float amp, float nx, float nz) {
+  if (type == SVGP_K_SE || type == SVGP_K_EXPSIN) return amp * amp;
+  if (type == SVGP_K_LINEAR) return nx * nz;
+  return 1.0f;
+}
+__device__ __forceinline__ float plane_scale(Spec sp, Hyp h, const float* ks) {
+  float b = factor_bound(sp.ta, h.amp_a, ks[2], ks[4]) * factor_bound(sp.tb, h.amp_b, ks[3], ks[5]);
+  if (!(b > 0.f) || !isfinite(b)) return 1.0f;
+  int e;
+  frexpf(b, &e);                       // b = m 2^e, m in [0.5, 1)
+  e = 14 - e;
+  if (e > 100) e = 100;
+  if (e < -100) e = -100;
+  return ldexpf(1.0f, e);
+}
+
+// max Euclidean norms of the two feature blocks over the rows of F -> ks[slot], ks[slot + 1] (float bits, >= 0)
+__global__ void feature_norm_kernel(const float* __restrict__ F, int64_t ld, int64_t rows, Spec sp, float* ks, int slot) {
+  float ma = 0.f, mb = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < rows; i += (int64_t)gridDim.x * blockDim.x) {
+    float sa = 0.f, sb = 0.f;
+    for (int f = 0; f < sp.da; ++f) { float v = F[i * ld + f]; sa = fmaf(v, v, sa); }
+    for (int f = 0; f < sp.db; ++f) { float v = F[i * ld + sp.da + f]; sb = fmaf(v, v, sb); }
+    ma = fmaxf(ma, sqrtf(sa)); mb = fmaxf(mb, sqrtf(sb));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<int*>(ks + slot), __float_as_int(ma));
+    atomicMax(reinterpret_cast<int*>(ks + slot + 1), __float_as_int(mb));
+  }
+}
+
 __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
     const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz, int64_t M,
-    Spec sp, const float* __restrict__ hyp, float* __restrict__ K, float* __restrict__ K_lo, int64_t ldk,
-    float* __restrict__ Kt, float* __restrict__ Kt_lo, int64_t ldkt) {
+    Spec sp, const float* __restrict__ hyp, float* __restrict__ K, int64_t ldk, __half* __restrict__ Kh,
+    __half* __restrict__ Kl, int64_t ldkh, __half* __restrict__ Kth, __half* __restrict__ Ktl, int64_t ldkt,
+    float* __restrict__ kscale) {
   extern __shared__ float smem[];
   const int d = sp.da + sp.db, dp = d | 1;
   float* xs = smem;                    // [TILE][dp]
@@ -154,6 +195,11 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
   const Hyp h = load_hyp(hyp);
   const int64_t col0 = (int64_t)blockIdx.x * TILE;
   const int64_t ntiles_r = (N + TILE - 1) / TILE;
+  float scale = 1.0f;
+  if (Kh || Kth) {
+    scale = plane_scale(sp, h, kscale);
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { kscale[0] = scale; kscale[1] = 1.0f / scale; }
+  }
 
   load_features(Fz, ldz, col0, M, d, dp, sp, zs, nza, nzb);
   const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;   // 4 row groups
@@ -168,24 +214,24 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
       tile[r * (TILE + 1) + c] = ka * kb;
     }
     __syncthreads();
-    if (K) {
+    if (K || Kh) {
 #pragma unroll 4
       for (int j = 0; j < TILE / 4; ++j) {
         int r = rg + 4 * j;
         int64_t gr = row0 + r, gc = col0 + c;
         if (gr < N && gc < M) {
           float v = tile[r * (TILE + 1) + c];
-          if (K_lo) {
-            float hi = to_tf32(v);
-            K[gr * ldk + gc] = hi;
-            K_lo[gr * ldk + gc] = to_tf32(v - hi);
-          } else {
-            K[gr * ldk + gc] = v;
+          if (K) K[gr * ldk + gc] = v;
+          if (Kh) {
+            float vs = v * scale;
+            __half hi = __float2half_rn(vs);
+            Kh[gr * ldkh + gc] = hi;
+            Kl[gr * ldkh + gc] = __float2half_rn(vs - __half2float(hi));
           }
         }
       }
     }
-    if (Kt) {
+    if (Kth) {
       // transposed write: consecutive threads walk consecutive datapoints of one inducing column
       const int r = threadIdx.x % TILE, cg = threadIdx.x / TILE;
 #pragma unroll 4
@@ -193,14 +239,10 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
         int cc = cg + 4 * j;
         int64_t gr = row0 + r, gc = col0 + cc;
         if (gr < N && gc < M) {
-          float v = tile[r * (TILE + 1) + cc];
-          if (Kt_lo) {
-            float hi = to_tf32(v);
-            Kt[gc * ldkt + gr] = hi;
-            Kt_lo[gc * ldkt + gr] = to_tf32(v - hi);
-          } else {
-            Kt[gc * ldkt + gr] = v;
-          }
+          float vs = tile[r * (TILE + 1) + cc] * scale;
+          __half hi = __float2half_rn(vs);
+          Kth[gc * ldkt + gr] = hi;
+          Ktl[gc * ldkt + gr] = __float2half_rn(vs - __half2float(hi));
         }
       }
     }
@@ -471,7 +513,7 @@ using namespace svgp;
 
 extern "C" {
 
-int svgp_version(void) { return 100; }
+int svgp_version(void) { return 200; }
 const char* svgp_last_error(void) { return svgp::last_error(); }
 int svgp_device_ok(void) {
   int dev = 0;
@@ -484,14 +526,28 @@ int svgp_device_ok(void) {
 }
 
 int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a,
-                    int dim_a, int type_b, int dim_b, const float* hyp, float* K, float* K_lo, int64_t ldk,
-                    float* Kt, float* Kt_lo, int64_t ldkt, void* stream) {
+                    int dim_a, int type_b, int dim_b, const float* hyp, float* K, int64_t ldk, void* Kh, void* Kl,
+                    int64_t ldkh, void* Kth, void* Ktl, int64_t ldkt, float* kscale, void* stream) {
   SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
   SVGP_REQUIRE(Fx && Fz && hyp && N >= 0 && M >= 0, "null input");
-  SVGP_REQUIRE((K || Kt), "no output requested");
-  SVGP_REQUIRE(!(K_lo && !K) && !(Kt_lo && !Kt), "lo plane without hi plane");
+  SVGP_REQUIRE((K || Kh || Kth), "no output requested");
+  SVGP_REQUIRE(!(Kh && !Kl) && !(Kth && !Ktl), "fp16 planes come in hi/lo pairs");
+  SVGP_REQUIRE(!(Kh || Kth) || kscale, "fp16 planes need the kscale buffer");
   if (N == 0 || M == 0) return SVGP_OK;
   Spec sp{type_a, dim_a, type_b, dim_b};
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Kh || Kth) {
+    if (cudaMemsetAsync(kscale, 0, 8 * sizeof(float), st) != cudaSuccess) return check_launch("svgp_kernel_fwd(memset)");
+    if (type_a == SVGP_K_LINEAR || type_b == SVGP_K_LINEAR) {
+      int64_t bx = ceil_div(N, 256), bz = ceil_div(M, 256);
+      if (bx > 148 * 8) bx = 148 * 8;
+      if (bz > 148 * 8) bz = 148 * 8;
+      feature_norm_kernel<<<(unsigned)bx, 256, 0, st>>>(Fx, ldx, N, sp, kscale, 2);
+      feature_norm_kernel<<<(unsigned)bz, 256, 0, st>>>(Fz, ldz, M, sp, kscale, 4);
+      int rc = check_launch("svgp_kernel_fwd(norms)");
+      if (rc) return rc;
+    }
+  }
   int64_t ntc = ceil_div(M, TILE), ntr = ceil_div(N, TILE);
   // grid.y strides over row tiles; keep >= ~8 CTAs per SM in flight without exceeding the 65535 limit
   int64_t gy = ntr;
@@ -500,8 +556,8 @@ int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, in
   if (gy < 1) gy = 1;
   if (gy > 65535) gy = 65535;
   dim3 grid((unsigned)ntc, (unsigned)gy);
-  kernel_fwd_kernel<<<grid, THREADS, fwd_smem(dim_a + dim_b), (cudaStream_t)stream>>>(
-      Fx, ldx, N, Fz, ldz, M, sp, hyp, K, K_lo, ldk, Kt, Kt_lo, ldkt);
+  kernel_fwd_kernel<<<grid, THREADS, fwd_smem(dim_a + dim_b), st>>>(
+      Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
   return check_launch("svgp_kernel_fwd");
 }
 

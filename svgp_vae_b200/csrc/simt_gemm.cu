@@ -11,6 +11,8 @@
 // and a sibling kernel does the row-wise quadratic forms svgp_rowquad (:336-337, :284).
 // Operands are fp32, every product and accumulation is fp64 (the S_l / Kinv operands have large
 // cancelling entries), reductions over datapoints are folded across chunks with double atomics.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace svgp {
@@ -84,23 +86,31 @@ struct SyrkOp {     // z = l * nchunk + chunk
     atomicAdd(&A[((int64_t)(z / nchunk) * M + m) * M + n], v);
   }
 };
+// K_nm element for the skinny products: plain fp32, or reassembled from the fp16 planes of a TC operand
+struct KAccess {
+  const float* K; const __half* Kh; const __half* Kl; int64_t ld; const float* kscale;
+  __device__ float operator()(int64_t i, int64_t a) const {
+    if (K) return K[i * ld + a];
+    return (__half2float(Kh[i * ld + a]) + __half2float(Kl[i * ld + a])) * kscale[1];
+  }
+};
 struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
   static constexpr bool A_K_CONTIG = false, B_K_CONTIG = false;
-  const float* K; int64_t ldk; const float* X; int64_t ldx; double* V; int64_t N, M, chunk;
+  KAccess Ka; const float* X; int64_t ldx; double* V; int64_t N, M, chunk;
   int64_t Mr, Nc;
   __device__ void krange(int z, int64_t& k0, int64_t& k1) const { k0 = (int64_t)z * chunk; k1 = min(N, k0 + chunk); }
   __device__ float a(int z, int64_t m, int64_t k) const { return X[k * ldx + m]; }
-  __device__ float b(int z, int64_t k, int64_t n) const { return K[k * ldk + n]; }
+  __device__ float b(int z, int64_t k, int64_t n) const { return Ka(k, n); }
   __device__ void store(int z, int64_t m, int64_t n, double v) const { atomicAdd(&V[m * M + n], v); }
 };
 struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
-  const float* K; int64_t ldk; const float* Wm; int64_t ldwm; float* out; int64_t ldo; int64_t M;
+  KAccess Ka; int64_t row0; const float* Wm; int64_t ldwm; float* out; int64_t ldo; int64_t M;
   int64_t Mr, Nc;
   __device__ void krange(int z, int64_t& k0, int64_t& k1) const { k0 = 0; k1 = M; }
-  __device__ float a(int z, int64_t m, int64_t k) const { return K[m * ldk + k]; }
+  __device__ float a(int z, int64_t m, int64_t k) const { return Ka(row0 + m, k); }
   __device__ float b(int z, int64_t k, int64_t n) const { return Wm[n * ldwm + k]; }
-  __device__ void store(int z, int64_t m, int64_t n, double v) const { out[m * ldo + n] = (float)v; }
+  __device__ void store(int z, int64_t m, int64_t n, double v) const { out[(row0 + m) * ldo + n] = (float)v; }
 };
 struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
@@ -203,12 +213,73 @@ __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restric
   }
 }
 
-__global__ void split_tf32_kernel(const double* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    double v = x[i];
-    float h = to_tf32((float)v);
-    hi[i] = h;
-    if (lo) lo[i] = to_tf32((float)(v - (double)h));
+// ---- fp16 operand planes ------------------------------------------------------------------------
+// per-matrix max |x| (as float bits) -> scratch[b]
+__global__ void absmax_f64_kernel(const double* __restrict__ x, int64_t count, float* __restrict__ scratch) {
+  const double* xb = x + (int64_t)blockIdx.y * count;
+  float m = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf((float)xb[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<int*>(scratch + blockIdx.y), __float_as_int(m));
+}
+// scale 2^(target - e) for max = m 2^e (m in [0.5, 1)); 1 for an all-zero / non-finite matrix
+__device__ __forceinline__ float pow2_scale(float mx, int target) {
+  if (!(mx > 0.f) || !isfinite(mx)) return 1.0f;
+  int e;
+  frexpf(mx, &e);
+  e = target - e;
+  if (e > 100) e = 100;
+  if (e < -100) e = -100;
+  return ldexpf(1.0f, e);
+}
+__global__ void split_f16_kernel(const double* __restrict__ x, int64_t count, __half* __restrict__ hi, __half* __restrict__ lo,
+                                 float* __restrict__ inv_scale, int64_t nb) {
+  const int64_t b = blockIdx.y;
+  const float s = pow2_scale(inv_scale[nb + b], 14);
+  const double sd = (double)s;
+  const double* xb = x + b * count;
+  __half* hb = hi + b * count;
+  __half* lb = lo + b * count;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+    const double v = xb[i] * sd;
+    const __half h = __float2half_rn((float)v);
+    hb[i] = h;
+    lb[i] = __float2half_rn((float)(v - (double)__half2float(h)));
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) inv_scale[b] = 1.0f / s;
+}
+
+// SYRK weights: column max of |W| -> per-channel power-of-two scale (|w s_l| <= 1), then the channel-major,
+// zero-padded, pre-scaled copy Wt (L x ldwt) the operand transform reads with 128-bit loads
+__global__ void colabsmax_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t L, float* __restrict__ mx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int64_t l0 = 0; l0 < L; l0 += 32) {
+    const int64_t l = l0 + lane;
+    float m = 0.f;
+    if (l < L)
+      for (int64_t i = (int64_t)blockIdx.x * nwarp + warp; i < N; i += (int64_t)gridDim.x * nwarp) m = fmaxf(m, fabsf(W[i * ldw + l]));
+    if (l < L && m > 0.f) atomicMax(reinterpret_cast<int*>(mx + l), __float_as_int(m));
+  }
+}
+__global__ void transpose_scale_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t L, const float* __restrict__ mx,
+                                       float* __restrict__ Wt, int64_t ldwt, float* __restrict__ winv) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32, l0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    int64_t n = n0 + r, l = l0 + tx;
+    tile[r][tx] = (n < N && l < L) ? W[n * ldw + l] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    int64_t l = l0 + r, n = n0 + tx;
+    if (l < L && n < ldwt) {
+      const float s = pow2_scale(mx[l], 0);                         // max * s in [0.5, 1)
+      Wt[l * ldwt + n] = tile[tx][r] * s;
+      if (blockIdx.x == 0 && tx == 0) winv[l] = 1.0f / s;
+    }
   }
 }
 
@@ -222,12 +293,20 @@ static int launch_tile(Op op, int64_t nz, cudaStream_t st, const char* name) {
 }
 
 // entry points of the tcgen05 implementation (tc_engine.cu)
-int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, int64_t L, double* A, int64_t chunk_rows, cudaStream_t st);
-int tc_rowquad(const svgp_kop* kop, const float* S_hi, const float* S_lo, int64_t L, int tri, float* q, int64_t ldq,
-               cudaStream_t st);
-int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const float* G_hi, const float* G_lo, int64_t L,
-                   float* out, int64_t ldo, int accumulate, cudaStream_t st);
+int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows,
+            cudaStream_t st);
+int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
+               int64_t ldq, cudaStream_t st);
+int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo, const float* G_inv,
+                   int64_t L, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
+                   cudaStream_t st);
 bool tc_shape_ok(const svgp_kop* kop);
+
+static inline int64_t pad8(int64_t n) { return (n + 7) / 8 * 8; }
+static inline KAccess kaccess(const svgp_kop* kop) {
+  if (kop->K) return KAccess{kop->K, nullptr, nullptr, kop->ldk, nullptr};
+  return KAccess{nullptr, (const __half*)kop->Kh, (const __half*)kop->Kl, kop->ldkh, kop->kscale};
+}
 
 }  // namespace svgp
 
@@ -236,85 +315,110 @@ using namespace svgp;
 static bool use_tc(const svgp_kop* kop, int impl) {
   if (impl == SVGP_IMPL_SIMT) return false;
   if (impl == SVGP_IMPL_TC) return true;
-  return kop->K_lo && kop->Kt && kop->Kt_lo && tc_shape_ok(kop);
+  return kop->Kh && kop->Kl && kop->Kth && kop->Ktl && kop->kscale && tc_shape_ok(kop);
 }
 
 extern "C" {
 
-int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, const float* Wt, int64_t ldwt, int64_t L, double* A,
-              int impl, int64_t chunk_rows, void* stream) {
-  SVGP_REQUIRE(kop && kop->K && A && L >= 1, "null argument");
+int64_t svgp_syrk_ws_floats(int64_t N, int64_t L) { return L * pad8(N) + 2 * L; }
+
+int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, int impl, int64_t chunk_rows,
+              float* ws, void* stream) {
+  SVGP_REQUIRE(kop && W && A && L >= 1, "null argument");
   if (kop->N == 0 || kop->M == 0) return SVGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(kop, impl)) {
-    SVGP_REQUIRE(Wt != nullptr, "TC path needs the channel-major weights Wt");
-    return tc_syrk(kop, Wt, ldwt, L, A, chunk_rows, (cudaStream_t)stream);
+    SVGP_REQUIRE(ws != nullptr, "TC path needs the workspace (svgp_syrk_ws_floats)");
+    const int64_t ldwt = pad8(kop->N);
+    float* Wt = ws;
+    float* mx = ws + L * ldwt;
+    float* winv = mx + L;
+    if (cudaMemsetAsync(mx, 0, L * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(memset)");
+    int64_t blocks = ceil_div(kop->N, 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    colabsmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, kop->N, L, mx);
+    dim3 grid((unsigned)ceil_div(ldwt, 32), (unsigned)ceil_div(L, 32));
+    transpose_scale_kernel<<<grid, 256, 0, st>>>(W, ldw, kop->N, L, mx, Wt, ldwt, winv);
+    int rc = check_launch("svgp_syrk(prep)");
+    if (rc) return rc;
+    return tc_syrk(kop, Wt, ldwt, winv, L, A, chunk_rows, st);
   }
-  SVGP_REQUIRE(W != nullptr, "SIMT path needs W (N x L)");
+  SVGP_REQUIRE(kop->K != nullptr, "SIMT path needs the fp32 K");
   int64_t chunk = chunk_rows > 0 ? chunk_rows : 2048;
   // keep the z-grid (L x chunks) within limits and the atomic traffic modest
   int64_t nchunk = ceil_div(kop->N, chunk);
   while (L * nchunk > 65535) { chunk *= 2; nchunk = ceil_div(kop->N, chunk); }
   SyrkOp op{kop->K, kop->ldk, W, ldw, A, kop->N, kop->M, L, chunk, nchunk, kop->M, kop->M};
-  return launch_tile(op, L * nchunk, (cudaStream_t)stream, "svgp_syrk");
+  return launch_tile(op, L * nchunk, st, "svgp_syrk");
 }
 
 int svgp_gemm_tn(const svgp_kop* kop, const float* X, int64_t ldx, int64_t L, double* V, void* stream) {
-  SVGP_REQUIRE(kop && kop->K && X && V && L >= 1, "null argument");
+  SVGP_REQUIRE(kop && (kop->K || (kop->Kh && kop->Kl && kop->kscale)) && X && V && L >= 1, "null argument");
   if (kop->N == 0 || kop->M == 0) return SVGP_OK;
   int64_t chunk = 2048, nchunk = ceil_div(kop->N, chunk);
   while (nchunk > 65535) { chunk *= 2; nchunk = ceil_div(kop->N, chunk); }
-  TnOp op{kop->K, kop->ldk, X, ldx, V, kop->N, kop->M, chunk, L, kop->M};
+  TnOp op{kaccess(kop), X, ldx, V, kop->N, kop->M, chunk, L, kop->M};
   return launch_tile(op, nchunk, (cudaStream_t)stream, "svgp_gemm_tn");
 }
 
 int svgp_gemm_nn(const svgp_kop* kop, const float* Wm, int64_t ldwm, int64_t L, float* out, int64_t ldo, void* stream) {
-  SVGP_REQUIRE(kop && kop->K && Wm && out && L >= 1, "null argument");
+  SVGP_REQUIRE(kop && (kop->K || (kop->Kh && kop->Kl && kop->kscale)) && Wm && out && L >= 1, "null argument");
   if (kop->N == 0) return SVGP_OK;
-  if (kop->N > 65535LL * BM) {   // walk row slabs
-    int64_t slab = 65535LL * BM;
-    for (int64_t r0 = 0; r0 < kop->N; r0 += slab) {
-      int64_t rows = kop->N - r0 < slab ? kop->N - r0 : slab;
-      NnOp op{kop->K + r0 * kop->ldk, kop->ldk, Wm, ldwm, out + r0 * ldo, ldo, kop->M, rows, L};
-      int rc = launch_tile(op, 1, (cudaStream_t)stream, "svgp_gemm_nn");
-      if (rc) return rc;
-    }
-    return SVGP_OK;
+  const int64_t slab = 65535LL * BM;   // walk row slabs (grid.y limit)
+  for (int64_t r0 = 0; r0 < kop->N; r0 += slab) {
+    int64_t rows = kop->N - r0 < slab ? kop->N - r0 : slab;
+    NnOp op{kaccess(kop), r0, Wm, ldwm, out, ldo, kop->M, rows, L};
+    int rc = launch_tile(op, 1, (cudaStream_t)stream, "svgp_gemm_nn");
+    if (rc) return rc;
   }
-  NnOp op{kop->K, kop->ldk, Wm, ldwm, out, ldo, kop->M, kop->N, L};
-  return launch_tile(op, 1, (cudaStream_t)stream, "svgp_gemm_nn");
+  return SVGP_OK;
 }
 
-int svgp_rowquad(const svgp_kop* kop, const float* S_hi, const float* S_lo, int64_t L, int tri, float* q, int64_t ldq,
-                 int impl, void* stream) {
-  SVGP_REQUIRE(kop && kop->K && S_hi && q && L >= 1, "null argument");
+int svgp_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
+                 int64_t ldq, int impl, void* stream) {
+  SVGP_REQUIRE(kop && S_hi && q && L >= 1, "null argument");
   if (kop->N == 0) return SVGP_OK;
   if (use_tc(kop, impl)) {
-    SVGP_REQUIRE(S_lo != nullptr, "TC path needs the lo plane of S");
-    return tc_rowquad(kop, S_hi, S_lo, L, tri, q, ldq, (cudaStream_t)stream);
+    SVGP_REQUIRE(S_lo != nullptr && S_inv != nullptr, "TC path needs the fp16 planes and scales of S (svgp_split_f16)");
+    return tc_rowquad(kop, S_hi, S_lo, S_inv, L, tri, q, ldq, (cudaStream_t)stream);
   }
   SVGP_REQUIRE(L <= 65535, "too many channels");
-  // SIMT: planes are summed on the fly only if a lo plane is given -- keep it simple: hi plane must be plain fp32
-  SVGP_REQUIRE(S_lo == nullptr, "SIMT path takes a single fp32 plane");
+  SVGP_REQUIRE(kop->K != nullptr && S_lo == nullptr && S_inv == nullptr, "SIMT path takes fp32 K and a single fp32 plane");
   dim3 grid((unsigned)ceil_div(kop->N, BM), (unsigned)L);
-  rowquad_simt_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(kop->K, kop->ldk, kop->N, kop->M, S_hi, tri, q, ldq);
+  rowquad_simt_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(kop->K, kop->ldk, kop->N, kop->M, (const float*)S_hi, tri, q, ldq);
   return check_launch("svgp_rowquad");
 }
 
-int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const float* G_hi, const float* G_lo, int64_t L,
-                     float* out, int64_t ldo, int accumulate, int impl, void* stream) {
-  SVGP_REQUIRE(kop && kop->K && W && G_hi && out && L >= 1, "null argument");
+int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo, const float* G_inv,
+                     int64_t L, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, int impl,
+                     void* stream) {
+  SVGP_REQUIRE(kop && W && G_hi && out && L >= 1, "null argument");
+  SVGP_REQUIRE(!dots || (ndot >= 0 && ndot <= L && lddots >= ndot), "bad dots argument");
   if (kop->N == 0 || kop->M == 0) return SVGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(kop, impl)) {
-    SVGP_REQUIRE(G_lo != nullptr, "TC path needs the lo plane of G");
-    return tc_scaled_gemm(kop, W, ldw, G_hi, G_lo, L, out, ldo, accumulate, (cudaStream_t)stream);
+    SVGP_REQUIRE(G_lo != nullptr && G_inv != nullptr, "TC path needs the fp16 planes and scales of G (svgp_split_f16)");
+    return tc_scaled_gemm(kop, W, ldw, G_hi, G_lo, G_inv, L, out, ldo, accumulate, dots, lddots, ndot, st);
   }
-  SVGP_REQUIRE(G_lo == nullptr, "SIMT path takes a single fp32 plane");
+  SVGP_REQUIRE(kop->K != nullptr && G_lo == nullptr && G_inv == nullptr, "SIMT path takes fp32 K and a single fp32 plane");
   int64_t slab = 65535LL * BM;
   for (int64_t r0 = 0; r0 < kop->N; r0 += slab) {
     int64_t rows = kop->N - r0 < slab ? kop->N - r0 : slab;
-    ScaledOp op{kop->K + r0 * kop->ldk, kop->ldk, W + r0 * ldw, ldw, G_hi, out + r0 * ldo, ldo, kop->M, L, accumulate, rows, kop->M};
-    int rc = launch_tile(op, 1, (cudaStream_t)stream, "svgp_scaled_gemm");
+    ScaledOp op{kop->K + r0 * kop->ldk, kop->ldk, W + r0 * ldw, ldw, (const float*)G_hi, out + r0 * ldo, ldo, kop->M, L, accumulate, rows, kop->M};
+    int rc = launch_tile(op, 1, st, "svgp_scaled_gemm");
     if (rc) return rc;
+  }
+  if (dots && ndot > 0) {
+    // no fused epilogue on the SIMT path: k^T G_l k comes from the row-quad kernel, which OVERWRITES dots
+    // (equal to the documented accumulate-into-zeroed-buffer contract)
+    SVGP_REQUIRE(ndot <= 65535, "too many channels");
+    for (int64_t r0 = 0; r0 < kop->N; r0 += slab) {
+      int64_t rows = kop->N - r0 < slab ? kop->N - r0 : slab;
+      dim3 grid((unsigned)ceil_div(rows, BM), (unsigned)ndot);
+      rowquad_simt_kernel<<<grid, NT, 0, st>>>(kop->K + r0 * kop->ldk, kop->ldk, rows, kop->M, (const float*)G_hi, 0,
+                                               dots + r0 * lddots, lddots);
+    }
+    return check_launch("svgp_scaled_gemm(dots)");
   }
   return SVGP_OK;
 }
@@ -332,13 +436,18 @@ int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t ld
   return SVGP_OK;
 }
 
-int svgp_split_tf32(const double* x, float* hi, float* lo, int64_t n, void* stream) {
-  SVGP_REQUIRE(x && hi && n >= 0, "bad argument");
-  if (n == 0) return SVGP_OK;
-  int64_t blocks = ceil_div(n, 256);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  split_tf32_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, hi, lo, n);
-  return check_launch("svgp_split_tf32");
+int svgp_split_f16(const double* x, int64_t nb, int64_t count, void* hi, void* lo, float* inv_scale, void* stream) {
+  SVGP_REQUIRE(x && hi && lo && inv_scale && nb >= 0 && count >= 0 && nb <= 65535, "bad argument");
+  if (nb == 0 || count == 0) return SVGP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(inv_scale + nb, 0, nb * sizeof(float), st) != cudaSuccess) return check_launch("svgp_split_f16(memset)");
+  int64_t bx = ceil_div(count, 256 * 8);
+  if (bx > 148 * 4) bx = 148 * 4;
+  if (bx < 1) bx = 1;
+  dim3 grid((unsigned)bx, (unsigned)nb);
+  absmax_f64_kernel<<<grid, 256, 0, st>>>(x, count, inv_scale + nb);
+  split_f16_kernel<<<grid, 256, 0, st>>>(x, count, (__half*)hi, (__half*)lo, inv_scale, nb);
+  return check_launch("svgp_split_f16");
 }
 
 }  // extern "C"

@@ -1,52 +1,58 @@
 // tcgen05 / TMEM / TMA implementation of the three O(N M^2 L) contractions of the SVGP step
-// (sm_100a only).  fp32-accurate on TF32 tensor cores through the 3xTF32 split: every fp32 operand
-// lives in memory as a TF32 pair x = hi + lo (written by K1 / svgp_split_tf32) and each k-step issues
+// (sm_100a only).  fp32-accurate products on the FP16 tensor-core path through a 3-term split:
+// every operand lives in memory as an fp16 pair  x * s = hi + lo  (s a power of two chosen per
+// matrix so that max|x| s < 2^14: 22 significand bits down to 2^-17 of the maximum, see
+// svgp_split_f16 / svgp_kernel_fwd) and each k-step issues
 //     D += A_lo * B_hi;   D += A_hi * B_lo;   D += A_hi * B_hi          (fp32 accumulators in TMEM)
+// at twice the TF32 rate and half the operand bytes of a 3xTF32 scheme.
 //
-//   MODE_SYRK    A_l[a,b]  += sum_n (w[n,l] Kt[a,n]) * Kt[b,n]   K2, SVGPVAE_model.py:328-330 and the
-//                                                                adjoint of the row-wise quadratic forms
-//   MODE_ROWQUAD q[i,l]     = sum_c (sum_a K[i,a] B_l[c,a]) * X   K4, :336-337, :284   (X = same product when
-//                                                                B_l is a triangular factor, else K[i,c])
-//   MODE_SCALED  out[i,c]   = sum_l sum_a (w[i,l] K[i,a]) G_l[c,a]   dObjective/dK_nm
+//   MODE_SYRK    A_l[a,b] += sum_n (w[n,l] Kt[a,n]) * Kt[b,n]       K2, SVGPVAE_model.py:328-330, and the
+//                                                                   adjoint of the row-wise quadratic forms
+//   MODE_QUAD    q[i,l]    = sum_c T_l[i,c] * X[i,c],  T_l = K B_l^T   K4, :336-337, :284
+//                                                                   (X = T_l when B_l is a triangular factor, else K)
+//   MODE_SCALED  out[i,c]  = sum_s w[i,s] T_s[i,c],   dots[i,s] = sum_c T_s[i,c] K[i,c]
+//                                                                   dObjective/dK_nm and dObjective/dp in one pass
 //
 // One persistent CTA per SM, 10 warps with fixed roles:
-//   warp 0      TMA producer: four 2-D tensor maps (A_hi, A_lo, B_hi, B_lo), 128B-swizzled K-major boxes
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 8 TF32 atoms)
+//   warp 0      TMA producer: four 2-D tensor maps (A_hi, A_lo, B_hi, B_lo), swizzled K-major boxes
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (128 x BN x 16 FP16 atoms)
 //   warps 2-5   epilogue: tcgen05.ld the accumulator (one TMEM lane == one output row per thread)
-//   warps 6-9   operand transform (SYRK / SCALED only): the per-channel diag(w) scaling cannot be
-//               precomputed for L channels, so the TMA-landed tile is rescaled and re-split into a TF32
-//               pair in place in shared memory, then handed to the MMA warp through a second mbarrier
+//   warps 6-9   SYRK: operand transform -- the per-channel diag(w) scaling sits on the reduction index, so the
+//               TMA-landed A tile is rescaled and re-split into an fp16 pair in place in shared memory and
+//               handed to the MMA warp through a second mbarrier;
+//               SCALED: four more epilogue warps (each warp owns half of the tile's columns: the running
+//               sum over the sub-tiles lives in registers, the per-row weights are applied in the epilogue)
 // Pipelines: smem stages (full -> [ready] -> empty) and two TMEM accumulator buffers (tmem_full/empty)
-// so that the epilogue of one tile overlaps the MMAs of the next.
+// so that the epilogue of one sub-tile overlaps the MMAs of the next.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace svgp {
 
-constexpr int MODE_SYRK = 0, MODE_ROWQUAD = 1, MODE_SCALED = 2;
+constexpr int MODE_SYRK = 0, MODE_QUAD = 1, MODE_SCALED = 2;
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;                 // 32 TF32 = 128 bytes = one swizzle row
-constexpr int UMMA_K = 8;
+constexpr int UMMA_K = 16;                  // fp16 elements per MMA k-step (32 bytes)
 constexpr int NUM_THREADS = 320;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
+constexpr int SYRK_STAGING_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose tiles (4 warps x 32 x 33 floats)
 
 // ---------------------------------------------------------------------------------------------
-// PTX wrappers
+// PTX wrappers (all shared-memory operands are 32-bit shared-window addresses)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
     asm volatile(
@@ -56,15 +62,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
   } while (!done);
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int32_t c0, int32_t c1) {
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1) {
   asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
@@ -74,18 +79,18 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -102,60 +107,89 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void sts32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO)
+// K-major swizzled operand tile: rows of RB (= 128 or 64) bytes, 8-row groups 8*RB bytes apart (SBO)
+template <int RB>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, 16-byte units
   d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset
+  d |= (uint64_t)((8 * RB) >> 4) << 32;           // stride byte offset
   d |= (uint64_t)1 << 46;                         // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                         // SWIZZLE_128B
+  d |= (uint64_t)(RB == 128 ? 2 : 4) << 61;       // SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
   return (1u << 4)                 // D format: F32
-         | (2u << 7)               // A format: TF32
-         | (2u << 10)              // B format: TF32
+         | (0u << 7)               // A format: F16
+         | (0u << 10)              // B format: F16
          | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// scale an fp16 pair (hi + lo) by w and split the product into a new pair
+__device__ __forceinline__ void rescale_pair(uint32_t& hi2, uint32_t& lo2, float w0, float w1) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo2));
+  const float y0 = (h.x + l.x) * w0, y1 = (h.y + l.y) * w1;
+  const __half2 nh = __floats2half2_rn(y0, y1);
+  const float2 nhf = __half22float2(nh);
+  const __half2 nl = __floats2half2_rn(y0 - nhf.x, y1 - nhf.y);
+  hi2 = *reinterpret_cast<const uint32_t*>(&nh);
+  lo2 = *reinterpret_cast<const uint32_t*>(&nl);
+}
+__device__ __forceinline__ float pair_dot2(uint32_t hi2, uint32_t lo2, float v0, float v1, float acc) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+  const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo2));
+  acc = fmaf(v0, h.x + l.x, acc);
+  return fmaf(v1, h.y + l.y, acc);
 }
 
 // ---------------------------------------------------------------------------------------------
 // kernel parameters
 // ---------------------------------------------------------------------------------------------
 struct TcParams {
-  int64_t N, M, L;
+  int64_t N, M, L;            // L = number of channels (SYRK / QUAD) or of stacked matrices (SCALED)
+  const float* kscale;        // {scale, 1/scale} of the K planes
+  const float* binv;          // 1/scale per B matrix (QUAD / SCALED); per channel weight 1/scale (SYRK)
   // SYRK
-  const float* Wt;        // (L, ldwt) channel-major weights, contiguous in n
+  const float* Wt;            // (L, ldwt) channel-major weights, pre-scaled, zero padded
   int64_t ldwt;
-  double* A;              // (L, M, M) accumulated
+  double* A;                  // (L, M, M) accumulated
   int64_t chunk_rows, nchunk;
-  int ntile;              // number of (ta, tb) tile pairs
-  // ROWQUAD
+  int ntile;                  // number of (ta, tb) tile pairs
+  // QUAD
   int tri;
-  const float* K_hi;      // for the DOT epilogue
-  const float* K_lo;
-  int64_t ldk;
+  const __half* K_hi;         // for the DOT epilogues
+  const __half* K_lo;
+  int64_t ldkh;
   float* q;
   int64_t ldq;
-  int lgroup;             // channels scheduled together (L2 residency of their B planes)
+  int lgroup;                 // channels scheduled together (L2 residency of their B planes)
   // SCALED
-  const float* W;         // (N, ldw)
+  const float* W;             // (N, ldw)
   int64_t ldw;
   float* out;
   int64_t ldo;
   int accumulate;
-  int lflush;             // channels per TMEM accumulation chain
+  float* dots;                // (N, lddots) or null
+  int64_t lddots, ndot;
   int64_t n_items;
-};
-
-template <int BN, int STAGES>
-struct SmemLayout {
-  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 4;      // one plane
-  static constexpr int B_BYTES = BN * BLOCK_K * 4;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;      // barriers + tmem ptr + alignment slack
 };
 
 // SYRK tile pairs: a-tiles of 128 rows, b-tiles of BN columns, kept when the tile touches the lower triangle
@@ -175,36 +209,59 @@ __device__ inline void syrk_tile_decode(int idx, int64_t M, int BN, int& ta_out,
   ta_out = tb_out = 0;
 }
 
-template <int MODE, int BN, int STAGES>
+// 32 columns [c, c + 32) of row i of the fp16 K planes dotted with v (columns >= M masked by the caller's zero v)
+__device__ __forceinline__ float dot_k_planes(const __half* __restrict__ Kh, const __half* __restrict__ Kl, int64_t ldkh,
+                                              int64_t i, int64_t c, const float (&v)[32], float acc) {
+  const uint4* ph = reinterpret_cast<const uint4*>(Kh + i * ldkh + c);
+  const uint4* pl = reinterpret_cast<const uint4*>(Kl + i * ldkh + c);
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    if (c + 8 * g + 8 <= ldkh) {
+      const uint4 h = __ldg(ph + g), l = __ldg(pl + g);
+      acc = pair_dot2(h.x, l.x, v[8 * g + 0], v[8 * g + 1], acc);
+      acc = pair_dot2(h.y, l.y, v[8 * g + 2], v[8 * g + 3], acc);
+      acc = pair_dot2(h.z, l.z, v[8 * g + 4], v[8 * g + 5], acc);
+      acc = pair_dot2(h.w, l.w, v[8 * g + 6], v[8 * g + 7], acc);
+    }
+  }
+  return acc;
+}
+
+template <int MODE, int BN, int BK, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
           const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams P) {
-  using SL = SmemLayout<BN, STAGES>;
-  constexpr bool HAS_XFORM = (MODE != MODE_ROWQUAD);
+  constexpr int RB = BK * 2;                                   // bytes per operand row of one k-block
+  constexpr int A_BYTES = BLOCK_M * RB, B_BYTES = BN * RB;     // one plane
+  constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr bool HAS_XFORM = (MODE == MODE_SYRK);
+  constexpr int EPI_WARPS = (MODE == MODE_SCALED) ? 8 : 4;
   constexpr int ACC_BUFS = (2 * BN <= 512) ? 2 : 1;
   constexpr uint32_t IDESC = make_idesc(BN);
+  static_assert(RB == 128 || RB == 64, "one swizzle row per k-block row");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = (uint64_t*)(smem + SL::BAR_OFFSET);
-  uint64_t* full = bars;                         // [STAGES]
-  uint64_t* ready = bars + STAGES;               // [STAGES]
-  uint64_t* empty = bars + 2 * STAGES;           // [STAGES]
-  uint64_t* tmem_full = bars + 3 * STAGES;       // [2]
-  uint64_t* tmem_empty = bars + 3 * STAGES + 2;  // [2]
-  uint32_t* tmem_ptr = (uint32_t*)(bars + 3 * STAGES + 4);
+  const uint32_t smem = (smem_u32(smem_raw) + 1023u) & ~1023u;      // shared-window address, 1024-byte aligned
+  const uint32_t bars = smem + STAGES * STAGE_BYTES;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto ready = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto tmem_full = [&](int t) { return bars + 8u * (3 * STAGES + t); };
+  auto tmem_empty = [&](int t) { return bars + 8u * (3 * STAGES + 2 + t); };
+  const uint32_t tmem_ptr_addr = bars + 8u * (3 * STAGES + 4);
+  const uint32_t staging = bars + 256u;                             // SYRK epilogue transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&ready[s], 4);
-      mbar_init(&empty[s], 1);
+      mbar_init(full(s), 1);
+      mbar_init(ready(s), 4);
+      mbar_init(empty(s), 1);
     }
     for (int t = 0; t < 2; ++t) {
-      mbar_init(&tmem_full[t], 1);
-      mbar_init(&tmem_empty[t], 4);
+      mbar_init(tmem_full(t), 1);
+      mbar_init(tmem_empty(t), EPI_WARPS);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -212,48 +269,44 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     prefetch_tmap(&mapA_hi); prefetch_tmap(&mapA_lo); prefetch_tmap(&mapB_hi); prefetch_tmap(&mapB_lo);
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(512));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr_addr), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
 
   // ---- work decomposition -------------------------------------------------------------------
   // Every role walks the same sequence: item -> sub-tiles -> k-blocks.  One TMEM accumulator buffer
   // holds one sub-tile; its MMA chain is kept short on purpose: the tensor core accumulates with
-  // truncation, so a chain of n MMAs carries a bias of up to ~n * 2^-24.  Long reductions (SYRK over
-  // N datapoints, SCALED over L * M) are therefore cut into sub-tiles that the epilogue folds into a
-  // CTA-owned global tile (double for SYRK, float for SCALED) with ordinary round-to-nearest adds.
-  //   SYRK    item = (tile pair, channel)      sub = chunk of `chunk_rows` datapoints
-  //   ROWQUAD item = (row tile, channel)       sub = column tile of B_l
-  //   SCALED  item = (row tile, column tile)   sub = group of `lflush` channels
+  // truncation, so a chain of n MMAs carries a bias of up to ~n * 2^-24.  Long reductions are cut
+  // into sub-tiles that the epilogue folds with ordinary round-to-nearest adds.
+  //   SYRK    item = (tile pair, channel)      sub = chunk of `chunk_rows` datapoints  -> double tile in L2
+  //   QUAD    item = (row tile, channel)       sub = column tile of B_l                -> row sum in a register
+  //   SCALED  item = (row tile, column tile)   sub = one stacked matrix                -> tile sum in registers
   const int64_t M = P.M;
   const int nct = (int)((M + BN - 1) / BN);
-  const int kb_full = (int)((M + BLOCK_K - 1) / BLOCK_K);
+  const int kb_full = (int)((M + BK - 1) / BK);
 
   auto item_subtiles = [&]() -> int {
     if (MODE == MODE_SYRK) return (int)P.nchunk;
-    if (MODE == MODE_ROWQUAD) return nct;
-    return (int)((P.L + P.lflush - 1) / P.lflush);
+    if (MODE == MODE_QUAD) return nct;
+    return (int)P.L;
   };
   auto subtile_kblocks = [&](int sub) -> int {
     if (MODE == MODE_SYRK) {
       int64_t n0 = (int64_t)sub * P.chunk_rows;
       int64_t n1 = n0 + P.chunk_rows < P.N ? n0 + P.chunk_rows : P.N;
-      return (int)((n1 - n0 + BLOCK_K - 1) / BLOCK_K);
-    } else if (MODE == MODE_ROWQUAD) {
+      return (int)((n1 - n0 + BK - 1) / BK);
+    } else if (MODE == MODE_QUAD) {
       if (!P.tri) return kb_full;
       int64_t kend = (int64_t)(sub + 1) * BN < M ? (int64_t)(sub + 1) * BN : M;
-      return (int)((kend + BLOCK_K - 1) / BLOCK_K);
-    } else {
-      int64_t l0 = (int64_t)sub * P.lflush;
-      int64_t nl = l0 + P.lflush < P.L ? P.lflush : P.L - l0;
-      return (int)(nl * kb_full);
+      return (int)((kend + BK - 1) / BK);
     }
+    return kb_full;
   };
-  // item -> coordinates
   struct Item { int64_t l, itile; int a_row0, b_row0; };
   auto decode = [&](int64_t item) -> Item {
     Item it{0, 0, 0, 0};
@@ -262,7 +315,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       int ta, tb;
       syrk_tile_decode((int)(item / P.L), M, BN, ta, tb);
       it.a_row0 = ta * BLOCK_M; it.b_row0 = tb * BN;
-    } else if (MODE == MODE_ROWQUAD) {
+    } else if (MODE == MODE_QUAD) {
       int64_t ntile_r = (P.N + BLOCK_M - 1) / BLOCK_M;
       int64_t per_group = ntile_r * P.lgroup;
       int64_t g = item / per_group, rem = item % per_group;
@@ -285,22 +338,21 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         for (int sub = 0; sub < nsub; ++sub) {
           const int nkb = subtile_kblocks(sub);
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(&empty[stage], phase ^ 1);
-            uint8_t* st = smem + stage * SL::STAGE_BYTES;
+            mbar_wait(empty(stage), phase ^ 1);
+            const uint32_t st = smem + stage * STAGE_BYTES;
             int32_t ak, ar, bk, br;
             if (MODE == MODE_SYRK) {
-              ak = (int32_t)((int64_t)sub * P.chunk_rows) + kb * BLOCK_K; ar = it.a_row0; bk = ak; br = it.b_row0;
-            } else if (MODE == MODE_ROWQUAD) {
-              ak = kb * BLOCK_K; ar = it.a_row0; bk = ak; br = (int32_t)(it.l * M + (int64_t)sub * BN);
+              ak = (int32_t)((int64_t)sub * P.chunk_rows) + kb * BK; ar = it.a_row0; bk = ak; br = it.b_row0;
+            } else if (MODE == MODE_QUAD) {
+              ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)(it.l * M + (int64_t)sub * BN);
             } else {
-              int lc = sub * P.lflush + kb / kb_full, kk = kb % kb_full;
-              ak = kk * BLOCK_K; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)lc * M + it.b_row0);
+              ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)sub * M + it.b_row0);
             }
-            mbar_expect_tx(&full[stage], SL::STAGE_BYTES);
-            tma_load_2d(st, &mapA_hi, &full[stage], ak, ar);
-            tma_load_2d(st + SL::A_BYTES, &mapA_lo, &full[stage], ak, ar);
-            tma_load_2d(st + 2 * SL::A_BYTES, &mapB_hi, &full[stage], bk, br);
-            tma_load_2d(st + 2 * SL::A_BYTES + SL::B_BYTES, &mapB_lo, &full[stage], bk, br);
+            mbar_expect_tx(full(stage), STAGE_BYTES);
+            tma_load_2d(st, &mapA_hi, full(stage), ak, ar);
+            tma_load_2d(st + A_BYTES, &mapA_lo, full(stage), ak, ar);
+            tma_load_2d(st + 2 * A_BYTES, &mapB_hi, full(stage), bk, br);
+            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), bk, br);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -314,26 +366,26 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       const int nsub = item_subtiles();
       for (int sub = 0; sub < nsub; ++sub) {
         const int nkb = subtile_kblocks(sub);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(tmem_empty(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          if (HAS_XFORM) mbar_wait(&ready[stage], phase);
+          mbar_wait(full(stage), phase);
+          if (HAS_XFORM) mbar_wait(ready(stage), phase);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t sa = smem_u32(smem + stage * SL::STAGE_BYTES);
-            const uint64_t a_hi = make_smem_desc(sa), a_lo = make_smem_desc(sa + SL::A_BYTES);
-            const uint64_t b_hi = make_smem_desc(sa + 2 * SL::A_BYTES), b_lo = make_smem_desc(sa + 2 * SL::A_BYTES + SL::B_BYTES);
+            const uint32_t sa = smem + stage * STAGE_BYTES;
+            const uint64_t a_hi = make_smem_desc<RB>(sa), a_lo = make_smem_desc<RB>(sa + A_BYTES);
+            const uint64_t b_hi = make_smem_desc<RB>(sa + 2 * A_BYTES), b_lo = make_smem_desc<RB>(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-            for (int ks = 0; ks < BLOCK_K / UMMA_K; ++ks) {
-              const uint64_t adv = (uint64_t)((ks * UMMA_K * 4) >> 4);
-              umma_tf32(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-              umma_tf32(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-              umma_tf32(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+            for (int ks = 0; ks < BK / UMMA_K; ++ks) {
+              const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
             }
-            umma_commit(&empty[stage]);
-            if (kb == nkb - 1) umma_commit(&tmem_full[acc]);
+            umma_commit(empty(stage));
+            if (kb == nkb - 1) umma_commit(tmem_full(acc));
           }
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -341,123 +393,176 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + EPI_WARPS) {
     // =============================== epilogue ====================================================
     const int qd = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;                  // output row inside the tile
+    const int half = (warp - 2) >> 2;                // SCALED: which half of the tile's columns
+    const float inv_ks = P.kscale[1];
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
-      float qsum = 0.f;
       const int nsub = item_subtiles();
-      for (int sub = 0; sub < nsub; ++sub) {
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN);
+      if (MODE == MODE_SYRK) {
+        // CTA-owned tile of the double accumulator in L2: read-modify-write, lower triangle only.  A TMEM lane is an
+        // output ROW, so a thread holds 32 consecutive columns of one row; the 32 x 32 block of a warp is transposed
+        // through a padded shared-memory tile so that every global access is one row segment of 32 consecutive
+        // doubles (256 contiguous bytes per warp instruction instead of 32 scattered sectors).
+        const double sc = (double)inv_ks * (double)inv_ks * (double)P.binv[it.l];
+        const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (32 * 33 * 4);
+        const int64_t a0 = (int64_t)it.a_row0 + qd * 32;                  // first row of this warp's block
+        for (int sub = 0; sub < nsub; ++sub) {
+          mbar_wait(tmem_full(acc), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          if (MODE == MODE_SYRK) {
-            // CTA-owned tile of the double accumulator: plain read-modify-write, lower triangle only
-            const int64_t a = it.a_row0 + row;
-            if (a < M) {
-              double* Arow = P.A + (it.l * M + a) * M + it.b_row0 + c0;
-              const int64_t bmax = a - (it.b_row0 + c0);          // columns j <= bmax are on/below the diagonal
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            const int64_t col0 = (int64_t)it.b_row0 + c0;
+            if (col0 > a0 + 31 || a0 >= M) break;                         // whole block above the diagonal / out of range
+            float v[32];
+            tmem_ld32(taddr + c0, v);
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j <= bmax) Arow[j] += (double)v[j];
+            for (int j = 0; j < 32; ++j) sts32(my_stage + (uint32_t)(lane * 33 + j) * 4, v[j]);
+            __syncwarp();
+            const int64_t col = col0 + lane;
+            double* Acol = P.A + (it.l * M + a0) * M + col;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const float x = lds32(my_stage + (uint32_t)(r * 33 + lane) * 4);
+              if (a0 + r < M && col <= a0 + r) Acol[(int64_t)r * M] += (double)x * sc;
             }
-          } else if (MODE == MODE_ROWQUAD) {
-            const int64_t i = it.itile * BLOCK_M + row;
+            __syncwarp();
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(acc));
+          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+        }
+      } else if (MODE == MODE_QUAD) {
+        const int64_t i = it.itile * BLOCK_M + row;
+        const bool live = (i < P.N) && (it.l < P.L);
+        const float bs = (it.l < P.L) ? P.binv[it.l] : 0.f;
+        float qsum = 0.f;
+        for (int sub = 0; sub < nsub; ++sub) {
+          mbar_wait(tmem_full(acc), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
             const int64_t cbase = (int64_t)sub * BN + c0;
+            if (cbase >= M) break;
+            float v[32];
+            tmem_ld32(taddr + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j >= M) v[j] = 0.f;
             if (P.tri) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < M) qsum = fmaf(v[j], v[j], qsum);
-            } else if (i < P.N) {
-              const float* kh = P.K_hi + i * P.ldk + cbase;
-              const float* kl = P.K_lo + i * P.ldk + cbase;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (cbase + j < M) qsum = fmaf(v[j], kh[j] + kl[j], qsum);
-            }
-          } else {
-            const int64_t i = it.itile * BLOCK_M + row;
-            if (i < P.N) {
-              float* o = P.out + i * P.ldo + it.b_row0 + c0;
-              const bool add = (sub > 0) || P.accumulate;
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if ((int64_t)it.b_row0 + c0 + j < M) o[j] = add ? o[j] + v[j] : v[j];
+              for (int j = 0; j < 32; ++j) qsum = fmaf(v[j], v[j], qsum);
+            } else if (live) {
+              qsum = dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, qsum);
             }
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(acc));
+          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
-      }
-      if (MODE == MODE_ROWQUAD) {
+        if (live) {
+          const float s1 = inv_ks * bs;
+          P.q[i * P.ldq + it.l] = P.tri ? qsum * s1 * s1 : qsum * s1 * inv_ks;
+        }
+      } else {
+        constexpr int NCH = BN / 64;                   // 32-column chunks owned by this warp
         const int64_t i = it.itile * BLOCK_M + row;
-        if (i < P.N && it.l < P.L) P.q[i * P.ldq + it.l] = qsum;
+        const bool live = i < P.N;
+        float run[NCH][32];
+#pragma unroll
+        for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
+        for (int sub = 0; sub < nsub; ++sub) {
+          const float bs = P.binv[sub];
+          const float wgt = live ? P.W[i * P.ldw + sub] * inv_ks * bs : 0.f;
+          const bool want_dot = (P.dots != nullptr) && (sub < P.ndot) && live;
+          float dsum = 0.f;
+          mbar_wait(tmem_full(acc), acc_phase);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const int64_t cbase = (int64_t)it.b_row0 + half * (BN / 2) + ch * 32;
+            if (cbase < M) {
+              float v[32];
+              tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (cbase + j >= M) v[j] = 0.f;
+                run[ch][j] = fmaf(wgt, v[j], run[ch][j]);
+              }
+              if (want_dot) dsum = dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, dsum);
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty(acc));
+          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+          if (want_dot) atomicAdd(&P.dots[i * P.lddots + sub], dsum * inv_ks * inv_ks * bs);
+        }
+        if (live) {
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const int64_t cbase = (int64_t)it.b_row0 + half * (BN / 2) + ch * 32;
+            float* o = P.out + i * P.ldo + cbase;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (cbase + j < M) o[j] = P.accumulate ? o[j] + run[ch][j] : run[ch][j];
+          }
+        }
       }
     }
   } else if (HAS_XFORM) {
-    // =============================== operand transform ===========================================
+    // =============================== operand transform (SYRK) ====================================
+    // The A tile (128 rows a x BK datapoints n) is rescaled by the channel's weights w[n] in place.  A thread
+    // owns one logical 16-byte chunk (8 consecutive n) of CPR rows: its 8 weights are loaded once per k-block.
+    // Swizzle: the physical chunk is the logical one XORed with (row & 7) [128-byte rows] or ((row >> 1) & 3)
+    // [64-byte rows]; both are constant over the rows a thread visits, and a quarter-warp always covers
+    // 128 contiguous bytes, so the 128-bit accesses are bank-conflict free.
+    constexpr int CPR = RB / 16;                     // chunks per row
+    constexpr int RSTEP = BLOCK_M / CPR;             // rows between two visits of a thread
     const int t = threadIdx.x - 6 * 32;              // 0..127
+    const int lchunk = t % CPR, rbase = t / CPR;
+    const int pchunk = (RB == 128) ? (lchunk ^ (rbase & 7)) : (lchunk ^ ((rbase >> 1) & 3));
     int stage = 0; uint32_t phase = 0;
-    // SW128: the 16-byte chunk index is XORed with (row & 7); this thread always sits on physical chunk t%8 of
-    // rows t/8 + 16*it, so its logical chunk (= k offset / 4) is the same for every row it touches
-    const int pchunk = t & 7, rbase = t >> 3;
-    const int lchunk = pchunk ^ (rbase & 7);
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
-      float rs[8];                                    // SCALED: per-row weights of the current channel
-      int cur_l = -1;
       const int nsub = item_subtiles();
       for (int sub = 0; sub < nsub; ++sub) {
         const int nkb = subtile_kblocks(sub);
         for (int kb = 0; kb < nkb; ++kb) {
-          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (MODE == MODE_SYRK) {
-            const int64_t n = (int64_t)sub * P.chunk_rows + (int64_t)kb * BLOCK_K + lchunk * 4;
-            const float* wp = P.Wt + it.l * P.ldwt + n;
-            if (n + 3 < P.N) wv = *reinterpret_cast<const float4*>(wp);
-            else { if (n < P.N) wv.x = wp[0]; if (n + 1 < P.N) wv.y = wp[1]; if (n + 2 < P.N) wv.z = wp[2]; }
-          } else {
-            int lc = sub * P.lflush + kb / kb_full;
-            if (lc != cur_l) {
-              cur_l = lc;
-#pragma unroll
-              for (int r = 0; r < 8; ++r) {
-                int64_t i = it.itile * BLOCK_M + rbase + 16 * r;
-                rs[r] = (i < P.N) ? P.W[i * P.ldw + lc] : 0.f;
-              }
-            }
+          const int64_t n = (int64_t)sub * P.chunk_rows + (int64_t)kb * BK + lchunk * 8;
+          float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
+          if (n + 8 <= P.ldwt) {
+            const float4* wp = reinterpret_cast<const float4*>(P.Wt + it.l * P.ldwt + n);
+            w0 = __ldg(wp); w1 = __ldg(wp + 1);
           }
-          mbar_wait(&full[stage], phase);
-          uint8_t* st = smem + stage * SL::STAGE_BYTES;
-          // both modes rescale the 128-row A operand (for the SYRK the weight may sit on either factor of
-          // k_a k_b; the A tile is half the size of the B tile, which halves the shared-memory traffic here)
-          constexpr int ROWS = BLOCK_M;
-          uint8_t* hi_p = st;
-          uint8_t* lo_p = st + SL::A_BYTES;
+          mbar_wait(full(stage), phase);
+          const uint32_t hi_p = smem + stage * STAGE_BYTES + rbase * RB + pchunk * 16;
+          const uint32_t lo_p = hi_p + A_BYTES;
 #pragma unroll
-          for (int r = 0; r < ROWS / 16; ++r) {
-            const int off = (rbase + 16 * r) * 128 + pchunk * 16;
-            float4 h = *reinterpret_cast<float4*>(hi_p + off);
-            float4 lo4 = *reinterpret_cast<float4*>(lo_p + off);
-            float4 s = (MODE == MODE_SYRK) ? wv : make_float4(rs[r & 7], rs[r & 7], rs[r & 7], rs[r & 7]);
-            float y0 = (h.x + lo4.x) * s.x, y1 = (h.y + lo4.y) * s.y, y2 = (h.z + lo4.z) * s.z, y3 = (h.w + lo4.w) * s.w;
-            float4 nh = make_float4(to_tf32(y0), to_tf32(y1), to_tf32(y2), to_tf32(y3));
-            float4 nl = make_float4(to_tf32(y0 - nh.x), to_tf32(y1 - nh.y), to_tf32(y2 - nh.z), to_tf32(y3 - nh.w));
-            *reinterpret_cast<float4*>(hi_p + off) = nh;
-            *reinterpret_cast<float4*>(lo_p + off) = nl;
+          for (int r = 0; r < CPR; ++r) {
+            const uint32_t off = r * RSTEP * RB;
+            uint4 h = lds128(hi_p + off), l = lds128(lo_p + off);
+            rescale_pair(h.x, l.x, w0.x, w0.y);
+            rescale_pair(h.y, l.y, w0.z, w0.w);
+            rescale_pair(h.z, l.z, w1.x, w1.y);
+            rescale_pair(h.w, l.w, w1.z, w1.w);
+            sts128(hi_p + off, h);
+            sts128(lo_p + off, l);
           }
           fence_async_smem();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&ready[stage]);
+          if (lane == 0) mbar_arrive(ready(stage));
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -500,17 +605,18 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-// 2-D fp32 tensor (rows x cols, leading dimension ld elements), box = box_rows x 32 columns, 128B swizzle
-static int make_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+// 2-D fp16 tensor (rows x cols, leading dimension ld elements), box = box_rows x bk columns, swizzle = row bytes
+static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows, int bk) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SVGP_ERR_CUDA; }
-  if (((uintptr_t)base & 15) || (ld * 4) % 16) { set_error("TMA operand needs 16-byte aligned base and row pitch"); return SVGP_ERR_ARG; }
+  if (((uintptr_t)base & 15) || (ld * 2) % 16) { set_error("TMA operand needs 16-byte aligned base and row pitch"); return SVGP_ERR_ARG; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return SVGP_ERR_CUDA; }
   return SVGP_OK;
 }
@@ -526,64 +632,68 @@ static int num_sms() {
   return n;
 }
 
-// tile configuration: 128 x 256 x 32 with two smem stages (default) or 128 x 128 x 32 with three (SVGP_TC_BN=128)
-static int tc_bn() {
-  static int bn = 0;
-  if (!bn) {
-    const char* e = getenv("SVGP_TC_BN");
-    bn = (e && atoi(e) == 128) ? 128 : 256;
+// k-block depth: 64 fp16 (128-byte swizzle rows, 2 smem stages of 96 KB; default: measured faster in every mode,
+// profiles/r01_tc_probe_fp16_v1.jsonl) or 32 (64-byte rows, 4 stages of 48 KB) with SVGP_TC_BK=32.
+static int tc_bk() {
+  static int bk = 0;
+  if (!bk) {
+    const char* e = getenv("SVGP_TC_BK");
+    bk = (e && atoi(e) == 32) ? 32 : 64;
   }
-  return bn;
+  return bk;
 }
 
-template <int MODE, int BN, int STAGES>
+template <int MODE, int BN, int BK, int STAGES>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcParams& P, cudaStream_t st, const char* name) {
-  using SL = SmemLayout<BN, STAGES>;
-  static_assert(SL::TOTAL <= TC_SMEM_LIMIT, "shared memory budget");
-  auto kern = tc_kernel<MODE, BN, STAGES>;
+  constexpr int SMEM_TOTAL = STAGES * (2 * BLOCK_M * BK * 2 + 2 * BN * BK * 2) + 256 + 1024 +
+                             (MODE == MODE_SYRK ? SYRK_STAGING_BYTES : 0);
+  static_assert(SMEM_TOTAL <= TC_SMEM_LIMIT, "shared memory budget");
+  auto kern = tc_kernel<MODE, BN, BK, STAGES>;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::TOTAL) != cudaSuccess) return check_launch(name);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) return check_launch(name);
     attr_done = true;
   }
   int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
   if (grid <= 0) return SVGP_OK;
-  kern<<<(unsigned)grid, NUM_THREADS, SL::TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, P);
+  kern<<<(unsigned)grid, NUM_THREADS, SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, P);
   return check_launch(name);
 }
 
 template <int MODE>
-static int dispatch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
+static int dispatch_tc(int bk, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const TcParams& P, cudaStream_t st, const char* name) {
-  if (tc_bn() == 128) return launch_tc<MODE, 128, 3>(a_hi, a_lo, b_hi, b_lo, P, st, name);
-  return launch_tc<MODE, 256, 2>(a_hi, a_lo, b_hi, b_lo, P, st, name);
+  if (bk == 32) return launch_tc<MODE, 256, 32, 4>(a_hi, a_lo, b_hi, b_lo, P, st, name);
+  return launch_tc<MODE, 256, 64, 2>(a_hi, a_lo, b_hi, b_lo, P, st, name);
 }
 
 bool tc_shape_ok(const svgp_kop* kop) {
   // worth it only when tiles are mostly full; TMA needs 16-byte pitches
-  return kop->M >= 128 && kop->N >= 2048 && (kop->ldk % 4) == 0 && (kop->ldkt % 4) == 0;
+  return kop->M >= 128 && kop->N >= 2048 && (kop->ldkh % 8) == 0 && (kop->ldkt % 8) == 0;
 }
 
-int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, int64_t L, double* A, int64_t chunk_rows, cudaStream_t st) {
-  if (!kop->Kt || !kop->Kt_lo) { set_error("tc_syrk: transposed TF32 planes missing"); return SVGP_ERR_ARG; }
-  if (((uintptr_t)Wt & 15) || (ldwt % 4)) { set_error("tc_syrk: weights need 16-byte alignment"); return SVGP_ERR_ARG; }
-  const int BN = tc_bn();
+int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows,
+            cudaStream_t st) {
+  if (!kop->Kth || !kop->Ktl || !kop->kscale) { set_error("tc_syrk: transposed fp16 planes missing"); return SVGP_ERR_ARG; }
+  if (((uintptr_t)Wt & 15) || (ldwt % 8)) { set_error("tc_syrk: weights need 16-byte alignment"); return SVGP_ERR_ARG; }
+  const int BN = 256, bk = tc_bk();
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = make_map(&a_hi, kop->Kt, kop->M, kop->N, kop->ldkt, BLOCK_M))) return rc;
-  if ((rc = make_map(&a_lo, kop->Kt_lo, kop->M, kop->N, kop->ldkt, BLOCK_M))) return rc;
-  if ((rc = make_map(&b_hi, kop->Kt, kop->M, kop->N, kop->ldkt, BN))) return rc;
-  if ((rc = make_map(&b_lo, kop->Kt_lo, kop->M, kop->N, kop->ldkt, BN))) return rc;
+  if ((rc = make_map(&a_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BLOCK_M, bk))) return rc;
+  if ((rc = make_map(&a_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BLOCK_M, bk))) return rc;
+  if ((rc = make_map(&b_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
+  if ((rc = make_map(&b_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
   TcParams P{};
-  P.N = kop->N; P.M = kop->M; P.L = L;
+  P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = winv;
   P.Wt = Wt; P.ldwt = ldwt; P.A = A;
-  int64_t chunk = chunk_rows > 0 ? chunk_rows : 1024;
-  chunk = (chunk + BLOCK_K - 1) / BLOCK_K * BLOCK_K;
+  // one accumulation chain = chunk / 16 k-steps x 3 MMAs; 2048 rows -> 384 MMAs (truncation bias ~1e-5 worst case)
+  int64_t chunk = chunk_rows > 0 ? chunk_rows : 2048;
+  chunk = (chunk + 63) / 64 * 64;
   P.chunk_rows = chunk; P.nchunk = ceil_div(kop->N, chunk);
   P.ntile = syrk_tile_count(kop->M, BN);
   P.n_items = (int64_t)P.ntile * L;
-  rc = dispatch_tc<MODE_SYRK>(a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
+  rc = dispatch_tc<MODE_SYRK>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
   if (rc) return rc;
   int64_t blocks = ceil_div(L * kop->M * kop->M, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -591,53 +701,48 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, int64_t L, doubl
   return check_launch("svgp_syrk(mirror)");
 }
 
-int tc_rowquad(const svgp_kop* kop, const float* S_hi, const float* S_lo, int64_t L, int tri, float* q, int64_t ldq,
-               cudaStream_t st) {
-  const int BN = tc_bn();
+int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
+               int64_t ldq, cudaStream_t st) {
+  if (!kop->Kh || !kop->Kl || !kop->kscale) { set_error("tc_rowquad: fp16 planes missing"); return SVGP_ERR_ARG; }
+  const int BN = 256, bk = tc_bk();
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = make_map(&a_hi, kop->K, kop->N, kop->M, kop->ldk, BLOCK_M))) return rc;
-  if ((rc = make_map(&a_lo, kop->K_lo, kop->N, kop->M, kop->ldk, BLOCK_M))) return rc;
-  if ((rc = make_map(&b_hi, S_hi, L * kop->M, kop->M, kop->M, BN))) return rc;
-  if ((rc = make_map(&b_lo, S_lo, L * kop->M, kop->M, kop->M, BN))) return rc;
+  if ((rc = make_map(&a_hi, kop->Kh, kop->N, kop->M, kop->ldkh, BLOCK_M, bk))) return rc;
+  if ((rc = make_map(&a_lo, kop->Kl, kop->N, kop->M, kop->ldkh, BLOCK_M, bk))) return rc;
+  if ((rc = make_map(&b_hi, S_hi, L * kop->M, kop->M, kop->M, BN, bk))) return rc;
+  if ((rc = make_map(&b_lo, S_lo, L * kop->M, kop->M, kop->M, BN, bk))) return rc;
   TcParams P{};
-  P.N = kop->N; P.M = kop->M; P.L = L;
-  P.tri = tri; P.K_hi = kop->K; P.K_lo = kop->K_lo; P.ldk = kop->ldk; P.q = q; P.ldq = ldq;
-  // channels whose factor planes (2 * M*M*4 bytes each) share ~half of the 126 MB L2
-  int64_t per = 2 * kop->M * kop->M * 4;
+  P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = S_inv;
+  P.tri = tri; P.K_hi = (const __half*)kop->Kh; P.K_lo = (const __half*)kop->Kl; P.ldkh = kop->ldkh; P.q = q; P.ldq = ldq;
+  // channels whose factor planes (2 * M*M*2 bytes each) share ~half of the 126 MB L2
+  int64_t per = 2 * kop->M * kop->M * 2;
   int64_t g = (64LL << 20) / (per > 0 ? per : 1);
   if (g < 1) g = 1;
   if (g > L) g = L;
   while (L % g) --g;                       // keep groups uniform
   P.lgroup = (int)g;
   P.n_items = ceil_div(kop->N, BLOCK_M) * L;
-  return dispatch_tc<MODE_ROWQUAD>(a_hi, a_lo, b_hi, b_lo, P, st, "svgp_rowquad(tc)");
+  return dispatch_tc<MODE_QUAD>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_rowquad(tc)");
 }
 
-int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const float* G_hi, const float* G_lo, int64_t L, float* out,
-                   int64_t ldo, int accumulate, cudaStream_t st) {
-  const int BN = tc_bn();
+int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo, const float* G_inv,
+                   int64_t L, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
+                   cudaStream_t st) {
+  if (!kop->Kh || !kop->Kl || !kop->kscale) { set_error("tc_scaled_gemm: fp16 planes missing"); return SVGP_ERR_ARG; }
+  const int BN = 256, bk = tc_bk();
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = make_map(&a_hi, kop->K, kop->N, kop->M, kop->ldk, BLOCK_M))) return rc;
-  if ((rc = make_map(&a_lo, kop->K_lo, kop->N, kop->M, kop->ldk, BLOCK_M))) return rc;
-  if ((rc = make_map(&b_hi, G_hi, L * kop->M, kop->M, kop->M, BN))) return rc;
-  if ((rc = make_map(&b_lo, G_lo, L * kop->M, kop->M, kop->M, BN))) return rc;
+  if ((rc = make_map(&a_hi, kop->Kh, kop->N, kop->M, kop->ldkh, BLOCK_M, bk))) return rc;
+  if ((rc = make_map(&a_lo, kop->Kl, kop->N, kop->M, kop->ldkh, BLOCK_M, bk))) return rc;
+  if ((rc = make_map(&b_hi, G_hi, L * kop->M, kop->M, kop->M, BN, bk))) return rc;
+  if ((rc = make_map(&b_lo, G_lo, L * kop->M, kop->M, kop->M, BN, bk))) return rc;
   TcParams P{};
-  P.N = kop->N; P.M = kop->M; P.L = L;
+  P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = G_inv;
+  P.K_hi = (const __half*)kop->Kh; P.K_lo = (const __half*)kop->Kl; P.ldkh = kop->ldkh;
   P.W = W; P.ldw = ldw; P.out = out; P.ldo = ldo; P.accumulate = accumulate;
-  {
-    // keep one accumulation chain to ~768 MMAs (measured truncation bias ~2.7e-8 per MMA -> ~2e-5):
-    // lflush channels x (M/32) k-blocks x 12 MMAs
-    int64_t kb = ceil_div(kop->M, BLOCK_K);
-    int64_t lf = 64 / (kb > 0 ? kb : 1);
-    const char* e = getenv("SVGP_TC_LFLUSH");
-    if (e && atoi(e) > 0) lf = atoi(e);
-    if (lf < 1) lf = 1;
-    P.lflush = (int)lf;
-  }
+  P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
   P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(kop->M, BN);
-  return dispatch_tc<MODE_SCALED>(a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");
+  return dispatch_tc<MODE_SCALED>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");
 }
 
 }  // namespace svgp

@@ -4,15 +4,16 @@ Replaces the per-channel Python loop of forward_pass_SVGPVAE (SVGPVAE_model.py:8
 two methods it calls per channel (approximate_posterior_params :303-343, variational_loss
 :220-301, gauss_cross_entropy utils.py:483-504).  Same mathematics, reorganised:
 
-  pass A   K1 builds K_nm (TF32 planes when large), K_mm, kappa; row stats; the only reductions
+  pass A   K1 builds K_nm (scaled fp16 hi/lo planes when large), K_mm, kappa; row stats; the only reductions
            over datapoints: A_l = sum_i p_il k_i k_i^T (K2, tcgen05 SYRK) and v_l = sum_i p_il y_il k_i
            -> all-reduce over the N-shards -> replicated float64 M x M stage (K3)
   pass B   per-row predictive moments p_m = K_nm w_l, p_v = kappa - h + |R_l^-1 k_i|^2 (K4)
   [decoder / caller]
   pass C   adjoints of p_m, p_v: weighted SYRK + skinny GEMM -> all-reduce -> adjoint of the
            M x M stage (torch autograd over ops.bmm64 / spd_inverse_logdet / spd_logdet)
-  pass D   dK_nm = sum_l diag(w_l) K_nm G_l (one tcgen05 GEMM over 2L+1 stacked channels), the
-           row-dots k_i^T dA_l k_i, and K1's adjoint into features / inducing points / hypers.
+  pass D   dK_nm = sum_s diag(w_s) K_nm G_s over the 2L+1 stacked matrices [dA+dA^T ; S ; Kinv] and the
+           row-dots k_i^T dA_l k_i from the same tcgen05 products (weights and dots live in the epilogue),
+           then K1's adjoint into features / inducing points / hypers.
 
 Every sum over datapoints inside L3 and the cross entropy is taken against A_l / v_l (e.g.
 sum_i p_il k_i^T W_l k_i = <W_l, A_l>), so the (b, m, m) tensor of :286-294 never exists and the
@@ -178,16 +179,17 @@ class _SVGPStep(torch.autograd.Function):
         gsums = torch.zeros_like(sums_) if gsums is None else gsums
 
         # ---- pass D: back to the rows ------------------------------------------------------------
-        # dK_nm: one stacked GEMM over [p | 2 dq1 | 2 dh] x [dA + dA^T ; S ; Kinv]
+        # dK_nm and k^T (dA + dA^T) k from ONE pass over the products K G_s: stacked matrices
+        # [dA + dA^T ; S ; Kinv] with per-row weights [p | 2 dq1 | 2 dh] applied in the epilogue
         Wstack = torch.cat([p, 2.0 * G_q1, (-2.0 * G_kappa)[:, None]], dim=1).contiguous()
         Gstack = torch.cat([gA + gA.transpose(-1, -2), S, Kinv], dim=0).contiguous()
-        G_K = be.scaled_gemm(kop, Wstack, Gstack)
+        G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
         del Wstack, Gstack
         py = p * y
         be.gemm_f32(py.contiguous(), gV.float().contiguous(), out=G_K)          # via v_l
         be.gemm_f32(g_pm, w.float().contiguous(), out=G_K)                       # via p_m
         # dp, dy, dnoise
-        G_p = be.rowquad(kop, ops._sym(gA).contiguous())                         # k^T dA k
+        G_p = 0.5 * kGk                                                          # k^T dA k
         G_py = be.gemm_nn(kop, gV.float().contiguous())
         gs = gsums.float()
         G_p = G_p + y * G_py + kappa[:, None] * gs[0][None, :] + (y * y) * gs[1][None, :]

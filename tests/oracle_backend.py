@@ -99,12 +99,14 @@ class OracleBackend:
             return (T * T).sum(-1).float()
         return torch.einsum('ia,lab,ib->il', K, S64, K).float()
 
-    def scaled_gemm(self, kop, W, G64, out=None, impl=0):
+    def scaled_gemm(self, kop, W, G64, out=None, ndot=0, impl=0):
         K = kop.value().to(F64)
         r = torch.einsum('il,ia,lac->ic', W.to(F64), K, G64).float()
         if out is not None:
             out += r
-            return out
+            r = out
+        if ndot:
+            return r, torch.einsum('ia,lab,ib->il', K, G64[:ndot], K).float()
         return r
 
     def gemm_f32(self, A, B, out=None):

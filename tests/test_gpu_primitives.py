@@ -38,7 +38,8 @@ def test_kernel_fwd_bwd(cuda_backend, name, shape):
     assert rel_err(kop.K, ref) < 5e-6                     # element-wise op: far tighter than the 1e-4 bar
     kopt = be.kernel_fwd(spec, Fx.cuda(), Fz.cuda(), hyp.cuda(), tc=True)
     assert rel_err(kopt.value(), ref) < 5e-6
-    assert rel_err((kopt.Kt + kopt.Kt_lo)[:M, :N], ref.t()) < 5e-6
+    assert rel_err((kopt.Kth.float() + kopt.Ktl.float())[:M, :N] * kopt.kscale[1], ref.t()) < 5e-6
+    assert float(kopt.value().abs().max() * kopt.kscale[0]) < 2 ** 14 + 1
     G = torch.randn(N, M, generator=torch.Generator().manual_seed(1))
     rx, rz, rh = ORA.kernel_bwd(spec, Fx, Fz, hyp, G)
     dx, dz, dh = be.kernel_bwd(spec, Fx.cuda(), Fz.cuda(), hyp.cuda(), G.cuda())
@@ -89,8 +90,9 @@ def test_simt_gemm_family(cuda_backend, shape):
     assert rel_err(be.rowquad(kop, Lt.cuda(), tri=True), ORA.rowquad(kop_c, Lt, tri=True)) < 1e-5
     assert rel_err(be.scaled_gemm(kop, W.cuda(), S.cuda()), ORA.scaled_gemm(kop_c, W, S)) < 1e-5
     out = torch.ones(N, M).cuda()
-    be.scaled_gemm(kop, W.cuda(), S.cuda(), out=out)
+    _, dots = be.scaled_gemm(kop, W.cuda(), S.cuda(), out=out, ndot=L)
     assert rel_err(out - 1, ORA.scaled_gemm(kop_c, W, S)) < 1e-5
+    assert rel_err(dots, ORA.rowquad(kop_c, S)) < 1e-5
     B = torch.randn(L, M, generator=g)
     assert rel_err(be.gemm_f32(W.cuda(), B.cuda()), ORA.gemm_f32(W, B)) < 1e-5
 

@@ -1,4 +1,4 @@
-"""tcgen05 engine (3xTF32) against float64 on the device and against the SIMT kernels."""
+"""tcgen05 engine (3 x FP16 split) against float64 on the device and against the SIMT kernels."""
 import pytest
 import torch
 
@@ -27,14 +27,18 @@ def test_tc_syrk(cuda_backend, shape):
     kop, K64, W, g = _setup(be, N, M, L)
     ref = torch.einsum('il,ia,ib->lab', W.double(), K64, K64)
     # the tensor core accumulates with truncation: the bias grows ~2.7e-8 per MMA of a chain (measured,
-    # profiles/r01_accuracy.md), so short chains (chunk_rows=128 -> 48 MMAs) reach fp32-level accuracy and
-    # the default chain (1024 rows -> 384 MMAs) stays ~1e-5
+    # profiles/r01_accuracy.md), so short chains (chunk_rows=128 -> 24 MMAs) reach fp32-level accuracy and
+    # the default chain (2048 rows -> 384 MMAs) stays ~1e-5
     assert rel_err(be.syrk(kop, W, chunk_rows=128), ref) < 3e-6
     A = be.syrk(kop, W)
     assert rel_err(A, ref) < 3e-5
     assert rel_err(A, A.transpose(1, 2)) == 0.0
     A2 = be.syrk(Kop(kop.value().contiguous()), W, impl=IMPL_SIMT)
     assert rel_err(A2, ref) < 1e-6 and rel_err(A, A2) < 3e-5
+    # weights spanning six decades (p = 1/noise with the reference's clip [1e-3, 10]): per-channel power-of-two scaling
+    Wp = torch.exp(torch.empty(N, L, device="cuda").uniform_(-4.6, 9.2, generator=g))
+    refp = torch.einsum('il,ia,ib->lab', Wp.double(), K64, K64)
+    assert rel_err(be.syrk(kop, Wp), refp) < 3e-5
 
 
 @pytest.mark.parametrize("shape", [(4096, 256, 3), (3000, 200, 2), (2304, 1024, 2)])
@@ -44,13 +48,32 @@ def test_tc_rowquad_scaled(cuda_backend, shape):
     kop, K64, W, g = _setup(be, N, M, L, seed=1)
     S = torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64)
     S = (S + S.transpose(1, 2)).contiguous()
+    S[0] *= 1e4                                      # per-matrix scaling of the fp16 planes
     Lt = torch.tril(torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64)).contiguous()
+    Lt[-1] *= 1e-3
     ref = torch.einsum('ia,lab,ib->il', K64, S, K64)
     assert rel_err(be.rowquad(kop, S), ref) < 3e-5
     T = torch.einsum('ia,lca->ilc', K64, Lt)
-    assert rel_err(be.rowquad(kop, Lt, tri=True), (T * T).sum(-1)) < 3e-5
-    ref = torch.einsum('il,ia,lac->ic', W.double(), K64, S)
-    out = be.scaled_gemm(kop, W, S)
-    assert rel_err(out, ref) < 3e-5
+    for l in range(L):
+        assert rel_err(be.rowquad(kop, Lt, tri=True)[:, l], (T * T).sum(-1)[:, l]) < 3e-5
+    refo = torch.einsum('il,ia,lac->ic', W.double(), K64, S)
+    out, dots = be.scaled_gemm(kop, W, S, ndot=L)
+    assert rel_err(out, refo) < 3e-5
+    for l in range(L):
+        assert rel_err(dots[:, l], ref[:, l]) < 3e-5
     be.scaled_gemm(kop, W, S, out=out)
-    assert rel_err(out, 2 * ref) < 3e-5
+    assert rel_err(out, 2 * refo) < 3e-5
+    out1, dots1 = be.scaled_gemm(kop, W, S, ndot=1)
+    assert rel_err(out1, refo) < 3e-5 and rel_err(dots1[:, 0], ref[:, 0]) < 3e-5
+
+
+def test_tc_planes_roundtrip(cuda_backend):
+    be = cuda_backend
+    g = torch.Generator(device="cuda").manual_seed(3)
+    X = torch.randn(3, 64, 64, generator=g, device="cuda", dtype=torch.float64)
+    X[1] *= 1e-6
+    X[2] = 0
+    pl = be.planes(X)
+    back = (pl.hi.double() + pl.lo.double()) * pl.inv[:3, None, None].double()
+    assert rel_err(back[0], X[0]) < 1e-6 and rel_err(back[1], X[1]) < 1e-6 and float(back[2].abs().max()) == 0.0
+    assert float(pl.hi.abs().max()) <= 2 ** 14

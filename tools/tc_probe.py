@@ -29,22 +29,28 @@ def main():
     hyp = torch.ones(4, device="cuda")
     spec = (1, 4, 1, 4)
     t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=True))
-    print(json.dumps(dict(op="kernel_fwd_planes", N=N, M=M, ms=t, GBs=4 * N * M * 4 / t / 1e6)), flush=True)
+    print(json.dumps(dict(op="kernel_fwd_planes", N=N, M=M, ms=t, GBs=4 * N * M * 2 / t / 1e6)), flush=True)
     t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=False))
     print(json.dumps(dict(op="kernel_fwd_f32", N=N, M=M, ms=t, GBs=N * M * 4 / t / 1e6)), flush=True)
     kop = be.kernel_fwd(spec, Fx, Fz, hyp, tc=True)
     W = torch.randn(N, L, generator=g, device="cuda")
     S = torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64); S = (S + S.transpose(1, 2)).contiguous()
     Lt = torch.tril(S).contiguous()
-    for chunk in (2048, 8192, 32768):
+    tag = os.environ.get("SVGP_TC_BK", "default")
+    for chunk in (1024, 4096, 16384):
         t = timeit(lambda: be.syrk(kop, W, chunk_rows=chunk))
-        print(json.dumps(dict(op="syrk_tc", chunk=chunk, N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
-    t = timeit(lambda: be.rowquad(kop, S))
-    print(json.dumps(dict(op="rowquad_tc_full", N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
-    t = timeit(lambda: be.rowquad(kop, Lt, tri=True))
-    print(json.dumps(dict(op="rowquad_tc_tri", N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
-    t = timeit(lambda: be.scaled_gemm(kop, W, S))
-    print(json.dumps(dict(op="scaled_gemm_tc", N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
+        print(json.dumps(dict(op="syrk_tc", bk=tag, chunk=chunk, N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
+    Spl, Ltpl = be.planes(S), be.planes(Lt)
+    t = timeit(lambda: be.planes(S))
+    print(json.dumps(dict(op="split_f16", M=M, L=L, ms=t)), flush=True)
+    t = timeit(lambda: be.rowquad(kop, Spl))
+    print(json.dumps(dict(op="rowquad_tc_full", bk=tag, N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
+    t = timeit(lambda: be.rowquad(kop, Ltpl, tri=True))
+    print(json.dumps(dict(op="rowquad_tc_tri", bk=tag, N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
+    t = timeit(lambda: be.scaled_gemm(kop, W, Spl))
+    print(json.dumps(dict(op="scaled_gemm_tc", bk=tag, N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
+    t = timeit(lambda: be.scaled_gemm(kop, W, Spl, ndot=L))
+    print(json.dumps(dict(op="scaled_gemm_tc_dots", bk=tag, N=N, M=M, L=L, ms=t, alg_TFLOPs=2 * N * M * M * L / t / 1e9)), flush=True)
     G = torch.randn(N, M, generator=g, device="cuda")
     t = timeit(lambda: be.kernel_bwd(spec, Fx, Fz, hyp, G))
     print(json.dumps(dict(op="kernel_bwd", N=N, M=M, ms=t)), flush=True)
