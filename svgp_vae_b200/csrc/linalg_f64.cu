@@ -201,12 +201,114 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(int transA, int transB, i
     }
 }
 
+// Large-matrix variant: 128 x 128 x 16 tiles, 256 threads, 8 x 8 doubles per thread (one LDS.128 per 4 DFMA),
+// next k-tile prefetched into registers while the current one is multiplied.  A thread's 8 rows are
+// {ty*4 .. ty*4+3} and {64 + ty*4 ..}, its 8 columns likewise in tx: every shared-memory read is a 16-byte
+// access whose quarter-warp covers consecutive banks.
+constexpr int GM = 128, GN = 128, GK = 16;
+template <bool transA, bool transB>
+__global__ void __launch_bounds__(256) gemm_f64_big_kernel(int64_t Mr, int64_t Nc, int64_t Kd, double alpha,
+                                                           const double* __restrict__ A, int64_t lda, int64_t strideA,
+                                                           const double* __restrict__ B, int64_t ldb, int64_t strideB, double beta,
+                                                           double* __restrict__ C, int64_t ldc, int64_t strideC, int lower_only) {
+  const int64_t m0 = (int64_t)blockIdx.y * GM, n0 = (int64_t)blockIdx.x * GN;
+  if (lower_only && n0 > m0 + GM - 1) return;
+  __shared__ __align__(16) double As[GK][GM];
+  __shared__ __align__(16) double Bs[GK][GN];
+  const double* Ab = A + (int64_t)blockIdx.z * strideA;
+  const double* Bb = B + (int64_t)blockIdx.z * strideB;
+  double* Cb = C + (int64_t)blockIdx.z * strideC;
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+  double ra[8], rb[8];
+  // element e of this thread inside a k-tile: idx = tid + 256 e  (0 .. 2047)
+  auto fetch = [&](int64_t kb) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      int kk, mm, nn;
+      if (!transA) { kk = idx % GK; mm = idx / GK; } else { mm = idx % GM; kk = idx / GM; }
+      int64_t gk = kb + kk;
+      const int64_t gm = m0 + mm;
+      ra[e] = (gk < Kd && gm < Mr) ? (transA ? Ab[gk * lda + gm] : Ab[gm * lda + gk]) : 0.0;
+      if (!transB) { nn = idx % GN; kk = idx / GN; } else { kk = idx % GK; nn = idx / GK; }
+      gk = kb + kk;
+      const int64_t gn = n0 + nn;
+      rb[e] = (gk < Kd && gn < Nc) ? (transB ? Bb[gn * ldb + gk] : Bb[gk * ldb + gn]) : 0.0;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int idx = threadIdx.x + e * 256;
+      int kk, mm, nn;
+      if (!transA) { kk = idx % GK; mm = idx / GK; } else { mm = idx % GM; kk = idx / GM; }
+      As[kk][mm] = ra[e];
+      if (!transB) { nn = idx % GN; kk = idx / GN; } else { kk = idx % GK; nn = idx / GK; }
+      Bs[kk][nn] = rb[e];
+    }
+  };
+  fetch(0);
+  for (int64_t kb = 0; kb < Kd; kb += GK) {
+    stash();
+    __syncthreads();
+    if (kb + GK < Kd) fetch(kb + GK);
+#pragma unroll
+    for (int kk = 0; kk < GK; ++kk) {
+      double a[8], b[8];
+      const double2 a0 = *reinterpret_cast<const double2*>(&As[kk][ty * 4]), a1 = *reinterpret_cast<const double2*>(&As[kk][ty * 4 + 2]);
+      const double2 a2 = *reinterpret_cast<const double2*>(&As[kk][64 + ty * 4]), a3 = *reinterpret_cast<const double2*>(&As[kk][64 + ty * 4 + 2]);
+      const double2 b0 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4]), b1 = *reinterpret_cast<const double2*>(&Bs[kk][tx * 4 + 2]);
+      const double2 b2 = *reinterpret_cast<const double2*>(&Bs[kk][64 + tx * 4]), b3 = *reinterpret_cast<const double2*>(&Bs[kk][64 + tx * 4 + 2]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y; b[4] = b2.x; b[5] = b2.y; b[6] = b3.x; b[7] = b3.y;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    if (gm >= Mr) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int64_t gn = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + j - 4);
+      if (gn < Nc) {
+        double* c = Cb + gm * ldc + gn;
+        *c = (beta == 0.0) ? alpha * acc[i][j] : fma(alpha, acc[i][j], beta * (*c));
+      }
+    }
+  }
+}
+
 static int gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, double alpha, const double* A, int64_t lda,
                     int64_t strideA, const double* B, int64_t ldb, int64_t strideB, double beta, double* C, int64_t ldc,
                     int64_t strideC, int64_t batch, int lower_only, cudaStream_t st) {
   if (Mr <= 0 || Nc <= 0 || batch <= 0) return SVGP_OK;
+  const bool big = Mr >= 96 && Nc >= 96 && Kd >= 32;
   for (int64_t b0 = 0; b0 < batch; b0 += 65535) {
     int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
+    if (big) {
+      dim3 gridb((unsigned)ceil_div(Nc, GN), (unsigned)ceil_div(Mr, GM), (unsigned)nb);
+#define SVGP_BIG(TA, TB)                                                                                                 \
+  gemm_f64_big_kernel<TA, TB><<<gridb, 256, 0, st>>>(Mr, Nc, Kd, alpha, A + b0 * strideA, lda, strideA, B + b0 * strideB, ldb, \
+                                                      strideB, beta, C + b0 * strideC, ldc, strideC, lower_only)
+      if (transA && transB) SVGP_BIG(true, true);
+      else if (transA) SVGP_BIG(true, false);
+      else if (transB) SVGP_BIG(false, true);
+      else SVGP_BIG(false, false);
+#undef SVGP_BIG
+      int rcb = check_launch("svgp_gemm_f64");
+      if (rcb) return rcb;
+      continue;
+    }
     dim3 grid((unsigned)ceil_div(Nc, DN), (unsigned)ceil_div(Mr, DM), (unsigned)nb);
     gemm_f64_kernel<<<grid, 256, 0, st>>>(transA, transB, Mr, Nc, Kd, alpha, A + b0 * strideA, lda, strideA, B + b0 * strideB,
                                           ldb, strideB, beta, C + b0 * strideC, ldc, strideC, lower_only);

@@ -34,9 +34,10 @@ namespace svgp {
 constexpr int MODE_SYRK = 0, MODE_QUAD = 1, MODE_SCALED = 2;
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;                  // fp16 elements per MMA k-step (32 bytes)
-constexpr int NUM_THREADS = 320;
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-constexpr int SYRK_STAGING_BYTES = 4 * 32 * 33 * 4;   // epilogue transpose tiles (4 warps x 32 x 33 floats)
+// threads per CTA: QUAD / SCALED run 10 warps; SYRK runs 4 warpgroups (register budgets are re-split
+// between them with setmaxnreg, see the kernel prologue)
+__host__ __device__ constexpr int tc_threads(int mode) { return mode == 0 ? 512 : 320; }
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (all shared-memory operands are 32-bit shared-window addresses)
@@ -173,6 +174,7 @@ struct TcParams {
   double* A;                  // (L, M, M) accumulated
   int64_t chunk_rows, nchunk;
   int ntile;                  // number of (ta, tb) tile pairs
+  int flush_every;            // chunks folded in fp32 registers between two float64 read-modify-writes of the tile
   // QUAD
   int tri;
   const __half* K_hi;         // for the DOT epilogues
@@ -228,14 +230,16 @@ __device__ __forceinline__ float dot_k_planes(const __half* __restrict__ Kh, con
 }
 
 template <int MODE, int BN, int BK, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(MODE), 1)
 tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
           const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams P) {
   constexpr int RB = BK * 2;                                   // bytes per operand row of one k-block
   constexpr int A_BYTES = BLOCK_M * RB, B_BYTES = BN * RB;     // one plane
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr bool HAS_XFORM = (MODE == MODE_SYRK);
-  constexpr int EPI_WARPS = (MODE == MODE_SCALED) ? 8 : 4;
+  constexpr int EPI_WARPS = (MODE == MODE_QUAD) ? 4 : 8;
+  constexpr int EPI_WARP0 = (MODE == MODE_SYRK) ? 8 : 2;       // first epilogue warp (SYRK: warpgroups 2 and 3)
+  constexpr int XF_WARP0 = 4;                                  // SYRK: warpgroup 1 transforms the A operand
   constexpr int ACC_BUFS = (2 * BN <= 512) ? 2 : 1;
   constexpr uint32_t IDESC = make_idesc(BN);
   static_assert(RB == 128 || RB == 64, "one swizzle row per k-block row");
@@ -249,7 +253,6 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   auto tmem_full = [&](int t) { return bars + 8u * (3 * STAGES + t); };
   auto tmem_empty = [&](int t) { return bars + 8u * (3 * STAGES + 2 + t); };
   const uint32_t tmem_ptr_addr = bars + 8u * (3 * STAGES + 4);
-  const uint32_t staging = bars + 256u;                             // SYRK epilogue transpose tiles
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -328,7 +331,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     return it;
   };
 
-  if (warp == 0) {
+  auto role_producer = [&]() {
     // =============================== TMA producer ===============================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
@@ -358,7 +361,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         }
       }
     }
-  } else if (warp == 1) {
+  };
+  auto role_mma = [&]() {
     // =============================== MMA issuer ==================================================
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
@@ -393,50 +397,80 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else if (warp < 2 + EPI_WARPS) {
+  };
+  auto role_epilogue = [&]() {
     // =============================== epilogue ====================================================
     const int qd = warp & 3;                         // TMEM lane quarter this warp may access
     const int row = qd * 32 + lane;                  // output row inside the tile
-    const int half = (warp - 2) >> 2;                // SCALED: which half of the tile's columns
+    const int half = (warp - EPI_WARP0) >> 2;        // SYRK / SCALED: which half of the tile's columns
     const float inv_ks = P.kscale[1];
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
       const int nsub = item_subtiles();
-      if (MODE == MODE_SYRK) {
-        // CTA-owned tile of the double accumulator in L2: read-modify-write, lower triangle only.  A TMEM lane is an
-        // output ROW, so a thread holds 32 consecutive columns of one row; the 32 x 32 block of a warp is transposed
-        // through a padded shared-memory tile so that every global access is one row segment of 32 consecutive
-        // doubles (256 contiguous bytes per warp instruction instead of 32 scattered sectors).
+      if constexpr (MODE == MODE_SYRK) {
+        // The tile's running sum lives in REGISTERS: warp (quarter qd, column half) owns rows [a0, a0 + 32) x 128
+        // columns, one row per thread, 128 fp32 sums.  Every chunk (one short, truncating MMA chain in TMEM) is
+        // folded with round-to-nearest adds; every `flush_every` chunks -- and at the end of the item -- the sums
+        // are added into the float64 tile of A_l (owned by this CTA: plain read-modify-write, lower triangle only)
+        // and cleared.  Per chunk the epilogue costs 4 tcgen05.ld + 128 FADD per thread; global traffic is
+        // 1 / flush_every of a per-chunk write-back.
         const double sc = (double)inv_ks * (double)inv_ks * (double)P.binv[it.l];
-        const uint32_t my_stage = staging + (uint32_t)(warp - 2) * (32 * 33 * 4);
-        const int64_t a0 = (int64_t)it.a_row0 + qd * 32;                  // first row of this warp's block
+        const int64_t a0 = (int64_t)it.a_row0 + qd * 32;                   // first row of this warp's block
+        const int64_t r = a0 + lane;                                       // this thread's output row
+        const int64_t cw0 = (int64_t)it.b_row0 + half * (BN / 2);          // first column of this warp
+        int nlive = 0;                                                     // 32-column chunks touching the lower triangle
+        if (a0 < M) {
+#pragma unroll
+          for (int ch = 0; ch < BN / 64; ++ch)
+            if (cw0 + 32 * ch <= a0 + 31 && cw0 + 32 * ch < M) nlive = ch + 1;
+        }
+        float run[BN / 64][32];
+#pragma unroll
+        for (int ch = 0; ch < BN / 64; ++ch)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
+        int pending = 0;
         for (int sub = 0; sub < nsub; ++sub) {
           mbar_wait(tmem_full(acc), acc_phase);
           tc_fence_after();
-          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
-            const int64_t col0 = (int64_t)it.b_row0 + c0;
-            if (col0 > a0 + 31 || a0 >= M) break;                         // whole block above the diagonal / out of range
-            float v[32];
-            tmem_ld32(taddr + c0, v);
+          const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sts32(my_stage + (uint32_t)(lane * 33 + j) * 4, v[j]);
-            __syncwarp();
-            const int64_t col = col0 + lane;
-            double* Acol = P.A + (it.l * M + a0) * M + col;
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const float x = lds32(my_stage + (uint32_t)(r * 33 + lane) * 4);
-              if (a0 + r < M && col <= a0 + r) Acol[(int64_t)r * M] += (double)x * sc;
+          for (int ch = 0; ch < BN / 64; ++ch) {
+            if (ch < nlive) {
+              float v[32];
+              tmem_ld32(taddr + ch * 32, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) run[ch][j] += v[j];
             }
-            __syncwarp();
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(acc));
           if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+          if (++pending == P.flush_every || sub == nsub - 1) {
+            pending = 0;
+#pragma unroll
+            for (int ch = 0; ch < BN / 64; ++ch) {
+              if (ch < nlive) {
+                const int64_t c0 = cw0 + 32 * ch;
+                double* dst = P.A + (it.l * M + r) * M + c0;
+                const int64_t nv64 = (r < M) ? r - c0 + 1 : 0;             // columns c0 .. min(c0 + 31, r) of row r
+                const int nv = nv64 > 32 ? 32 : (int)nv64;
+#pragma unroll
+                for (int j0 = 0; j0 < 32; j0 += 8) {
+                  double t[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) t[j] = (j0 + j < nv) ? dst[j0 + j] : 0.0;
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (j0 + j < nv) dst[j0 + j] = t[j] + (double)run[ch][j0 + j] * sc;
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
+              }
+            }
+          }
         }
       } else if (MODE == MODE_QUAD) {
         const int64_t i = it.itile * BLOCK_M + row;
@@ -521,7 +555,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         }
       }
     }
-  } else if (HAS_XFORM) {
+  };
+  auto role_transform = [&]() {
     // =============================== operand transform (SYRK) ====================================
     // The A tile (128 rows a x BK datapoints n) is rescaled by the channel's weights w[n] in place.  A thread
     // owns one logical 16-byte chunk (8 consecutive n) of CPR rows: its 8 weights are loaded once per k-block.
@@ -530,7 +565,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     // 128 contiguous bytes, so the 128-bit accesses are bank-conflict free.
     constexpr int CPR = RB / 16;                     // chunks per row
     constexpr int RSTEP = BLOCK_M / CPR;             // rows between two visits of a thread
-    const int t = threadIdx.x - 6 * 32;              // 0..127
+    const int t = threadIdx.x - XF_WARP0 * 32;       // 0..127
     const int lchunk = t % CPR, rbase = t / CPR;
     const int pchunk = (RB == 128) ? (lchunk ^ (rbase & 7)) : (lchunk ^ ((rbase >> 1) & 3));
     int stage = 0; uint32_t phase = 0;
@@ -567,6 +602,28 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         }
       }
     }
+  };
+
+  if constexpr (MODE == MODE_SYRK) {
+    // 512 threads start with 128 registers each.  The TMA / MMA warpgroup and the transform warpgroup hand
+    // registers to the two epilogue warpgroups, whose threads each keep 128 fp32 running sums of the output
+    // tile.  setmaxnreg is executed by all four warps of a warpgroup at the top of that warpgroup's branch.
+    const int wg = warp >> 2;
+    if (wg == 0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+      if (warp == 0) role_producer();
+      else if (warp == 1) role_mma();
+    } else if (wg == 1) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+      role_transform();
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+      role_epilogue();
+    }
+  } else {
+    if (warp == 0) role_producer();
+    else if (warp == 1) role_mma();
+    else if (warp >= EPI_WARP0 && warp < EPI_WARP0 + EPI_WARPS) role_epilogue();
   }
 
   tc_fence_before();
@@ -643,11 +700,21 @@ static int tc_bk() {
   return bk;
 }
 
+// chunks folded in fp32 registers between two float64 write-backs of a SYRK tile (16 x 2048 rows by default:
+// sqrt(16) half-ulp random error per group, groups are summed in float64); SVGP_SYRK_FLUSH overrides.
+static int syrk_flush_every() {
+  static int f = 0;
+  if (!f) {
+    const char* e = getenv("SVGP_SYRK_FLUSH");
+    f = (e && atoi(e) > 0) ? atoi(e) : 16;
+  }
+  return f;
+}
+
 template <int MODE, int BN, int BK, int STAGES>
 static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                      const TcParams& P, cudaStream_t st, const char* name) {
-  constexpr int SMEM_TOTAL = STAGES * (2 * BLOCK_M * BK * 2 + 2 * BN * BK * 2) + 256 + 1024 +
-                             (MODE == MODE_SYRK ? SYRK_STAGING_BYTES : 0);
+  constexpr int SMEM_TOTAL = STAGES * (2 * BLOCK_M * BK * 2 + 2 * BN * BK * 2) + 256 + 1024;
   static_assert(SMEM_TOTAL <= TC_SMEM_LIMIT, "shared memory budget");
   auto kern = tc_kernel<MODE, BN, BK, STAGES>;
   static bool attr_done = false;
@@ -657,7 +724,7 @@ static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUt
   }
   int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
   if (grid <= 0) return SVGP_OK;
-  kern<<<(unsigned)grid, NUM_THREADS, SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, P);
+  kern<<<(unsigned)grid, tc_threads(MODE), SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, P);
   return check_launch(name);
 }
 
@@ -692,6 +759,7 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
   chunk = (chunk + 63) / 64 * 64;
   P.chunk_rows = chunk; P.nchunk = ceil_div(kop->N, chunk);
   P.ntile = syrk_tile_count(kop->M, BN);
+  P.flush_every = syrk_flush_every();
   P.n_items = (int64_t)P.ntile * L;
   rc = dispatch_tc<MODE_SYRK>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
   if (rc) return rc;

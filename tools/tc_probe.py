@@ -23,23 +23,29 @@ def timeit(fn, reps=3):
 
 def main():
     N, M, L = (int(x) for x in sys.argv[1:4]) if len(sys.argv) >= 4 else (131072, 1024, 8)
+    only = sys.argv[4] if len(sys.argv) >= 5 else None          # "syrk": time the SYRK only
     be = backend.get_backend()
     g = torch.Generator(device="cuda").manual_seed(0)
     Fx = torch.randn(N, 8, generator=g, device="cuda"); Fz = torch.randn(M, 8, generator=g, device="cuda")
     hyp = torch.ones(4, device="cuda")
     spec = (1, 4, 1, 4)
-    t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=True))
-    print(json.dumps(dict(op="kernel_fwd_planes", N=N, M=M, ms=t, GBs=4 * N * M * 2 / t / 1e6)), flush=True)
-    t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=False))
-    print(json.dumps(dict(op="kernel_fwd_f32", N=N, M=M, ms=t, GBs=N * M * 4 / t / 1e6)), flush=True)
+    if not only:
+        t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=True))
+        print(json.dumps(dict(op="kernel_fwd_planes", N=N, M=M, ms=t, GBs=4 * N * M * 2 / t / 1e6)), flush=True)
+        t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=False))
+        print(json.dumps(dict(op="kernel_fwd_f32", N=N, M=M, ms=t, GBs=N * M * 4 / t / 1e6)), flush=True)
     kop = be.kernel_fwd(spec, Fx, Fz, hyp, tc=True)
     W = torch.randn(N, L, generator=g, device="cuda")
     S = torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64); S = (S + S.transpose(1, 2)).contiguous()
     Lt = torch.tril(S).contiguous()
     tag = os.environ.get("SVGP_TC_BK", "default")
-    for chunk in (1024, 4096, 16384):
+    flush = os.environ.get("SVGP_SYRK_FLUSH", "default")
+    for chunk in (1024, 2048, 4096, 16384):
         t = timeit(lambda: be.syrk(kop, W, chunk_rows=chunk))
-        print(json.dumps(dict(op="syrk_tc", bk=tag, chunk=chunk, N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
+        print(json.dumps(dict(op="syrk_tc", bk=tag, flush=flush, chunk=chunk, N=N, M=M, L=L, ms=t,
+                              alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
+    if only == "syrk":
+        return
     Spl, Ltpl = be.planes(S), be.planes(Lt)
     t = timeit(lambda: be.planes(S))
     print(json.dumps(dict(op="split_f16", M=M, L=L, ms=t)), flush=True)
