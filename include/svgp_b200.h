@@ -61,7 +61,9 @@ int svgp_device_ok(void);          /* 1 if the current device is compute capabil
  * Outputs (each group may be NULL):
  *   K   (N x M fp32, ld = ldk)                         plain matrix for the SIMT consumers
  *   Kh, Kl   (N x M fp16 planes, ld = ldkh elements)   operand planes of the tcgen05 consumers:
- *   Kth, Ktl (M x N fp16 planes, ld = ldkt elements)   value * scale = fp16 hi + fp16 lo (22 bits),
+ *   Kth, Ktl (transposed planes, datapoint-blocked:    value * scale = fp16 hi + fp16 lo (22 bits),
+ *            element (m, n) at [n / 64] * ldkt + m * 64 + n % 64, ldkt >= 64 M; ceil(N / 64) blocks, the
+ *            datapoints past N in the last block are written as zeros)
  *            with scale = the power of two that puts the kernel's upper bound (amplitudes, max
  *            feature norms) just below 2^14; kscale (device float[8], required with the planes)
  *            receives {scale, 1/scale, ...scratch}.  Rows/columns beyond N / M up to ld stay untouched.
@@ -101,8 +103,8 @@ typedef struct svgp_kop {
   const float* K;      /* N x M fp32, ld = ldk (SIMT operand; may be NULL when the planes are given) */
   const void* Kh;      /* N x M fp16 hi plane, ld = ldkh                                            */
   const void* Kl;      /* N x M fp16 lo plane                                                       */
-  const void* Kth;     /* M x N fp16 hi plane of the transpose, ld = ldkt                           */
-  const void* Ktl;     /* M x N fp16 lo plane                                                       */
+  const void* Kth;     /* fp16 hi plane of the transpose, blocked [ceil(N/64)][M][64], block stride ldkt */
+  const void* Ktl;     /* fp16 lo plane, same layout                                                */
   const float* kscale; /* device float[>=2]: {scale, 1/scale} of the planes                         */
   int64_t N, M, ldk, ldkh, ldkt;
 } svgp_kop;
@@ -116,12 +118,14 @@ int svgp_split_f16(const double* x, int64_t nb, int64_t count, void* hi, void* l
 
 /* K2  batched weighted SYRK   A[l] = sum_i W[i,l] k_i k_i^T   (L x M x M, double, ACCUMULATED:
  * caller zeroes; both triangles written).  W is N x L fp32 (any sign).  The TC path needs the
- * workspace ws (float[svgp_syrk_ws_floats(N, L)]): it holds the channel-major copy of W scaled
- * per channel by a power of two (|w s_l| <= 1, so that w * k stays inside fp16 range) and 1/s_l.
+ * workspace ws (float[svgp_syrk_ws_floats(N, M, L)]): it holds the channel-major copy of W scaled
+ * per channel by a power of two (|w s_l| <= 1, so that w * k stays inside fp16 range), 1/s_l, and
+ * the lock words guarding the float64 tiles of A (datapoints are walked in L2-sized super-chunks;
+ * CTAs working on different super-chunks of one tile add into it under a spin lock).
  * chunk_rows: datapoints per TMEM accumulation chain (0 = default 2048).
  * replaces: K_mn (K_nm * 1/sigma^2) SVGPVAE_model.py:328-330 (:160 for the ball) and, as the
  * adjoint of svgp_rowquad, the (b,m,m) trace pattern :286-294.                               */
-int64_t svgp_syrk_ws_floats(int64_t N, int64_t L);
+int64_t svgp_syrk_ws_floats(int64_t N, int64_t M, int64_t L);
 int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, int impl,
               int64_t chunk_rows, float* ws, void* stream);
 

@@ -40,7 +40,7 @@ SIGNATURES = {
     "svgp_kernel_diag_bwd": [_P, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, _P, _P, _P, _P],
     "svgp_gather_rows": [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, _P],
     "svgp_scatter_add_rows": [_P, c_int64, _P, c_int64, c_int64, c_int64, _P, c_int64, _P],
-    "svgp_syrk_ws_floats": [c_int64, c_int64],
+    "svgp_syrk_ws_floats": [c_int64, c_int64, c_int64],
     "svgp_syrk": [POINTER(KopStruct), _P, c_int64, c_int64, _P, c_int, c_int64, _P, _P],
     "svgp_gemm_tn": [POINTER(KopStruct), _P, c_int64, c_int64, _P, _P],
     "svgp_gemm_nn": [POINTER(KopStruct), _P, c_int64, c_int64, _P, c_int64, _P],

@@ -42,6 +42,11 @@ class Kop:
             return self.K[: self.N, : self.M]
         return (self.Kh[: self.N, : self.M].float() + self.Kl[: self.N, : self.M].float()) * self.kscale[1]
 
+    def value_t(self):
+        """K_nm^T (M x N) reassembled from the datapoint-blocked transposed planes."""
+        t = (self.Kth.float() + self.Ktl.float()) * self.kscale[1]            # (nblk, M, 64)
+        return t.permute(1, 0, 2).reshape(self.M, -1)[:, : self.N]
+
     def struct(self):
         s = KopStruct()
         s.K = self.K.data_ptr() if self.K is not None else None
@@ -141,13 +146,15 @@ class CudaBackend:
         ta, da, tb, db = spec
         dev = Fx.device
         if tc:
-            ldkh, ldkt = _pad(M, 8), _pad(N, 8)
+            ldkh = _pad(M, 8)
             alloc = torch.zeros if (ldkh != M) else torch.empty
             Kh = alloc((N, ldkh), device=dev, dtype=torch.float16)
             Kl = alloc((N, ldkh), device=dev, dtype=torch.float16)
-            alloc = torch.zeros if (ldkt != N) else torch.empty
-            Kth = alloc((M, ldkt), device=dev, dtype=torch.float16)
-            Ktl = alloc((M, ldkt), device=dev, dtype=torch.float16)
+            # transposed planes, blocked by 64 datapoints: [ceil(N / 64)][M][64] (the kernel zeroes the ragged tail)
+            nblk = (N + 63) // 64
+            Kth = torch.empty((nblk, M, 64), device=dev, dtype=torch.float16)
+            Ktl = torch.empty((nblk, M, 64), device=dev, dtype=torch.float16)
+            ldkt = M * 64
             kscale = torch.empty(8, device=dev, dtype=torch.float32)
             kop = Kop(None, Kh, Kl, Kth, Ktl, kscale, N, M)
             _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
@@ -227,7 +234,7 @@ class CudaBackend:
         use_tc = kop.tc and impl != IMPL_SIMT
         ws = None
         if use_tc:
-            ws = torch.empty(int(_lib.load().svgp_syrk_ws_floats(kop.N, L)), device=W.device, dtype=torch.float32)
+            ws = torch.empty(int(_lib.load().svgp_syrk_ws_floats(kop.N, kop.M, L)), device=W.device, dtype=torch.float32)
         s = kop.struct()
         _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), L, _ptr(A), IMPL_TC if use_tc else IMPL_SIMT, chunk_rows,
               _ptr(ws), _stream())

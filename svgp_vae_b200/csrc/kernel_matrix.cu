@@ -232,17 +232,21 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
       }
     }
     if (Kth) {
-      // transposed write: consecutive threads walk consecutive datapoints of one inducing column
+      // transposed, datapoint-blocked write  Kt[n / 64][m][n % 64]  (block stride ldkt): this 64 x 64 tile is one
+      // contiguous 8 KB run, and the SYRK's TMA boxes (rows x 64 datapoints) are contiguous too -- a plain M x N
+      // transpose puts every row of a box on its own 2 MB page.  Datapoints past N in the last block are zeroed.
+      static_assert(TILE == 64, "the blocked transpose is laid out in 64-datapoint blocks");
       const int r = threadIdx.x % TILE, cg = threadIdx.x / TILE;
 #pragma unroll 4
       for (int j = 0; j < TILE / 4; ++j) {
         int cc = cg + 4 * j;
         int64_t gr = row0 + r, gc = col0 + cc;
-        if (gr < N && gc < M) {
-          float vs = tile[r * (TILE + 1) + cc] * scale;
+        if (gc < M) {
+          float vs = gr < N ? tile[r * (TILE + 1) + cc] * scale : 0.f;
           __half hi = __float2half_rn(vs);
-          Kth[gc * ldkt + gr] = hi;
-          Ktl[gc * ldkt + gr] = __float2half_rn(vs - __half2float(hi));
+          const int64_t o = rt * ldkt + gc * TILE + r;
+          Kth[o] = hi;
+          Ktl[o] = __float2half_rn(vs - __half2float(hi));
         }
       }
     }

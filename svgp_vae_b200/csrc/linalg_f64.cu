@@ -213,8 +213,10 @@ __global__ void __launch_bounds__(256) gemm_f64_big_kernel(int64_t Mr, int64_t N
                                                            double* __restrict__ C, int64_t ldc, int64_t strideC, int lower_only) {
   const int64_t m0 = (int64_t)blockIdx.y * GM, n0 = (int64_t)blockIdx.x * GN;
   if (lower_only && n0 > m0 + GM - 1) return;
-  __shared__ __align__(16) double As[GK][GM];
-  __shared__ __align__(16) double Bs[GK][GN];
+  // +2 doubles per row: the transposing stores (16 consecutive kk of one column) then land 16 bytes apart
+  // (2-way instead of 16-way bank conflicts) and every row start stays 16-byte aligned for the LDS.128 reads
+  __shared__ __align__(16) double As[GK][GM + 2];
+  __shared__ __align__(16) double Bs[GK][GN + 2];
   const double* Ab = A + (int64_t)blockIdx.z * strideA;
   const double* Bb = B + (int64_t)blockIdx.z * strideB;
   double* Cb = C + (int64_t)blockIdx.z * strideC;

@@ -293,7 +293,8 @@ static int launch_tile(Op op, int64_t nz, cudaStream_t st, const char* name) {
 }
 
 // entry points of the tcgen05 implementation (tc_engine.cu)
-int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows,
+int64_t tc_syrk_lock_words(int64_t M, int64_t L);
+int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows, int* locks,
             cudaStream_t st);
 int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
                int64_t ldq, cudaStream_t st);
@@ -320,7 +321,7 @@ static bool use_tc(const svgp_kop* kop, int impl) {
 
 extern "C" {
 
-int64_t svgp_syrk_ws_floats(int64_t N, int64_t L) { return L * pad8(N) + 2 * L; }
+int64_t svgp_syrk_ws_floats(int64_t N, int64_t M, int64_t L) { return L * pad8(N) + 2 * L + tc_syrk_lock_words(M, L); }
 
 int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, int impl, int64_t chunk_rows,
               float* ws, void* stream) {
@@ -341,7 +342,7 @@ int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, doubl
     transpose_scale_kernel<<<grid, 256, 0, st>>>(W, ldw, kop->N, L, mx, Wt, ldwt, winv);
     int rc = check_launch("svgp_syrk(prep)");
     if (rc) return rc;
-    return tc_syrk(kop, Wt, ldwt, winv, L, A, chunk_rows, st);
+    return tc_syrk(kop, Wt, ldwt, winv, L, A, chunk_rows, reinterpret_cast<int*>(winv + L), st);
   }
   SVGP_REQUIRE(kop->K != nullptr, "SIMT path needs the fp32 K");
   int64_t chunk = chunk_rows > 0 ? chunk_rows : 2048;

@@ -73,6 +73,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -154,6 +160,26 @@ __device__ __forceinline__ void rescale_pair(uint32_t& hi2, uint32_t& lo2, float
   hi2 = *reinterpret_cast<const uint32_t*>(&nh);
   lo2 = *reinterpret_cast<const uint32_t*>(&nl);
 }
+// the same in packed-half arithmetic, with the weight itself given as an fp16 pair w = wh + wl:
+//   (hi + lo)(wh + wl) = hi wh + [lo wh + hi wl] + O(2^-22);   nh = rn(hi wh), and fma(hi, wh, -nh) is the EXACT
+// rounding residual of that product (it has at most 11 significant bits), so nh + nl carries 22 bits again.
+__device__ __forceinline__ void rescale_pair_h2(uint32_t& hi2, uint32_t& lo2, uint32_t wh2, uint32_t wl2) {
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi2), l = *reinterpret_cast<const __half2*>(&lo2);
+  const __half2 wh = *reinterpret_cast<const __half2*>(&wh2), wl = *reinterpret_cast<const __half2*>(&wl2);
+  const __half2 nh = __hmul2(h, wh);
+  __half2 nl = __hfma2(h, wh, __hneg2(nh));
+  nl = __hfma2(l, wh, nl);
+  nl = __hfma2(h, wl, nl);
+  hi2 = *reinterpret_cast<const uint32_t*>(&nh);
+  lo2 = *reinterpret_cast<const uint32_t*>(&nl);
+}
+__device__ __forceinline__ void split_weights(float a, float b, uint32_t& wh2, uint32_t& wl2) {
+  const __half2 wh = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(wh);
+  const __half2 wl = __floats2half2_rn(a - f.x, b - f.y);
+  wh2 = *reinterpret_cast<const uint32_t*>(&wh);
+  wl2 = *reinterpret_cast<const uint32_t*>(&wl);
+}
 __device__ __forceinline__ float pair_dot2(uint32_t hi2, uint32_t lo2, float v0, float v1, float acc) {
   const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
   const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lo2));
@@ -172,9 +198,14 @@ struct TcParams {
   const float* Wt;            // (L, ldwt) channel-major weights, pre-scaled, zero padded
   int64_t ldwt;
   double* A;                  // (L, M, M) accumulated
-  int64_t chunk_rows, nchunk;
+  int64_t chunk_rows;         // datapoints per MMA chain (one TMEM sub-tile)
+  int64_t sc_rows;            // datapoints per super-chunk: an item covers one super-chunk of one (tile pair, channel)
+  int nsc;                    // number of super-chunks
   int ntile;                  // number of (ta, tb) tile pairs
+  int* locks;                 // one word per (tile pair, channel, epilogue warp): guards the float64 read-modify-write
   int flush_every;            // chunks folded in fp32 registers between two float64 read-modify-writes of the tile
+  int debug;                  // experiments (SVGP_TC_DEBUG): bit 0 = skip the operand transform arithmetic (wrong results),
+                              // bit 1 = fp32 transform instead of the packed-half one
   // QUAD
   int tri;
   const __half* K_hi;         // for the DOT epilogues
@@ -253,12 +284,14 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   auto tmem_full = [&](int t) { return bars + 8u * (3 * STAGES + t); };
   auto tmem_empty = [&](int t) { return bars + 8u * (3 * STAGES + 2 + t); };
   const uint32_t tmem_ptr_addr = bars + 8u * (3 * STAGES + 4);
+  auto fullA = [&](int s) { return bars + 8u * (3 * STAGES + 5 + s); };    // SYRK: the A planes land (and are transformed) first
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
+      mbar_init(fullA(s), 1);
       mbar_init(ready(s), 4);
       mbar_init(empty(s), 1);
     }
@@ -293,31 +326,21 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   const int nct = (int)((M + BN - 1) / BN);
   const int kb_full = (int)((M + BK - 1) / BK);
 
-  auto item_subtiles = [&]() -> int {
-    if (MODE == MODE_SYRK) return (int)P.nchunk;
-    if (MODE == MODE_QUAD) return nct;
-    return (int)P.L;
-  };
-  auto subtile_kblocks = [&](int sub) -> int {
-    if (MODE == MODE_SYRK) {
-      int64_t n0 = (int64_t)sub * P.chunk_rows;
-      int64_t n1 = n0 + P.chunk_rows < P.N ? n0 + P.chunk_rows : P.N;
-      return (int)((n1 - n0 + BK - 1) / BK);
-    } else if (MODE == MODE_QUAD) {
-      if (!P.tri) return kb_full;
-      int64_t kend = (int64_t)(sub + 1) * BN < M ? (int64_t)(sub + 1) * BN : M;
-      return (int)((kend + BK - 1) / BK);
-    }
-    return kb_full;
-  };
-  struct Item { int64_t l, itile; int a_row0, b_row0; };
+  struct Item { int64_t l, itile, n0, n1; int a_row0, b_row0, tile; };
   auto decode = [&](int64_t item) -> Item {
-    Item it{0, 0, 0, 0};
+    Item it{0, 0, 0, 0, 0, 0, 0};
     if (MODE == MODE_SYRK) {
-      it.l = item % P.L;
+      // super-chunk major: all (tile pair, channel) items of one window of datapoints are scheduled together, so the
+      // CTAs in flight stream the same <= ~48 MB slice of K^T out of L2 instead of thrashing it with M x N planes
+      const int64_t per_sc = (int64_t)P.ntile * P.L;
+      const int64_t sc = item / per_sc, rem = item - sc * per_sc;
+      it.l = rem % P.L;
+      it.tile = (int)(rem / P.L);
       int ta, tb;
-      syrk_tile_decode((int)(item / P.L), M, BN, ta, tb);
+      syrk_tile_decode(it.tile, M, BN, ta, tb);
       it.a_row0 = ta * BLOCK_M; it.b_row0 = tb * BN;
+      it.n0 = sc * P.sc_rows;
+      it.n1 = it.n0 + P.sc_rows < P.N ? it.n0 + P.sc_rows : P.N;
     } else if (MODE == MODE_QUAD) {
       int64_t ntile_r = (P.N + BLOCK_M - 1) / BLOCK_M;
       int64_t per_group = ntile_r * P.lgroup;
@@ -330,6 +353,23 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     }
     return it;
   };
+  auto item_subtiles = [&](const Item& it) -> int {
+    if (MODE == MODE_SYRK) return (int)((it.n1 - it.n0 + P.chunk_rows - 1) / P.chunk_rows);
+    if (MODE == MODE_QUAD) return nct;
+    return (int)P.L;
+  };
+  auto subtile_kblocks = [&](const Item& it, int sub) -> int {
+    if (MODE == MODE_SYRK) {
+      int64_t c0 = it.n0 + (int64_t)sub * P.chunk_rows;
+      int64_t c1 = c0 + P.chunk_rows < it.n1 ? c0 + P.chunk_rows : it.n1;
+      return (int)((c1 - c0 + BK - 1) / BK);
+    } else if (MODE == MODE_QUAD) {
+      if (!P.tri) return kb_full;
+      int64_t kend = (int64_t)(sub + 1) * BN < M ? (int64_t)(sub + 1) * BN : M;
+      return (int)((kend + BK - 1) / BK);
+    }
+    return kb_full;
+  };
 
   auto role_producer = [&]() {
     // =============================== TMA producer ===============================================
@@ -337,25 +377,38 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode(item);
-        const int nsub = item_subtiles();
+        const int nsub = item_subtiles(it);
         for (int sub = 0; sub < nsub; ++sub) {
-          const int nkb = subtile_kblocks(sub);
+          const int nkb = subtile_kblocks(it, sub);
           for (int kb = 0; kb < nkb; ++kb) {
             mbar_wait(empty(stage), phase ^ 1);
             const uint32_t st = smem + stage * STAGE_BYTES;
             int32_t ak, ar, bk, br;
             if (MODE == MODE_SYRK) {
-              ak = (int32_t)((int64_t)sub * P.chunk_rows) + kb * BK; ar = it.a_row0; bk = ak; br = it.b_row0;
+              ak = (int32_t)(it.n0 + (int64_t)sub * P.chunk_rows) + kb * BK; ar = it.a_row0; bk = ak; br = it.b_row0;
             } else if (MODE == MODE_QUAD) {
               ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)(it.l * M + (int64_t)sub * BN);
             } else {
               ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)sub * M + it.b_row0);
             }
-            mbar_expect_tx(full(stage), STAGE_BYTES);
-            tma_load_2d(st, &mapA_hi, full(stage), ak, ar);
-            tma_load_2d(st + A_BYTES, &mapA_lo, full(stage), ak, ar);
-            tma_load_2d(st + 2 * A_BYTES, &mapB_hi, full(stage), bk, br);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), bk, br);
+            if (MODE == MODE_SYRK) {
+              // datapoint-blocked transposed planes [n / 64][m][n % 64]: a box is one contiguous run of rows.
+              // The A planes get their own barrier and go first: the transform warps rescale them while the
+              // (twice as large) B planes are still in flight.
+              const int32_t nb = ak >> 6, ni = ak & 63;
+              mbar_expect_tx(fullA(stage), 2 * A_BYTES);
+              tma_load_3d(st, &mapA_hi, fullA(stage), ni, ar, nb);
+              tma_load_3d(st + A_BYTES, &mapA_lo, fullA(stage), ni, ar, nb);
+              mbar_expect_tx(full(stage), 2 * B_BYTES);
+              tma_load_3d(st + 2 * A_BYTES, &mapB_hi, full(stage), ni, br, nb);
+              tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), ni, br, nb);
+            } else {
+              mbar_expect_tx(full(stage), STAGE_BYTES);
+              tma_load_2d(st, &mapA_hi, full(stage), ak, ar);
+              tma_load_2d(st + A_BYTES, &mapA_lo, full(stage), ak, ar);
+              tma_load_2d(st + 2 * A_BYTES, &mapB_hi, full(stage), bk, br);
+              tma_load_2d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), bk, br);
+            }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
         }
@@ -367,9 +420,10 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      const int nsub = item_subtiles();
+      const Item it = decode(item);
+      const int nsub = item_subtiles(it);
       for (int sub = 0; sub < nsub; ++sub) {
-        const int nkb = subtile_kblocks(sub);
+        const int nkb = subtile_kblocks(it, sub);
         mbar_wait(tmem_empty(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -407,7 +461,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     int acc = 0; uint32_t acc_phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
-      const int nsub = item_subtiles();
+      const int nsub = item_subtiles(it);
       if constexpr (MODE == MODE_SYRK) {
         // The tile's running sum lives in REGISTERS: warp (quarter qd, column half) owns rows [a0, a0 + 32) x 128
         // columns, one row per thread, 128 fp32 sums.  Every chunk (one short, truncating MMA chain in TMEM) is
@@ -450,25 +504,38 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
           if (++pending == P.flush_every || sub == nsub - 1) {
             pending = 0;
-#pragma unroll
-            for (int ch = 0; ch < BN / 64; ++ch) {
-              if (ch < nlive) {
-                const int64_t c0 = cw0 + 32 * ch;
-                double* dst = P.A + (it.l * M + r) * M + c0;
-                const int64_t nv64 = (r < M) ? r - c0 + 1 : 0;             // columns c0 .. min(c0 + 31, r) of row r
-                const int nv = nv64 > 32 ? 32 : (int)nv64;
-#pragma unroll
-                for (int j0 = 0; j0 < 32; j0 += 8) {
-                  double t[8];
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) t[j] = (j0 + j < nv) ? dst[j0 + j] : 0.0;
-#pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    if (j0 + j < nv) dst[j0 + j] = t[j] + (double)run[ch][j0 + j] * sc;
-                }
-#pragma unroll
-                for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
+            if (nlive > 0) {
+              // Other CTAs add other super-chunks of the same tile: the 32 x 128 block of this warp is guarded by a
+              // spin lock (contention is rare: same-tile items are ntile * L items apart) and accessed through L2 only.
+              int* lock = P.locks + ((int64_t)it.tile * P.L + it.l) * 8 + (warp - EPI_WARP0);
+              if (lane == 0) {
+                while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
+                __threadfence();
               }
+              __syncwarp();
+#pragma unroll
+              for (int ch = 0; ch < BN / 64; ++ch) {
+                if (ch < nlive) {
+                  const int64_t c0 = cw0 + 32 * ch;
+                  double* dst = P.A + (it.l * M + r) * M + c0;
+                  const int64_t nv64 = (r < M) ? r - c0 + 1 : 0;           // columns c0 .. min(c0 + 31, r) of row r
+                  const int nv = nv64 > 32 ? 32 : (int)nv64;
+#pragma unroll
+                  for (int j0 = 0; j0 < 32; j0 += 8) {
+                    double t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = (j0 + j < nv) ? __ldcg(dst + j0 + j) : 0.0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                      if (j0 + j < nv) __stcg(dst + j0 + j, t[j] + (double)run[ch][j0 + j] * sc);
+                  }
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
+                }
+              }
+              __threadfence();
+              __syncwarp();
+              if (lane == 0) atomicExch(lock, 0);
             }
           }
         }
@@ -571,29 +638,50 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     int stage = 0; uint32_t phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
-      const int nsub = item_subtiles();
+      const int nsub = item_subtiles(it);
       for (int sub = 0; sub < nsub; ++sub) {
-        const int nkb = subtile_kblocks(sub);
+        const int nkb = subtile_kblocks(it, sub);
         for (int kb = 0; kb < nkb; ++kb) {
-          const int64_t n = (int64_t)sub * P.chunk_rows + (int64_t)kb * BK + lchunk * 8;
+          const int64_t n = it.n0 + (int64_t)sub * P.chunk_rows + (int64_t)kb * BK + lchunk * 8;
           float4 w0 = make_float4(0.f, 0.f, 0.f, 0.f), w1 = w0;
           if (n + 8 <= P.ldwt) {
             const float4* wp = reinterpret_cast<const float4*>(P.Wt + it.l * P.ldwt + n);
             w0 = __ldg(wp); w1 = __ldg(wp + 1);
           }
-          mbar_wait(full(stage), phase);
+          // the thread's 8 weights as fp16 pairs (|w| <= 1 after the per-channel scaling)
+          uint32_t wh[4], wl[4];
+          split_weights(w0.x, w0.y, wh[0], wl[0]);
+          split_weights(w0.z, w0.w, wh[1], wl[1]);
+          split_weights(w1.x, w1.y, wh[2], wl[2]);
+          split_weights(w1.z, w1.w, wh[3], wl[3]);
+          mbar_wait(fullA(stage), phase);
           const uint32_t hi_p = smem + stage * STAGE_BYTES + rbase * RB + pchunk * 16;
           const uint32_t lo_p = hi_p + A_BYTES;
+          if (P.debug & 2) {
+            // reference variant: rescale in fp32 and re-split (3.5x the instructions of the packed-half path)
 #pragma unroll
-          for (int r = 0; r < CPR; ++r) {
-            const uint32_t off = r * RSTEP * RB;
-            uint4 h = lds128(hi_p + off), l = lds128(lo_p + off);
-            rescale_pair(h.x, l.x, w0.x, w0.y);
-            rescale_pair(h.y, l.y, w0.z, w0.w);
-            rescale_pair(h.z, l.z, w1.x, w1.y);
-            rescale_pair(h.w, l.w, w1.z, w1.w);
-            sts128(hi_p + off, h);
-            sts128(lo_p + off, l);
+            for (int r = 0; r < CPR; ++r) {
+              const uint32_t off = r * RSTEP * RB;
+              uint4 h = lds128(hi_p + off), l = lds128(lo_p + off);
+              rescale_pair(h.x, l.x, w0.x, w0.y);
+              rescale_pair(h.y, l.y, w0.z, w0.w);
+              rescale_pair(h.z, l.z, w1.x, w1.y);
+              rescale_pair(h.w, l.w, w1.z, w1.w);
+              sts128(hi_p + off, h);
+              sts128(lo_p + off, l);
+            }
+          } else if (!(P.debug & 1)) {
+#pragma unroll
+            for (int r = 0; r < CPR; ++r) {
+              const uint32_t off = r * RSTEP * RB;
+              uint4 h = lds128(hi_p + off), l = lds128(lo_p + off);
+              rescale_pair_h2(h.x, l.x, wh[0], wl[0]);
+              rescale_pair_h2(h.y, l.y, wh[1], wl[1]);
+              rescale_pair_h2(h.z, l.z, wh[2], wl[2]);
+              rescale_pair_h2(h.w, l.w, wh[3], wl[3]);
+              sts128(hi_p + off, h);
+              sts128(lo_p + off, l);
+            }
           }
           fence_async_smem();
           __syncwarp();
@@ -678,6 +766,22 @@ static int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t co
   return SVGP_OK;
 }
 
+// datapoint-blocked transposed plane [nblk][rows][64] fp16 (block stride ldb elements), box = box_rows x bk datapoints
+static int make_map_blocked(CUtensorMap* map, const void* base, int64_t rows, int64_t N, int64_t ldb, int box_rows, int bk) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SVGP_ERR_CUDA; }
+  if (((uintptr_t)base & 15) || (ldb * 2) % 16 || ldb < rows * 64) { set_error("TMA operand: bad blocked transposed plane"); return SVGP_ERR_ARG; }
+  cuuint64_t dims[3] = {64, (cuuint64_t)rows, (cuuint64_t)((N + 63) / 64)};
+  cuuint64_t strides[2] = {128, (cuuint64_t)ldb * 2};
+  cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (blocked) failed (%d)", (int)r); return SVGP_ERR_CUDA; }
+  return SVGP_OK;
+}
+
 static int num_sms() {
   static int n = 0;
   if (!n) {
@@ -740,27 +844,42 @@ bool tc_shape_ok(const svgp_kop* kop) {
   return kop->M >= 128 && kop->N >= 2048 && (kop->ldkh % 8) == 0 && (kop->ldkt % 8) == 0;
 }
 
+// super-chunk length: the K^T slice of one super-chunk (M rows x sc datapoints x hi/lo fp16) should occupy well under
+// half of the 126 MB L2, because items of two consecutive super-chunks are in flight around a boundary
+static int64_t syrk_superchunk_rows(int64_t M, int64_t chunk) {
+  const char* e = getenv("SVGP_SYRK_SC");
+  int64_t sc = (e && atoll(e) > 0) ? atoll(e) : (48LL << 20) / (M * 4);
+  sc = sc / chunk * chunk;
+  return sc < chunk ? chunk : sc;
+}
+
+int64_t tc_syrk_lock_words(int64_t M, int64_t L) { return (int64_t)syrk_tile_count(M, 256) * L * 8; }
+
 int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows,
-            cudaStream_t st) {
+            int* locks, cudaStream_t st) {
   if (!kop->Kth || !kop->Ktl || !kop->kscale) { set_error("tc_syrk: transposed fp16 planes missing"); return SVGP_ERR_ARG; }
   if (((uintptr_t)Wt & 15) || (ldwt % 8)) { set_error("tc_syrk: weights need 16-byte alignment"); return SVGP_ERR_ARG; }
   const int BN = 256, bk = tc_bk();
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
-  if ((rc = make_map(&a_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BLOCK_M, bk))) return rc;
-  if ((rc = make_map(&a_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BLOCK_M, bk))) return rc;
-  if ((rc = make_map(&b_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
-  if ((rc = make_map(&b_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
+  if ((rc = make_map_blocked(&a_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BLOCK_M, bk))) return rc;
+  if ((rc = make_map_blocked(&a_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BLOCK_M, bk))) return rc;
+  if ((rc = make_map_blocked(&b_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
+  if ((rc = make_map_blocked(&b_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
   TcParams P{};
   P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = winv;
-  P.Wt = Wt; P.ldwt = ldwt; P.A = A;
+  P.Wt = Wt; P.ldwt = ldwt; P.A = A; P.locks = locks;
   // one accumulation chain = chunk / 16 k-steps x 3 MMAs; 2048 rows -> 384 MMAs (truncation bias ~1e-5 worst case)
   int64_t chunk = chunk_rows > 0 ? chunk_rows : 2048;
   chunk = (chunk + 63) / 64 * 64;
-  P.chunk_rows = chunk; P.nchunk = ceil_div(kop->N, chunk);
+  P.chunk_rows = chunk;
+  P.sc_rows = syrk_superchunk_rows(kop->M, chunk);
+  P.nsc = (int)ceil_div(kop->N, P.sc_rows);
   P.ntile = syrk_tile_count(kop->M, BN);
   P.flush_every = syrk_flush_every();
-  P.n_items = (int64_t)P.ntile * L;
+  { const char* e = getenv("SVGP_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
+  P.n_items = (int64_t)P.nsc * P.ntile * L;
+  if (cudaMemsetAsync(locks, 0, sizeof(int) * tc_syrk_lock_words(kop->M, L), st) != cudaSuccess) return check_launch("svgp_syrk(locks)");
   rc = dispatch_tc<MODE_SYRK>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
   if (rc) return rc;
   int64_t blocks = ceil_div(L * kop->M * kop->M, 256);

@@ -42,7 +42,7 @@ def test_kernel_fwd_bwd(cuda_backend, name, shape):
     floor = 2.0 ** -24 * float(kopt.kscale[1])
     refc = ref.cuda()
     assert float((kopt.value().double() - refc).abs().max()) < 5e-6 * float(refc.abs().max()) + floor
-    Kt = (kopt.Kth.float() + kopt.Ktl.float())[:M, :N] * kopt.kscale[1]
+    Kt = kopt.value_t()
     assert float((Kt.double() - refc.t()).abs().max()) < 5e-6 * float(refc.abs().max()) + floor
     assert float(kopt.value().abs().max() * kopt.kscale[0]) < 2 ** 14 + 1
     G = torch.randn(N, M, generator=torch.Generator().manual_seed(1))
@@ -120,6 +120,13 @@ def test_linalg_f64(cuda_backend, M, B):
             B_ = Y.transpose(1, 2).contiguous() if tB else Y
             assert rel_err(be.bmm64(A_.cuda(), B_.cuda(), tA, tB), X @ Y) < 1e-12
     assert rel_err(be.bmm64(X[:1].cuda(), Y.cuda()), X[:1] @ Y) < 1e-12       # broadcast batch of one
+    if M >= 96:                                                                # 128 x 128 register-tiled kernel, ragged edges
+        Z = torch.randn(B, M, M - 5, generator=g, dtype=torch.float64)
+        for tA in (False, True):
+            for tB in (False, True):
+                A_ = X.transpose(1, 2).contiguous() if tA else X
+                B_ = Z.transpose(1, 2).contiguous() if tB else Z
+                assert rel_err(be.bmm64(A_.cuda(), B_.cuda(), tA, tB), X @ Z) < 1e-12
     # a non-PD matrix is reported, not silently NaN-propagated
     bad = X.clone()
     bad[0, M - 1, M - 1] = -1.0

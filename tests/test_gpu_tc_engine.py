@@ -41,6 +41,22 @@ def test_tc_syrk(cuda_backend, shape):
     assert rel_err(be.syrk(kop, Wp), refp) < 3e-5
 
 
+@pytest.mark.parametrize("shape", [(9000, 256, 1), (20000, 384, 3)])
+def test_tc_syrk_superchunks(cuda_backend, shape, monkeypatch):
+    """Datapoints are walked in L2-sized super-chunks; different CTAs add different super-chunks of one tile into the
+    float64 accumulator under a lock.  Force many small super-chunks (L = 1: same-tile items run concurrently)."""
+    be = cuda_backend
+    N, M, L = shape
+    kop, K64, W, g = _setup(be, N, M, L, seed=5)
+    ref = torch.einsum('il,ia,ib->lab', W.double(), K64, K64)
+    monkeypatch.setenv("SVGP_SYRK_SC", "512")
+    for _ in range(3):
+        A = be.syrk(kop, W, chunk_rows=256)
+        assert rel_err(A, ref) < 3e-6
+    monkeypatch.setenv("SVGP_SYRK_SC", "4096")
+    assert rel_err(be.syrk(kop, W), ref) < 3e-5
+
+
 @pytest.mark.parametrize("shape", [(4096, 256, 3), (3000, 200, 2), (2304, 1024, 2)])
 def test_tc_rowquad_scaled(cuda_backend, shape):
     be = cuda_backend
