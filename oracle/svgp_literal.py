@@ -20,6 +20,7 @@ PARITY UNPINNED (see oracle/__init__.py).
 """
 import math
 
+import numpy as np
 import torch
 
 from . import tfp_kernels as tfk
@@ -68,7 +69,10 @@ class BallSVGP:
         self.num_inducing_points = num_inducing_points
         self.jitter = jitter
         lo, hi = (tmin, tmax) if fixed_inducing_points else (ip_min, ip_max)
-        self.inducing_index_points = torch.linspace(lo, hi, num_inducing_points, dtype=F64)
+        # :46 / :49 -- the reference builds the grid with np.linspace(..., dtype=np.float32): the inducing times ARE
+        # float32 numbers (3.0714285...), so the float64 oracle starts from the same rounded values
+        self.inducing_index_points = torch.from_numpy(
+            np.linspace(lo, hi, num_inducing_points, dtype=np.float32).astype(np.float64))
         self.l_GP = as64(vidlt if fixed_gp_params else GP_init)
         # :60 amplitude=None
         self.kernel = tfk.ExponentiatedQuadratic(amplitude=None, length_scale=self.l_GP)

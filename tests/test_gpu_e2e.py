@@ -152,3 +152,74 @@ def test_ball(cuda_backend):
     g0 = torch.autograd.grad(r0["KL_term"].sum() + (gm * r0["p_m"]).sum() + (gv * r0["p_v"]).sum(), [y64, n64])
     (KL_term.sum() + (gm.cuda().float() * pm).sum() + (gv.cuda().float() * pv).sum()).backward()
     assert rel_err(yc.grad, g0[0]) < TOL and rel_err(nc.grad, g0[1]) < TOL
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CUDA path vs tests/golden/reference_golden.npz: outputs of the unmodified reference source executed under the
+# TensorFlow-API shim (tests/golden/make_reference_golden.py) -- no oracle in between.
+# ----------------------------------------------------------------------------------------------------------
+REF_CASES = [
+    ("mnist", "mnist", lambda: configs.mnist_inputs(MNIST_FIXTURE, L=4), False),
+    ("mnist_norm", "mnist", lambda: configs.mnist_inputs(MNIST_FIXTURE, L=4, normalize=True), False),
+    ("mnist_train_last", "mnist", lambda: configs.mnist_inputs(MNIST_FIXTURE, L=2, b=210, rows="train", batch_index=15), False),
+    ("sprites72", "sprites", lambda: configs.sprites_inputs(M=72, L=4), True),
+    ("sprites72_raw", "sprites", lambda: configs.sprites_inputs(M=72, L=4, normalize=False), True),
+]
+
+
+@pytest.mark.parametrize("name,kind,maker,clip", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_against_reference_source_golden(cuda_backend, name, kind, maker, clip):
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    cfg = maker()
+    _, s, _, sp = refs.make_pair(kind, cfg, "cuda")
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda(), clip_pv=clip)
+    T = lambda k: torch.from_numpy(gold[name + "/" + k])
+    assert rel_err(r1["p_m"], T("p_m")) < TOL and rel_err(r1["p_v"], T("p_v")) < TOL
+    sc = gold[name + "/scalars"]
+    for k, ref_v in zip(("inside_elbo_recon", "inside_elbo_kl", "ce_term", "KL_term"), sc[:4]):
+        assert abs(float(r1[k]) - ref_v) <= TOL * abs(ref_v), (k, float(r1[k]), ref_v)
+    assert abs(float(J1) - sc[4]) <= TOL * abs(sc[4])
+    names = ["y", "noise", "Z", "table"] + (["amplitude", "length"] if kind == "mnist" else [])
+    for gname, g in zip(names, g1):
+        ref_g = T("grad_" + gname)
+        if ref_g.abs().max() > 0:
+            assert rel_err(g, ref_g) < TOL, gname
+    auxc = cfg["aux"].cuda()
+    K = s.kernel_matrix(auxc, s.inducing_index_points, x_inducing=False)
+    assert rel_err(K, T("K_nm")) < 1e-6
+    assert rel_err(s.kernel_matrix(auxc, auxc, x_inducing=False, y_inducing=False, diag_only=True), T("K_nn_diag")) < 1e-6
+    if kind == "sprites":                                       # prediction-time entry, SVGPVAE_model.py:610-635
+        mean, B = s.approximate_posterior_params_precomputed_GP_posterior_params(
+            auxc, T("pred_mean_term").cuda(), T("pred_sigma_term").cuda())
+        assert rel_err(mean, T("pred_mean")) < TOL and rel_err(B, T("pred_B")) < TOL
+
+
+def test_ball_against_reference_source_golden(cuda_backend):
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    cfg = configs.ball_inputs()
+    sx, sy = pkg.SVGP(name="x", **cfg["ctor"]).cuda(), pkg.SVGP(name="y", **cfg["ctor"]).cuda()
+    xc, yc, nc = cfg["x"].cuda(), cfg["y"].cuda().requires_grad_(True), cfg["noise"].cuda().requires_grad_(True)
+    rec = kl = 0.0
+    pms, pvs = [], []
+    for ch, s in enumerate((sx, sy)):
+        pm, B, mu, Ah = s.approximate_posterior_params(xc, y=yc[:, :, ch], noise=nc[:, :, ch])
+        a, b = s.variational_loss(xc, yc[:, :, ch], nc[:, :, ch], mu_hat=mu, A_hat=Ah)
+        if ch == 0:
+            assert rel_err(B, torch.from_numpy(gold["ball/B_x"])) < TOL and rel_err(mu, torch.from_numpy(gold["ball/mu_hat_x"])) < TOL
+            assert rel_err(Ah, torch.from_numpy(gold["ball/A_hat_x"])) < TOL
+        rec, kl = rec + a, kl + b
+        pms.append(pm); pvs.append(torch.diagonal(B, dim1=-2, dim2=-1))
+    pm, pv = torch.stack(pms, 2), torch.stack(pvs, 2)
+    assert rel_err(pm, torch.from_numpy(gold["ball/p_m"])) < TOL and rel_err(pv, torch.from_numpy(gold["ball/p_v"])) < TOL
+    assert rel_err(rec, torch.from_numpy(gold["ball/recon"])) < TOL and rel_err(kl, torch.from_numpy(gold["ball/kl"])) < TOL
+    KL_term = -pkg.gauss_cross_entropy(pm, pv, yc, nc).sum((1, 2)) + rec - kl
+    assert rel_err(KL_term, torch.from_numpy(gold["ball/KL_term"])) < TOL
+    gm, gv = refs.upstream((35, 30, 2))
+    (KL_term.sum() + (gm.cuda().float() * pm).sum() + (gv.cuda().float() * pv).sum()).backward()
+    assert rel_err(yc.grad, torch.from_numpy(gold["ball/grad_y"])) < TOL and rel_err(nc.grad, torch.from_numpy(gold["ball/grad_noise"])) < TOL

@@ -74,12 +74,14 @@ def test_survey_appendix_B2_ball():
     s = lit.BallSVGP(False, 15, True, 1, 30, 2.0, True, "x", 1e-9, 1, 30, 2.0)
     mean, B, mu_hat, A_hat = s.approximate_posterior_params(x, y, noise)
     assert mean.shape == (35, 30) and B.shape == (35, 30, 30) and mu_hat.shape == (35, 15) and A_hat.shape == (35, 15, 15)
-    assert np.allclose(mean[0, :3].numpy(), [0.0575036480, 0.2709499525, 0.5303067273], rtol=1e-8)
-    assert np.allclose(torch.diagonal(B[0])[:3].numpy(), [0.1291471822, 0.0866073092, 0.0658024436], rtol=1e-8)
+    # The survey's probe used a float64 inducing grid; the reference builds it with np.linspace(dtype=float32)
+    # (SVGPVAE_model.py:46), which the oracle now follows (pinned by reference_golden.npz): agreement is ~1e-7.
+    assert np.allclose(mean[0, :3].numpy(), [0.0575036480, 0.2709499525, 0.5303067273], rtol=2e-6)
+    assert np.allclose(torch.diagonal(B[0])[:3].numpy(), [0.1291471822, 0.0866073092, 0.0658024436], rtol=2e-6)
     L3, KL = s.variational_loss(x, y, noise, mu_hat, A_hat)
-    assert np.allclose(L3[:3].numpy(), [-0.4421172586, 1.1807586738, 2.2101319702], rtol=1e-8)
-    assert np.allclose(KL[:3].numpy(), [836.2227133929, 836.1091974550, 836.0499025487], rtol=1e-9)   # the quirky KL
-    assert abs(float((L3 - KL).sum()) + 29244.9691106253) < 1e-5
+    assert np.allclose(L3[:3].numpy(), [-0.4421172586, 1.1807586738, 2.2101319702], rtol=2e-6)
+    assert np.allclose(KL[:3].numpy(), [836.2227133929, 836.1091974550, 836.0499025487], rtol=1e-7)   # the quirky KL
+    assert abs(float((L3 - KL).sum()) + 29244.9691106253) < 1e-2
 
 
 def test_exact_gp_limit():
@@ -136,3 +138,71 @@ def test_oracle_reproduces_committed_golden_vectors():
     # edge cases of the restatement itself
     assert float(lit.recip_no_nan(torch.tensor([0.0, 2.0], dtype=F64))[0]) == 0.0
     assert torch.equal(lit.add_jitter(torch.zeros(2, 3, 3, dtype=F64), 0.5)[1], 0.5 * torch.eye(3, dtype=F64))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The oracle against the REFERENCE SOURCE: tests/golden/reference_golden.npz holds the outputs of the unmodified
+# /root/reference/SVGPVAE_model.py (forward_pass_SVGPVAE, mnistSVGP, spritesSVGP, SVGP) executed under the
+# TensorFlow-API shim of tests/golden/tf_shim.py on the same seeded inputs (tests/golden/make_reference_golden.py).
+# ----------------------------------------------------------------------------------------------------------
+REF_CASES = [
+    ("mnist", "mnist", lambda: configs.mnist_inputs(MNIST_FIXTURE, L=4), False, ["Z", "table", "amplitude", "length"]),
+    ("mnist_norm", "mnist", lambda: configs.mnist_inputs(MNIST_FIXTURE, L=4, normalize=True), False, ["Z", "table", "amplitude", "length"]),
+    ("mnist_train_last", "mnist", lambda: configs.mnist_inputs(MNIST_FIXTURE, L=2, b=210, rows="train", batch_index=15), False,
+     ["Z", "table", "amplitude", "length"]),
+    ("sprites72", "sprites", lambda: configs.sprites_inputs(M=72, L=4), True, ["Z", "table"]),
+    ("sprites72_raw", "sprites", lambda: configs.sprites_inputs(M=72, L=4, normalize=False), True, ["Z", "table"]),
+    ("sprites72_se", "sprites", lambda: configs.sprites_inputs(M=72, L=3, K_SE=True), True,
+     ["Z", "table", "sigma_action", "l_action", "sigma_character", "l_character"]),
+]
+
+
+def _close(a, b, rtol):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b).max() <= rtol * max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name,kind,maker,clip,pnames", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_oracle_matches_reference_source(name, kind, maker, clip, pnames):
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    cfg = maker()
+    o, _, op, _ = refs.make_pair(kind, cfg, "cpu")
+    r, J, g = refs.oracle_objective(o, op, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=clip)
+    assert _close(r["p_m"].detach(), gold[name + "/p_m"], 1e-10)
+    assert _close(r["p_v"].detach(), gold[name + "/p_v"], 1e-10)
+    sc = gold[name + "/scalars"]
+    for k, ref_v in zip(("inside_elbo_recon", "inside_elbo_kl", "ce_term"), sc[:3]):
+        assert abs(float(r[k]) - ref_v) <= 1e-11 * abs(ref_v), k
+    # KL_term and J are cancelling combinations of the above: compare at the scale of their summands
+    assert abs(float(r["KL_term"]) - sc[3]) <= 1e-11 * abs(sc[2])
+    assert abs(float(J) - sc[4]) <= 1e-11 * abs(sc[2])
+    for t, n in zip(g, ["y", "noise"] + pnames):
+        ref_g = gold[name + "/grad_" + n]
+        assert _close(torch.zeros(1) if t is None else t, ref_g, 1e-8), n
+    aux, Z = cfg["aux"].double(), o.inducing_index_points
+    assert _close(o.kernel_matrix(aux, Z, x_inducing=False).detach(), gold[name + "/K_nm"], 1e-12)
+    assert _close(o.kernel_matrix(aux, aux, False, False, True).detach(), gold[name + "/K_nn_diag"], 1e-12)
+    if kind == "mnist":
+        y0, n0 = cfg["y"].double()[:, 0], cfg["noise"].double()[:, 0]
+        m, B, mu_hat, A_hat = o.approximate_posterior_params(aux, aux, y0, n0)
+        L3, KL = o.variational_loss(aux, y0, mu_hat, A_hat, n0)
+        assert _close(mu_hat.detach(), gold[name + "/ch0_mu_hat"], 1e-10) and _close(A_hat.detach(), gold[name + "/ch0_A_hat"], 1e-10)
+        assert _close(torch.stack([L3, KL]).detach(), gold[name + "/ch0_L3_KL"], 1e-11)
+
+
+def test_oracle_ball_matches_reference_source():
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    cfg = configs.ball_inputs()
+    ox, oy = lit.BallSVGP(name="x", **cfg["ctor"]), lit.BallSVGP(name="y", **cfg["ctor"])
+    y = cfg["y"].double().requires_grad_(True)
+    nz = cfg["noise"].double().requires_grad_(True)
+    r = lit.ball_glue(ox, oy, y, nz)
+    gm, gv = refs.upstream(tuple(y.shape))
+    J = r["KL_term"].sum() + (gm * r["p_m"]).sum() + (gv * r["p_v"]).sum()
+    gy, gn = torch.autograd.grad(J, [y, nz])
+    for k, gk in (("p_m", "ball/p_m"), ("p_v", "ball/p_v"), ("inside_elbo_recon", "ball/recon"), ("inside_elbo_kl", "ball/kl"),
+                  ("B_0", "ball/B_x"), ("mu_hat_0", "ball/mu_hat_x"), ("A_hat_0", "ball/A_hat_x")):
+        assert _close(r[k].detach(), gold[gk], 1e-9), k
+    assert np.abs(r["KL_term"].detach().numpy() - gold["ball/KL_term"]).max() <= 1e-10 * np.abs(gold["ball/kl"]).max()
+    assert abs(float(J) - float(gold["ball/J"][0])) <= 1e-10 * abs(float(gold["ball/J"][0]))
+    assert _close(gy, gold["ball/grad_y"], 1e-7) and _close(gn, gold["ball/grad_noise"], 1e-7)
