@@ -136,6 +136,11 @@ int svgp_gemm_tn(const svgp_kop* kop, const float* X, int64_t ldx, int64_t L, do
 int svgp_gemm_nn(const svgp_kop* kop, const float* Wm, int64_t ldwm, int64_t L, float* out,
                  int64_t ldo, void* stream);
 
+/* the same product on the tensor cores: Wm given as the fp16 planes + 1/scale of svgp_split_f16(Wm, nb = 1,
+ * count = L * M); needs the fp16 planes of K_nm in kop.                                        */
+int svgp_gemm_nn_tc(const svgp_kop* kop, const void* Wm_hi, const void* Wm_lo, const float* Wm_inv, int64_t L,
+                    float* out, int64_t ldo, void* stream);
+
 /* K4  row-wise quadratic forms  q[i,l] = k_i^T S_l k_i  (N x L fp32).
  * S (L x M x M, symmetric): SIMT takes one fp32 plane S_hi (S_lo, S_inv NULL); TC takes the fp16
  * planes + inv_scale of svgp_split_f16.  If `tri` != 0 the planes hold a lower-triangular factor

@@ -44,6 +44,7 @@ SIGNATURES = {
     "svgp_syrk": [POINTER(KopStruct), _P, c_int64, c_int64, _P, c_int, c_int64, _P, _P],
     "svgp_gemm_tn": [POINTER(KopStruct), _P, c_int64, c_int64, _P, _P],
     "svgp_gemm_nn": [POINTER(KopStruct), _P, c_int64, c_int64, _P, c_int64, _P],
+    "svgp_gemm_nn_tc": [POINTER(KopStruct), _P, _P, _P, c_int64, _P, c_int64, _P],
     "svgp_rowquad": [POINTER(KopStruct), _P, _P, _P, c_int64, c_int, _P, c_int64, c_int, _P],
     "svgp_scaled_gemm": [POINTER(KopStruct), _P, c_int64, _P, _P, _P, c_int64, _P, c_int64, c_int, _P, c_int64, c_int64,
                          c_int, _P],

@@ -250,11 +250,16 @@ class CudaBackend:
         self.launches += 1
         return V
 
-    def gemm_nn(self, kop, Wm):
-        Wm = _f32c(Wm)
+    def gemm_nn(self, kop, Wm, impl=IMPL_AUTO):
         L = Wm.shape[0]
         out = torch.empty((kop.N, L), device=Wm.device, dtype=torch.float32)
         s = kop.struct()
+        if kop.tc and impl != IMPL_SIMT and kop.M >= 128 and kop.N >= self.tc_min_rows:
+            pl = self.planes(Wm.double().contiguous().unsqueeze(0))          # (1, L, M) -> one scale for the whole matrix
+            _call("svgp_gemm_nn_tc", ctypes.byref(s), _ptr(pl.hi), _ptr(pl.lo), _ptr(pl.inv), L, _ptr(out), out.stride(0), _stream())
+            self.launches += 1
+            return out
+        Wm = _f32c(Wm.float().contiguous())
         _call("svgp_gemm_nn", ctypes.byref(s), _ptr(Wm), Wm.stride(0), L, _ptr(out), out.stride(0), _stream())
         self.launches += 1
         return out

@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(THREADS) kernel_bwd_kernel(
 #pragma unroll
     for (int q = 0; q < MAXD / 4; ++q) acc[q] = 0.f;
     float own_acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float hy[4] = {0.f, 0.f, 0.f, 0.f};
+    // hyper-parameter gradients are heavily cancelling sums over all N x M entries: accumulate them in double
+    double hy[4] = {0.0, 0.0, 0.0, 0.0};
     if (threadIdx.x < 4) hred[threadIdx.x] = 0.f;
     if (PASS_X) load_features(Fx, ldx, ot * TILE, N, d, dp, sp, xs, nxa, nxb);
     else        load_features(Fz, ldz, ot * TILE, M, d, dp, sp, zs, nza, nzb);
@@ -382,11 +383,11 @@ __global__ void __launch_bounds__(THREADS) kernel_bwd_kernel(
       if (!PASS_X) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          float s = warp_sum(hy[k]);
-          if ((threadIdx.x & 31) == 0) atomicAdd(&hred[k], s);
+          double s = hy[k];
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+          if ((threadIdx.x & 31) == 0) atomicAdd(&dhyp[k], s);          // one double atomic per warp per owned tile
         }
-        __syncthreads();
-        if (threadIdx.x < 4) atomicAdd(&dhyp[threadIdx.x], (double)hred[threadIdx.x]);
       }
       __syncthreads();
     }
@@ -418,7 +419,7 @@ __global__ void kernel_diag_bwd_kernel(const float* __restrict__ Fx, int64_t ldx
                                        const float* __restrict__ g, float* __restrict__ dFx, float* __restrict__ dFy,
                                        double* __restrict__ dhyp) {
   const Hyp h = load_hyp(hyp);
-  float hy[4] = {0.f, 0.f, 0.f, 0.f};
+  double hy[4] = {0.0, 0.0, 0.0, 0.0};
   const int d = sp.da + sp.db;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
     float x[MAXD], y[MAXD];
@@ -443,8 +444,10 @@ __global__ void kernel_diag_bwd_kernel(const float* __restrict__ Fx, int64_t ldx
   }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
-    float s = warp_sum(hy[k]);
-    if ((threadIdx.x & 31) == 0 && s != 0.f) atomicAdd(&dhyp[k], (double)s);
+    double s = hy[k];
+#pragma unroll
+    for (int o2 = 16; o2 > 0; o2 >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o2);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(&dhyp[k], s);
   }
 }
 

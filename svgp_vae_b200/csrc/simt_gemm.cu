@@ -299,7 +299,7 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
 int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
                int64_t ldq, cudaStream_t st);
 int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo, const float* G_inv,
-                   int64_t L, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
+                   int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
                    cudaStream_t st);
 bool tc_shape_ok(const svgp_kop* kop);
 
@@ -375,6 +375,15 @@ int svgp_gemm_nn(const svgp_kop* kop, const float* Wm, int64_t ldwm, int64_t L, 
   return SVGP_OK;
 }
 
+int svgp_gemm_nn_tc(const svgp_kop* kop, const void* Wm_hi, const void* Wm_lo, const float* Wm_inv, int64_t L, float* out,
+                    int64_t ldo, void* stream) {
+  SVGP_REQUIRE(kop && Wm_hi && Wm_lo && Wm_inv && out && L >= 1 && ldo >= L, "null argument");
+  SVGP_REQUIRE(kop->Kh && kop->Kl && kop->kscale && tc_shape_ok(kop), "needs the fp16 planes of K_nm and a tensor-core sized problem");
+  if (kop->N == 0) return SVGP_OK;
+  // one "stacked matrix" of L rows: out[i, l] = sum_c K[i, c] Wm[l, c]
+  return tc_scaled_gemm(kop, nullptr, 0, Wm_hi, Wm_lo, Wm_inv, 1, L, out, ldo, 0, nullptr, 0, 0, (cudaStream_t)stream);
+}
+
 int svgp_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
                  int64_t ldq, int impl, void* stream) {
   SVGP_REQUIRE(kop && S_hi && q && L >= 1, "null argument");
@@ -399,7 +408,7 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
   cudaStream_t st = (cudaStream_t)stream;
   if (use_tc(kop, impl)) {
     SVGP_REQUIRE(G_lo != nullptr && G_inv != nullptr, "TC path needs the fp16 planes and scales of G (svgp_split_f16)");
-    return tc_scaled_gemm(kop, W, ldw, G_hi, G_lo, G_inv, L, out, ldo, accumulate, dots, lddots, ndot, st);
+    return tc_scaled_gemm(kop, W, ldw, G_hi, G_lo, G_inv, L, kop->M, out, ldo, accumulate, dots, lddots, ndot, st);
   }
   SVGP_REQUIRE(kop->K != nullptr && G_lo == nullptr && G_inv == nullptr, "SIMT path takes fp32 K and a single fp32 plane");
   int64_t slab = 65535LL * BM;

@@ -122,6 +122,14 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
   asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ double ld_stream_f64(const double* p, uint64_t policy) {
+  double v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(p), "l"(policy) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_stream_f64(double* p, double v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -215,7 +223,8 @@ struct TcParams {
   int64_t ldq;
   int lgroup;                 // channels scheduled together (L2 residency of their B planes)
   // SCALED
-  const float* W;             // (N, ldw)
+  int64_t Mc;                 // output columns = rows of each stacked B matrix (M for the dK_nm product, L for K Wm^T)
+  const float* W;             // (N, ldw) per-row weights, or null (all ones)
   int64_t ldw;
   float* out;
   int64_t ldo;
@@ -323,12 +332,13 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   //   QUAD    item = (row tile, channel)       sub = column tile of B_l                -> row sum in a register
   //   SCALED  item = (row tile, column tile)   sub = one stacked matrix                -> tile sum in registers
   const int64_t M = P.M;
-  const int nct = (int)((M + BN - 1) / BN);
+  const int64_t Mc = (MODE == MODE_SCALED) ? P.Mc : M;          // output columns (rows of one B matrix)
+  const int nct = (int)((Mc + BN - 1) / BN);
   const int kb_full = (int)((M + BK - 1) / BK);
 
-  struct Item { int64_t l, itile, n0, n1; int a_row0, b_row0, tile; };
+  struct Item { int64_t l, itile, n0, n1; int a_row0, b_row0, tile; bool half_tile; };
   auto decode = [&](int64_t item) -> Item {
-    Item it{0, 0, 0, 0, 0, 0, 0};
+    Item it{0, 0, 0, 0, 0, 0, 0, false};
     if (MODE == MODE_SYRK) {
       // super-chunk major: all (tile pair, channel) items of one window of datapoints are scheduled together, so the
       // CTAs in flight stream the same <= ~48 MB slice of K^T out of L2 instead of thrashing it with M x N planes
@@ -339,6 +349,9 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       int ta, tb;
       syrk_tile_decode(it.tile, M, BN, ta, tb);
       it.a_row0 = ta * BLOCK_M; it.b_row0 = tb * BN;
+      // a tile whose right half lies entirely above the diagonal (128-row tile on the diagonal of a 256-column tile)
+      // only needs its first BN / 2 columns: half the B rows are loaded and the MMAs run with N = BN / 2
+      it.half_tile = (BN == 2 * BLOCK_M) && (it.b_row0 >= it.a_row0);
       it.n0 = sc * P.sc_rows;
       it.n1 = it.n0 + P.sc_rows < P.N ? it.n0 + P.sc_rows : P.N;
     } else if (MODE == MODE_QUAD) {
@@ -389,7 +402,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
             } else if (MODE == MODE_QUAD) {
               ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)(it.l * M + (int64_t)sub * BN);
             } else {
-              ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)sub * M + it.b_row0);
+              ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)sub * Mc + it.b_row0);
             }
             if (MODE == MODE_SYRK) {
               // datapoint-blocked transposed planes [n / 64][m][n % 64]: a box is one contiguous run of rows.
@@ -399,9 +412,15 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
               mbar_expect_tx(fullA(stage), 2 * A_BYTES);
               tma_load_3d(st, &mapA_hi, fullA(stage), ni, ar, nb);
               tma_load_3d(st + A_BYTES, &mapA_lo, fullA(stage), ni, ar, nb);
-              mbar_expect_tx(full(stage), 2 * B_BYTES);
-              tma_load_3d(st + 2 * A_BYTES, &mapB_hi, full(stage), ni, br, nb);
-              tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), ni, br, nb);
+              if (it.half_tile) {                       // BN / 2 == BLOCK_M rows: the A maps have the right box
+                mbar_expect_tx(full(stage), 2 * A_BYTES);
+                tma_load_3d(st + 2 * A_BYTES, &mapA_hi, full(stage), ni, br, nb);
+                tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapA_lo, full(stage), ni, br, nb);
+              } else {
+                mbar_expect_tx(full(stage), 2 * B_BYTES);
+                tma_load_3d(st + 2 * A_BYTES, &mapB_hi, full(stage), ni, br, nb);
+                tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), ni, br, nb);
+              }
             } else {
               mbar_expect_tx(full(stage), STAGE_BYTES);
               tma_load_2d(st, &mapA_hi, full(stage), ak, ar);
@@ -422,6 +441,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
       const int nsub = item_subtiles(it);
+      const uint32_t idesc = it.half_tile ? make_idesc(BN / 2) : IDESC;
       for (int sub = 0; sub < nsub; ++sub) {
         const int nkb = subtile_kblocks(it, sub);
         mbar_wait(tmem_empty(acc), acc_phase ^ 1);
@@ -438,9 +458,9 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
             for (int ks = 0; ks < BK / UMMA_K; ++ks) {
               const uint64_t adv = (uint64_t)((ks * UMMA_K * 2) >> 4);
-              umma_f16(d_tmem, a_lo + adv, b_hi + adv, IDESC, (kb > 0 || ks > 0) ? 1u : 0u);
-              umma_f16(d_tmem, a_hi + adv, b_lo + adv, IDESC, 1u);
-              umma_f16(d_tmem, a_hi + adv, b_hi + adv, IDESC, 1u);
+              umma_f16(d_tmem, a_lo + adv, b_hi + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
+              umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
             }
             umma_commit(empty(stage));
             if (kb == nkb - 1) umma_commit(tmem_full(acc));
@@ -507,6 +527,10 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
             if (nlive > 0) {
               // Other CTAs add other super-chunks of the same tile: the 32 x 128 block of this warp is guarded by a
               // spin lock (contention is rare: same-tile items are ntile * L items apart) and accessed through L2 only.
+              // the float64 tiles stream through L2 once per super-chunk: evict-first + no L1 allocation, so that they
+              // do not push the K^T slice (re-read by every tile pair of the super-chunk) out of the cache
+              uint64_t pol;
+              asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
               int* lock = P.locks + ((int64_t)it.tile * P.L + it.l) * 8 + (warp - EPI_WARP0);
               if (lane == 0) {
                 while (atomicCAS(lock, 0, 1) != 0) __nanosleep(100);
@@ -524,10 +548,10 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                   for (int j0 = 0; j0 < 32; j0 += 8) {
                     double t[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) t[j] = (j0 + j < nv) ? __ldcg(dst + j0 + j) : 0.0;
+                    for (int j = 0; j < 8; ++j) t[j] = (j0 + j < nv) ? ld_stream_f64(dst + j0 + j, pol) : 0.0;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                      if (j0 + j < nv) __stcg(dst + j0 + j, t[j] + (double)run[ch][j0 + j] * sc);
+                      if (j0 + j < nv) st_stream_f64(dst + j0 + j, t[j] + (double)run[ch][j0 + j] * sc, pol);
                   }
 #pragma unroll
                   for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
@@ -584,7 +608,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
         for (int sub = 0; sub < nsub; ++sub) {
           const float bs = P.binv[sub];
-          const float wgt = live ? P.W[i * P.ldw + sub] * inv_ks * bs : 0.f;
+          const float wgt = live ? (P.W ? P.W[i * P.ldw + sub] : 1.f) * inv_ks * bs : 0.f;
           const bool want_dot = (P.dots != nullptr) && (sub < P.ndot) && live;
           float dsum = 0.f;
           mbar_wait(tmem_full(acc), acc_phase);
@@ -593,12 +617,12 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
           for (int ch = 0; ch < NCH; ++ch) {
             const int64_t cbase = (int64_t)it.b_row0 + half * (BN / 2) + ch * 32;
-            if (cbase < M) {
+            if (cbase < Mc) {
               float v[32];
               tmem_ld32(taddr + ch * 32, v);
 #pragma unroll
               for (int j = 0; j < 32; ++j) {
-                if (cbase + j >= M) v[j] = 0.f;
+                if (cbase + j >= Mc) v[j] = 0.f;
                 run[ch][j] = fmaf(wgt, v[j], run[ch][j]);
               }
               if (want_dot) dsum = dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, dsum);
@@ -617,7 +641,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
             float* o = P.out + i * P.ldo + cbase;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (cbase + j < M) o[j] = P.accumulate ? o[j] + run[ch][j] : run[ch][j];
+              if (cbase + j < Mc) o[j] = P.accumulate ? o[j] + run[ch][j] : run[ch][j];
           }
         }
       }
@@ -913,22 +937,23 @@ int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const fl
 }
 
 int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo, const float* G_inv,
-                   int64_t L, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
+                   int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
                    cudaStream_t st) {
   if (!kop->Kh || !kop->Kl || !kop->kscale) { set_error("tc_scaled_gemm: fp16 planes missing"); return SVGP_ERR_ARG; }
+  if (dots && Mc != kop->M) { set_error("tc_scaled_gemm: the k-dots need square M x M matrices"); return SVGP_ERR_ARG; }
   const int BN = 256, bk = tc_bk();
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
   int rc;
   if ((rc = make_map(&a_hi, kop->Kh, kop->N, kop->M, kop->ldkh, BLOCK_M, bk))) return rc;
   if ((rc = make_map(&a_lo, kop->Kl, kop->N, kop->M, kop->ldkh, BLOCK_M, bk))) return rc;
-  if ((rc = make_map(&b_hi, G_hi, L * kop->M, kop->M, kop->M, BN, bk))) return rc;
-  if ((rc = make_map(&b_lo, G_lo, L * kop->M, kop->M, kop->M, BN, bk))) return rc;
+  if ((rc = make_map(&b_hi, G_hi, L * Mc, kop->M, kop->M, BN, bk))) return rc;       // rows past L * Mc are zero-filled by TMA
+  if ((rc = make_map(&b_lo, G_lo, L * Mc, kop->M, kop->M, BN, bk))) return rc;
   TcParams P{};
-  P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = G_inv;
+  P.N = kop->N; P.M = kop->M; P.L = L; P.Mc = Mc; P.kscale = kop->kscale; P.binv = G_inv;
   P.K_hi = (const __half*)kop->Kh; P.K_lo = (const __half*)kop->Kl; P.ldkh = kop->ldkh;
   P.W = W; P.ldw = ldw; P.out = out; P.ldo = ldo; P.accumulate = accumulate;
   P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
-  P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(kop->M, BN);
+  P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(Mc, BN);
   return dispatch_tc<MODE_SCALED>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");
 }
 

@@ -83,6 +83,19 @@ def test_tc_rowquad_scaled(cuda_backend, shape):
     assert rel_err(out1, refo) < 3e-5 and rel_err(dots1[:, 0], ref[:, 0]) < 3e-5
 
 
+@pytest.mark.parametrize("shape", [(4096, 256, 3), (3000, 200, 64), (2304, 1024, 70), (2500, 384, 300)])
+def test_tc_gemm_nn(cuda_backend, shape):
+    """out = K Wm^T on the tensor cores (SCALED mode with L output columns) against float64 and the SIMT kernel."""
+    be = cuda_backend
+    N, M, L = shape
+    kop, K64, _, g = _setup(be, N, M, 1, seed=7)
+    Wm = torch.randn(L, M, generator=g, device="cuda") * torch.exp(torch.randn(L, 1, generator=g, device="cuda") * 3)
+    ref = K64 @ Wm.double().t()
+    out = be.gemm_nn(kop, Wm)
+    assert out.shape == (N, L) and rel_err(out, ref) < 3e-5
+    assert rel_err(be.gemm_nn(Kop(kop.value().contiguous()), Wm, impl=IMPL_SIMT), ref) < 1e-5
+
+
 def test_tc_planes_roundtrip(cuda_backend):
     be = cuda_backend
     g = torch.Generator(device="cuda").manual_seed(3)
