@@ -311,7 +311,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:           # CPU leg: rank 0 of the single-GPU run only
             line["cpu_baseline"] = cpu_baseline(args, n_total)
         print(json.dumps(line), flush=True)
     if group is not None:

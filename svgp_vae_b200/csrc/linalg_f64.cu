@@ -9,6 +9,9 @@
 // Panel factorisation: one warp per 32 x 32 diagonal block, lane r owns row r in registers and
 // columns are exchanged with warp shuffles (no shared memory, no block barrier).  The same warp
 // also inverts the block so that the panel solve below it becomes a multiply.
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 
 namespace svgp {
@@ -290,6 +293,106 @@ __global__ void __launch_bounds__(256) gemm_f64_big_kernel(int64_t Mr, int64_t N
   }
 }
 
+// Tensor-pipe variant (DMMA.8x8x4, the FP64 MMA shape native to sm_100: a probe of the FP64 pipes measures 37 TFLOP/s
+// for both DFMA and DMMA on B200, but the MMA form needs 1/64 of the register-file operand traffic per FMA).
+// CTA tile 128 x 128 x 16, 16 warps in a 4 x 4 grid, warp tile 32 x 32 = 4 x 4 fragments of 8 x 8 (32 doubles / thread).
+// Each operand tile sits in shared memory in the orientation it has in global memory (no transposing stores); the
+// row pitches (20 resp. 132 doubles, both = 4 mod 16) make every fragment load -- 4 k-values x 8 rows or columns per
+// warp -- hit 16 distinct 8-byte banks per half-warp.
+//   mma.m8n8k4.row.col.f64:  a = A[lane / 4][lane % 4]   b = B[lane % 4][lane / 4]   c{0,1} = C[lane / 4][2 (lane % 4) + {0,1}]
+constexpr int PK = GK + 4;      // pitch of a k-contiguous tile   [128][PK]
+constexpr int PM = GM + 4;      // pitch of an m/n-contiguous tile [GK][PM]
+constexpr int TILE_DOUBLES = (GM * PK > GK * PM) ? GM * PK : GK * PM;
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <bool transA, bool transB>
+__global__ void __launch_bounds__(512, 1) gemm_f64_mma_kernel(int64_t Mr, int64_t Nc, int64_t Kd, double alpha,
+                                                              const double* __restrict__ A, int64_t lda, int64_t strideA,
+                                                              const double* __restrict__ B, int64_t ldb, int64_t strideB, double beta,
+                                                              double* __restrict__ C, int64_t ldc, int64_t strideC, int lower_only) {
+  const int64_t m0 = (int64_t)blockIdx.y * GM, n0 = (int64_t)blockIdx.x * GN;
+  if (lower_only && n0 > m0 + GM - 1) return;
+  __shared__ __align__(16) double As[TILE_DOUBLES];
+  __shared__ __align__(16) double Bs[TILE_DOUBLES];
+  const double* Ab = A + (int64_t)blockIdx.z * strideA;
+  const double* Bb = B + (int64_t)blockIdx.z * strideB;
+  double* Cb = C + (int64_t)blockIdx.z * strideC;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 32;       // warp tile origin inside the CTA tile
+  const int lr = lane >> 2, lk = lane & 3;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  double ra[4], rb[4];
+  // element e of this thread inside a k-tile: idx = tid + 512 e (0 .. 2047); k-contiguous operands walk k fastest
+  auto fetch = [&](int64_t kb) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = threadIdx.x + e * 512;
+      {
+        const int kk = transA ? idx / GM : idx % GK, mm = transA ? idx % GM : idx / GK;
+        const int64_t gk = kb + kk, gm = m0 + mm;
+        ra[e] = (gk < Kd && gm < Mr) ? (transA ? Ab[gk * lda + gm] : Ab[gm * lda + gk]) : 0.0;
+      }
+      {
+        const int kk = transB ? idx % GK : idx / GN, nn = transB ? idx / GK : idx % GN;
+        const int64_t gk = kb + kk, gn = n0 + nn;
+        rb[e] = (gk < Kd && gn < Nc) ? (transB ? Bb[gn * ldb + gk] : Bb[gk * ldb + gn]) : 0.0;
+      }
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int idx = threadIdx.x + e * 512;
+      if (transA) As[(idx / GM) * PM + idx % GM] = ra[e]; else As[(idx / GK) * PK + idx % GK] = ra[e];
+      if (transB) Bs[(idx / GK) * PK + idx % GK] = rb[e]; else Bs[(idx / GN) * PM + idx % GN] = rb[e];
+    }
+  };
+  fetch(0);
+  for (int64_t kb = 0; kb < Kd; kb += GK) {
+    stash();
+    __syncthreads();
+    if (kb + GK < Kd) fetch(kb + GK);
+#pragma unroll
+    for (int k0 = 0; k0 < GK; k0 += 4) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        a[i] = transA ? As[(k0 + lk) * PM + wm + i * 8 + lr] : As[(wm + i * 8 + lr) * PK + k0 + lk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        b[j] = transB ? Bs[(wn + j * 8 + lr) * PK + k0 + lk] : Bs[(k0 + lk) * PM + wn + j * 8 + lr];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t gm = m0 + wm + i * 8 + lr;
+    if (gm >= Mr) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const int64_t gn = n0 + wn + j * 8 + 2 * lk + t;
+        if (gn < Nc) {
+          double* c = Cb + gm * ldc + gn;
+          *c = (beta == 0.0) ? alpha * acc[i][j][t] : fma(alpha, acc[i][j][t], beta * (*c));
+        }
+      }
+    }
+  }
+}
+
 static int gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, double alpha, const double* A, int64_t lda,
                     int64_t strideA, const double* B, int64_t ldb, int64_t strideB, double beta, double* C, int64_t ldc,
                     int64_t strideC, int64_t batch, int lower_only, cudaStream_t st) {
@@ -299,9 +402,16 @@ static int gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, 
     int64_t nb = batch - b0 < 65535 ? batch - b0 : 65535;
     if (big) {
       dim3 gridb((unsigned)ceil_div(Nc, GN), (unsigned)ceil_div(Mr, GM), (unsigned)nb);
-#define SVGP_BIG(TA, TB)                                                                                                 \
-  gemm_f64_big_kernel<TA, TB><<<gridb, 256, 0, st>>>(Mr, Nc, Kd, alpha, A + b0 * strideA, lda, strideA, B + b0 * strideB, ldb, \
-                                                      strideB, beta, C + b0 * strideC, ldc, strideC, lower_only)
+      static const bool use_simt = getenv("SVGP_DGEMM") && !strcmp(getenv("SVGP_DGEMM"), "simt");
+#define SVGP_BIG(TA, TB)                                                                                                     \
+  do {                                                                                                                       \
+    if (use_simt)                                                                                                            \
+      gemm_f64_big_kernel<TA, TB><<<gridb, 256, 0, st>>>(Mr, Nc, Kd, alpha, A + b0 * strideA, lda, strideA, B + b0 * strideB,  \
+                                                          ldb, strideB, beta, C + b0 * strideC, ldc, strideC, lower_only);    \
+    else                                                                                                                     \
+      gemm_f64_mma_kernel<TA, TB><<<gridb, 512, 0, st>>>(Mr, Nc, Kd, alpha, A + b0 * strideA, lda, strideA, B + b0 * strideB,  \
+                                                          ldb, strideB, beta, C + b0 * strideC, ldc, strideC, lower_only);    \
+  } while (0)
       if (transA && transB) SVGP_BIG(true, true);
       else if (transA) SVGP_BIG(true, false);
       else if (transB) SVGP_BIG(false, true);

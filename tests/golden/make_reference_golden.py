@@ -97,6 +97,16 @@ def mnist_case(out, name, cfg):
     out[name + "/ch0_mu_hat"], out[name + "/ch0_A_hat"] = mu_hat.detach().numpy(), A_hat.detach().numpy()
     out[name + "/ch0_L3_KL"] = np.array([float(L3), float(KL)])
     out[name + "/ch0_bias_mean"] = svgp.mean_vector_bias_analysis(aux, mu[:, 0], var[:, 0]).detach().numpy()
+    # conditional generation: test index points against training encodings, the L-loop of
+    # bacthing_predict_SVGPVAE_rotated_mnist (:1048-1050); test rows = the first 48 rows with the view angle shifted
+    with torch.no_grad():
+        test_aux = aux[:48].clone()
+        test_aux[:, 1] = test_aux[:, 1] + 0.3
+        pm, pv = [], []
+        for l in range(mu.shape[1]):
+            m_l, v_l, _, _ = svgp.approximate_posterior_params(test_aux, aux, mu[:, l], var[:, l])
+            pm.append(m_l); pv.append(v_l)
+        out[name + "/cgen_p_m"], out[name + "/cgen_p_v"] = tf.stack(pm, axis=1).numpy(), tf.stack(pv, axis=1).numpy()
 
 
 def sprites_case(out, name, cfg, clip=True):
@@ -149,6 +159,15 @@ def sprites_case(out, name, cfg, clip=True):
         mean_vec, Bdiag = svgp.approximate_posterior_params_precomputed_GP_posterior_params(aux, mean_term, sigma_l_inv)
     out[name + "/pred_mean_term"], out[name + "/pred_sigma_term"] = mean_term.numpy(), sigma_l_inv.numpy()
     out[name + "/pred_mean"], out[name + "/pred_B"] = mean_vec.numpy(), Bdiag.numpy()
+    # the reference's own precompute over all channels (:989-1023) and the per-channel predictions from it (:1165-1168)
+    with torch.no_grad():
+        mean_terms, inv_sigmas = ref.precompute_GP_params_SVGPVAE(qnet_mu, qnet_var, aux, svgp)
+        pm, pv = [], []
+        for l in range(qnet_mu.shape[1]):
+            m_l, v_l = svgp.approximate_posterior_params_precomputed_GP_posterior_params(aux[:100], mean_terms[l], inv_sigmas[l])
+            pm.append(m_l); pv.append(v_l)
+    out[name + "/precomp_mean_terms"], out[name + "/precomp_inv_sigma"] = mean_terms.numpy(), inv_sigmas.numpy()
+    out[name + "/precomp_p_m"], out[name + "/precomp_p_v"] = tf.stack(pm, axis=1).numpy(), tf.stack(pv, axis=1).numpy()
 
 
 def ball_case(out, cfg):

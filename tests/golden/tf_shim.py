@@ -194,6 +194,7 @@ class _Math(types.ModuleType):
         return torch.sqrt((x * x).sum(dim=axis, keepdim=keepdims))
 
     log = staticmethod(log)
+    multiply = staticmethod(multiply)
 
 
 class _Random(types.ModuleType):

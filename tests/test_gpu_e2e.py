@@ -227,3 +227,25 @@ def test_ball_against_reference_source_golden(cuda_backend):
     gm, gv = refs.upstream((35, 30, 2))
     (KL_term.sum() + (gm.cuda().float() * pm).sum() + (gv.cuda().float() * pv).sum()).backward()
     assert rel_err(yc.grad, torch.from_numpy(gold["ball/grad_y"])) < TOL and rel_err(nc.grad, torch.from_numpy(gold["ball/grad_noise"])) < TOL
+
+
+def test_prediction_path_against_reference_source(cuda_backend):
+    """Prediction-time entries (SVGPVAE_model.py:989-1023, :610-635, :1048-1050) on the device vs the reference source."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    T = lambda k: torch.from_numpy(gold[k])
+    cfg = configs.sprites_inputs(M=72, L=4)
+    _, s, _, _ = refs.make_pair("sprites", cfg, "cuda")
+    aux, y, nz = cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda()
+    mt, si = pkg.precompute_GP_params_SVGPVAE(y, nz, aux, s)
+    assert rel_err(mt, T("sprites72/precomp_mean_terms")) < TOL and rel_err(si, T("sprites72/precomp_inv_sigma")) < TOL
+    pm, pv = pkg.predict_from_precomputed(s, aux[:100], T("sprites72/precomp_mean_terms").cuda(), T("sprites72/precomp_inv_sigma").cuda())
+    assert rel_err(pm, T("sprites72/precomp_p_m")) < TOL and rel_err(pv, T("sprites72/precomp_p_v")) < TOL
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=4)
+    _, s, _, _ = refs.make_pair("mnist", cfg, "cuda")
+    test_aux = cfg["aux"][:48].clone()
+    test_aux[:, 1] += 0.3
+    pm, pv = pkg.posterior_predict(s, test_aux.cuda(), cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda())
+    assert rel_err(pm, T("mnist/cgen_p_m")) < TOL and rel_err(pv, T("mnist/cgen_p_v")) < TOL

@@ -149,3 +149,23 @@ def test_primitive_adjoints_against_autograd(oracle_backend):
         assert rel_err(ga[0], gb[0]) < 1e-12 and rel_err(ga[1], gb[1]) < 1e-12
     with pytest.raises(ops.NotPositiveDefinite):
         ops.spd_logdet(-torch.eye(3, dtype=torch.float64)[None])
+
+
+def test_prediction_path_against_reference_source(oracle_backend):
+    """precompute_GP_params_SVGPVAE (:989-1023), the precomputed-posterior entry (:610-635) and the conditional-generation
+    loop (:1048-1050), batched over the channels, against the outputs of the reference source (reference_golden.npz)."""
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    T = lambda k: torch.from_numpy(gold[k])
+    cfg = configs.sprites_inputs(M=72, L=4)
+    _, s, _, _ = refs.make_pair("sprites", cfg, "cpu")
+    mt, si = pkg.precompute_GP_params_SVGPVAE(cfg["y"], cfg["noise"], cfg["aux"], s)
+    assert mt.shape == (4, 72) and si.shape == (4, 72, 72)
+    assert rel_err(mt, T("sprites72/precomp_mean_terms")) < TOL and rel_err(si, T("sprites72/precomp_inv_sigma")) < TOL
+    pm, pv = pkg.predict_from_precomputed(s, cfg["aux"][:100], mt, si)
+    assert rel_err(pm, T("sprites72/precomp_p_m")) < TOL and rel_err(pv, T("sprites72/precomp_p_v")) < TOL
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=4)
+    _, s, _, _ = refs.make_pair("mnist", cfg, "cpu")
+    test_aux = cfg["aux"][:48].clone()
+    test_aux[:, 1] += 0.3
+    pm, pv = pkg.posterior_predict(s, test_aux, cfg["aux"], cfg["y"], cfg["noise"])
+    assert pm.shape == (48, 4) and rel_err(pm, T("mnist/cgen_p_m")) < TOL and rel_err(pv, T("mnist/cgen_p_v")) < TOL
