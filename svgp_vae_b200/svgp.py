@@ -128,14 +128,22 @@ class mainSVGP(_KernelBase):
 
     def variational_loss(self, x, y, mu_hat, A_hat, noise=None):
         """:220-301, Hensman branch -> (L_3 sum term, KL term)."""
-        if self.titsias:
-            raise NotImplementedError("Titsias L_2 branch (SVGPVAE_model.py:246-259) is not built yet")
         hyp, spec = self._hyp(), self._spec()
         b, m = float(x.shape[0]), float(self.nr_inducing)
         Fz, K_mm, K_mm_inv, ldK = self._inducing_factors()
         Fx = self._features(x, False)
         K_nn = ops.kernel_diag(Fx, Fx, hyp, spec).double()
         K_nm = ops.kernel_matrix(Fx, Fz, hyp, spec)
+        if self.titsias:
+            # :246-259 -- L_2 of Titsias: a (b x b) Gaussian log-density, small batches only (as in the reference)
+            Kd = K_nm.double().unsqueeze(0)
+            Q = ops.bmm64(ops.bmm64(Kd, K_mm_inv), Kd, False, True)[0]                       # K_nm Kinv K_mn   (b, b)
+            yd, nd = y.double(), noise.double()
+            cov_j = _add_diagonal_jitter(torch.diag(nd) + Q, self.jitter)                    # :248, :251-252
+            cov_inv, cov_logdet, _ = ops.spd_inverse_logdet(cov_j.unsqueeze(0))
+            trace_term = reciprocal_no_nan(nd) * (K_nn - torch.diagonal(Q))                  # :249-250
+            L2 = -0.5 * (b * math.log(2 * math.pi) + cov_logdet[0] + (yd * (cov_inv[0] @ yd)).sum() + trace_term.sum())
+            return L2.to(self.dtype), torch.zeros((), dtype=self.dtype, device=L2.device)    # :255-259
         mu64, A64 = mu_hat.double(), A_hat.double()
         a = ops.bmv64(K_mm_inv, mu64.unsqueeze(0))                                 # Kinv mu_hat
         mean_vector = ops.k_matmul(K_nm, a)[:, 0].double()                         # :264-265
@@ -174,7 +182,7 @@ class mainSVGP(_KernelBase):
         inside_elbo_kl, inside_elbo, ce_term, KL_term).  ``clip_pv`` mirrors :891-892.
         """
         if self.titsias:
-            raise NotImplementedError("Titsias branch not built yet")
+            return self._elbo_step_per_channel(aux_data, qnet_mu, qnet_var, clip_pv)
         Fx = self._features(aux_data, False)
         Fz = self._features(self.inducing_index_points, True)
         res = svgp_step(self._spec(), Fx, Fz, self._hyp(), qnet_mu, qnet_var, N_train=self.N_train,
@@ -184,6 +192,28 @@ class mainSVGP(_KernelBase):
             b = b * torch.distributed.get_world_size(group)      # equal shards
         res.update(elbo_terms(res, b, self.N_train))
         return res
+
+
+    def _elbo_step_per_channel(self, aux_data, qnet_mu, qnet_var, clip_pv=False):
+        """The reference's own loop (:868-898) over the per-channel methods.  Used for the Titsias bound, whose
+        (b x b) Gaussian term has no channel-batched kernel here (it is a small-batch formulation by construction)."""
+        recon, kl, pms, pvs, mus, Ahs = [], [], [], [], [], []
+        for l in range(qnet_mu.shape[1]):
+            pm, pv, mu_hat, A_hat = self.approximate_posterior_params(aux_data, aux_data, qnet_mu[:, l], qnet_var[:, l])
+            r_l, k_l = self.variational_loss(x=aux_data, y=qnet_mu[:, l], noise=qnet_var[:, l], mu_hat=mu_hat, A_hat=A_hat)
+            recon.append(r_l.double()); kl.append(k_l.double()); pms.append(pm); pvs.append(pv)
+            mus.append(mu_hat); Ahs.append(A_hat)
+        p_m, p_v = torch.stack(pms, 1), torch.stack(pvs, 1)
+        if clip_pv:
+            p_v = torch.clamp(p_v, 1e-4, 100.0)                                            # :891-892
+        recon_l, kl_l = torch.stack(recon), torch.stack(kl)
+        ce_l = gauss_cross_entropy(p_m.double(), p_v.double(), qnet_mu.double(), qnet_var.double()).sum(0)
+        rec, k, ce = recon_l.sum(), kl_l.sum(), ce_l.sum()
+        b = float(aux_data.shape[0])
+        inside = rec - k if self.titsias else rec - (b / self.N_train) * k                 # :883-886
+        return dict(p_m=p_m, p_v=p_v, recon_l=recon_l, kl_l=kl_l, ce_l=ce_l, mu_hat=torch.stack(mus).detach(),
+                    A_hat=torch.stack(Ahs).detach(), inside_elbo_recon=rec, inside_elbo_kl=k, inside_elbo=inside,
+                    ce_term=ce, KL_term=-ce + inside)
 
 
 # --------------------------------------------------------------------------------------
@@ -399,11 +429,20 @@ class SVGP(_KernelBase):
 
     def variational_loss(self, x, y, noise, mu_hat, A_hat):
         """:62-139, Hensman branch -> ((B,), (B,))."""
-        if self.titsias:
-            raise NotImplementedError("Titsias L_2 branch (SVGPVAE_model.py:89-101) is not built yet")
         Bn, T, Fx, K_mm, K_mm_inv, ldK, K_nm = self._mats(x)
         m = float(self.inducing_index_points.shape[0])
         prec = reciprocal_no_nan(noise).double()
+        if self.titsias:
+            # :89-101 -- per-video (T x T) Gaussian log-density
+            Kb = K_nm.double().reshape(Bn, T, -1)
+            Q = ops.bmm64(ops.bmm64(Kb, K_mm_inv), Kb, False, True)                          # (B, T, T)
+            cov_j = _add_diagonal_jitter(torch.diag_embed(noise.double()) + Q, self.jitter)
+            cov_inv, cov_logdet, _ = ops.spd_inverse_logdet(cov_j)
+            K_nn_diag = ops.kernel_diag(Fx, Fx, self._hyp(), self._spec()).double().reshape(Bn, T)
+            trace_term = prec * (K_nn_diag - torch.diagonal(Q, dim1=-2, dim2=-1))
+            yd = y.double()
+            L2 = -0.5 * (T * math.log(2 * math.pi) + cov_logdet + (yd * ops.bmv64(cov_inv, yd)).sum(1) + trace_term.sum(1))
+            return L2.to(self.dtype), torch.zeros((), dtype=self.dtype, device=L2.device)
         mu64, A64 = mu_hat.double(), A_hat.double()
         a = ops.bmm64(mu64.unsqueeze(0), K_mm_inv)[0]                                    # (B,m) = Kinv mu_hat (Kinv symmetric)
         mean_vector = self._own(ops.k_matmul(K_nm, a), Bn, T).double()                   # :106

@@ -202,6 +202,33 @@ def ball_case(out, cfg):
     out["ball/grad_y"], out["ball/grad_noise"] = gy.numpy(), gn.numpy()
 
 
+def titsias_cases(out, fx):
+    """The L_2 (Titsias) branch of both classes: SVGPVAE_model.py:246-259 through forward_pass_SVGPVAE, :89-101 direct."""
+    cfg = configs.mnist_inputs(fx, L=2, b=64)
+    ctor = dict(cfg["ctor"], titsias=True)
+    svgp = ref.mnistSVGP(name="ref", **ctor)
+    aux = cfg["aux"].to(F64)
+    mu, var = _leaf(cfg["y"]), _leaf(cfg["noise"])
+    images = torch.zeros(aux.shape[0], 28, 28, 1, dtype=F64)
+    r = ref.forward_pass_SVGPVAE((images, aux), beta=1.0, vae=StubVAE(mu, var), svgp=svgp, C_ma=0.0, lagrange_mult=1.0,
+                                 alpha=0.99, kappa=0.02, clipping_qs=False, GECO=False)
+    elbo, recon_loss, KL_term, inside_elbo, ce_term, p_m, p_v, _, _, _, rec, kl = r[:12]
+    res = dict(p_m=p_m, p_v=p_v, inside_elbo_recon=rec, inside_elbo_kl=kl, ce_term=ce_term, KL_term=KL_term)
+    gm, gv = refs.upstream(tuple(mu.shape))
+    J = KL_term + (gm * p_m).sum() + (gv * p_v).sum()
+    grads = torch.autograd.grad(J, [mu, var, svgp.inducing_index_points, svgp.object_vectors, svgp.amplitude, svgp.l_GP], allow_unused=True)
+    _pack(out, "mnist_titsias", res, J, grads, ["y", "noise", "Z", "table", "amplitude", "length"])
+    cfgb = configs.ball_inputs()
+    sb = ref.SVGP(name="x", **dict(cfgb["ctor"], titsias=True))
+    y, nz = _leaf(cfgb["y"][:, :, 0]), _leaf(cfgb["noise"][:, :, 0])
+    batch_T = tf.tile(tf.expand_dims(tf.range(30, dtype=np.float64) + 1.0, 0), (y.shape[0], 1))
+    _, _, mu_hat, A_hat = sb.approximate_posterior_params(index_points=batch_T, y=y, noise=nz)
+    L2, zero = sb.variational_loss(x=batch_T, y=y, noise=nz, mu_hat=mu_hat, A_hat=A_hat)
+    gy, gn = torch.autograd.grad(L2.sum(), [y, nz])
+    out["ball_titsias/L2"] = L2.detach().numpy()
+    out["ball_titsias/grad_y"], out["ball_titsias/grad_noise"] = gy.numpy(), gn.numpy()
+
+
 def main():
     fx = os.path.join(HERE, "mnist_aux.npz")
     out = {}
@@ -212,6 +239,7 @@ def main():
     sprites_case(out, "sprites72_raw", configs.sprites_inputs(M=72, L=4, normalize=False))
     sprites_case(out, "sprites72_se", configs.sprites_inputs(M=72, L=3, K_SE=True))
     ball_case(out, configs.ball_inputs())
+    titsias_cases(out, fx)
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "with", len(out), "arrays;", os.path.getsize(path), "bytes")

@@ -249,3 +249,27 @@ def test_prediction_path_against_reference_source(cuda_backend):
     test_aux[:, 1] += 0.3
     pm, pv = pkg.posterior_predict(s, test_aux.cuda(), cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda())
     assert rel_err(pm, T("mnist/cgen_p_m")) < TOL and rel_err(pv, T("mnist/cgen_p_v")) < TOL
+
+
+def test_titsias_branch_against_reference_source(cuda_backend):
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    T = lambda k: torch.from_numpy(gold[k])
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=2, b=64)
+    cfg["ctor"]["titsias"] = True
+    _, s, _, sp = refs.make_pair("mnist", cfg, "cuda")
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda())
+    sc = gold["mnist_titsias/scalars"]
+    assert abs(float(r1["inside_elbo_recon"]) - sc[0]) < TOL * abs(sc[0]) and abs(float(r1["KL_term"]) - sc[3]) < TOL * abs(sc[3])
+    assert rel_err(r1["p_m"], T("mnist_titsias/p_m")) < TOL and rel_err(r1["p_v"], T("mnist_titsias/p_v")) < TOL
+    for g, n in zip(g1, ["y", "noise", "Z", "table"]):
+        assert rel_err(g, T("mnist_titsias/grad_" + n)) < 3 * TOL, n
+    cfgb = configs.ball_inputs()
+    sb = pkg.SVGP(name="x", **dict(cfgb["ctor"], titsias=True)).cuda()
+    xc = cfgb["x"].cuda()
+    y, nz = cfgb["y"][:, :, 0].cuda().requires_grad_(True), cfgb["noise"][:, :, 0].cuda().requires_grad_(True)
+    _, _, mu_hat, A_hat = sb.approximate_posterior_params(xc, y=y, noise=nz)
+    L2, zero = sb.variational_loss(xc, y, nz, mu_hat=mu_hat, A_hat=A_hat)
+    assert rel_err(L2, T("ball_titsias/L2")) < TOL

@@ -169,3 +169,27 @@ def test_prediction_path_against_reference_source(oracle_backend):
     test_aux[:, 1] += 0.3
     pm, pv = pkg.posterior_predict(s, test_aux, cfg["aux"], cfg["y"], cfg["noise"])
     assert pm.shape == (48, 4) and rel_err(pm, T("mnist/cgen_p_m")) < TOL and rel_err(pv, T("mnist/cgen_p_v")) < TOL
+
+
+def test_titsias_branch_against_reference_source(oracle_backend):
+    """titsias=True: variational_loss returns (L_2, 0) (:246-259, ball :89-101); elbo_step falls back to the per-channel loop."""
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    T = lambda k: torch.from_numpy(gold[k])
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=2, b=64)
+    cfg["ctor"]["titsias"] = True
+    _, s, _, sp = refs.make_pair("mnist", cfg, "cpu")
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"])
+    sc = gold["mnist_titsias/scalars"]
+    assert float(r1["inside_elbo_kl"]) == 0.0
+    assert abs(float(r1["inside_elbo_recon"]) - sc[0]) < TOL * abs(sc[0]) and abs(float(r1["KL_term"]) - sc[3]) < TOL * abs(sc[3])
+    assert rel_err(r1["p_m"], T("mnist_titsias/p_m")) < TOL and rel_err(r1["p_v"], T("mnist_titsias/p_v")) < TOL
+    for g, n in zip(g1, ["y", "noise", "Z", "table", "amplitude", "length"]):
+        assert rel_err(g, T("mnist_titsias/grad_" + n)) < 5 * TOL, n
+    cfgb = configs.ball_inputs()
+    sb = pkg.SVGP(name="x", **dict(cfgb["ctor"], titsias=True))
+    y, nz = cfgb["y"][:, :, 0].clone().requires_grad_(True), cfgb["noise"][:, :, 0].clone().requires_grad_(True)
+    _, _, mu_hat, A_hat = sb.approximate_posterior_params(cfgb["x"], y=y, noise=nz)
+    L2, zero = sb.variational_loss(cfgb["x"], y, nz, mu_hat=mu_hat, A_hat=A_hat)
+    assert float(zero) == 0.0 and rel_err(L2, T("ball_titsias/L2")) < TOL
+    L2.sum().backward()
+    assert rel_err(y.grad, T("ball_titsias/grad_y")) < 5 * TOL and rel_err(nz.grad, T("ball_titsias/grad_noise")) < 5 * TOL

@@ -206,3 +206,24 @@ def test_oracle_ball_matches_reference_source():
     assert np.abs(r["KL_term"].detach().numpy() - gold["ball/KL_term"]).max() <= 1e-10 * np.abs(gold["ball/kl"]).max()
     assert abs(float(J) - float(gold["ball/J"][0])) <= 1e-10 * abs(float(gold["ball/J"][0]))
     assert _close(gy, gold["ball/grad_y"], 1e-7) and _close(gn, gold["ball/grad_noise"], 1e-7)
+
+
+def test_oracle_titsias_matches_reference_source():
+    """L_2 (Titsias) branch: SVGPVAE_model.py:246-259 (mini-batched, through forward_pass_SVGPVAE) and :89-101 (ball)."""
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=2, b=64)
+    cfg["ctor"]["titsias"] = True
+    o, _, op, _ = refs.make_pair("mnist", cfg, "cpu")
+    r, J, g = refs.oracle_objective(o, op, cfg["aux"], cfg["y"], cfg["noise"])
+    sc = gold["mnist_titsias/scalars"]
+    assert float(r["inside_elbo_kl"]) == 0.0 and sc[1] == 0.0
+    assert abs(float(r["inside_elbo_recon"]) - sc[0]) <= 1e-10 * abs(sc[0]) and abs(float(r["KL_term"]) - sc[3]) <= 1e-10 * abs(sc[2])
+    for t, n in zip(g, ["y", "noise", "Z", "table", "amplitude", "length"]):
+        assert _close(t, gold["mnist_titsias/grad_" + n], 1e-7), n
+    cfgb = configs.ball_inputs()
+    sb = lit.BallSVGP(name="x", **dict(cfgb["ctor"], titsias=True))
+    y, nz = cfgb["y"][:, :, 0].double(), cfgb["noise"][:, :, 0].double()
+    x = cfgb["x"].double()
+    _, _, mu_hat, A_hat = sb.approximate_posterior_params(x, y, nz)
+    L2, _ = sb.variational_loss(x, y, nz, mu_hat, A_hat)
+    assert _close(L2, gold["ball_titsias/L2"], 1e-10)
