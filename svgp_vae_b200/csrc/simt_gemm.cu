@@ -27,11 +27,14 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   int64_t k0, k1;
   op.krange(blockIdx.z, k0, k1);
-  double acc[4][4];      // fp32 products, fp64 accumulation: S_l / Kinv have large cancelling entries (cond ~1e3..1e5)
+  // fp32 products; accumulation type per operator: double where the operand matrices have large cancelling entries
+  // (S_l / Kinv, cond ~1e3..1e5), float for the short / chunked sums whose partials are folded in double afterwards
+  using Acc = typename Op::Acc;
+  Acc acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[i][j] = (Acc)0;
 
   for (int64_t kb = k0; kb < k1; kb += BK) {
     // A tile: BK x BM, B tile: BK x BN; each thread loads 4 + 4 elements
@@ -51,11 +54,11 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      double a[4], b[4];
+      Acc a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = (double)As[kk][ty * 4 + i];
+      for (int i = 0; i < 4; ++i) a[i] = (Acc)As[kk][ty * 4 + i];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = (double)Bs[kk][tx * 4 + j];
+      for (int j = 0; j < 4; ++j) b[j] = (Acc)Bs[kk][tx * 4 + j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -74,6 +77,7 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
 
 // ---- operand functors -------------------------------------------------------------------------
 struct SyrkOp {     // z = l * nchunk + chunk
+  using Acc = double;
   static constexpr bool A_K_CONTIG = false, B_K_CONTIG = false;
   const float* K; int64_t ldk; const float* W; int64_t ldw; double* A; int64_t N, M, L, chunk, nchunk;
   int64_t Mr, Nc;
@@ -95,6 +99,7 @@ struct KAccess {
   }
 };
 struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
+  using Acc = float;
   static constexpr bool A_K_CONTIG = false, B_K_CONTIG = false;
   KAccess Ka; const float* X; int64_t ldx; double* V; int64_t N, M, chunk;
   int64_t Mr, Nc;
@@ -104,6 +109,7 @@ struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
   __device__ void store(int z, int64_t m, int64_t n, double v) const { atomicAdd(&V[m * M + n], v); }
 };
 struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
+  using Acc = double;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
   KAccess Ka; int64_t row0; const float* Wm; int64_t ldwm; float* out; int64_t ldo; int64_t M;
   int64_t Mr, Nc;
@@ -113,6 +119,7 @@ struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
   __device__ void store(int z, int64_t m, int64_t n, double v) const { out[(row0 + m) * ldo + n] = (float)v; }
 };
 struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
+  using Acc = double;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
   const float* K; int64_t ldk; const float* W; int64_t ldw; const float* G; float* out; int64_t ldo;
   int64_t M, L; int accumulate;
@@ -129,6 +136,7 @@ struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
   }
 };
 struct PlainOp {
+  using Acc = float;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
   const float* A; int64_t lda; const float* B; int64_t ldb; float* C; int64_t ldc; int64_t Kd; int accumulate;
   int64_t Mr, Nc;

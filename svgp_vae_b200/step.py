@@ -186,8 +186,8 @@ class _SVGPStep(torch.autograd.Function):
         G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
         del Wstack, Gstack
         py = p * y
-        be.gemm_f32(py.contiguous(), gV.float().contiguous(), out=G_K)          # via v_l
-        be.gemm_f32(g_pm, w.float().contiguous(), out=G_K)                       # via p_m
+        # rank-2L part of dK_nm in one pass over it: [p*y | g_pm] (N, 2L) @ [dV ; w] (2L, M)   (via v_l and via p_m)
+        be.gemm_f32(torch.cat([py, g_pm], dim=1), torch.cat([gV.float(), w.float()], dim=0).contiguous(), out=G_K)
         # dp, dy, dnoise
         G_p = 0.5 * kGk                                                          # k^T dA k
         G_py = be.gemm_nn(kop, gV.float().contiguous())
