@@ -142,7 +142,8 @@ int svgp_gemm_nn_tc(const svgp_kop* kop, const void* Wm_hi, const void* Wm_lo, c
                     float* out, int64_t ldo, void* stream);
 
 /* K4  row-wise quadratic forms  q[i,l] = k_i^T S_l k_i  (N x L fp32).
- * S (L x M x M, symmetric): SIMT takes one fp32 plane S_hi (S_lo, S_inv NULL); TC takes the fp16
+ * S (L x M x M, symmetric): SIMT takes the float64 matrices themselves (S_hi = const double*, S_lo and
+ * S_inv NULL: fp32 K entries times float64 S entries, float64 accumulation); TC takes the fp16
  * planes + inv_scale of svgp_split_f16.  If `tri` != 0 the planes hold a lower-triangular factor
  * Rinv_l instead and q[i,l] = |Rinv_l k_i|^2 (half the work, a sum of squares: no cancellation).
  * L may be 1 with N x 1 output (h_i = k^T Kinv k).

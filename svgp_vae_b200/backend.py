@@ -269,8 +269,8 @@ class CudaBackend:
         if use_tc:
             pl = S64 if isinstance(S64, Planes) else self.planes(S64)
             return _ptr(pl.hi), _ptr(pl.lo), _ptr(pl.inv), pl
-        S32 = _f64c(S64).to(torch.float32)
-        return _ptr(S32), None, None, S32
+        S64 = _f64c(S64 if S64.is_contiguous() else S64.contiguous())      # SIMT kernels read the float64 matrices directly
+        return _ptr(S64), None, None, S64
 
     def rowquad(self, kop, S64, tri=False, impl=IMPL_AUTO):
         L = (S64.hi if isinstance(S64, Planes) else S64).shape[0]

@@ -21,8 +21,9 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 
 template <class Op>
 __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
+  using BT = typename Op::BT;                 // element type of the B operand (double for the M x M matrices)
   __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ BT Bs[BK][BN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
   int64_t k0, k1;
@@ -49,7 +50,7 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
       if (Op::B_K_CONTIG) { kk = idx % BK; nn = idx / BK; } else { nn = idx % BN; kk = idx / BN; }
       gk = kb + kk;
       int64_t gn = n0 + nn;
-      Bs[kk][nn] = (gk < k1 && gn < op.Nc) ? op.b(blockIdx.z, gk, gn) : 0.f;
+      Bs[kk][nn] = (gk < k1 && gn < op.Nc) ? op.b(blockIdx.z, gk, gn) : (BT)0;
     }
     __syncthreads();
 #pragma unroll
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(NT) tile_gemm_kernel(Op op) {
 
 // ---- operand functors -------------------------------------------------------------------------
 struct SyrkOp {     // z = l * nchunk + chunk
+  using BT = float;
   using Acc = double;
   static constexpr bool A_K_CONTIG = false, B_K_CONTIG = false;
   const float* K; int64_t ldk; const float* W; int64_t ldw; double* A; int64_t N, M, L, chunk, nchunk;
@@ -98,8 +100,10 @@ struct KAccess {
     return (__half2float(Kh[i * ld + a]) + __half2float(Kl[i * ld + a])) * kscale[1];
   }
 };
-struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
-  using Acc = float;
+template <class AccT>
+struct TnOpT {       // rows = channel l, cols = inducing index; z = chunk
+  using BT = float;
+  using Acc = AccT;
   static constexpr bool A_K_CONTIG = false, B_K_CONTIG = false;
   KAccess Ka; const float* X; int64_t ldx; double* V; int64_t N, M, chunk;
   int64_t Mr, Nc;
@@ -109,6 +113,7 @@ struct TnOp {       // rows = channel l, cols = inducing index; z = chunk
   __device__ void store(int z, int64_t m, int64_t n, double v) const { atomicAdd(&V[m * M + n], v); }
 };
 struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
+  using BT = float;
   using Acc = double;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = true;
   KAccess Ka; int64_t row0; const float* Wm; int64_t ldwm; float* out; int64_t ldo; int64_t M;
@@ -119,9 +124,10 @@ struct NnOp {       // out[i,l] = sum_a K[i,a] Wm[l,a]
   __device__ void store(int z, int64_t m, int64_t n, double v) const { out[(row0 + m) * ldo + n] = (float)v; }
 };
 struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
+  using BT = double;
   using Acc = double;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
-  const float* K; int64_t ldk; const float* W; int64_t ldw; const float* G; float* out; int64_t ldo;
+  const float* K; int64_t ldk; const float* W; int64_t ldw; const double* G; float* out; int64_t ldo;
   int64_t M, L; int accumulate;
   int64_t Mr, Nc;
   __device__ void krange(int z, int64_t& k0, int64_t& k1) const { k0 = 0; k1 = L * M; }
@@ -129,13 +135,14 @@ struct ScaledOp {   // out[i,c] = sum_{l,a} W[i,l] K[i,a] G[l,a,c]
     int64_t l = k / M, aa = k - l * M;
     return W[m * ldw + l] * K[m * ldk + aa];
   }
-  __device__ float b(int z, int64_t k, int64_t n) const { return G[k * M + n]; }   // (l*M + a)*M + c
+  __device__ double b(int z, int64_t k, int64_t n) const { return G[k * M + n]; }   // (l*M + a)*M + c
   __device__ void store(int z, int64_t m, int64_t n, double v) const {
     float* o = out + m * ldo + n;
     *o = accumulate ? (float)((double)*o + v) : (float)v;
   }
 };
 struct PlainOp {
+  using BT = float;
   using Acc = float;
   static constexpr bool A_K_CONTIG = true, B_K_CONTIG = false;
   const float* A; int64_t lda; const float* B; int64_t ldb; float* C; int64_t ldc; int64_t Kd; int accumulate;
@@ -153,14 +160,14 @@ struct PlainOp {
 // block = 64 datapoints x one channel; walks the column tiles of S_l, forms U = K_tile S_l[:, tile] in
 // registers and folds it straight into q (DOT: sum_b U_ib K_ib; SQUARE/tri: sum_c U_ic^2).
 __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restrict__ K, int64_t ldk, int64_t N, int64_t M,
-                                                          const float* __restrict__ S, int tri, float* __restrict__ q,
+                                                          const double* __restrict__ S, int tri, float* __restrict__ q,
                                                           int64_t ldq) {
   __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ double Bs[BK][BN + 4];
   const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int l = blockIdx.y;
-  const float* Sl = S + (int64_t)l * M * M;
+  const double* Sl = S + (int64_t)l * M * M;
   double qacc[4] = {0.0, 0.0, 0.0, 0.0};
   for (int64_t n0 = 0; n0 < M; n0 += BN) {
     double acc[4][4];
@@ -178,9 +185,9 @@ __global__ void __launch_bounds__(NT) rowquad_simt_kernel(const float* __restric
         As[kk][mm] = (gk < M && gm < N) ? K[gm * ldk + gk] : 0.f;
         int64_t gn;
         if (tri) { kk = idx % BK; int nn = idx / BK; gk = kb + kk; gn = n0 + nn;
-                   Bs[kk][nn] = (gk < M && gn < M) ? Sl[gn * M + gk] : 0.f; }
+                   Bs[kk][nn] = (gk < M && gn < M) ? Sl[gn * M + gk] : 0.0; }
         else     { int nn = idx % BN; kk = idx / BN; gk = kb + kk; gn = n0 + nn;
-                   Bs[kk][nn] = (gk < M && gn < M) ? Sl[gk * M + gn] : 0.f; }
+                   Bs[kk][nn] = (gk < M && gn < M) ? Sl[gk * M + gn] : 0.0; }
       }
       __syncthreads();
 #pragma unroll
@@ -366,7 +373,13 @@ int svgp_gemm_tn(const svgp_kop* kop, const float* X, int64_t ldx, int64_t L, do
   if (kop->N == 0 || kop->M == 0) return SVGP_OK;
   int64_t chunk = 2048, nchunk = ceil_div(kop->N, chunk);
   while (nchunk > 65535) { chunk *= 2; nchunk = ceil_div(kop->N, chunk); }
-  TnOp op{kaccess(kop), X, ldx, V, kop->N, kop->M, chunk, L, kop->M};
+  // fp32 chunk partials are fine once many of them are folded in double (their rounding errors average out, same
+  // accuracy class as the tensor-core SYRK); a short reduction keeps double accumulators throughout
+  if (nchunk >= 32) {
+    TnOpT<float> op{kaccess(kop), X, ldx, V, kop->N, kop->M, chunk, L, kop->M};
+    return launch_tile(op, nchunk, (cudaStream_t)stream, "svgp_gemm_tn");
+  }
+  TnOpT<double> op{kaccess(kop), X, ldx, V, kop->N, kop->M, chunk, L, kop->M};
   return launch_tile(op, nchunk, (cudaStream_t)stream, "svgp_gemm_tn");
 }
 
@@ -401,9 +414,9 @@ int svgp_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const 
     return tc_rowquad(kop, S_hi, S_lo, S_inv, L, tri, q, ldq, (cudaStream_t)stream);
   }
   SVGP_REQUIRE(L <= 65535, "too many channels");
-  SVGP_REQUIRE(kop->K != nullptr && S_lo == nullptr && S_inv == nullptr, "SIMT path takes fp32 K and a single fp32 plane");
+  SVGP_REQUIRE(kop->K != nullptr && S_lo == nullptr && S_inv == nullptr, "SIMT path takes fp32 K and the float64 matrices themselves (G_lo = G_inv = NULL)");
   dim3 grid((unsigned)ceil_div(kop->N, BM), (unsigned)L);
-  rowquad_simt_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(kop->K, kop->ldk, kop->N, kop->M, (const float*)S_hi, tri, q, ldq);
+  rowquad_simt_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(kop->K, kop->ldk, kop->N, kop->M, (const double*)S_hi, tri, q, ldq);
   return check_launch("svgp_rowquad");
 }
 
@@ -418,11 +431,11 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
     SVGP_REQUIRE(G_lo != nullptr && G_inv != nullptr, "TC path needs the fp16 planes and scales of G (svgp_split_f16)");
     return tc_scaled_gemm(kop, W, ldw, G_hi, G_lo, G_inv, L, kop->M, out, ldo, accumulate, dots, lddots, ndot, st);
   }
-  SVGP_REQUIRE(kop->K != nullptr && G_lo == nullptr && G_inv == nullptr, "SIMT path takes fp32 K and a single fp32 plane");
+  SVGP_REQUIRE(kop->K != nullptr && G_lo == nullptr && G_inv == nullptr, "SIMT path takes fp32 K and the float64 matrices themselves (G_lo = G_inv = NULL)");
   int64_t slab = 65535LL * BM;
   for (int64_t r0 = 0; r0 < kop->N; r0 += slab) {
     int64_t rows = kop->N - r0 < slab ? kop->N - r0 : slab;
-    ScaledOp op{kop->K + r0 * kop->ldk, kop->ldk, W + r0 * ldw, ldw, (const float*)G_hi, out + r0 * ldo, ldo, kop->M, L, accumulate, rows, kop->M};
+    ScaledOp op{kop->K + r0 * kop->ldk, kop->ldk, W + r0 * ldw, ldw, (const double*)G_hi, out + r0 * ldo, ldo, kop->M, L, accumulate, rows, kop->M};
     int rc = launch_tile(op, 1, st, "svgp_scaled_gemm");
     if (rc) return rc;
   }
@@ -433,7 +446,7 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
     for (int64_t r0 = 0; r0 < kop->N; r0 += slab) {
       int64_t rows = kop->N - r0 < slab ? kop->N - r0 : slab;
       dim3 grid((unsigned)ceil_div(rows, BM), (unsigned)ndot);
-      rowquad_simt_kernel<<<grid, NT, 0, st>>>(kop->K + r0 * kop->ldk, kop->ldk, rows, kop->M, (const float*)G_hi, 0,
+      rowquad_simt_kernel<<<grid, NT, 0, st>>>(kop->K + r0 * kop->ldk, kop->ldk, rows, kop->M, (const double*)G_hi, 0,
                                                dots + r0 * lddots, lddots);
     }
     return check_launch("svgp_scaled_gemm(dots)");

@@ -79,6 +79,25 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// the same load, multicast to the CTAs of `mask` in this cluster: data and the complete_tx signal land at the same
+// shared-memory offsets in every destination CTA
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2,
+                                               uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -98,6 +117,10 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -269,10 +292,15 @@ __device__ __forceinline__ float dot_k_planes(const __half* __restrict__ Kh, con
   return acc;
 }
 
-template <int MODE, int BN, int BK, int STAGES>
+// CL = CTAs per cluster (SYRK only: 2).  The two CTAs of a cluster work on the same (tile pair, super-chunk) for two
+// adjacent channels: they need the SAME K^T boxes, so each loads half of the rows of every box and TMA-multicasts
+// them into both shared memories -- half the L2 -> SM traffic per CTA.  mapH_* are the half-height (64-row) boxes.
+template <int MODE, int BN, int BK, int STAGES, int CL>
 __global__ void __launch_bounds__(tc_threads(MODE), 1)
 tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ CUtensorMap mapA_lo,
-          const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo, const TcParams P) {
+          const __grid_constant__ CUtensorMap mapB_hi, const __grid_constant__ CUtensorMap mapB_lo,
+          const __grid_constant__ CUtensorMap mapH_hi, const __grid_constant__ CUtensorMap mapH_lo, const TcParams P) {
+  static_assert(CL == 1 || (CL == 2 && MODE == MODE_SYRK), "clusters are used by the SYRK only");
   constexpr int RB = BK * 2;                                   // bytes per operand row of one k-block
   constexpr int A_BYTES = BLOCK_M * RB, B_BYTES = BN * RB;     // one plane
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -296,13 +324,15 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   auto fullA = [&](int s) { return bars + 8u * (3 * STAGES + 5 + s); };    // SYRK: the A planes land (and are transformed) first
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full(s), 1);
       mbar_init(fullA(s), 1);
       mbar_init(ready(s), 4);
-      mbar_init(empty(s), 1);
+      mbar_init(empty(s), CL);          // a stage is free when the MMAs of EVERY CTA of the cluster have read it
     }
     for (int t = 0; t < 2; ++t) {
       mbar_init(tmem_full(t), 1);
@@ -319,6 +349,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr_addr));
@@ -409,6 +440,26 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
               // The A planes get their own barrier and go first: the transform warps rescale them while the
               // (twice as large) B planes are still in flight.
               const int32_t nb = ak >> 6, ni = ak & 63;
+              if (CL == 2) {
+                // this CTA fetches rows [crank * h, (crank + 1) * h) of every box and multicasts them to both CTAs;
+                // each CTA's barriers still expect the full box (its own half + the peer's)
+                const int32_t ha = crank * (BLOCK_M / 2);
+                const uint32_t oa = crank * (A_BYTES / 2);
+                mbar_expect_tx(fullA(stage), 2 * A_BYTES);
+                tma_load_3d_mc(st + oa, &mapH_hi, fullA(stage), ni, ar + ha, nb, MC_MASK);
+                tma_load_3d_mc(st + A_BYTES + oa, &mapH_lo, fullA(stage), ni, ar + ha, nb, MC_MASK);
+                if (it.half_tile) {
+                  mbar_expect_tx(full(stage), 2 * A_BYTES);
+                  tma_load_3d_mc(st + 2 * A_BYTES + oa, &mapH_hi, full(stage), ni, br + ha, nb, MC_MASK);
+                  tma_load_3d_mc(st + 2 * A_BYTES + B_BYTES + oa, &mapH_lo, full(stage), ni, br + ha, nb, MC_MASK);
+                } else {
+                  const int32_t hb = crank * (BN / 2);
+                  const uint32_t ob = crank * (B_BYTES / 2);
+                  mbar_expect_tx(full(stage), 2 * B_BYTES);
+                  tma_load_3d_mc(st + 2 * A_BYTES + ob, &mapA_hi, full(stage), ni, br + hb, nb, MC_MASK);    // BN / 2 == BLOCK_M rows
+                  tma_load_3d_mc(st + 2 * A_BYTES + B_BYTES + ob, &mapA_lo, full(stage), ni, br + hb, nb, MC_MASK);
+                }
+              } else {
               mbar_expect_tx(fullA(stage), 2 * A_BYTES);
               tma_load_3d(st, &mapA_hi, fullA(stage), ni, ar, nb);
               tma_load_3d(st + A_BYTES, &mapA_lo, fullA(stage), ni, ar, nb);
@@ -420,6 +471,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 mbar_expect_tx(full(stage), 2 * B_BYTES);
                 tma_load_3d(st + 2 * A_BYTES, &mapB_hi, full(stage), ni, br, nb);
                 tma_load_3d(st + 2 * A_BYTES + B_BYTES, &mapB_lo, full(stage), ni, br, nb);
+              }
               }
             } else {
               mbar_expect_tx(full(stage), STAGE_BYTES);
@@ -462,7 +514,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
               umma_f16(d_tmem, a_hi + adv, b_lo + adv, idesc, 1u);
               umma_f16(d_tmem, a_hi + adv, b_hi + adv, idesc, 1u);
             }
-            umma_commit(empty(stage));
+            if (CL == 2) umma_commit_mc(empty(stage), MC_MASK); else umma_commit(empty(stage));
             if (kb == nkb - 1) umma_commit(tmem_full(acc));
           }
           __syncwarp();
@@ -740,6 +792,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // nobody leaves while the peer may still multicast into / signal this CTA
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
@@ -839,28 +892,54 @@ static int syrk_flush_every() {
   return f;
 }
 
-template <int MODE, int BN, int BK, int STAGES>
-static int launch_tc(const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
-                     const TcParams& P, cudaStream_t st, const char* name) {
+template <int MODE, int BN, int BK, int STAGES, int CL>
+static int launch_tc(const CUtensorMap* maps, const TcParams& P, cudaStream_t st, const char* name) {
   constexpr int SMEM_TOTAL = STAGES * (2 * BLOCK_M * BK * 2 + 2 * BN * BK * 2) + 256 + 1024;
   static_assert(SMEM_TOTAL <= TC_SMEM_LIMIT, "shared memory budget");
-  auto kern = tc_kernel<MODE, BN, BK, STAGES>;
+  auto kern = tc_kernel<MODE, BN, BK, STAGES, CL>;
   static bool attr_done = false;
+  static int max_ctas = 0;             // CTAs that can be co-resident (CL == 2: 2 x the number of active clusters)
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(tc_threads(MODE), 1, 1);
+  cfg.dynamicSmemBytes = SMEM_TOTAL;
+  cfg.stream = st;
+  if (CL > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
   if (!attr_done) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL) != cudaSuccess) return check_launch(name);
+    max_ctas = num_sms();
+    if (CL > 1) {
+      // a persistent grid must be fully co-resident: ask how many clusters fit (GPCs with an odd number of usable
+      // SMs leave one SM without a partner)
+      int nclusters = 0;
+      cfg.gridDim = dim3(num_sms() / CL * CL, 1, 1);
+      if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) != cudaSuccess || nclusters <= 0) {
+        cudaGetLastError();
+        set_error("%s: no co-resident clusters of %d CTAs available", name, CL);
+        return SVGP_ERR_CUDA;
+      }
+      max_ctas = nclusters * CL;
+    }
     attr_done = true;
   }
-  int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
+  int64_t grid = P.n_items < max_ctas ? P.n_items : max_ctas;
+  grid = grid / CL * CL;
   if (grid <= 0) return SVGP_OK;
-  kern<<<(unsigned)grid, tc_threads(MODE), SMEM_TOTAL, st>>>(a_hi, a_lo, b_hi, b_lo, P);
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  if (cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], P) != cudaSuccess) return check_launch(name);
   return check_launch(name);
 }
 
 template <int MODE>
 static int dispatch_tc(int bk, const CUtensorMap& a_hi, const CUtensorMap& a_lo, const CUtensorMap& b_hi, const CUtensorMap& b_lo,
                        const TcParams& P, cudaStream_t st, const char* name) {
-  if (bk == 32) return launch_tc<MODE, 256, 32, 4>(a_hi, a_lo, b_hi, b_lo, P, st, name);
-  return launch_tc<MODE, 256, 64, 2>(a_hi, a_lo, b_hi, b_lo, P, st, name);
+  const CUtensorMap maps[6] = {a_hi, a_lo, b_hi, b_lo, a_hi, a_lo};
+  if (bk == 32) return launch_tc<MODE, 256, 32, 4, 1>(maps, P, st, name);
+  return launch_tc<MODE, 256, 64, 2, 1>(maps, P, st, name);
 }
 
 bool tc_shape_ok(const svgp_kop* kop) {
@@ -904,7 +983,20 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
   { const char* e = getenv("SVGP_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.n_items = (int64_t)P.nsc * P.ntile * L;
   if (cudaMemsetAsync(locks, 0, sizeof(int) * tc_syrk_lock_words(kop->M, L), st) != cudaSuccess) return check_launch("svgp_syrk(locks)");
-  rc = dispatch_tc<MODE_SYRK>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
+  // even channel counts run as clusters of two CTAs (adjacent channels of one tile pair) sharing their loads by TMA
+  // multicast; SVGP_SYRK_CLUSTER=1 forces the single-CTA kernel
+  const char* ecl = getenv("SVGP_SYRK_CLUSTER");
+  const bool pair = (L % 2 == 0) && !(ecl && atoi(ecl) == 1);
+  if (pair) {
+    CUtensorMap h_hi, h_lo;
+    if ((rc = make_map_blocked(&h_hi, kop->Kth, kop->M, kop->N, kop->ldkt, BLOCK_M / 2, bk))) return rc;
+    if ((rc = make_map_blocked(&h_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BLOCK_M / 2, bk))) return rc;
+    const CUtensorMap maps[6] = {a_hi, a_lo, b_hi, b_lo, h_hi, h_lo};
+    rc = (bk == 32) ? launch_tc<MODE_SYRK, 256, 32, 4, 2>(maps, P, st, "svgp_syrk(tc, cluster)")
+                    : launch_tc<MODE_SYRK, 256, 64, 2, 2>(maps, P, st, "svgp_syrk(tc, cluster)");
+  } else {
+    rc = dispatch_tc<MODE_SYRK>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_syrk(tc)");
+  }
   if (rc) return rc;
   int64_t blocks = ceil_div(L * kop->M * kop->M, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;

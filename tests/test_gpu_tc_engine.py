@@ -41,7 +41,7 @@ def test_tc_syrk(cuda_backend, shape):
     assert rel_err(be.syrk(kop, Wp), refp) < 3e-5
 
 
-@pytest.mark.parametrize("shape", [(9000, 256, 1), (20000, 384, 3)])
+@pytest.mark.parametrize("shape", [(9000, 256, 1), (20000, 384, 3), (20000, 384, 4), (70000, 1024, 2)])
 def test_tc_syrk_superchunks(cuda_backend, shape, monkeypatch):
     """Datapoints are walked in L2-sized super-chunks; different CTAs add different super-chunks of one tile into the
     float64 accumulator under a lock.  Force many small super-chunks (L = 1: same-tile items run concurrently)."""

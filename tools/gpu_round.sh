@@ -20,11 +20,11 @@ for s in $STAGES; do
       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file $OUT/launches.csv \
         python bench.py --steps 1 --warmup 1 --n 262144 --no-cpu-baseline > $OUT/launches_bench.log 2>&1 ;;
     full)
-      # one launch of each tcgen05 mode (tc_probe launch order: 12 syrk, 4 rowquad full, 4 rowquad tri, 4 scaled)
-      for spec in syrk:1 rowquad_full:13 rowquad_tri:17 scaled:21; do
+      # one launch of each tcgen05 mode (tc_probe launch order: 16 syrk, 4 rowquad full, 4 rowquad tri, 4 scaled, 4 scaled+dots)
+      for spec in syrk:5 rowquad_full:17 rowquad_tri:21 scaled:25 scaled_dots:29; do
         name=${spec%%:*}; skip=${spec##*:}
         timeout 600 ncu --set full --clock-control none --import-source on -k regex:tc_kernel --launch-skip $skip --launch-count 1 \
-          -o $OUT/prof_$name python tools/tc_probe.py 65536 1024 8 > $OUT/full_$name.log 2>&1
+          -o $OUT/prof_$name python tools/tc_probe.py 131072 1024 16 > $OUT/full_$name.log 2>&1
         ncu -i $OUT/prof_$name.ncu-rep --page raw --csv > $OUT/prof_$name.raw.csv 2>/dev/null
         ncu -i $OUT/prof_$name.ncu-rep --page details --csv > $OUT/prof_$name.details.csv 2>/dev/null
         ncu -i $OUT/prof_$name.ncu-rep --page source --csv > $OUT/prof_$name.source.csv 2>/dev/null
