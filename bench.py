@@ -288,6 +288,14 @@ def run_gpu(args):
         kern_alg = {"svgp_scaled_gemm": 2.0 * N * M * M * (2 * L + 1), "svgp_syrk": 1.0 * N * M * M * L,
                     "svgp_rowquad": 1.0 * N * M * M * L}
         top_flops = kern_alg.get(top_name, float("nan"))
+        # DRAM bytes of one launch of that kernel from the committed ncu capture of this exact workload (else null)
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            if (N, M, L) == (N_PER_GPU, M_IND, L_CH):
+                traffic = tr.get(top_name)
+        except Exception:  # noqa: BLE001
+            pass
         achieved = 3.0 * top_flops / (top_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": n_total / t_s, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -297,7 +305,7 @@ def run_gpu(args):
                        "l2": "inputs_exceed_l2 (K_nm fp16 hi/lo planes + transpose = %.1f GB per GPU)" % (4 * N * M * 2 / 1e9),
                        "parallelism": "N-sharded x%d, all-reduce of A_l/v_l and their adjoints" % world},
             "roofline": {"bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
                          "note": "achieved = e x algorithmic FLOPs of the kernel's launch / its CUDA-event duration inside the step, e = 3 FP16 MMAs "
                                  "per algorithmic MAC (fp32-emulating split); peak = %s; fp16 cuBLAS 8192^3 timed in this run: %.1f TFLOP/s"
                                  % (peak_src, f16_run),

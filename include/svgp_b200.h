@@ -176,6 +176,9 @@ int svgp_chol_f64(double* A, int64_t M, int64_t ld, int64_t stride, int64_t batc
 /* Linv = inverse of the lower-triangular factor (strict upper triangle of Linv zeroed)        */
 int svgp_trinv_f64(const double* Lf, double* Linv, int64_t M, int64_t ld, int64_t stride,
                    int64_t batch, double* ws, void* stream);
+/* S = T^T T for lower-triangular T (both triangles of S written): X^-1 = Linv^T Linv after the two calls above.
+ * Skips the structurally zero part of the reduction (about a quarter of a full product).      */
+int svgp_ltl_f64(const double* T, double* S, int64_t M, int64_t ld, int64_t stride, int64_t batch, void* stream);
 /* C[b] = alpha op(A[b]) op(B[b]) + beta C[b]; row-major, trans flags 0/1, stride 0 broadcasts */
 int svgp_gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, double alpha,
                   const double* A, int64_t lda, int64_t strideA, const double* B, int64_t ldb,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "svgp_split_f16": [_P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_chol_f64": [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P],
     "svgp_trinv_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P],
+    "svgp_ltl_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P],
     "svgp_gemm_f64": [c_int, c_int, c_int64, c_int64, c_int64, c_double, _P, c_int64, c_int64, _P, c_int64,
                       c_int64, c_double, _P, c_int64, c_int64, c_int64, _P],
     "svgp_rowstats_fwd": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P],

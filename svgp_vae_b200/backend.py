@@ -333,6 +333,15 @@ class CudaBackend:
         self.launches += 2 * nblk + 2
         return Linv
 
+    def ltl(self, T):
+        """T^T T for a batch of lower-triangular float64 matrices (X^-1 from the inverse Cholesky factor)."""
+        T = _f64c(T)
+        B, M, _ = T.shape
+        S = torch.empty_like(T)
+        _call("svgp_ltl_f64", _ptr(T), _ptr(S), M, M, M * M, B, _stream())
+        self.launches += 2
+        return S
+
     def bmm64(self, A, B, transA=False, transB=False):
         """C[b] = op(A[b]) op(B[b]); a leading batch of 1 broadcasts against the other operand."""
         A, B = _f64c(A), _f64c(B)

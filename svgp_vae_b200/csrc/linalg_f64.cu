@@ -354,8 +354,11 @@ __global__ void __launch_bounds__(512, 1) gemm_f64_mma_kernel(int64_t Mr, int64_
       if (transB) Bs[(idx / GK) * PK + idx % GK] = rb[e]; else Bs[(idx / GN) * PM + idx % GN] = rb[e];
     }
   };
-  fetch(0);
-  for (int64_t kb = 0; kb < Kd; kb += GK) {
+  // lower_only == 2: C = T^T T with T lower-triangular (S = Linv^T Linv): entries of a lower tile only receive
+  // contributions from k >= its first row
+  const int64_t kb0 = (lower_only == 2) ? (m0 / GK) * GK : 0;
+  fetch(kb0);
+  for (int64_t kb = kb0; kb < Kd; kb += GK) {
     stash();
     __syncthreads();
     if (kb + GK < Kd) fetch(kb + GK);
@@ -442,6 +445,25 @@ int svgp_gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, do
   SVGP_REQUIRE(A && B && C && Mr >= 0 && Nc >= 0 && Kd >= 0 && batch >= 0, "bad argument");
   return gemm_f64(transA, transB, Mr, Nc, Kd, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC, batch, 0,
                   (cudaStream_t)stream);
+}
+
+// copy the lower triangle of every matrix onto its upper triangle
+__global__ void mirror_lower_f64_kernel(double* __restrict__ A, int64_t M, int64_t ld, int64_t stride) {
+  double* Ab = A + (int64_t)blockIdx.y * stride;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < M * M; idx += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = idx / M, c = idx - r * M;
+    if (c > r) Ab[r * ld + c] = Ab[c * ld + r];
+  }
+}
+
+int svgp_ltl_f64(const double* T, double* S, int64_t M, int64_t ld, int64_t stride, int64_t batch, void* stream) {
+  SVGP_REQUIRE(T && S && M >= 1 && ld >= M && batch >= 1 && batch <= 65535, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = gemm_f64(1, 0, M, M, M, 1.0, T, ld, stride, T, ld, stride, 0.0, S, ld, stride, batch, 2, st);
+  if (rc) return rc;
+  dim3 g((unsigned)(ceil_div(M * M, 256) < 1024 ? ceil_div(M * M, 256) : 1024), (unsigned)batch);
+  mirror_lower_f64_kernel<<<g, 256, 0, st>>>(S, M, ld, stride);
+  return check_launch("svgp_ltl_f64");
 }
 
 int svgp_chol_f64(double* A, int64_t M, int64_t ld, int64_t stride, int64_t batch, int* status, double* ws, void* stream) {

@@ -35,9 +35,9 @@ constexpr int MODE_SYRK = 0, MODE_QUAD = 1, MODE_SCALED = 2;
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;                  // fp16 elements per MMA k-step (32 bytes)
 constexpr int TC_SMEM_LIMIT = 227 * 1024;
-// threads per CTA: QUAD / SCALED run 10 warps; SYRK runs 4 warpgroups (register budgets are re-split
-// between them with setmaxnreg, see the kernel prologue)
-__host__ __device__ constexpr int tc_threads(int mode) { return mode == 0 ? 512 : 320; }
+// threads per CTA: QUAD runs 10 warps; SYRK runs 4 warpgroups and SCALED 3 (register budgets are re-split between
+// the warpgroups with setmaxnreg at the top of each role branch)
+__host__ __device__ constexpr int tc_threads(int mode) { return mode == 0 ? 512 : (mode == 2 ? 384 : 320); }
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers (all shared-memory operands are 32-bit shared-window addresses)
@@ -306,7 +306,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   constexpr bool HAS_XFORM = (MODE == MODE_SYRK);
   constexpr int EPI_WARPS = (MODE == MODE_QUAD) ? 4 : 8;
-  constexpr int EPI_WARP0 = (MODE == MODE_SYRK) ? 8 : 2;       // first epilogue warp (SYRK: warpgroups 2 and 3)
+  constexpr int EPI_WARP0 = (MODE == MODE_SYRK) ? 8 : (MODE == MODE_SCALED ? 4 : 2);   // SYRK: warpgroups 2-3, SCALED: 1-2
   constexpr int XF_WARP0 = 4;                                  // SYRK: warpgroup 1 transforms the A operand
   constexpr int ACC_BUFS = (2 * BN <= 512) ? 2 : 1;
   constexpr uint32_t IDESC = make_idesc(BN);
@@ -782,6 +782,17 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       role_transform();
     } else {
       asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
+      role_epilogue();
+    }
+  } else if constexpr (MODE == MODE_SCALED) {
+    // 384 threads start with 168 registers each; the TMA / MMA warpgroup hands registers to the two epilogue
+    // warpgroups (128 running sums + the k-dot operands per thread)
+    if ((warp >> 2) == 0) {
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+      if (warp == 0) role_producer();
+      else if (warp == 1) role_mma();
+    } else {
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
       role_epilogue();
     }
   } else {

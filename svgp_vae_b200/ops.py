@@ -86,7 +86,7 @@ class _SPDInverseLogdet(torch.autograd.Function):
         if check:
             _check_status(status, "spd_inverse_logdet")
         Linv = be.trinv(Lf)
-        Xinv = be.bmm64(Linv, Linv, True, False)
+        Xinv = be.ltl(Linv)
         logdet = 2.0 * torch.log(torch.diagonal(Lf, dim1=-2, dim2=-1)).sum(-1)
         ctx.save_for_backward(Xinv)
         ctx.mark_non_differentiable(Linv)
@@ -126,7 +126,7 @@ class _SPDLogdet(torch.autograd.Function):
         (Lf,) = ctx.saved_tensors
         be = get_backend()
         Linv = be.trinv(Lf)
-        Xinv = be.bmm64(Linv, Linv, True, False)
+        Xinv = be.ltl(Linv)
         return g[:, None, None] * Xinv, None
 
 

@@ -125,6 +125,9 @@ class OracleBackend:
         eye = torch.eye(Lf.shape[-1], dtype=Lf.dtype).expand_as(Lf)
         return torch.linalg.solve_triangular(Lf, eye, upper=False)
 
+    def ltl(self, T):
+        return T.transpose(-1, -2) @ T
+
     def bmm64(self, A, B, transA=False, transB=False):
         A = A.transpose(-1, -2) if transA else A
         B = B.transpose(-1, -2) if transB else B

@@ -113,6 +113,7 @@ def test_linalg_f64(cuda_backend, M, B):
     assert rel_err(Lf, torch.linalg.cholesky(X)) < 1e-11
     Linv = be.trinv(Lf)
     assert rel_err(Linv, ORA.trinv(torch.linalg.cholesky(X))) < 1e-10
+    assert rel_err(be.ltl(Linv), torch.linalg.inv(X)) < 1e-9                  # S = Linv^T Linv (triangular-aware)
     Y = torch.randn(B, M, 7, generator=g, dtype=torch.float64)
     for tA in (False, True):
         for tB in (False, True):
