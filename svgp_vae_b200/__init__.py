@@ -9,6 +9,7 @@ CPU fallback -- importing is cheap, the first kernel call raises if the library 
 from .svgp import (SVGP, _add_diagonal_jitter, gauss_cross_entropy, mainSVGP, mnistSVGP, productSVGP,  # noqa: F401
                    reciprocal_no_nan, spritesSVGP)
 from .step import elbo_terms, svgp_step  # noqa: F401
+from .glue import aux_data_SVGPVAE_sprites, forward_pass_SVGPVAE  # noqa: F401
 from .predict import posterior_predict, precompute_GP_params_SVGPVAE, predict_from_precomputed  # noqa: F401
 
 __version__ = "0.1.0"

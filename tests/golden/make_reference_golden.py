@@ -202,6 +202,51 @@ def ball_case(out, cfg):
     out["ball/grad_y"], out["ball/grad_noise"] = gy.numpy(), gn.numpy()
 
 
+class GlueVAE(StubVAE):
+    """Deterministic stand-in decoder so that elbo / recon_loss / GECO state depend on the latent samples."""
+
+    def decode(self, z):
+        base = torch.linspace(-1.0, 1.0, 28 * 28, dtype=F64).reshape(1, 28, 28, 1)
+        return torch.tanh(z.sum(1)).reshape(-1, 1, 1, 1) * base + 0.1 * z[:, :1].reshape(-1, 1, 1, 1)
+
+
+def glue_images(b):
+    i = torch.arange(b, dtype=F64).reshape(-1, 1, 1, 1)
+    base = torch.linspace(0.0, 1.0, 28 * 28, dtype=F64).reshape(1, 28, 28, 1)
+    return torch.sin(0.1 * i + 3.0 * base)
+
+
+def glue_cases(out, fx):
+    """The rest of forward_pass_SVGPVAE (:900-936: sampling, decoder, beta-ELBO and GECO) and aux_data_SVGPVAE_sprites
+    (:1086-1115), for svgp_vae_b200/glue.py."""
+    cfg = configs.mnist_inputs(fx, L=4)
+    aux = cfg["aux"].to(F64)
+    images = glue_images(aux.shape[0])
+    for geco in (False, True):
+        svgp = ref.mnistSVGP(name="ref", **dict(cfg["ctor"]))
+        mu, var = _leaf(cfg["y"]), _leaf(cfg["noise"])
+        r = ref.forward_pass_SVGPVAE((images, aux), beta=0.7, vae=GlueVAE(mu, var), svgp=svgp, C_ma=0.3, lagrange_mult=1.5,
+                                     alpha=0.99, kappa=0.02, clipping_qs=True, GECO=geco)
+        tag = "glue_geco" if geco else "glue_beta"
+        out[tag + "/elbo"] = np.array([float(r[0])])
+        out[tag + "/recon_loss"] = np.array([float(r[1])])
+        out[tag + "/latent_samples"] = r[12].detach().numpy()
+        out[tag + "/C_ma"] = np.array([float(r[13])])
+        out[tag + "/lagrange_mult"] = np.array([float(r[14])])
+        g = torch.autograd.grad(r[0], [mu, var, svgp.inducing_index_points])
+        out[tag + "/grad_y"], out[tag + "/grad_noise"], out[tag + "/grad_Z"] = (t.numpy() for t in g)
+    out["glue/epsilon"] = tf.random.normal(shape=(aux.shape[0], 4)).numpy()
+
+    class Repr:
+        def repr_nn(self, images):
+            return images.reshape(images.shape[0], -1)[:, :16] * 2.0 + 0.5
+    b = 12
+    imgs = glue_images(b)
+    action_ids = torch.tensor([3, 7, 1, 0, 5, 5, 2, 71, 9, 4, 6, 8])
+    seg, rep = [0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2], [5, 3, 4]
+    out["sprites_aux/aux"] = ref.aux_data_SVGPVAE_sprites((imgs, action_ids), Repr(), seg, rep).numpy()
+
+
 def titsias_cases(out, fx):
     """The L_2 (Titsias) branch of both classes: SVGPVAE_model.py:246-259 through forward_pass_SVGPVAE, :89-101 direct."""
     cfg = configs.mnist_inputs(fx, L=2, b=64)
@@ -240,6 +285,7 @@ def main():
     sprites_case(out, "sprites72_se", configs.sprites_inputs(M=72, L=3, K_SE=True))
     ball_case(out, configs.ball_inputs())
     titsias_cases(out, fx)
+    glue_cases(out, fx)
     path = os.path.join(HERE, "reference_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "with", len(out), "arrays;", os.path.getsize(path), "bytes")

@@ -131,8 +131,21 @@ def gather(params, indices):
 
 
 def repeat(x, repeats, axis):
-    r = repeats[0] if isinstance(repeats, (list, tuple)) else repeats
-    return torch.repeat_interleave(x, int(r), dim=axis)
+    r = torch.as_tensor(repeats).reshape(-1).long()
+    if r.numel() == 1:
+        return torch.repeat_interleave(x, int(r[0]), dim=axis)
+    return torch.repeat_interleave(x, r, dim=axis)
+
+
+def segment_mean(data, segment_ids):
+    ids = torch.as_tensor(segment_ids).long()
+    n = int(ids.max()) + 1
+    sums = torch.zeros((n,) + tuple(data.shape[1:]), dtype=data.dtype).index_add(0, ids, data)
+    return sums / torch.bincount(ids, minlength=n).to(data.dtype).reshape((n,) + (1,) * (data.dim() - 1))
+
+
+def concat(values, axis=0):
+    return torch.cat(list(values), dim=axis)
 
 
 def stack(values, axis=0):
@@ -291,7 +304,7 @@ def install():
     g = globals()
     for k in ("float32", "float64", "int32", "int64", "newaxis", "constant", "Variable", "cast", "shape", "log", "exp", "sqrt",
               "matmul", "multiply", "expand_dims", "reduce_sum", "reduce_mean", "transpose", "trace", "gather", "repeat", "stack",
-              "clip_by_value", "stop_gradient", "tile"):
+              "clip_by_value", "stop_gradient", "tile", "segment_mean", "concat"):
         setattr(tf, k, g[k])
     tf.range = _tf_range
     tf.linalg, tf.math, tf.random = _Linalg("tensorflow.linalg"), _Math("tensorflow.math"), _Random("tensorflow.random")

@@ -273,3 +273,26 @@ def test_titsias_branch_against_reference_source(cuda_backend):
     _, _, mu_hat, A_hat = sb.approximate_posterior_params(xc, y=y, noise=nz)
     L2, zero = sb.variational_loss(xc, y, nz, mu_hat=mu_hat, A_hat=A_hat)
     assert rel_err(L2, T("ball_titsias/L2")) < TOL
+
+
+@pytest.mark.parametrize("geco", [False, True])
+def test_forward_pass_glue_against_reference_source(cuda_backend, geco):
+    """glue.forward_pass_SVGPVAE on the device vs the reference's forward_pass_SVGPVAE (:823-936) under the TF shim."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN
+    from test_host_logic import _GlueVAE, _glue_images
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    tag = "glue_geco" if geco else "glue_beta"
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=4)
+    _, s, _, _ = refs.make_pair("mnist", cfg, "cuda")
+    mu, var = cfg["y"].cuda().requires_grad_(True), cfg["noise"].cuda().requires_grad_(True)
+    r = pkg.forward_pass_SVGPVAE((_glue_images(256).cuda(), cfg["aux"].cuda()), beta=0.7, vae=_GlueVAE(mu, var), svgp=s, C_ma=0.3,
+                                 lagrange_mult=1.5, alpha=0.99, kappa=0.02, clipping_qs=True, GECO=geco,
+                                 epsilon=torch.from_numpy(gold["glue/epsilon"]).cuda())
+    for idx, key in ((0, "elbo"), (1, "recon_loss"), (13, "C_ma"), (14, "lagrange_mult")):
+        assert abs(float(r[idx]) - float(gold[tag + "/" + key][0])) < TOL * abs(float(gold[tag + "/" + key][0])), key
+    assert rel_err(r[12], torch.from_numpy(gold[tag + "/latent_samples"])) < TOL
+    g = torch.autograd.grad(r[0], [mu, var, s.inducing_index_points])
+    for t, n in zip(g, ("y", "noise", "Z")):
+        assert rel_err(t, torch.from_numpy(gold[tag + "/grad_" + n])) < TOL, n

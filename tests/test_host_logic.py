@@ -193,3 +193,54 @@ def test_titsias_branch_against_reference_source(oracle_backend):
     assert float(zero) == 0.0 and rel_err(L2, T("ball_titsias/L2")) < TOL
     L2.sum().backward()
     assert rel_err(y.grad, T("ball_titsias/grad_y")) < 5 * TOL and rel_err(nz.grad, T("ball_titsias/grad_noise")) < 5 * TOL
+
+
+class _GlueVAE:
+    dtype = torch.float64
+
+    def __init__(self, mu, var):
+        self.mu, self.var = mu, var
+
+    def encode(self, images):
+        return self.mu, self.var
+
+    def decode(self, z):
+        base = torch.linspace(-1.0, 1.0, 28 * 28, dtype=z.dtype, device=z.device).reshape(1, 28, 28, 1)
+        return torch.tanh(z.sum(1)).reshape(-1, 1, 1, 1) * base + 0.1 * z[:, :1].reshape(-1, 1, 1, 1)
+
+
+def _glue_images(b, dtype=torch.float64):
+    i = torch.arange(b, dtype=dtype).reshape(-1, 1, 1, 1)
+    base = torch.linspace(0.0, 1.0, 28 * 28, dtype=dtype).reshape(1, 28, 28, 1)
+    return torch.sin(0.1 * i + 3.0 * base)
+
+
+@pytest.mark.parametrize("geco", [False, True])
+def test_forward_pass_glue_against_reference_source(oracle_backend, geco):
+    """glue.forward_pass_SVGPVAE vs the reference's own forward_pass_SVGPVAE (:823-936) run under the TF shim."""
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    tag = "glue_geco" if geco else "glue_beta"
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=4)
+    _, s, _, _ = refs.make_pair("mnist", cfg, "cpu")
+    mu, var = cfg["y"].clone().requires_grad_(True), cfg["noise"].clone().requires_grad_(True)
+    r = pkg.forward_pass_SVGPVAE((_glue_images(256), cfg["aux"]), beta=0.7, vae=_GlueVAE(mu, var), svgp=s, C_ma=0.3,
+                                 lagrange_mult=1.5, alpha=0.99, kappa=0.02, clipping_qs=True, GECO=geco,
+                                 epsilon=torch.from_numpy(gold["glue/epsilon"]))
+    assert len(r) == 16
+    for idx, key in ((0, "elbo"), (1, "recon_loss"), (13, "C_ma"), (14, "lagrange_mult")):
+        assert abs(float(r[idx]) - float(gold[tag + "/" + key][0])) < TOL * abs(float(gold[tag + "/" + key][0])), key
+    assert rel_err(r[12], torch.from_numpy(gold[tag + "/latent_samples"])) < TOL
+    g = torch.autograd.grad(r[0], [mu, var, s.inducing_index_points])
+    for t, n in zip(g, ("y", "noise", "Z")):
+        assert rel_err(t, torch.from_numpy(gold[tag + "/grad_" + n])) < 5 * TOL, n
+
+
+def test_sprites_aux_data_against_reference_source():
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+
+    class Repr:
+        def repr_nn(self, images):
+            return images.reshape(images.shape[0], -1)[:, :16] * 2.0 + 0.5
+    action_ids = torch.tensor([3, 7, 1, 0, 5, 5, 2, 71, 9, 4, 6, 8])
+    aux = pkg.aux_data_SVGPVAE_sprites((_glue_images(12), action_ids), Repr(), [0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2], [5, 3, 4])
+    assert aux.shape == (12, 17) and rel_err(aux, torch.from_numpy(gold["sprites_aux/aux"])) < 1e-12
