@@ -39,6 +39,7 @@ def parse():
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="datapoints per GPU (default: the named workload)")
     ap.add_argument("--m", type=int, default=M_IND)
     ap.add_argument("--l", type=int, default=L_CH)
+    ap.add_argument("--mm-chunk", type=int, default=0, help="channels per chunk of the float64 M x M stage (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1024)
     return ap.parse_args()
@@ -213,7 +214,7 @@ def run_gpu(args):
         y_d.requires_grad_(True); nz_d.requires_grad_(True)
         for p in params:
             p.grad = None
-        res = svgp.elbo_step(aux_d, y_d, nz_d, group=group)
+        res = svgp.elbo_step(aux_d, y_d, nz_d, group=group, mm_chunk=args.mm_chunk or None, return_A_hat=False)
         # per-rank loss = local decoder stand-in + this rank's share of the replicated global scalar
         J = (gm * res["p_m"]).sum().double() + (gv * res["p_v"]).sum().double() + res["KL_term"] / world
         J.backward()
@@ -312,6 +313,10 @@ def run_gpu(args):
                          "kernel_ms": top_ms, "kernel_algorithmic_tflops": top_flops / (top_ms * 1e-3) / 1e12,
                          "step_algorithmic_tflops": f_alg / t_s / 1e12, "step_issued_tflops": 3 * f_alg / t_s / 1e12,
                          "step_frac_of_peak": 3 * f_alg / t_s / 1e12 / peak if peak else None, "e": 3,
+                         # what the tensor kernels of this implementation really issue per step: 2 SYRKs + 1 triangular row quad
+                         # (N M^2 L FLOP each) + the (2L+1)-matrix product of pass D, times e
+                         "step_tensor_flops_launched": 3 * (3.0 * L + 2.0 * (2 * L + 1)) * N * M * M,
+                         "step_tensor_tflops_launched": 3 * (3.0 * L + 2.0 * (2 * L + 1)) * N * M * M / t_s / 1e12,
                          "f16_cublas_tflops_in_run": f16_run},
             "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "kernels_calls": {k: v["calls"] for k, v in prof.items()},

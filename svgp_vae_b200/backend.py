@@ -227,6 +227,15 @@ class CudaBackend:
         self.launches += 2
         return Planes(hi, lo, inv)
 
+    def planes_into(self, S64, hi, lo, inv, at):
+        """svgp_split_f16 of a (b, M, M) float64 batch into rows [at, at + b) of preallocated plane buffers."""
+        S64 = _f64c(S64 if S64.is_contiguous() else S64.contiguous())
+        nb = S64.shape[0]
+        tmp = torch.empty(2 * nb, device=S64.device, dtype=torch.float32)      # [1/scale | abs-max scratch]
+        _call("svgp_split_f16", _ptr(S64), nb, S64[0].numel(), _ptr(hi[at:at + nb]), _ptr(lo[at:at + nb]), _ptr(tmp), _stream())
+        inv[at:at + nb] = tmp[:nb]
+        self.launches += 2
+
     def syrk(self, kop, W, impl=IMPL_AUTO, chunk_rows=0):
         W = _f32c(W)
         L = W.shape[1]
@@ -272,11 +281,17 @@ class CudaBackend:
         S64 = _f64c(S64 if S64.is_contiguous() else S64.contiguous())      # SIMT kernels read the float64 matrices directly
         return _ptr(S64), None, None, S64
 
-    def rowquad(self, kop, S64, tri=False, impl=IMPL_AUTO):
+    def rowquad(self, kop, S64, tri=False, impl=IMPL_AUTO, out=None):
+        """q[i, l] = k_i^T S_l k_i (or |T_l k_i|^2 for a triangular factor T_l); ``out``: an (N, L) fp32 view
+        with unit column stride to write into (e.g. a column slice of a wider matrix)."""
         L = (S64.hi if isinstance(S64, Planes) else S64).shape[0]
         use_tc = kop.tc and impl != IMPL_SIMT
         hi, lo, inv, keep = self._operand(S64, use_tc)
-        q = torch.empty((kop.N, L), device=kop.device, dtype=torch.float32)
+        if out is None:
+            q = torch.empty((kop.N, L), device=kop.device, dtype=torch.float32)
+        else:
+            q = out
+            assert q.is_cuda and q.dtype == torch.float32 and q.shape == (kop.N, L) and q.stride(1) == 1, (q.shape, q.stride())
         s = kop.struct()
         _call("svgp_rowquad", ctypes.byref(s), hi, lo, inv, L, int(bool(tri)), _ptr(q), q.stride(0),
               IMPL_TC if use_tc else IMPL_SIMT, _stream())

@@ -24,7 +24,7 @@ import math
 import torch
 
 from . import ops
-from .backend import get_backend
+from .backend import Planes, get_backend
 
 LOG_2PI = 1.8378770664093453      # utils.py:498
 LOG_2PI_RT = math.log(2.0 * math.pi)
@@ -40,18 +40,19 @@ def _world(group):
     return 1 if group is None else torch.distributed.get_world_size(group)
 
 
-def mm_stage(A, V, sums, K, jitter, c, b_total):
-    """Replicated float64 M x M stage (SVGPVAE_model.py:318-319, 328-331, 339-341, 264-279).
+def mm_shared(K, jitter):
+    """Channel-independent part of the M x M stage: (K + jI)^-1, its log-det and inverse Cholesky factor (:318-319)."""
+    M = K.shape[-1]
+    eye = torch.eye(M, dtype=K.dtype, device=K.device)
+    return ops.spd_inverse_logdet(K.unsqueeze(0) + jitter * eye)
 
-    A (L,M,M), V (L,M), sums (3,L) = [sum p kappa, sum p y^2, sum log noise], K (M,M).
-    Differentiable w.r.t. all four.  The jitter placement is the reference's: Sigma is built from the
-    un-jittered K and jittered before inversion; mu_hat / A_hat use the un-jittered K; Kinv is the
-    inverse of K + jI.
-    """
+
+def mm_channels(A, V, sums, K, Kinv_b, ldK, jitter, c, b_total):
+    """Per-channel part of the M x M stage for the channels held by A (Lc, M, M), V (Lc, M), sums (3, Lc)
+    (SVGPVAE_model.py:328-331, 339-341, 264-279).  Differentiable w.r.t. A, V, sums, K, Kinv_b, ldK."""
     L, M, _ = A.shape
     eye = torch.eye(M, dtype=A.dtype, device=A.device)
     Kb = K.unsqueeze(0)
-    Kinv_b, ldK, LinvK = ops.spd_inverse_logdet(Kb + jitter * eye)
     Sigma = Kb + c * A + jitter * eye
     S, _, Linv = ops.spd_inverse_logdet(Sigma)
     w = c * ops.bmv64(S, V)                                   # p_m = K_nm w
@@ -72,7 +73,44 @@ def mm_stage(A, V, sums, K, jitter, c, b_total):
     Aw = ops.bmv64(A, w)
     s_ppv = s_pk - s_ph + (S * A).sum((-1, -2))
     ce = -0.5 * (b_total * LOG_2PI + s_log + s_ppv + (w * Aw).sum(-1) - 2.0 * (w * V).sum(-1) + s_pyy)
-    return dict(S=S, w=w, Kinv=Kinv_b, Linv=Linv, LinvK=LinvK, recon=recon, kl=kl, ce=ce, mu_hat=mu_hat, A_hat=A_hat)
+    return dict(S=S, w=w, Linv=Linv, recon=recon, kl=kl, ce=ce, mu_hat=mu_hat, A_hat=A_hat)
+
+
+def mm_stage(A, V, sums, K, jitter, c, b_total):
+    """Replicated float64 M x M stage (SVGPVAE_model.py:318-319, 328-331, 339-341, 264-279).
+
+    A (L,M,M), V (L,M), sums (3,L) = [sum p kappa, sum p y^2, sum log noise], K (M,M).
+    Differentiable w.r.t. all four.  The jitter placement is the reference's: Sigma is built from the
+    un-jittered K and jittered before inversion; mu_hat / A_hat use the un-jittered K; Kinv is the
+    inverse of K + jI.
+    """
+    Kinv_b, ldK, LinvK = mm_shared(K, jitter)
+    mm = mm_channels(A, V, sums, K, Kinv_b, ldK, jitter, c, b_total)
+    mm.update(Kinv=Kinv_b, LinvK=LinvK)
+    return mm
+
+
+# autograd state of mm_channels: about this many (M, M) float64 matrices per channel stay alive between its
+# forward and backward (A, Sigma, S, KS, A_hat, its Cholesky factor, Kinv A_hat, Wm, products saved twice ...)
+_MM_LIVE_MATRICES = 16
+
+
+def mm_chunk_channels(L, M, device, override=None):
+    """Channels per chunk of the M x M stage.  One chunk (= the whole stage, fastest) whenever its autograd state
+    fits the budget; otherwise the stage runs chunk by chunk -- forward without a graph, re-materialised chunk by
+    chunk in the backward -- so that L x M x M float64 state is bounded (configs[4]: M = 4096, L = 128 is 17 GB per
+    (L, M, M) tensor)."""
+    if override:
+        return max(1, min(L, int(override)))
+    budget = 48e9
+    if device.type == "cuda":
+        budget = min(budget, 0.2 * torch.cuda.get_device_properties(device).total_memory)
+    per_channel = _MM_LIVE_MATRICES * 8.0 * M * M
+    if per_channel * L <= budget:
+        return L
+    lc = max(1, int(budget // per_channel))
+    nchunk = -(-L // lc)
+    return -(-L // nchunk)
 
 
 class _SVGPStep(torch.autograd.Function):
@@ -102,35 +140,65 @@ class _SVGPStep(torch.autograd.Function):
         b_total = float(count.item()) if group is not None else float(N)
         c = N_train / b_total
 
-        with torch.enable_grad():
-            leaves = [t.detach().requires_grad_(True) for t in (A, V, sums, Kmm.double())]
-            mm = mm_stage(leaves[0], leaves[1], leaves[2], leaves[3], jitter, c, b_total)
-
-        # pass B
-        S, w, Kinv, Linv = mm["S"].detach(), mm["w"].detach(), mm["Kinv"].detach(), mm["Linv"]
-        # quadratic forms through the Cholesky factors: |R^-1 k|^2 is a sum of squares (half the MMA work and
-        # no cancellation between the large entries of S_l / Kinv)
-        if cfg.get("tri", True):
-            h = be.rowquad(kop, mm["LinvK"], tri=True).squeeze(1)
-            q1 = be.rowquad(kop, Linv, tri=True)
+        lc = mm_chunk_channels(L, M, y32.device, cfg.get("mm_chunk"))
+        tri = cfg.get("tri", True)
+        K64 = Kmm.double()
+        if lc >= L:
+            with torch.enable_grad():
+                leaves = [t.detach().requires_grad_(True) for t in (A, V, sums, K64)]
+                mm = mm_stage(leaves[0], leaves[1], leaves[2], leaves[3], jitter, c, b_total)
+            # pass B
+            S, w, Kinv, Linv = mm["S"].detach(), mm["w"].detach(), mm["Kinv"].detach(), mm["Linv"]
+            # quadratic forms through the Cholesky factors: |R^-1 k|^2 is a sum of squares (half the MMA work and
+            # no cancellation between the large entries of S_l / Kinv)
+            if tri:
+                h = be.rowquad(kop, mm["LinvK"], tri=True).squeeze(1)
+                q1 = be.rowquad(kop, Linv, tri=True)
+            else:
+                h = be.rowquad(kop, Kinv).squeeze(1)
+                q1 = be.rowquad(kop, S)
+            recon, kl, ce0 = mm["recon"].detach().clone(), mm["kl"].detach().clone(), mm["ce"].detach()
+            mu_hat, A_hat = mm["mu_hat"].detach(), mm["A_hat"].detach()
         else:
-            h = be.rowquad(kop, Kinv).squeeze(1)
-            q1 = be.rowquad(kop, S)
+            # chunked M x M stage: no graph in the forward (the backward re-materialises it chunk by chunk); S is
+            # the only (L, M, M) result that stays (pass D reads it), the factors feed the row quads chunk by chunk
+            leaves, mm = (A, V, sums, K64), None
+            want_Ahat = cfg.get("return_A_hat", True)
+            S = torch.empty_like(A)
+            A_hat = torch.empty_like(A) if want_Ahat else None
+            w = torch.empty_like(V)
+            mu_hat = torch.empty_like(V)
+            recon, kl, ce0 = (torch.empty(L, dtype=torch.float64, device=A.device) for _ in range(3))
+            q1 = torch.empty((N, L), dtype=torch.float32, device=A.device)
+            with torch.no_grad():
+                Kinv, ldK, LinvK = mm_shared(K64, jitter)
+                h = (be.rowquad(kop, LinvK, tri=True) if tri else be.rowquad(kop, Kinv)).squeeze(1)
+                for l0 in range(0, L, lc):
+                    sl = slice(l0, min(L, l0 + lc))
+                    mc = mm_channels(A[sl], V[sl], sums[:, sl].contiguous(), K64, Kinv, ldK, jitter, c, b_total)
+                    S[sl], w[sl], mu_hat[sl] = mc["S"], mc["w"], mc["mu_hat"]
+                    recon[sl], kl[sl], ce0[sl] = mc["recon"], mc["kl"], mc["ce"]
+                    if want_Ahat:
+                        A_hat[sl] = mc["A_hat"]
+                    be.rowquad(kop, mc["Linv"] if tri else mc["S"], tri=tri, out=q1[:, sl])
+                    del mc
         pm = be.gemm_nn(kop, w.float().contiguous())
         pv, clipsum, mask = be.predictive(kappa, h, q1, p, clip)
-        ce = mm["ce"].detach().clone()
+        ce = ce0.clone()
         if clip:
             _allreduce(clipsum, group)
             ce = ce - 0.5 * clipsum
 
-        ctx.cfg, ctx.kop, ctx.mm, ctx.leaves = cfg, kop, mm, leaves
+        ctx.cfg, ctx.kop, ctx.mm, ctx.leaves, ctx.lc = cfg, kop, mm, leaves, lc
         ctx.b_total, ctx.c = b_total, c
         ctx.save_for_backward(Fx32, Fz32, hyp32, y32, n32, p, kappa, h, pv, q1 if clip else pv, mask if clip else pv, S, w, Kinv)
         ctx.in_dtypes = (Fx.dtype, Fz.dtype, hyp.dtype, y.dtype, noise.dtype)
         out_dt = y.dtype
-        mu_hat, A_hat = mm["mu_hat"].detach(), mm["A_hat"].detach()
-        ctx.mark_non_differentiable(mu_hat, A_hat)
-        return pm.to(out_dt), pv.to(out_dt), mm["recon"].detach().clone(), mm["kl"].detach().clone(), ce, mu_hat, A_hat
+        if A_hat is None:
+            ctx.mark_non_differentiable(mu_hat)
+        else:
+            ctx.mark_non_differentiable(mu_hat, A_hat)
+        return pm.to(out_dt), pv.to(out_dt), recon, kl, ce, mu_hat, A_hat
 
     @staticmethod
     def backward(ctx, g_pm, g_pv, g_recon, g_kl, g_ce, _g_mu, _g_Ahat):
@@ -173,16 +241,61 @@ class _SVGPStep(torch.autograd.Function):
 
         # ---- adjoint of the replicated M x M stage -----------------------------------------------
         A_, V_, sums_, K_ = ctx.leaves
-        gA, gV, gsums, gK = torch.autograd.grad(
-            [mm["S"], mm["w"], mm["Kinv"], mm["recon"], mm["kl"], mm["ce"]], [A_, V_, sums_, K_],
-            grad_outputs=[G_S, G_w, G_Kinv, g_recon, g_kl, g_ce], allow_unused=True)
-        gsums = torch.zeros_like(sums_) if gsums is None else gsums
+        lc = ctx.lc
+        if lc >= L:
+            gA, gV, gsums, gK = torch.autograd.grad(
+                [mm["S"], mm["w"], mm["Kinv"], mm["recon"], mm["kl"], mm["ce"]], [A_, V_, sums_, K_],
+                grad_outputs=[G_S, G_w, G_Kinv, g_recon, g_kl, g_ce], allow_unused=True)
+            gsums = torch.zeros_like(sums_) if gsums is None else gsums
+            # ---- pass D: back to the rows --------------------------------------------------------
+            # dK_nm and k^T (dA + dA^T) k from ONE pass over the products K G_s: stacked matrices
+            # [dA + dA^T ; S ; Kinv] with per-row weights [p | 2 dq1 | 2 dh] applied in the epilogue
+            Gstack = torch.cat([gA + gA.transpose(-1, -2), S, Kinv], dim=0).contiguous()
+            del gA
+        else:
+            # re-materialise the stage chunk by chunk; every chunk's dA_l + dA_l^T goes straight into the operand
+            # planes of pass D, so no second (L, M, M) float64 tensor is alive next to A, S and G_S
+            jitter, c, b_total = cfg["jitter"], ctx.c, ctx.b_total
+            if kop.tc:
+                hi = torch.empty((2 * L + 1, M, M), dtype=torch.float16, device=dev)
+                lo = torch.empty_like(hi)
+                inv = torch.empty(2 * L + 1, dtype=torch.float32, device=dev)
+                put = lambda X, at: be.planes_into(X, hi, lo, inv, at)
+            else:
+                G64 = torch.empty((2 * L + 1, M, M), dtype=torch.float64, device=dev)
 
-        # ---- pass D: back to the rows ------------------------------------------------------------
-        # dK_nm and k^T (dA + dA^T) k from ONE pass over the products K G_s: stacked matrices
-        # [dA + dA^T ; S ; Kinv] with per-row weights [p | 2 dq1 | 2 dh] applied in the epilogue
+                def put(X, at):
+                    G64[at:at + X.shape[0]] = X
+            gV, gsums = torch.empty_like(V_), torch.empty_like(sums_)
+            with torch.enable_grad():
+                K_leaf = K_.detach().requires_grad_(True)
+                Kinv_g, ldK_g, _ = mm_shared(K_leaf, jitter)
+            gK = torch.zeros_like(K_)
+            gKinv = G_Kinv.clone()
+            gldK = torch.zeros_like(ldK_g)
+            for l0 in range(0, L, lc):
+                sl = slice(l0, min(L, l0 + lc))
+                with torch.enable_grad():
+                    lv = [t.detach().requires_grad_(True) for t in (A_[sl], V_[sl], sums_[:, sl].contiguous(), K_, Kinv_g, ldK_g)]
+                    mc = mm_channels(*lv, jitter, c, b_total)
+                g = torch.autograd.grad([mc["S"], mc["w"], mc["recon"], mc["kl"], mc["ce"]], lv,
+                                        grad_outputs=[G_S[sl], G_w[sl], g_recon[sl], g_kl[sl], g_ce[sl]], allow_unused=True)
+                del mc, lv
+                put(g[0] + g[0].transpose(-1, -2), l0)
+                gV[sl] = g[1]
+                gsums[:, sl] = g[2] if g[2] is not None else 0.0
+                gK += g[3]
+                gKinv += g[4]
+                gldK += g[5]
+                del g
+            (gK_sh,) = torch.autograd.grad([Kinv_g, ldK_g], [K_leaf], grad_outputs=[gKinv, gldK])
+            gK += gK_sh
+            del G_S, gKinv
+            for l0 in range(0, L, lc):
+                put(S[l0:l0 + lc], L + l0)
+            put(Kinv, 2 * L)
+            Gstack = Planes(hi, lo, inv) if kop.tc else G64
         Wstack = torch.cat([p, 2.0 * G_q1, (-2.0 * G_kappa)[:, None]], dim=1).contiguous()
-        Gstack = torch.cat([gA + gA.transpose(-1, -2), S, Kinv], dim=0).contiguous()
         G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
         del Wstack, Gstack
         py = p * y
@@ -222,7 +335,7 @@ class _SVGPStep(torch.autograd.Function):
 
 
 def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, group=None, tc=None, tri=True,
-              chunk_rows=0):
+              chunk_rows=0, mm_chunk=None, return_A_hat=True):
     """All-channel SVGP step on one shard of datapoints.
 
     Fx (N, d) data features, Fz (M, d) inducing features, hyp (4,) kernel hypers, y / noise (N, L)
@@ -231,11 +344,13 @@ def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, gro
 
     Returns dict(p_m, p_v (N, L); recon_l, kl_l, ce_l (L,) float64 -- GLOBAL sums, identical on all
     ranks; mu_hat (L, M), A_hat (L, M, M) float64, detached).
+    ``mm_chunk``: channels per chunk of the float64 M x M stage (default: one chunk while its state fits, see
+    mm_chunk_channels); ``return_A_hat=False`` skips the (L, M, M) A_hat output on the chunked path.
     Gradient convention when sharded: make each rank's loss ``local terms + global terms / world``;
     gradients of replicated parameters then come out as per-rank partial sums (sum them).
     """
     cfg = dict(spec=spec, N_train=float(N_train), jitter=float(jitter), clip_pv=clip_pv, group=group, tc=tc, tri=tri,
-               chunk_rows=chunk_rows)
+               chunk_rows=chunk_rows, mm_chunk=mm_chunk, return_A_hat=return_A_hat)
     pm, pv, recon, kl, ce, mu_hat, A_hat = _SVGPStep.apply(Fx, Fz, hyp, y, noise, cfg)
     return dict(p_m=pm, p_v=pv, recon_l=recon, kl_l=kl, ce_l=ce, mu_hat=mu_hat, A_hat=A_hat)
 

@@ -92,12 +92,17 @@ class OracleBackend:
     def gemm_nn(self, kop, Wm):
         return (kop.value().to(F64) @ Wm.to(F64).t()).float()
 
-    def rowquad(self, kop, S64, tri=False, impl=0):
+    def rowquad(self, kop, S64, tri=False, impl=0, out=None):
         K = kop.value().to(F64)
         if tri:
             T = torch.einsum('ia,lca->ilc', K, S64)
-            return (T * T).sum(-1).float()
-        return torch.einsum('ia,lab,ib->il', K, S64, K).float()
+            q = (T * T).sum(-1).float()
+        else:
+            q = torch.einsum('ia,lab,ib->il', K, S64, K).float()
+        if out is not None:
+            out.copy_(q)
+            return out
+        return q
 
     def scaled_gemm(self, kop, W, G64, out=None, ndot=0, impl=0):
         K = kop.value().to(F64)

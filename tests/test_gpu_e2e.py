@@ -74,6 +74,23 @@ def test_sweep_small(cuda_backend, tc):
     _check("sweep", configs.sweep_inputs(2304, 200, 3), tc=tc)
 
 
+@pytest.mark.parametrize("tc", [False, True])
+def test_chunked_mm_stage_matches_one_chunk(cuda_backend, tc):
+    """Channel-chunked float64 M x M stage (memory plan of configs[4]: M = 4096, L = 128) against the one-chunk
+    stage on the same kernels: identical factorisations per channel, so only the order of a few float64 sums differs."""
+    cfg = configs.sweep_inputs(4096, 256, 6)
+    o, s, op, sp = refs.make_pair("sweep", cfg, "cuda")
+    args = (cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda())
+    r0, J0, g0 = refs.product_objective(s, sp, *args, tc=tc)
+    r1, J1, g1 = refs.product_objective(s, sp, *args, tc=tc, mm_chunk=4)          # chunks of 4 + 2 channels
+    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "mu_hat", "A_hat"):
+        assert rel_err(r1[k], r0[k]) < 1e-6, k
+    for a, b in zip(g0, g1):
+        assert rel_err(b, a) < 1e-6
+    r2 = s.elbo_step(*args, tc=tc, mm_chunk=4, return_A_hat=False)
+    assert r2["A_hat"] is None and rel_err(r2["p_v"], r0["p_v"]) < 1e-6
+
+
 def test_sweep_subsample_tc_vs_streamlined(cuda_backend):
     """N = 16384, M = 256, L = 4 on the tcgen05 path against the streamlined float64 oracle (the literal form
     would need a 16384 x 256 x 256 tensor per channel)."""

@@ -50,6 +50,23 @@ def test_step_sweep_kernel(oracle_backend):
     _check("sweep", configs.sweep_inputs(500, 48, 3))
 
 
+@pytest.mark.parametrize("mm_chunk", [1, 2, 3])
+def test_step_chunked_mm_stage(oracle_backend, mm_chunk):
+    """The channel-chunked float64 M x M stage (no graph in the forward, re-materialised chunk by chunk in the
+    backward -- the memory plan of configs[4], M = 4096, L = 128) gives the same step as the one-chunk stage,
+    including a ragged last chunk (L = 5)."""
+    cfg = configs.sweep_inputs(300, 40, 5)
+    o, s, op, sp = refs.make_pair("sweep", cfg, "cpu")
+    r0, J0, g0 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"])
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"], mm_chunk=mm_chunk)
+    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "mu_hat", "A_hat"):
+        assert rel_err(r1[k], r0[k]) < 1e-10, k
+    for a, b in zip(g0, g1):
+        assert rel_err(b, a) < 1e-10
+    r2 = s.elbo_step(cfg["aux"], cfg["y"], cfg["noise"], mm_chunk=mm_chunk, return_A_hat=False)
+    assert r2["A_hat"] is None and rel_err(r2["p_v"], r0["p_v"]) < 1e-10
+
+
 def test_per_channel_api_matches_reference_signature(oracle_backend):
     cfg = configs.mnist_inputs(MNIST_FIXTURE, L=2)
     o, s, op, sp = refs.make_pair("mnist", cfg, "cpu")
