@@ -284,9 +284,9 @@ def run_gpu(args):
         # dominant kernel of the step = the entry point with the largest total device time; its launch = the longest call
         top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("", {"ms": float("nan"), "calls": 0, "max_ms": float("nan")})
         top_name, top_ms = top[0], top[1]["max_ms"]
-        # algorithmic FLOPs of that launch (2 x MACs): scaled_gemm = 2L+1 full N x M x M products; syrk = lower triangle
+        # algorithmic FLOPs of that launch (2 x MACs): scaled_gemm = 2L full N x M x M products; syrk = lower triangle
         # of L products N x M x M; rowquad (triangular factor) = half of L full products
-        kern_alg = {"svgp_scaled_gemm": 2.0 * N * M * M * (2 * L + 1), "svgp_syrk": 1.0 * N * M * M * L,
+        kern_alg = {"svgp_scaled_gemm": 2.0 * N * M * M * (2 * L), "svgp_syrk": 1.0 * N * M * M * L,
                     "svgp_rowquad": 1.0 * N * M * M * L}
         top_flops = kern_alg.get(top_name, float("nan"))
         # DRAM bytes of one launch of that kernel from the committed ncu capture of this exact workload (else null)
@@ -314,9 +314,9 @@ def run_gpu(args):
                          "step_algorithmic_tflops": f_alg / t_s / 1e12, "step_issued_tflops": 3 * f_alg / t_s / 1e12,
                          "step_frac_of_peak": 3 * f_alg / t_s / 1e12 / peak if peak else None, "e": 3,
                          # what the tensor kernels of this implementation really issue per step: 2 SYRKs + 1 triangular row quad
-                         # (N M^2 L FLOP each) + the (2L+1)-matrix product of pass D, times e
-                         "step_tensor_flops_launched": 3 * (3.0 * L + 2.0 * (2 * L + 1)) * N * M * M,
-                         "step_tensor_tflops_launched": 3 * (3.0 * L + 2.0 * (2 * L + 1)) * N * M * M / t_s / 1e12,
+                         # (N M^2 L FLOP each) + the 2L-matrix product of pass D, times e
+                         "step_tensor_flops_launched": 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M,
+                         "step_tensor_tflops_launched": 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M / t_s / 1e12,
                          "f16_cublas_tflops_in_run": f16_run},
             "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "kernels_calls": {k: v["calls"] for k, v in prof.items()},

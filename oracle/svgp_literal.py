@@ -38,7 +38,7 @@ def as64(x):
 def add_jitter(mat, jitter):
     """SVGPVAE_model.py:13-14 (set_diag(A, diag(A) + j))."""
     m = mat.shape[-1]
-    return mat + jitter * torch.eye(m, dtype=mat.dtype)
+    return mat + jitter * torch.eye(m, dtype=mat.dtype, device=mat.device)
 
 
 def recip_no_nan(x):

@@ -254,6 +254,131 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
   }
 }
 
+// Planes-only builder (the tcgen05 consumers' operand format: scaled fp16 hi/lo of K and of its datapoint-blocked
+// transpose).  HBM-write bound: 8 bytes leave the SM per kernel entry.  The 64 x 64 tile is kept in shared memory as
+// packed {hi, lo} words (pitch 65: conflict-free for the column-per-lane writes and for both read-outs below) and
+// every thread leaves with 16-byte stores -- 8 consecutive columns of a row of Kh / Kl, 8 consecutive datapoints of
+// a row of Kth / Ktl.  SE44 = product of two 4-feature SE factors (the SWEEP kernel): inducing features live in
+// registers, datapoint features are broadcast float4 loads, both factors share one ex2.
+template <bool SE44>
+__global__ void __launch_bounds__(THREADS) kernel_fwd_planes_kernel(
+    const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz, int64_t M,
+    Spec sp, const float* __restrict__ hyp, __half* __restrict__ Kh, __half* __restrict__ Kl, int64_t ldkh,
+    __half* __restrict__ Kth, __half* __restrict__ Ktl, int64_t ldkt, float* __restrict__ kscale) {
+  extern __shared__ float smem[];
+  const int d = sp.da + sp.db;
+  const int dpx = SE44 ? 8 : (d | 1), dpz = d | 1;
+  float* xs = smem;                                   // [TILE][dpx]   (16-byte aligned rows when SE44)
+  float* zs = xs + TILE * (SE44 ? 8 : dpz);           // [TILE][dpz]
+  uint32_t* tile = reinterpret_cast<uint32_t*>(zs + TILE * dpz);   // [TILE][TILE + 1] packed {hi | lo << 16}
+  float* nxa = reinterpret_cast<float*>(tile + TILE * (TILE + 1));
+  float* nxb = nxa + TILE;
+  float* nza = nxb + TILE;
+  float* nzb = nza + TILE;
+  constexpr int P = TILE + 1;
+  const Hyp h = load_hyp(hyp);
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int64_t ntiles_r = (N + TILE - 1) / TILE;
+  const float scale = plane_scale(sp, h, kscale);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { kscale[0] = scale; kscale[1] = 1.0f / scale; }
+
+  load_features(Fz, ldz, col0, M, d, dpz, sp, zs, nza, nzb);
+  const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;   // compute phase: one column, 16 rows per thread
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k4 = lane & 3, sub = lane >> 2;                   // read-out phase: 4 lanes x 8 entries = 32 entries
+  float zr[8];
+  float ca = 0.f, cb = 0.f, amp2s = 0.f;
+  if (SE44) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f) zr[f] = zs[c * dpz + f];
+    const float LOG2E = 1.4426950408889634f;
+    ca = -0.5f * LOG2E / (h.len_a * h.len_a);
+    cb = -0.5f * LOG2E / (h.len_b * h.len_b);
+    amp2s = h.amp_a * h.amp_a * h.amp_b * h.amp_b * scale;
+  }
+  const bool vec_rows = (ldkh % 8) == 0 && ((reinterpret_cast<uintptr_t>(Kh) | reinterpret_cast<uintptr_t>(Kl)) & 15) == 0;
+  const bool vec_cols = (ldkt % 8) == 0 && ((reinterpret_cast<uintptr_t>(Kth) | reinterpret_cast<uintptr_t>(Ktl)) & 15) == 0;
+
+  for (int64_t rt = blockIdx.y; rt < ntiles_r; rt += gridDim.y) {
+    const int64_t row0 = rt * TILE;
+    load_features(Fx, ldx, row0, N, d, dpx, sp, xs, nxa, nxb);
+#pragma unroll 4
+    for (int j = 0; j < TILE / 4; ++j) {
+      const int r = rg + 4 * j;
+      float vs;
+      if (SE44) {
+        const float4 xa = *reinterpret_cast<const float4*>(xs + r * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + r * 8 + 4);
+        float t, ra, rb;
+        t = xa.x - zr[0]; ra = t * t;
+        t = xa.y - zr[1]; ra = fmaf(t, t, ra);
+        t = xa.z - zr[2]; ra = fmaf(t, t, ra);
+        t = xa.w - zr[3]; ra = fmaf(t, t, ra);
+        t = xb.x - zr[4]; rb = t * t;
+        t = xb.y - zr[5]; rb = fmaf(t, t, rb);
+        t = xb.z - zr[6]; rb = fmaf(t, t, rb);
+        t = xb.w - zr[7]; rb = fmaf(t, t, rb);
+        vs = amp2s * exp2f(fmaf(ca, ra, cb * rb));
+      } else {
+        const float ka = factor_value(sp.ta, xs + r * dpx, zs + c * dpz, sp.da, h.amp_a, h.len_a, nxa[r], nza[c]);
+        const float kb = factor_value(sp.tb, xs + r * dpx + sp.da, zs + c * dpz + sp.da, sp.db, h.amp_b, h.len_b, nxb[r], nzb[c]);
+        vs = ka * kb * scale;
+      }
+      if (row0 + r >= N) vs = 0.f;                    // datapoints past N are zero in the blocked transpose
+      const __half hi = __float2half_rn(vs);
+      const __half lo = __float2half_rn(vs - __half2float(hi));
+      tile[r * P + c] = (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+    }
+    __syncthreads();
+    // read-out: a warp covers 8 tile rows (or columns) x 32 entries; bank = (line + 8 k4 + i) mod 32 -> conflict-free
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t w[8];
+      {   // Kh / Kl: row r, columns e0 .. e0 + 7
+        const int r = warp * 8 + sub, e0 = half * 32 + k4 * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = tile[r * P + e0 + i];
+        const int64_t gr = row0 + r, gc = col0 + e0;
+        if (gr < N && gc < M) {
+          const int64_t o = gr * ldkh + gc;
+          if (vec_rows && gc + 8 <= M) {
+            *reinterpret_cast<uint4*>(Kh + o) = make_uint4(__byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410),
+                                                           __byte_perm(w[4], w[5], 0x5410), __byte_perm(w[6], w[7], 0x5410));
+            *reinterpret_cast<uint4*>(Kl + o) = make_uint4(__byte_perm(w[0], w[1], 0x7632), __byte_perm(w[2], w[3], 0x7632),
+                                                           __byte_perm(w[4], w[5], 0x7632), __byte_perm(w[6], w[7], 0x7632));
+          } else {
+            for (int i = 0; i < 8 && gc + i < M; ++i) {
+              Kh[o + i] = __ushort_as_half((unsigned short)(w[i] & 0xffffu));
+              Kl[o + i] = __ushort_as_half((unsigned short)(w[i] >> 16));
+            }
+          }
+        }
+      }
+      {   // Kth / Ktl: column cc, datapoints e0 .. e0 + 7 of this 64-datapoint block (block stride ldkt)
+        const int cc = warp * 8 + sub, e0 = half * 32 + k4 * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = tile[(e0 + i) * P + cc];
+        const int64_t gc = col0 + cc;
+        if (gc < M) {
+          const int64_t o = rt * ldkt + gc * TILE + e0;
+          if (vec_cols) {
+            *reinterpret_cast<uint4*>(Kth + o) = make_uint4(__byte_perm(w[0], w[1], 0x5410), __byte_perm(w[2], w[3], 0x5410),
+                                                            __byte_perm(w[4], w[5], 0x5410), __byte_perm(w[6], w[7], 0x5410));
+            *reinterpret_cast<uint4*>(Ktl + o) = make_uint4(__byte_perm(w[0], w[1], 0x7632), __byte_perm(w[2], w[3], 0x7632),
+                                                            __byte_perm(w[4], w[5], 0x7632), __byte_perm(w[6], w[7], 0x7632));
+          } else {
+            for (int i = 0; i < 8; ++i) {
+              Kth[o + i] = __ushort_as_half((unsigned short)(w[i] & 0xffffu));
+              Ktl[o + i] = __ushort_as_half((unsigned short)(w[i] >> 16));
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // backward.  Two passes over the same tiles so that neither needs float atomics on N-sized data:
 //   pass X: one block per row tile walks every column tile      -> dFx rows (plain stores)
@@ -563,6 +688,17 @@ int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, in
   if (gy < 1) gy = 1;
   if (gy > 65535) gy = 65535;
   dim3 grid((unsigned)ntc, (unsigned)gy);
+  if (!K && Kh && Kth) {
+    // the tcgen05 consumers' operand format only: vectorised builder
+    const bool se44 = type_a == SVGP_K_SE && type_b == SVGP_K_SE && dim_a == 4 && dim_b == 4;
+    if (se44)
+      kernel_fwd_planes_kernel<true><<<grid, THREADS, fwd_smem(dim_a + dim_b), st>>>(
+          Fx, ldx, N, Fz, ldz, M, sp, hyp, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
+    else
+      kernel_fwd_planes_kernel<false><<<grid, THREADS, fwd_smem(dim_a + dim_b), st>>>(
+          Fx, ldx, N, Fz, ldz, M, sp, hyp, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
+    return check_launch("svgp_kernel_fwd(planes)");
+  }
   kernel_fwd_kernel<<<grid, THREADS, fwd_smem(dim_a + dim_b), st>>>(
       Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
   return check_launch("svgp_kernel_fwd");

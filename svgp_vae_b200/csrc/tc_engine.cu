@@ -254,6 +254,9 @@ struct TcParams {
   int accumulate;
   float* dots;                // (N, lddots) or null
   int64_t lddots, ndot;
+  int kseg, kseg2;            // k-blocks per MMA chain (0 = the whole reduction in one chain) for the matrices with a
+                              // k-dot (< ndot) / without: the reduction over M is cut into segments that the epilogue
+                              // folds with round-to-nearest FMAs (see "work decomposition")
   int64_t n_items;
 };
 
@@ -361,11 +364,30 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   // into sub-tiles that the epilogue folds with ordinary round-to-nearest adds.
   //   SYRK    item = (tile pair, channel)      sub = chunk of `chunk_rows` datapoints  -> double tile in L2
   //   QUAD    item = (row tile, channel)       sub = column tile of B_l                -> row sum in a register
-  //   SCALED  item = (row tile, column tile)   sub = one stacked matrix                -> tile sum in registers
+  //   SCALED  item = (row tile, column tile)   sub = (stacked matrix, k-segment)       -> tile sum in registers
   const int64_t M = P.M;
   const int64_t Mc = (MODE == MODE_SCALED) ? P.Mc : M;          // output columns (rows of one B matrix)
   const int nct = (int)((Mc + BN - 1) / BN);
   const int kb_full = (int)((M + BK - 1) / BK);
+  const int ksegA = (MODE == MODE_SCALED && P.kseg > 0 && P.kseg < kb_full) ? P.kseg : kb_full;
+  const int ksegB = (MODE == MODE_SCALED && P.kseg2 > 0 && P.kseg2 < kb_full) ? P.kseg2 : kb_full;
+  const int nsegA = (kb_full + ksegA - 1) / ksegA, nsegB = (kb_full + ksegB - 1) / ksegB;
+  const int nsubA = (MODE == MODE_SCALED) ? (int)P.ndot * nsegA : 0;      // sub-tiles of the matrices that carry a k-dot
+  struct SubInfo { int mat, k0, nkb; bool last; };
+  // SCALED: sub -> (stacked matrix, first k-block and length of this segment of its reduction, last segment?)
+  auto scaled_sub = [&](int sub) -> SubInfo {
+    SubInfo r;
+    int seg;
+    if (sub < nsubA) {
+      r.mat = sub / nsegA; seg = sub - r.mat * nsegA;
+      r.k0 = seg * ksegA; r.nkb = kb_full - r.k0 < ksegA ? kb_full - r.k0 : ksegA; r.last = seg == nsegA - 1;
+    } else {
+      const int t = sub - nsubA, m = t / nsegB;
+      r.mat = (int)P.ndot + m; seg = t - m * nsegB;
+      r.k0 = seg * ksegB; r.nkb = kb_full - r.k0 < ksegB ? kb_full - r.k0 : ksegB; r.last = seg == nsegB - 1;
+    }
+    return r;
+  };
 
   struct Item { int64_t l, itile, n0, n1; int a_row0, b_row0, tile; bool half_tile; };
   auto decode = [&](int64_t item) -> Item {
@@ -400,7 +422,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   auto item_subtiles = [&](const Item& it) -> int {
     if (MODE == MODE_SYRK) return (int)((it.n1 - it.n0 + P.chunk_rows - 1) / P.chunk_rows);
     if (MODE == MODE_QUAD) return nct;
-    return (int)P.L;
+    return nsubA + ((int)P.L - (int)P.ndot) * nsegB;      // SCALED: sub = (matrix, k-segment)
   };
   auto subtile_kblocks = [&](const Item& it, int sub) -> int {
     if (MODE == MODE_SYRK) {
@@ -412,7 +434,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
       int64_t kend = (int64_t)(sub + 1) * BN < M ? (int64_t)(sub + 1) * BN : M;
       return (int)((kend + BK - 1) / BK);
     }
-    return kb_full;
+    return scaled_sub(sub).nkb;
   };
 
   auto role_producer = [&]() {
@@ -433,7 +455,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
             } else if (MODE == MODE_QUAD) {
               ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)(it.l * M + (int64_t)sub * BN);
             } else {
-              ak = kb * BK; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)sub * Mc + it.b_row0);
+              const SubInfo si = scaled_sub(sub);
+              ak = (si.k0 + kb) * BK; ar = it.a_row0; bk = ak; br = (int32_t)((int64_t)si.mat * Mc + it.b_row0);
             }
             if (MODE == MODE_SYRK) {
               // datapoint-blocked transposed planes [n / 64][m][n % 64]: a box is one contiguous run of rows.
@@ -658,11 +681,14 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
           for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
+        float dsum = 0.f;
         for (int sub = 0; sub < nsub; ++sub) {
-          const float bs = P.binv[sub];
-          const float wgt = live ? (P.W ? P.W[i * P.ldw + sub] : 1.f) * inv_ks * bs : 0.f;
-          const bool want_dot = (P.dots != nullptr) && (sub < P.ndot) && live;
-          float dsum = 0.f;
+          const SubInfo si = scaled_sub(sub);
+          const int mat = si.mat;                                  // stacked matrix; this sub-tile = one k-segment of its reduction
+          const float bs = P.binv[mat];
+          const float wgt = live ? (P.W ? P.W[i * P.ldw + mat] : 1.f) * inv_ks * bs : 0.f;
+          const bool want_dot = (P.dots != nullptr) && (mat < P.ndot) && live;
+          if (si.k0 == 0) dsum = 0.f;
           mbar_wait(tmem_full(acc), acc_phase);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
@@ -684,7 +710,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(acc));
           if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
-          if (want_dot) atomicAdd(&P.dots[i * P.lddots + sub], dsum * inv_ks * inv_ks * bs);
+          if (want_dot && si.last) atomicAdd(&P.dots[i * P.lddots + mat], dsum * inv_ks * inv_ks * bs);
         }
         if (live) {
 #pragma unroll
@@ -892,15 +918,13 @@ static int tc_bk() {
   return bk;
 }
 
-// chunks folded in fp32 registers between two float64 write-backs of a SYRK tile (16 x 2048 rows by default:
-// sqrt(16) half-ulp random error per group, groups are summed in float64); SVGP_SYRK_FLUSH overrides.
-static int syrk_flush_every() {
-  static int f = 0;
-  if (!f) {
-    const char* e = getenv("SVGP_SYRK_FLUSH");
-    f = (e && atoi(e) > 0) ? atoi(e) : 16;
-  }
-  return f;
+// chunks folded in fp32 registers (round-to-nearest adds) between two float64 write-backs of a SYRK tile: one
+// write-back per 32768 datapoints whatever the chain length; SVGP_SYRK_FLUSH overrides (in chunks).
+static int syrk_flush_every(int64_t chunk) {
+  const char* e = getenv("SVGP_SYRK_FLUSH");
+  if (e && atoi(e) > 0) return atoi(e);
+  int64_t f = 32768 / chunk;
+  return f < 1 ? 1 : (int)f;
 }
 
 template <int MODE, int BN, int BK, int STAGES, int CL>
@@ -983,14 +1007,16 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
   TcParams P{};
   P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = winv;
   P.Wt = Wt; P.ldwt = ldwt; P.A = A; P.locks = locks;
-  // one accumulation chain = chunk / 16 k-steps x 3 MMAs; 2048 rows -> 384 MMAs (truncation bias ~1e-5 worst case)
-  int64_t chunk = chunk_rows > 0 ? chunk_rows : 2048;
+  // one accumulation chain = chunk / 16 k-steps x 3 MMAs.  The tensor core accumulates with truncation: measured on
+  // A_l (all terms positive) the bias is -1.8e-7 x chunk / 1024 of the largest entry (tools/accum_probe.py), and S_l =
+  // (K + c A_l + J)^-1 amplifies it by the condition number.  512 rows = 96 MMAs per chain costs ~3 % of SYRK time.
+  int64_t chunk = chunk_rows > 0 ? chunk_rows : 512;
   chunk = (chunk + 63) / 64 * 64;
   P.chunk_rows = chunk;
   P.sc_rows = syrk_superchunk_rows(kop->M, chunk);
   P.nsc = (int)ceil_div(kop->N, P.sc_rows);
   P.ntile = syrk_tile_count(kop->M, BN);
-  P.flush_every = syrk_flush_every();
+  P.flush_every = syrk_flush_every(chunk);
   { const char* e = getenv("SVGP_TC_DEBUG"); P.debug = e ? atoi(e) : 0; }
   P.n_items = (int64_t)P.nsc * P.ntile * L;
   if (cudaMemsetAsync(locks, 0, sizeof(int) * tc_syrk_lock_words(kop->M, L), st) != cudaSuccess) return check_launch("svgp_syrk(locks)");
@@ -1056,6 +1082,11 @@ int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void*
   P.K_hi = (const __half*)kop->Kh; P.K_lo = (const __half*)kop->Kl; P.ldkh = kop->ldkh;
   P.W = W; P.ldw = ldw; P.out = out; P.ldo = ldo; P.accumulate = accumulate;
   P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
+  // chain length: the tensor core accumulates with truncation (a bias of ~n 2^-24 after n MMAs, relative to the LARGEST
+  // partial sum of the chain -- and K G_s cancels by 1e3..1e4 against the entries of S_l).  4 k-blocks = 48 MMAs per
+  // chain; the segments are folded in fp32 registers with round-to-nearest FMAs.  SVGP_SCALED_KSEG overrides (0 = one chain).
+  { const char* e = getenv("SVGP_SCALED_KSEG"); P.kseg = e ? atoi(e) : 4 * 64 / bk; }
+  { const char* e = getenv("SVGP_SCALED_KSEG2"); P.kseg2 = e ? atoi(e) : P.kseg; }
   P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(Mc, BN);
   return dispatch_tc<MODE_SCALED>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");
 }

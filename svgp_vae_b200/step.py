@@ -11,7 +11,7 @@ two methods it calls per channel (approximate_posterior_params :303-343, variati
   [decoder / caller]
   pass C   adjoints of p_m, p_v: weighted SYRK + skinny GEMM -> all-reduce -> adjoint of the
            M x M stage (torch autograd over ops.bmm64 / spd_inverse_logdet / spd_logdet)
-  pass D   dK_nm = sum_s diag(w_s) K_nm G_s over the 2L+1 stacked matrices [dA+dA^T ; S ; Kinv] and the
+  pass D   dK_nm = sum_s diag(w_s) K_nm G_s over the 2L stacked matrices [dA+dA^T ; S - Kinv] and the
            row-dots k_i^T dA_l k_i from the same tcgen05 products (weights and dots live in the epilogue),
            then K1's adjoint into features / inducing points / hypers.
 
@@ -235,9 +235,13 @@ class _SVGPStep(torch.autograd.Function):
         G_kappa = G_q1.sum(1)                                    # d/d kappa_i  (and -d/d h_i)
         G_S = be.syrk(kop, G_q1, chunk_rows=cfg.get("chunk_rows", 0))
         G_w = be.gemm_tn(kop, g_pm)
-        G_Kinv = be.syrk(kop, (-G_kappa)[:, None].contiguous())
-        for t in (G_S, G_w, G_Kinv):
+        for t in (G_S, G_w):
             _allreduce(t, group)
+        # d/d Kinv of h_i = k_i^T Kinv k_i is sum_i (-G_kappa_i) k_i k_i^T = -sum_l G_S,l.  Taking it from G_S (instead
+        # of a separate single-channel SYRK) is not only free: both adjoints are amplified by the squared inverses
+        # downstream (-Kinv G Kinv and -S_l G S_l, |Kinv|, |S_l| ~ 1 / jitter in the directions the data does not
+        # see) and only cancel there if they carry the SAME rounding noise.
+        G_Kinv = -G_S.sum(0, keepdim=True)
 
         # ---- adjoint of the replicated M x M stage -----------------------------------------------
         A_, V_, sums_, K_ = ctx.leaves
@@ -249,20 +253,22 @@ class _SVGPStep(torch.autograd.Function):
             gsums = torch.zeros_like(sums_) if gsums is None else gsums
             # ---- pass D: back to the rows --------------------------------------------------------
             # dK_nm and k^T (dA + dA^T) k from ONE pass over the products K G_s: stacked matrices
-            # [dA + dA^T ; S ; Kinv] with per-row weights [p | 2 dq1 | 2 dh] applied in the epilogue
-            Gstack = torch.cat([gA + gA.transpose(-1, -2), S, Kinv], dim=0).contiguous()
+            # [dA + dA^T ; S - Kinv] with per-row weights [p | 2 dq1] applied in the epilogue.  p_v = kappa - k^T (Kinv - S_l) k:
+            # the difference is formed in float64 BEFORE the fp16 split, so the 1 / jitter-sized components that
+            # Kinv and S_l share never enter the tensor-core products
+            Gstack = torch.cat([gA + gA.transpose(-1, -2), S - Kinv], dim=0).contiguous()
             del gA
         else:
             # re-materialise the stage chunk by chunk; every chunk's dA_l + dA_l^T goes straight into the operand
             # planes of pass D, so no second (L, M, M) float64 tensor is alive next to A, S and G_S
             jitter, c, b_total = cfg["jitter"], ctx.c, ctx.b_total
             if kop.tc:
-                hi = torch.empty((2 * L + 1, M, M), dtype=torch.float16, device=dev)
+                hi = torch.empty((2 * L, M, M), dtype=torch.float16, device=dev)
                 lo = torch.empty_like(hi)
-                inv = torch.empty(2 * L + 1, dtype=torch.float32, device=dev)
+                inv = torch.empty(2 * L, dtype=torch.float32, device=dev)
                 put = lambda X, at: be.planes_into(X, hi, lo, inv, at)
             else:
-                G64 = torch.empty((2 * L + 1, M, M), dtype=torch.float64, device=dev)
+                G64 = torch.empty((2 * L, M, M), dtype=torch.float64, device=dev)
 
                 def put(X, at):
                     G64[at:at + X.shape[0]] = X
@@ -292,10 +298,9 @@ class _SVGPStep(torch.autograd.Function):
             gK += gK_sh
             del G_S, gKinv
             for l0 in range(0, L, lc):
-                put(S[l0:l0 + lc], L + l0)
-            put(Kinv, 2 * L)
+                put(S[l0:l0 + lc] - Kinv, L + l0)
             Gstack = Planes(hi, lo, inv) if kop.tc else G64
-        Wstack = torch.cat([p, 2.0 * G_q1, (-2.0 * G_kappa)[:, None]], dim=1).contiguous()
+        Wstack = torch.cat([p, 2.0 * G_q1], dim=1).contiguous()
         G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
         del Wstack, Gstack
         py = p * y

@@ -1,5 +1,5 @@
 """Per-tensor parity of the tcgen05 path against the streamlined float64 oracle for a list of shapes and SYRK
-chain lengths.  Usage: python tools/parity_probe.py N,M,L[,chunk_rows[,mm_chunk]] ...   -> one JSON line per case."""
+chain lengths.  Usage: python tools/parity_probe.py N,M,L[,chunk_rows[,mm_chunk[,tc]]] ...   -> one JSON line per case."""
 import json
 import os
 import sys
@@ -25,6 +25,7 @@ def main():
         N, M, L = v[:3]
         chunk = v[3] if len(v) > 3 else 0
         mmc = v[4] if len(v) > 4 else 0
+        tc = bool(v[5]) if len(v) > 5 else True
         cfg = configs.sweep_inputs(N, M, L)
         o, s, op, sp = refs.make_pair("sweep", cfg, "cuda")
         X, y, nz = cfg["aux"].double(), cfg["y"].double().requires_grad_(True), cfg["noise"].double().requires_grad_(True)
@@ -37,11 +38,11 @@ def main():
         gm, gv = refs.upstream(tuple(y.shape))
         J0 = g0["KL_term"] + (gm * t0["p_m"]).sum() + (gv * t0["p_v"]).sum()
         gr0 = torch.autograd.grad(J0, [y, nz] + op)
-        kw = dict(tc=True, chunk_rows=chunk)
+        kw = dict(tc=tc, chunk_rows=chunk)
         if mmc:
             kw["mm_chunk"] = mmc
         r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda(), **kw)
-        out = dict(N=N, M=M, L=L, chunk_rows=chunk, mm_chunk=mmc, p_m=rel(r1["p_m"], t0["p_m"]), p_v=rel(r1["p_v"], t0["p_v"]))
+        out = dict(N=N, M=M, L=L, chunk_rows=chunk, mm_chunk=mmc, tc=tc, p_m=rel(r1["p_m"], t0["p_m"]), p_v=rel(r1["p_v"], t0["p_v"]))
         for k in ("inside_elbo_recon", "inside_elbo_kl", "ce_term", "KL_term"):
             out[k] = abs(float(r1[k]) - float(g0[k])) / abs(float(g0[k]))
         for name, a, b in zip(["dy", "dnoise", "dZ", "dhyp"], gr0, g1):

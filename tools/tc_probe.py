@@ -40,7 +40,7 @@ def main():
     Lt = torch.tril(S).contiguous()
     tag = os.environ.get("SVGP_TC_BK", "default")
     flush = os.environ.get("SVGP_SYRK_FLUSH", "default")
-    for chunk in (1024, 2048, 4096, 16384):
+    for chunk in (128, 256, 512, 1024, 2048):
         t = timeit(lambda: be.syrk(kop, W, chunk_rows=chunk))
         print(json.dumps(dict(op="syrk_tc", bk=tag, flush=flush, chunk=chunk, N=N, M=M, L=L, ms=t,
                               alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
