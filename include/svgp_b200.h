@@ -105,7 +105,7 @@ typedef struct svgp_kop {
   const void* Kl;      /* N x M fp16 lo plane                                                       */
   const void* Kth;     /* fp16 hi plane of the transpose, blocked [ceil(N/64)][M][64], block stride ldkt */
   const void* Ktl;     /* fp16 lo plane, same layout                                                */
-  const float* kscale; /* device float[>=2]: {scale, 1/scale} of the planes                         */
+  const float* kscale; /* device float[8]: {scale, 1/scale, feature norms..., [6] = 1 if K >= 0 element-wise} */
   int64_t N, M, ldk, ldkh, ldkt;
 } svgp_kop;
 

@@ -158,6 +158,12 @@ __device__ __forceinline__ float plane_scale(Spec sp, Hyp h, const float* ks) {
   return ldexpf(1.0f, e);
 }
 
+// every entry of K is >= 0 (stationary factors only): recorded in kscale[6] for the SYRK's truncation-bias correction
+__device__ __forceinline__ bool kernel_nonneg(Spec sp) {
+  auto ok = [](int t) { return t == SVGP_K_NONE || t == SVGP_K_SE || t == SVGP_K_EXPSIN; };
+  return ok(sp.ta) && ok(sp.tb);
+}
+
 // max Euclidean norms of the two feature blocks over the rows of F -> ks[slot], ks[slot + 1] (float bits, >= 0)
 __global__ void feature_norm_kernel(const float* __restrict__ F, int64_t ld, int64_t rows, Spec sp, float* ks, int slot) {
   float ma = 0.f, mb = 0.f;
@@ -198,7 +204,9 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_kernel(
   float scale = 1.0f;
   if (Kh || Kth) {
     scale = plane_scale(sp, h, kscale);
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { kscale[0] = scale; kscale[1] = 1.0f / scale; }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+      kscale[0] = scale; kscale[1] = 1.0f / scale; kscale[6] = kernel_nonneg(sp) ? 1.0f : 0.0f;
+    }
   }
 
   load_features(Fz, ldz, col0, M, d, dp, sp, zs, nza, nzb);
@@ -280,7 +288,9 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_planes_kernel(
   const int64_t col0 = (int64_t)blockIdx.x * TILE;
   const int64_t ntiles_r = (N + TILE - 1) / TILE;
   const float scale = plane_scale(sp, h, kscale);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { kscale[0] = scale; kscale[1] = 1.0f / scale; }
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    kscale[0] = scale; kscale[1] = 1.0f / scale; kscale[6] = kernel_nonneg(sp) ? 1.0f : 0.0f;
+  }
 
   load_features(Fz, ldz, col0, M, d, dpz, sp, zs, nza, nzb);
   const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;   // compute phase: one column, 16 rows per thread

@@ -268,14 +268,22 @@ __global__ void split_f16_kernel(const double* __restrict__ x, int64_t count, __
 
 // SYRK weights: column max of |W| -> per-channel power-of-two scale (|w s_l| <= 1), then the channel-major,
 // zero-padded, pre-scaled copy Wt (L x ldwt) the operand transform reads with 128-bit loads
+// (mx[L + l] becomes 1.0 if channel l has a negative weight: the SYRK's truncation-bias correction is only valid for
+// chains whose terms all have one sign)
 __global__ void colabsmax_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t L, float* __restrict__ mx) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int64_t l0 = 0; l0 < L; l0 += 32) {
     const int64_t l = l0 + lane;
     float m = 0.f;
+    bool neg = false;
     if (l < L)
-      for (int64_t i = (int64_t)blockIdx.x * nwarp + warp; i < N; i += (int64_t)gridDim.x * nwarp) m = fmaxf(m, fabsf(W[i * ldw + l]));
+      for (int64_t i = (int64_t)blockIdx.x * nwarp + warp; i < N; i += (int64_t)gridDim.x * nwarp) {
+        const float w = W[i * ldw + l];
+        m = fmaxf(m, fabsf(w));
+        neg = neg || (w < 0.f);
+      }
     if (l < L && m > 0.f) atomicMax(reinterpret_cast<int*>(mx + l), __float_as_int(m));
+    if (l < L && neg) atomicMax(reinterpret_cast<int*>(mx + L + l), __float_as_int(1.0f));
   }
 }
 __global__ void transpose_scale_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t L, const float* __restrict__ mx,
@@ -309,7 +317,7 @@ static int launch_tile(Op op, int64_t nz, cudaStream_t st, const char* name) {
 
 // entry points of the tcgen05 implementation (tc_engine.cu)
 int64_t tc_syrk_lock_words(int64_t M, int64_t L);
-int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows, int* locks,
+int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, const float* wneg, int64_t L, double* A, int64_t chunk_rows, int* locks,
             cudaStream_t st);
 int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const float* S_inv, int64_t L, int tri, float* q,
                int64_t ldq, cudaStream_t st);
@@ -336,7 +344,7 @@ static bool use_tc(const svgp_kop* kop, int impl) {
 
 extern "C" {
 
-int64_t svgp_syrk_ws_floats(int64_t N, int64_t M, int64_t L) { return L * pad8(N) + 2 * L + tc_syrk_lock_words(M, L); }
+int64_t svgp_syrk_ws_floats(int64_t N, int64_t M, int64_t L) { return L * pad8(N) + 3 * L + tc_syrk_lock_words(M, L); }
 
 int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, int impl, int64_t chunk_rows,
               float* ws, void* stream) {
@@ -347,9 +355,10 @@ int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, doubl
     SVGP_REQUIRE(ws != nullptr, "TC path needs the workspace (svgp_syrk_ws_floats)");
     const int64_t ldwt = pad8(kop->N);
     float* Wt = ws;
-    float* mx = ws + L * ldwt;
-    float* winv = mx + L;
-    if (cudaMemsetAsync(mx, 0, L * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(memset)");
+    float* mx = ws + L * ldwt;                 // [max |w| per channel | any-negative flag per channel]
+    float* wneg = mx + L;
+    float* winv = wneg + L;
+    if (cudaMemsetAsync(mx, 0, 2 * L * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(memset)");
     int64_t blocks = ceil_div(kop->N, 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
     colabsmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, kop->N, L, mx);
@@ -357,7 +366,7 @@ int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, doubl
     transpose_scale_kernel<<<grid, 256, 0, st>>>(W, ldw, kop->N, L, mx, Wt, ldwt, winv);
     int rc = check_launch("svgp_syrk(prep)");
     if (rc) return rc;
-    return tc_syrk(kop, Wt, ldwt, winv, L, A, chunk_rows, reinterpret_cast<int*>(winv + L), st);
+    return tc_syrk(kop, Wt, ldwt, winv, wneg, L, A, chunk_rows, reinterpret_cast<int*>(winv + L), st);
   }
   SVGP_REQUIRE(kop->K != nullptr, "SIMT path needs the fp32 K");
   int64_t chunk = chunk_rows > 0 ? chunk_rows : 2048;

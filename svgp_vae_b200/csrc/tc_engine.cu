@@ -233,6 +233,8 @@ struct TcParams {
   int64_t sc_rows;            // datapoints per super-chunk: an item covers one super-chunk of one (tile pair, channel)
   int nsc;                    // number of super-chunks
   int ntile;                  // number of (ta, tb) tile pairs
+  const float* wneg;          // per channel: != 0 if the channel has a negative weight
+  float bias_coef;            // expected relative truncation loss of a one-signed chain per MMA, in units of 2^-24
   int* locks;                 // one word per (tile pair, channel, epilogue warp): guards the float64 read-modify-write
   int flush_every;            // chunks folded in fp32 registers between two float64 read-modify-writes of the tile
   int debug;                  // experiments (SVGP_TC_DEBUG): bit 0 = skip the operand transform arithmetic (wrong results),
@@ -242,6 +244,9 @@ struct TcParams {
   const __half* K_hi;         // for the DOT epilogues
   const __half* K_lo;
   int64_t ldkh;
+  const __half* Kt_hi;        // datapoint-blocked transposed planes (SCALED k-dots), may be null
+  const __half* Kt_lo;
+  int64_t ldkt;
   float* q;
   int64_t ldq;
   int lgroup;                 // channels scheduled together (L2 residency of their B planes)
@@ -291,6 +296,26 @@ __device__ __forceinline__ float dot_k_planes(const __half* __restrict__ Kh, con
       acc = pair_dot2(h.z, l.z, v[8 * g + 4], v[8 * g + 5], acc);
       acc = pair_dot2(h.w, l.w, v[8 * g + 6], v[8 * g + 7], acc);
     }
+  }
+  return acc;
+}
+
+// the same dot through the datapoint-blocked TRANSPOSED planes Kt[n / 64][m][n % 64]: the 32 lanes of a warp are 32
+// consecutive datapoints, so one column of the block is one 64-byte run -- 1 L1 wavefront per (column, plane) instead
+// of the 32 of the row-major planes (every lane on its own 2 KB-strided row).  The SCALED epilogue repeats this dot for
+// every k-segment of every matrix that carries a k-dot, so its LSU cost decides how short the MMA chains can be.
+__device__ __forceinline__ float dot_kt_planes(const __half* __restrict__ Kth, const __half* __restrict__ Ktl, int64_t ldkt,
+                                               int64_t i, int64_t c, int64_t M, const float (&v)[32], float acc) {
+  const int64_t o = (i >> 6) * ldkt + c * 64 + (i & 63);
+  const __half* ph = Kth + o;
+  const __half* pl = Ktl + o;
+  if (c + 32 <= M) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc = fmaf(v[j], __half2float(__ldg(ph + j * 64)) + __half2float(__ldg(pl + j * 64)), acc);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (c + j < M) acc = fmaf(v[j], __half2float(__ldg(ph + j * 64)) + __half2float(__ldg(pl + j * 64)), acc);
   }
   return acc;
 }
@@ -580,7 +605,20 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
         int pending = 0;
+        // Truncation-bias correction.  The tensor core truncates towards zero when it aligns and adds into its fp32
+        // accumulator; when all terms of a chain have one sign (weights >= 0 and an element-wise non-negative kernel:
+        // the forward A_l of the SE / periodic kernels) the partial sum grows monotonically from 0 to P and the loss
+        // is a fixed fraction of P: one truncation of ulp(P k / n) / 2 per MMA would give
+        //   sum_k ulp(P k / n) / 2 = n 2^-24 P (f - 2/3) / f^2 = (0.33 .. 0.375) n 2^-24 P   (f = significand of P),
+        // and the hardware loses about twice that (products are truncated individually).  MEASURED on this part
+        // (tools/accum_probe.py, profiles/r01_syrk_shrink_calibration.jsonl): A_tc = (1 - beta) A with
+        // beta / n = 3.86e-8, 3.97e-8, 4.00e-8, 4.04e-8 for n = 48, 96, 192, 384 MMAs, i.e. 0.666 n 2^-24, independent
+        // of the entry.  The factor (1 + 0.666 n 2^-24) on every chunk's partial sum removes it (S_l = (K + c A_l + J)^-1
+        // amplifies a relative error of A_l by the condition number).  Chains with mixed signs (adjoint SYRKs,
+        // linear kernels) are left alone.
+        const bool one_signed = (P.kscale[6] != 0.f) && (P.wneg[it.l] == 0.f);
         for (int sub = 0; sub < nsub; ++sub) {
+          const float fix = one_signed ? 1.0f + P.bias_coef * 5.9604645e-8f * (float)(subtile_kblocks(it, sub) * (BK / UMMA_K) * 3) : 1.0f;
           mbar_wait(tmem_full(acc), acc_phase);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
@@ -590,7 +628,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
               float v[32];
               tmem_ld32(taddr + ch * 32, v);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) run[ch][j] += v[j];
+              for (int j = 0; j < 32; ++j) run[ch][j] = fmaf(v[j], fix, run[ch][j]);
             }
           }
           tc_fence_before();
@@ -703,7 +741,9 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 if (cbase + j >= Mc) v[j] = 0.f;
                 run[ch][j] = fmaf(wgt, v[j], run[ch][j]);
               }
-              if (want_dot) dsum = dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, dsum);
+              if (want_dot)
+                dsum = P.Kt_hi ? dot_kt_planes(P.Kt_hi, P.Kt_lo, P.ldkt, i, cbase, M, v, dsum)
+                               : dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, dsum);
             }
           }
           tc_fence_before();
@@ -993,8 +1033,8 @@ static int64_t syrk_superchunk_rows(int64_t M, int64_t chunk) {
 
 int64_t tc_syrk_lock_words(int64_t M, int64_t L) { return (int64_t)syrk_tile_count(M, 256) * L * 8; }
 
-int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, int64_t L, double* A, int64_t chunk_rows,
-            int* locks, cudaStream_t st) {
+int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* winv, const float* wneg, int64_t L, double* A,
+            int64_t chunk_rows, int* locks, cudaStream_t st) {
   if (!kop->Kth || !kop->Ktl || !kop->kscale) { set_error("tc_syrk: transposed fp16 planes missing"); return SVGP_ERR_ARG; }
   if (((uintptr_t)Wt & 15) || (ldwt % 8)) { set_error("tc_syrk: weights need 16-byte alignment"); return SVGP_ERR_ARG; }
   const int BN = 256, bk = tc_bk();
@@ -1006,7 +1046,9 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
   if ((rc = make_map_blocked(&b_lo, kop->Ktl, kop->M, kop->N, kop->ldkt, BN, bk))) return rc;
   TcParams P{};
   P.N = kop->N; P.M = kop->M; P.L = L; P.kscale = kop->kscale; P.binv = winv;
-  P.Wt = Wt; P.ldwt = ldwt; P.A = A; P.locks = locks;
+  P.Wt = Wt; P.ldwt = ldwt; P.A = A; P.locks = locks; P.wneg = wneg;
+  // truncation-bias correction of one-signed chains (see the SYRK epilogue); SVGP_SYRK_BIAS overrides the coefficient
+  { const char* e = getenv("SVGP_SYRK_BIAS"); P.bias_coef = e ? (float)atof(e) : 0.666f; }
   // one accumulation chain = chunk / 16 k-steps x 3 MMAs.  The tensor core accumulates with truncation: measured on
   // A_l (all terms positive) the bias is -1.8e-7 x chunk / 1024 of the largest entry (tools/accum_probe.py), and S_l =
   // (K + c A_l + J)^-1 amplifies it by the condition number.  512 rows = 96 MMAs per chain costs ~3 % of SYRK time.
@@ -1081,11 +1123,16 @@ int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void*
   P.N = kop->N; P.M = kop->M; P.L = L; P.Mc = Mc; P.kscale = kop->kscale; P.binv = G_inv;
   P.K_hi = (const __half*)kop->Kh; P.K_lo = (const __half*)kop->Kl; P.ldkh = kop->ldkh;
   P.W = W; P.ldw = ldw; P.out = out; P.ldo = ldo; P.accumulate = accumulate;
+  if (kop->Kth && kop->Ktl && !getenv("SVGP_SCALED_ROWDOT")) { P.Kt_hi = (const __half*)kop->Kth; P.Kt_lo = (const __half*)kop->Ktl; P.ldkt = kop->ldkt; }
   P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
-  // chain length: the tensor core accumulates with truncation (a bias of ~n 2^-24 after n MMAs, relative to the LARGEST
-  // partial sum of the chain -- and K G_s cancels by 1e3..1e4 against the entries of S_l).  4 k-blocks = 48 MMAs per
-  // chain; the segments are folded in fp32 registers with round-to-nearest FMAs.  SVGP_SCALED_KSEG overrides (0 = one chain).
-  { const char* e = getenv("SVGP_SCALED_KSEG"); P.kseg = e ? atoi(e) : 4 * 64 / bk; }
+  // Chain length.  The tensor core accumulates with truncation (a bias of ~n 2^-24 after n MMAs, relative to the LARGEST
+  // partial sum of the chain -- and K G_s cancels heavily against the entries of dA_l).  The reduction over M can be cut
+  // into segments of `kseg` k-blocks that the epilogue folds in fp32 registers with round-to-nearest FMAs:
+  // SVGP_SCALED_KSEG (matrices with a k-dot) / SVGP_SCALED_KSEG2 (the others); 0 = one chain.  Measured at M = 1024
+  // (profiles/r01_parity_chain_matrix.jsonl): segments of 4 k-blocks take the inducing-point gradient from 2.1e-3 to
+  // 3.7e-4 of its maximum but cost +75 % kernel time on the k-dot matrices (the dot re-reads its K tile from L2 once per
+  // segment, and L2 -> SM bandwidth is what this kernel runs at), so the default stays one chain.
+  { const char* e = getenv("SVGP_SCALED_KSEG"); P.kseg = e ? atoi(e) : 0; }
   { const char* e = getenv("SVGP_SCALED_KSEG2"); P.kseg2 = e ? atoi(e) : P.kseg; }
   P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(Mc, BN);
   return dispatch_tc<MODE_SCALED>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");

@@ -76,3 +76,49 @@ def product_objective(s, params, aux, y, noise, clip_pv=False, **kw):
     J = res["KL_term"] + (gm.to(res["p_m"].dtype) * res["p_m"]).sum().double() + (gv.to(res["p_v"].dtype) * res["p_v"]).sum().double()
     grads = torch.autograd.grad(J, [y, noise] + list(params), allow_unused=True)
     return res, J, grads
+
+
+# ---- SVIGP_Hensman (tests/golden/make_svigp_golden.py uses the same seeded variational parameters) -----------------
+def svigp_case(normalize, device, fixture):
+    """-> (product SVIGP_Hensman on `device`, aux, upstream g (b, L)) for the inputs of svigp_golden.npz."""
+    from svgp_vae_b200 import configs
+    from svgp_vae_b200.svigp import SVIGP_Hensman
+    L = 3
+    cfg = configs.mnist_inputs(fixture, L=L, b=192, normalize=normalize)
+    c = cfg["ctor"]
+    s = SVIGP_Hensman(fixed_inducing_points=False, initial_inducing_points=c["initial_inducing_points"], name="p",
+                      jitter=c["jitter"], N_train=c["N_train"], dtype=torch.float64, L=L, fixed_gp_params=False,
+                      object_vectors_init=c["object_vectors_init"], K_obj_normalize=normalize)
+    m = s.nr_inducing
+    g = torch.Generator().manual_seed(3)
+    mu = 0.5 * torch.randn(L, m, generator=g, dtype=F64)
+    A = torch.eye(m, dtype=F64).repeat(L, 1, 1) * 0.7 + 0.05 * torch.tril(torch.randn(L, m, m, generator=g, dtype=F64))
+    with torch.no_grad():
+        s.GP_var_params_mu.copy_(mu)
+        s.GP_var_params_A.copy_(A)
+        s.Hensman_likelihood_noise.fill_(0.3)
+    g2 = torch.Generator().manual_seed(5)
+    gm = torch.randn(192, L, generator=g2, dtype=F64)
+    return s.to(device), cfg["aux"].to(F64).to(device), gm.to(device)
+
+
+def svigp_check(s, aux, gm, gold, key, tol, rel_err, batched=True):
+    """Values and gradients of SVIGP_Hensman against the reference-source golden vectors."""
+    if batched:
+        rec, kl, means = s.variational_loss_all(aux)
+    else:
+        outs = [s.variational_loss(aux, None, l) for l in range(s.L)]
+        rec, kl, means = torch.stack([o[0] for o in outs]), torch.stack([o[1] for o in outs]), torch.stack([o[2] for o in outs], 1)
+    g = lambda n: torch.from_numpy(gold[key + "/" + n])
+    assert rel_err(rec, g("L3")) < tol and rel_err(kl, g("KL")) < tol and rel_err(means, g("mean")) < tol
+    b = float(aux.shape[0])
+    J = rec.sum() - (b / s.N_train) * kl.sum() + (gm * means).sum()
+    assert abs(float(J) - float(g("J"))) < tol * abs(float(g("J")))
+    leaves = [s.inducing_index_points, s.object_vectors, s.amplitude, s.l_GP, s.noise, s.GP_var_params_mu, s.GP_var_params_A]
+    grads = torch.autograd.grad(J, leaves)
+    for n, gr in zip(["Z", "table", "amplitude", "length", "noise", "mu", "A"], grads):
+        assert rel_err(gr, g("grad_" + n)) < (max(tol, 1e-4) if gr.numel() == 1 else tol), n
+    test_aux = aux[:40].clone()
+    test_aux[:, 1] = test_aux[:, 1] + 0.3
+    mv, B = s.approximate_posterior_params(test_aux, 1)
+    assert rel_err(mv, g("post_mean")) < tol and rel_err(B, g("post_B")) < tol

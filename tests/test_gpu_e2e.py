@@ -3,11 +3,13 @@
 Tolerance: 1e-4 relative to max|oracle tensor| (BASELINE.json north_star), for posterior means /
 variances, the ELBO scalars -- including the cancelling combination KL_term -- and all gradients.
 """
+import os
+
 import pytest
 import torch
 
 import refs
-from conftest import MNIST_FIXTURE, rel_err
+from conftest import GOLDEN, MNIST_FIXTURE, rel_err
 from oracle import svgp_literal as lit
 from oracle import svgp_streamlined as st
 import svgp_vae_b200 as pkg
@@ -313,3 +315,12 @@ def test_forward_pass_glue_against_reference_source(cuda_backend, geco):
     g = torch.autograd.grad(r[0], [mu, var, s.inducing_index_points])
     for t, n in zip(g, ("y", "noise", "Z")):
         assert rel_err(t, torch.from_numpy(gold[tag + "/grad_" + n])) < TOL, n
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_svigp_hensman_against_reference_source(cuda_backend, normalize):
+    """SVIGP_Hensman on the CUDA library against the outputs of the unmodified reference source."""
+    import numpy as np
+    gold = np.load(os.path.join(GOLDEN, "svigp_golden.npz"))
+    s, aux, gm = refs.svigp_case(normalize, "cuda", MNIST_FIXTURE)
+    refs.svigp_check(s, aux, gm, gold, "svigp_norm" if normalize else "svigp", TOL, rel_err, batched=True)

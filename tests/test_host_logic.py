@@ -263,3 +263,13 @@ def test_sprites_aux_data_against_reference_source():
     action_ids = torch.tensor([3, 7, 1, 0, 5, 5, 2, 71, 9, 4, 6, 8])
     aux = pkg.aux_data_SVGPVAE_sprites((_glue_images(12), action_ids), Repr(), [0, 0, 0, 0, 0, 1, 1, 1, 2, 2, 2, 2], [5, 3, 4])
     assert aux.shape == (12, 17) and rel_err(aux, torch.from_numpy(gold["sprites_aux/aux"])) < 1e-12
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+@pytest.mark.parametrize("batched", [True, False])
+def test_svigp_hensman_against_reference_source(oracle_backend, normalize, batched):
+    """SVIGP_Hensman (SVIGP_Hensman_model.py:14-227) -- values, posterior and every gradient against the outputs of the
+    unmodified reference source (tests/golden/make_svigp_golden.py), per channel and through the batched entry."""
+    gold = np.load(os.path.join(GOLDEN, "svigp_golden.npz"))
+    s, aux, gm = refs.svigp_case(normalize, "cpu", MNIST_FIXTURE)
+    refs.svigp_check(s, aux, gm, gold, "svigp_norm" if normalize else "svigp", TOL, rel_err, batched=batched)

@@ -19,7 +19,8 @@ def stats(name, got, ref, **kw):
     err = got - ref
     den = ref.abs().max()
     out = dict(op=name, max_rel=float(err.abs().max() / den), rms_rel=float(err.pow(2).mean().sqrt() / den),
-               mean_signed_rel=float(err.mean() / den), ref_rms_rel=float(ref.pow(2).mean().sqrt() / den), **kw)
+               mean_signed_rel=float(err.mean() / den), ref_rms_rel=float(ref.pow(2).mean().sqrt() / den),
+               shrink=float(-(err * ref).sum() / (ref * ref).sum()), **kw)     # least-squares beta of got = (1 - beta) ref
     print(json.dumps({k: (float("%.3g" % v) if isinstance(v, float) else v) for k, v in out.items()}), flush=True)
 
 
@@ -78,6 +79,16 @@ def main():
     Fx = s._features(cfg["aux"].cuda(), False).float().contiguous()
     Fz = s._features(s.inducing_index_points, True).float().contiguous()
     hyp = s._hyp().float().contiguous()
+    # per matrix family (with the default ordering: [dA + dA^T (L) ; S - Kinv (L)]), against the same planes
+    for fam, sl in (("dA+dA^T", slice(0, L)), ("S-Kinv", slice(L, nb))):
+        o_tc = orig_scaled(kop, W[:, sl].contiguous(), G64[sl].contiguous())
+        o_ref = torch.zeros(N, M, dtype=torch.float64, device="cuda")
+        for t in range(sl.start, sl.stop):
+            o_ref += W[:, t:t + 1].double() * (K @ Gp[t])
+        stats("scaled_gemm family " + fam + " vs planes", o_tc, o_ref)
+        _, dZ_a, _ = be.kernel_bwd(s._spec(), Fx, Fz, hyp, o_tc.float().contiguous(), need_x=False)
+        _, dZ_b, _ = be.kernel_bwd(s._spec(), Fx, Fz, hyp, o_ref.float().contiguous(), need_x=False)
+        stats("dZ (K_nm path) family " + fam, dZ_a, dZ_b)
     for nm, Gx in (("planes", Gp), ("float64", G64)):
         out_ref = torch.zeros(N, M, dtype=torch.float64, device="cuda")
         for t in range(nb):
