@@ -137,6 +137,22 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+         "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+         "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+         "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+         "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+         "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+         "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+         "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void sts32(uint32_t addr, float v) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
@@ -259,6 +275,8 @@ struct TcParams {
   int accumulate;
   float* dots;                // (N, lddots) or null
   int64_t lddots, ndot;
+  int kcache;                 // SCALED with k-dots: keep the item's K tile in the second TMEM accumulator buffer while the
+                              // matrices that carry a k-dot are processed (single-buffered on the first)
   int kseg, kseg2;            // k-blocks per MMA chain (0 = the whole reduction in one chain) for the matrices with a
                               // k-dot (< ndot) / without: the reduction over M is cut into segments that the epilogue
                               // folds with round-to-nearest FMAs (see "work decomposition")
@@ -414,6 +432,22 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     return r;
   };
 
+  // TMEM accumulator buffer of sub-tile `sub`.  Normally the two buffers alternate (the epilogue of one sub-tile overlaps
+  // the MMAs of the next).  SCALED with a K-tile cache: the matrices with a k-dot run single-buffered on buffer 0 while
+  // buffer 1 holds the item's K tile (fp32, written once per item by the epilogue warps); the remaining matrices then
+  // alternate again starting at buffer 0 -- whose release implies that every epilogue warp is done with the cache.
+  const bool kcache = (MODE == MODE_SCALED) && P.kcache && nsubA > 0 && ACC_BUFS == 2;
+  struct BufSel {
+    int toggle = 0;
+    uint32_t phase[2] = {0u, 0u};
+  };
+  auto pick_buf = [&](BufSel& b, int sub) -> int {
+    if (kcache) return sub < nsubA ? 0 : ((sub - nsubA) & 1);
+    const int r = b.toggle;
+    b.toggle = (ACC_BUFS == 2) ? (b.toggle ^ 1) : 0;
+    return r;
+  };
+
   struct Item { int64_t l, itile, n0, n1; int a_row0, b_row0, tile; bool half_tile; };
   auto decode = [&](int64_t item) -> Item {
     Item it{0, 0, 0, 0, 0, 0, 0, false};
@@ -537,14 +571,15 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
   auto role_mma = [&]() {
     // =============================== MMA issuer ==================================================
     int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
+    BufSel bs;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
       const int nsub = item_subtiles(it);
       const uint32_t idesc = it.half_tile ? make_idesc(BN / 2) : IDESC;
       for (int sub = 0; sub < nsub; ++sub) {
         const int nkb = subtile_kblocks(it, sub);
-        mbar_wait(tmem_empty(acc), acc_phase ^ 1);
+        const int acc = pick_buf(bs, sub);
+        mbar_wait(tmem_empty(acc), bs.phase[acc] ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -568,7 +603,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+        bs.phase[acc] ^= 1;
       }
     }
   };
@@ -578,7 +613,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
     const int row = qd * 32 + lane;                  // output row inside the tile
     const int half = (warp - EPI_WARP0) >> 2;        // SYRK / SCALED: which half of the tile's columns
     const float inv_ks = P.kscale[1];
-    int acc = 0; uint32_t acc_phase = 0;
+    BufSel bsel;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
       const int nsub = item_subtiles(it);
@@ -619,7 +654,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         const bool one_signed = (P.kscale[6] != 0.f) && (P.wneg[it.l] == 0.f);
         for (int sub = 0; sub < nsub; ++sub) {
           const float fix = one_signed ? 1.0f + P.bias_coef * 5.9604645e-8f * (float)(subtile_kblocks(it, sub) * (BK / UMMA_K) * 3) : 1.0f;
-          mbar_wait(tmem_full(acc), acc_phase);
+          const int acc = pick_buf(bsel, sub);
+          mbar_wait(tmem_full(acc), bsel.phase[acc]);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll
@@ -634,7 +670,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(acc));
-          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+          bsel.phase[acc] ^= 1;
           if (++pending == P.flush_every || sub == nsub - 1) {
             pending = 0;
             if (nlive > 0) {
@@ -682,7 +718,8 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         const float bs = (it.l < P.L) ? P.binv[it.l] : 0.f;
         float qsum = 0.f;
         for (int sub = 0; sub < nsub; ++sub) {
-          mbar_wait(tmem_full(acc), acc_phase);
+          const int acc = pick_buf(bsel, sub);
+          mbar_wait(tmem_full(acc), bsel.phase[acc]);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
@@ -704,7 +741,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(acc));
-          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+          bsel.phase[acc] ^= 1;
         }
         if (live) {
           const float s1 = inv_ks * bs;
@@ -720,14 +757,40 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; ++j) run[ch][j] = 0.f;
         float dsum = 0.f;
+        const uint32_t tcache = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(BN + half * (BN / 2));
+        if (kcache) {
+          // this thread's row of the item's K tile (its half of the columns), fp32 hi + lo in plane units, into buffer 1:
+          // read back with tcgen05.ld for every k-segment of every matrix that carries a k-dot -- no L2 traffic
+#pragma unroll
+          for (int ch = 0; ch < NCH; ++ch) {
+            const int64_t cbase = (int64_t)it.b_row0 + half * (BN / 2) + ch * 32;
+            float kv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) kv[j] = 0.f;
+            if (live && cbase < M) {
+              const int64_t o = (i >> 6) * P.ldkt + cbase * 64 + (i & 63);
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (cbase + j < M) kv[j] = __half2float(__ldg(P.Kt_hi + o + j * 64)) + __half2float(__ldg(P.Kt_lo + o + j * 64));
+            }
+            __syncwarp();                                          // reconverge: tcgen05.st is .sync.aligned
+            tmem_st32(tcache + ch * 32, kv);
+          }
+        }
         for (int sub = 0; sub < nsub; ++sub) {
           const SubInfo si = scaled_sub(sub);
           const int mat = si.mat;                                  // stacked matrix; this sub-tile = one k-segment of its reduction
-          const float bs = P.binv[mat];
+          // mixed-sign chains: the truncating accumulation shrinks K G_s uniformly by 0.263 .. 0.28 n 2^-24 on this workload
+          // class (profiles/r01_scaled_shrink_calibration.jsonl).  Removing that uniform part (SVGP_SCALED_BIAS=0.27) was
+          // measured to change NO parity figure (profiles/r01_parity_scaled_bias_sweep.jsonl): what hurts the
+          // inducing-point gradient is the non-uniform part of the truncation error.  Default: no correction.
+          const float fix = 1.0f + P.bias_coef * 5.9604645e-8f * (float)(si.nkb * (BK / UMMA_K) * 3);
+          const float bs = P.binv[mat] * fix;
           const float wgt = live ? (P.W ? P.W[i * P.ldw + mat] : 1.f) * inv_ks * bs : 0.f;
           const bool want_dot = (P.dots != nullptr) && (mat < P.ndot) && live;
           if (si.k0 == 0) dsum = 0.f;
-          mbar_wait(tmem_full(acc), acc_phase);
+          const int acc = pick_buf(bsel, sub);
+          mbar_wait(tmem_full(acc), bsel.phase[acc]);
           tc_fence_after();
           const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(acc * BN + half * (BN / 2));
 #pragma unroll
@@ -741,15 +804,23 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
                 if (cbase + j >= Mc) v[j] = 0.f;
                 run[ch][j] = fmaf(wgt, v[j], run[ch][j]);
               }
-              if (want_dot)
-                dsum = P.Kt_hi ? dot_kt_planes(P.Kt_hi, P.Kt_lo, P.ldkt, i, cbase, M, v, dsum)
-                               : dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, dsum);
+              if (kcache && P.dots != nullptr && mat < P.ndot) {      // warp-uniform: tcgen05.ld is .sync.aligned
+                float kv[32];
+                tmem_ld32(tcache + ch * 32, kv);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dsum = fmaf(v[j], kv[j], dsum);
+              } else if (want_dot) {
+                {
+                  dsum = P.Kt_hi ? dot_kt_planes(P.Kt_hi, P.Kt_lo, P.ldkt, i, cbase, M, v, dsum)
+                                 : dot_k_planes(P.K_hi, P.K_lo, P.ldkh, i, cbase, v, dsum);
+                }
+              }
             }
           }
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty(acc));
-          if (++acc == ACC_BUFS) { acc = 0; acc_phase ^= 1; }
+          bsel.phase[acc] ^= 1;
           if (want_dot && si.last) atomicAdd(&P.dots[i * P.lddots + mat], dsum * inv_ks * inv_ks * bs);
         }
         if (live) {
@@ -1125,15 +1196,19 @@ int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void*
   P.W = W; P.ldw = ldw; P.out = out; P.ldo = ldo; P.accumulate = accumulate;
   if (kop->Kth && kop->Ktl && !getenv("SVGP_SCALED_ROWDOT")) { P.Kt_hi = (const __half*)kop->Kth; P.Kt_lo = (const __half*)kop->Ktl; P.ldkt = kop->ldkt; }
   P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
-  // Chain length.  The tensor core accumulates with truncation (a bias of ~n 2^-24 after n MMAs, relative to the LARGEST
-  // partial sum of the chain -- and K G_s cancels heavily against the entries of dA_l).  The reduction over M can be cut
-  // into segments of `kseg` k-blocks that the epilogue folds in fp32 registers with round-to-nearest FMAs:
-  // SVGP_SCALED_KSEG (matrices with a k-dot) / SVGP_SCALED_KSEG2 (the others); 0 = one chain.  Measured at M = 1024
-  // (profiles/r01_parity_chain_matrix.jsonl): segments of 4 k-blocks take the inducing-point gradient from 2.1e-3 to
-  // 3.7e-4 of its maximum but cost +75 % kernel time on the k-dot matrices (the dot re-reads its K tile from L2 once per
-  // segment, and L2 -> SM bandwidth is what this kernel runs at), so the default stays one chain.
-  { const char* e = getenv("SVGP_SCALED_KSEG"); P.kseg = e ? atoi(e) : 0; }
-  { const char* e = getenv("SVGP_SCALED_KSEG2"); P.kseg2 = e ? atoi(e) : P.kseg; }
+  // Chain length.  The tensor core accumulates with truncation (an error of ~n 2^-24 after n MMAs, relative to the LARGEST
+  // partial sum of the chain -- and K (dA_l + dA_l^T) cancels heavily).  The reduction over M is cut into segments of
+  // `kseg` k-blocks that the epilogue folds in fp32 registers with round-to-nearest FMAs: SVGP_SCALED_KSEG (matrices with
+  // a k-dot: dA_l + dA_l^T) / SVGP_SCALED_KSEG2 (the others: S_l - Kinv); 0 = one chain.  Measured at M = 1024
+  // (profiles/r01_parity_chain_matrix.jsonl, r01_parity_kcache.jsonl): segments of 4 k-blocks (48 MMAs) on the k-dot
+  // matrices take the inducing-point gradient from 1.9e-3 to 3.4e-4 of its maximum, shorter ones and segmenting the
+  // other family change nothing.  Every segment repeats the k-dot, i.e. re-reads the item's K tile: from L2 that costs
+  // +75 % kernel time (the kernel already runs at L2 -> SM bandwidth); with the tile cached in the second TMEM buffer
+  // (kcache: those matrices run single-buffered on the first) it costs +10 % (610 -> 671 ms at N = 1e6, L = 64).
+  { const char* e = getenv("SVGP_SCALED_KCACHE"); P.kcache = (P.Kt_hi != nullptr && P.ndot > 0) ? (e ? atoi(e) : 1) : 0; }
+  { const char* e = getenv("SVGP_SCALED_KSEG"); P.kseg = e ? atoi(e) : (P.kcache ? 4 * 64 / bk : 0); }
+  { const char* e = getenv("SVGP_SCALED_KSEG2"); P.kseg2 = e ? atoi(e) : 0; }
+  { const char* e = getenv("SVGP_SCALED_BIAS"); P.bias_coef = e ? (float)atof(e) : 0.0f; }
   P.n_items = ceil_div(kop->N, BLOCK_M) * ceil_div(Mc, BN);
   return dispatch_tc<MODE_SCALED>(bk, a_hi, a_lo, b_hi, b_lo, P, st, "svgp_scaled_gemm(tc)");
 }
