@@ -196,6 +196,7 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout (ONE JSON line)
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     be = backend.get_backend()

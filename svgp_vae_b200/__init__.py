@@ -12,6 +12,7 @@ from .svgp import (SVGP, _add_diagonal_jitter, gauss_cross_entropy, mainSVGP, mn
 from .step import elbo_terms, svgp_step  # noqa: F401
 from .glue import aux_data_SVGPVAE_sprites, forward_pass_SVGPVAE  # noqa: F401
 from .svigp import SVIGP_Hensman, forward_pass_deep_SVIGP_Hensman  # noqa: F401
+from .graphed import GraphedElboStep  # noqa: F401
 from .predict import posterior_predict, precompute_GP_params_SVGPVAE, predict_from_precomputed  # noqa: F401
 
 __version__ = "0.1.0"

@@ -72,6 +72,8 @@ class NotPositiveDefinite(RuntimeError):
 
 
 def _check_status(status, what):
+    if status.is_cuda and torch.cuda.is_current_stream_capturing():
+        return                      # no host synchronisation inside a CUDA graph (graphed.py): the caller checks eagerly
     bad = torch.nonzero(status)
     if bad.numel():
         b = int(bad[0, 0])

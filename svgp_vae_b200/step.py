@@ -134,10 +134,12 @@ class _SVGPStep(torch.autograd.Function):
         p, py, sums = be.rowstats(y32, n32, kappa)
         A = be.syrk(kop, p, chunk_rows=cfg.get("chunk_rows", 0))
         V = be.gemm_tn(kop, py)
-        count = torch.tensor([float(N)], dtype=torch.float64, device=y32.device)
-        for t in (A, V, sums, count):
-            _allreduce(t, group)
-        b_total = float(count.item()) if group is not None else float(N)
+        b_total = float(N)
+        if group is not None:
+            count = torch.tensor([float(N)], dtype=torch.float64, device=y32.device)
+            for t in (A, V, sums, count):
+                _allreduce(t, group)
+            b_total = float(count.item())
         c = N_train / b_total
 
         lc = mm_chunk_channels(L, M, y32.device, cfg.get("mm_chunk"))

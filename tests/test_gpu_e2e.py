@@ -324,3 +324,40 @@ def test_svigp_hensman_against_reference_source(cuda_backend, normalize):
     gold = np.load(os.path.join(GOLDEN, "svigp_golden.npz"))
     s, aux, gm = refs.svigp_case(normalize, "cuda", MNIST_FIXTURE)
     refs.svigp_check(s, aux, gm, gold, "svigp_norm" if normalize else "svigp", TOL, rel_err, batched=True)
+
+
+@pytest.mark.parametrize("kind", ["mnist", "sprites"])
+def test_cuda_graph_step_matches_eager(cuda_backend, kind):
+    """GraphedElboStep (forward and backward of elbo_step captured as CUDA graphs) replays the same numbers as the
+    eager step, also for new input values of the captured shapes."""
+    if kind == "mnist":
+        cfg = configs.mnist_inputs(MNIST_FIXTURE, L=16)
+        s = pkg.mnistSVGP(name="g", **cfg["ctor"]).cuda()
+        clip = False
+    else:
+        cfg = configs.sprites_inputs(M=72, L=8)
+        s = pkg.spritesSVGP(name="g", **cfg["ctor"]).cuda()
+        clip = True
+    aux, y, nz = cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda()
+    step = pkg.GraphedElboStep(s, aux, y, nz, clip_pv=clip)
+    params = [p for p in s.parameters()]
+    for scale in (1.0, 0.7):                      # second pass: different values through the same graphs
+        outs = []
+        for fn in (lambda a, b, c: s.elbo_step(a, b, c, clip_pv=clip), step):
+            yy, nn = (y * scale).clone().requires_grad_(True), (nz * (2.0 - scale)).clone().requires_grad_(True)
+            for p in params:
+                p.grad = None
+            r = fn(aux, yy, nn)
+            gm, gv = refs.upstream(tuple(yy.shape), "cuda")
+            J = r["KL_term"] + (gm.to(r["p_m"].dtype) * r["p_m"]).sum().double() + (gv.to(r["p_v"].dtype) * r["p_v"]).sum().double()
+            J.backward()
+            outs.append((r["p_m"].detach().clone(), r["p_v"].detach().clone(), J.detach().clone(), yy.grad.clone(), nn.grad.clone(),
+                         [None if p.grad is None else p.grad.clone() for p in params]))
+        e, g = outs
+        # same kernels on the same inputs; the float64 atomics of the reductions make the last digits order-dependent
+        for a, b in zip(e[:5], g[:5]):
+            assert rel_err(b, a) < 1e-6
+        for a, b in zip(e[5], g[5]):
+            assert (a is None) == (b is None)
+            if a is not None and a.abs().max() > 0:
+                assert rel_err(b, a) < 1e-6

@@ -26,14 +26,15 @@ def timeit(fn, reps=20):
     return a.elapsed_time(b) / reps
 
 
-def fused(svgp, cfg, clip):
+def fused(svgp, cfg, clip, graphed=False):
     aux, y, nz = cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda()
     g = torch.Generator(device="cuda").manual_seed(0)
     gm, gv = torch.randn(y.shape, generator=g, device="cuda"), torch.randn(y.shape, generator=g, device="cuda")
+    call = pkg.GraphedElboStep(svgp, aux, y, nz, clip_pv=clip) if graphed else (lambda a, b, c: svgp.elbo_step(a, b, c, clip_pv=clip))
 
     def step():
         yy, nn = y.clone().requires_grad_(True), nz.clone().requires_grad_(True)
-        res = svgp.elbo_step(aux, yy, nn, clip_pv=clip)
+        res = call(aux, yy, nn)
         J = res["KL_term"] + (gm.to(res["p_m"].dtype) * res["p_m"]).sum().double() + (gv.to(res["p_v"].dtype) * res["p_v"]).sum().double()
         J.backward()
     return step
@@ -50,6 +51,11 @@ def main():
         ms = timeit(fused(svgp, cfg, clip))
         b = cfg["aux"].shape[0]
         print(json.dumps({"config": name, "path": "elbo_step fwd+bwd", "ms": ms, "datapoints_per_s": b / ms * 1e3}), flush=True)
+        try:
+            ms = timeit(fused(svgp, cfg, clip, graphed=True), reps=100)
+            print(json.dumps({"config": name, "path": "GraphedElboStep fwd+bwd (CUDA graphs)", "ms": ms, "datapoints_per_s": b / ms * 1e3}), flush=True)
+        except Exception as e:  # noqa: BLE001
+            print(json.dumps({"config": name, "path": "GraphedElboStep", "error": repr(e)[:300]}), flush=True)
     # moving ball: two SVGP objects, the reference's per-object calls (batch 35 x tmax 30, m = 15)
     cfg = configs.ball_inputs()
     sx, sy = pkg.SVGP(name="x", **cfg["ctor"]).cuda(), pkg.SVGP(name="y", **cfg["ctor"]).cuda()
