@@ -646,7 +646,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
         // is a fixed fraction of P: one truncation of ulp(P k / n) / 2 per MMA would give
         //   sum_k ulp(P k / n) / 2 = n 2^-24 P (f - 2/3) / f^2 = (0.33 .. 0.375) n 2^-24 P   (f = significand of P),
         // and the hardware loses about twice that (products are truncated individually).  MEASURED on this part
-        // (tools/accum_probe.py, profiles/r01_syrk_shrink_calibration.jsonl): A_tc = (1 - beta) A with
+        // (tests/probes/accum_probe.py, profiles/r01_syrk_shrink_calibration.jsonl): A_tc = (1 - beta) A with
         // beta / n = 3.86e-8, 3.97e-8, 4.00e-8, 4.04e-8 for n = 48, 96, 192, 384 MMAs, i.e. 0.666 n 2^-24, independent
         // of the entry.  The factor (1 + 0.666 n 2^-24) on every chunk's partial sum removes it (S_l = (K + c A_l + J)^-1
         // amplifies a relative error of A_l by the condition number).  Chains with mixed signs (adjoint SYRKs,
@@ -1121,7 +1121,7 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
   // truncation-bias correction of one-signed chains (see the SYRK epilogue); SVGP_SYRK_BIAS overrides the coefficient
   { const char* e = getenv("SVGP_SYRK_BIAS"); P.bias_coef = e ? (float)atof(e) : 0.666f; }
   // one accumulation chain = chunk / 16 k-steps x 3 MMAs.  The tensor core accumulates with truncation: measured on
-  // A_l (all terms positive) the bias is -1.8e-7 x chunk / 1024 of the largest entry (tools/accum_probe.py), and S_l =
+  // A_l (all terms positive) the bias is -1.8e-7 x chunk / 1024 of the largest entry (tests/probes/accum_probe.py), and S_l =
   // (K + c A_l + J)^-1 amplifies it by the condition number.  512 rows = 96 MMAs per chain costs ~3 % of SYRK time.
   int64_t chunk = chunk_rows > 0 ? chunk_rows : 512;
   chunk = (chunk + 63) / 64 * 64;

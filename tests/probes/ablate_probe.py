@@ -1,6 +1,6 @@
 """Error attribution for the tcgen05 path: selected backend calls of one step are replaced by float64 torch
 computations ON THE SAME OPERAND PLANES (kop.value()), and the step's parity against the float64 oracle is
-reported for every subset.  Usage: python tools/ablate_probe.py N M L  -> JSON lines."""
+reported for every subset.  Usage: python tests/probes/ablate_probe.py N M L  -> JSON lines."""
 import itertools
 import json
 import os
@@ -8,7 +8,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refs  # noqa: E402

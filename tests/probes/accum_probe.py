@@ -1,13 +1,13 @@
 """Where the tcgen05 path loses accuracy: every tensor-core call of one real step is captured and re-computed in
 float64 from the SAME operand planes (so only the accumulation differs), and from the unsplit float64 operands
-(so the fp16 hi/lo split shows up).  Usage: python tools/accum_probe.py N M L [chunk_rows] -> JSON lines."""
+(so the fp16 hi/lo split shows up).  Usage: python tests/probes/accum_probe.py N M L [chunk_rows] -> JSON lines."""
 import json
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refs  # noqa: E402

@@ -2,14 +2,14 @@
 
 The streamlined oracle (oracle/svgp_streamlined.py) is device-agnostic torch float64; the product-SE kernel matrix is
 restated with the |x|^2 + |z|^2 - 2 x.z expansion in float64 (checked here against oracle/tfp_kernels on the first
-rows) so that no (N, M, d) tensor is needed.  Usage: python tools/parity_fullsize.py N M L [seed] -> one JSON line."""
+rows) so that no (N, M, d) tensor is needed.  Usage: python tests/probes/parity_fullsize.py N M L [seed] -> one JSON line."""
 import json
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle import svgp_streamlined as st  # noqa: E402

@@ -1,12 +1,12 @@
 """Per-tensor parity of the tcgen05 path against the streamlined float64 oracle for a list of shapes and SYRK
-chain lengths.  Usage: python tools/parity_probe.py N,M,L[,chunk_rows[,mm_chunk[,tc]]] ...   -> one JSON line per case."""
+chain lengths.  Usage: python tests/probes/parity_probe.py N,M,L[,chunk_rows[,mm_chunk[,tc]]] ...   -> one JSON line per case."""
 import json
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import refs  # noqa: E402

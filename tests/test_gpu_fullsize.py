@@ -92,7 +92,7 @@ def test_full_step_invariants(cuda_backend):
 
 def test_step_against_float64_oracle_on_the_gpu(cuda_backend):
     """The whole step at M = 1024 and N = 262144 rows against the streamlined float64 ORACLE evaluated on the GPU
-    (tools/parity_fullsize.py: oracle/svgp_streamlined.py is device-agnostic torch float64; the kernel matrix is
+    (tests/probes/parity_fullsize.py: oracle/svgp_streamlined.py is device-agnostic torch float64; the kernel matrix is
     restated with the squared-distance expansion in float64 and checked there against oracle/tfp_kernels).
 
     Tolerance 1e-4 of max|oracle tensor| (north_star) for the posterior moments, the ELBO sums, the cancelling
@@ -103,7 +103,7 @@ def test_step_against_float64_oracle_on_the_gpu(cuda_backend):
     (profiles/r01_parity_simt_path.jsonl)."""
     import os
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "probes"))
     import parity_fullsize
     o = parity_fullsize.run(262144, 1024, 2)
     print(o)

@@ -7,9 +7,9 @@ export PYTHONUNBUFFERED=1
 for cfg in "4 4 512" "0 4 512" "4 0 512" "2 2 512" "1 1 512" "4 4 128" "2 2 128" "1 1 128" "1 1 64"; do
   set -- $cfg
   echo "KSEG=$1 KSEG2=$2 chunk=$3" | tee -a $OUT/parity_matrix.jsonl
-  SVGP_SCALED_KSEG=$1 SVGP_SCALED_KSEG2=$2 timeout 300 python tools/parity_probe.py 32768,1024,2,$3 2>/dev/null | tee -a $OUT/parity_matrix.jsonl
+  SVGP_SCALED_KSEG=$1 SVGP_SCALED_KSEG2=$2 timeout 300 python tests/probes/parity_probe.py 32768,1024,2,$3 2>/dev/null | tee -a $OUT/parity_matrix.jsonl
 done
-timeout 600 python tools/parity_fullsize.py 262144 1024 2 > $OUT/parity_fullsize.jsonl 2> $OUT/parity_fullsize.err; cat $OUT/parity_fullsize.jsonl; tail -3 $OUT/parity_fullsize.err
+timeout 600 python tests/probes/parity_fullsize.py 262144 1024 2 > $OUT/parity_fullsize.jsonl 2> $OUT/parity_fullsize.err; cat $OUT/parity_fullsize.jsonl; tail -3 $OUT/parity_fullsize.err
 timeout 300 python tools/tc_probe.py 1000000 1024 64 syrk > $OUT/syrk_chunk_sweep.jsonl 2>&1; cat $OUT/syrk_chunk_sweep.jsonl
 for cfg in "0 0" "0 4" "0 2" "0 1" "4 4" "4 2" "2 2"; do
   set -- $cfg

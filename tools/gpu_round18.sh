@@ -3,7 +3,7 @@ TAG=${1:-r01x}
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 export PYTHONUNBUFFERED=1
-timeout 900 python tools/ablate_probe.py 32768 1024 2 > $OUT/ablate.jsonl 2> $OUT/ablate.err; cat $OUT/ablate.jsonl; tail -3 $OUT/ablate.err
+timeout 900 python tests/probes/ablate_probe.py 32768 1024 2 > $OUT/ablate.jsonl 2> $OUT/ablate.err; cat $OUT/ablate.jsonl; tail -3 $OUT/ablate.err
 for cfg in "0 0" "4 4" "2 4"; do
   set -- $cfg
   SVGP_SCALED_KSEG=$1 SVGP_SCALED_KSEG2=$2 timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/bench_k$1_$2.json 2> $OUT/bench_k$1_$2.err

@@ -6,7 +6,7 @@ export PYTHONUNBUFFERED=1
 for cfg in "1 0" "1 4" "1 2" "0 0"; do
   set -- $cfg
   echo "KCACHE=$1 KSEG=$2" | tee -a $OUT/parity_kcache.jsonl
-  SVGP_SCALED_KCACHE=$1 SVGP_SCALED_KSEG=$2 SVGP_SCALED_KSEG2=0 timeout 300 python tools/parity_probe.py 32768,1024,2 16384,256,4 2>&1 | grep -v Warn | tail -2 | tee -a $OUT/parity_kcache.jsonl
+  SVGP_SCALED_KCACHE=$1 SVGP_SCALED_KSEG=$2 SVGP_SCALED_KSEG2=0 timeout 300 python tests/probes/parity_probe.py 32768,1024,2 16384,256,4 2>&1 | grep -v Warn | tail -2 | tee -a $OUT/parity_kcache.jsonl
 done
 SVGP_SCALED_KSEG=4 SVGP_SCALED_KSEG2=0 timeout 600 python -m pytest tests -m gpu -q -x > $OUT/pytest_gpu.log 2>&1; tail -3 $OUT/pytest_gpu.log
 for cfg in "1 0" "1 4" "1 2" "1 8"; do
