@@ -299,6 +299,15 @@ def run_gpu(args):
         except Exception:  # noqa: BLE001
             pass
         achieved = 3.0 * top_flops / (top_ms * 1e-3) / 1e12
+        # K1 (the kernel-matrix builder) is the HBM-bound kernel of the path: 4 fp16 planes of N x M written once
+        k1_ms = prof.get("svgp_kernel_fwd", {}).get("max_ms")
+        hbm_peak = peaks.get("hbm_gbs")
+        k1 = None
+        if k1_ms:
+            k1_gbs = (4.0 * N * M * 2 + N * 8 * 4) / (k1_ms * 1e-3) / 1e9
+            k1 = {"bound": "hbm", "kernel": "svgp_kernel_fwd (planes builder)", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": k1_gbs / hbm_peak if hbm_peak else None, "kernel_ms": k1_ms,
+                  "algorithmic_bytes": 4.0 * N * M * 2 + N * 8 * 4}
         line = {
             "metric": METRIC, "value": n_total / t_s, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -319,6 +328,7 @@ def run_gpu(args):
                          "step_tensor_flops_launched": 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M,
                          "step_tensor_tflops_launched": 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M / t_s / 1e12,
                          "f16_cublas_tflops_in_run": f16_run},
+            "roofline_k1": k1,
             "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "kernels_calls": {k: v["calls"] for k, v in prof.items()},
             "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "datapoints/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,

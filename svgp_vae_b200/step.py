@@ -40,6 +40,29 @@ def _world(group):
     return 1 if group is None else torch.distributed.get_world_size(group)
 
 
+def _allgather0(t, group):
+    """Concatenate the ranks' equally shaped tensors along dim 0 (rank order)."""
+    t = t.contiguous()
+    W = _world(group)
+    out = torch.empty((W * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    try:
+        torch.distributed.all_gather_into_tensor(out, t, group=group)
+    except (RuntimeError, NotImplementedError):          # backends without the flat variant
+        torch.distributed.all_gather(list(out.chunk(W, 0)), t, group=group)
+    return out
+
+
+def _own_channels(L, group, enabled=True):
+    """Channel ownership of the float64 M x M stage when the datapoints are sharded over `group`: rank r runs K3 for
+    channels [r L / W, (r + 1) L / W) and the results are all-gathered (K3 is channel-parallel: per-channel
+    factorisations and products).  Needs L % W == 0, otherwise the stage stays replicated."""
+    W = _world(group)
+    if not enabled or W == 1 or L % W != 0:
+        return slice(0, L), False
+    r = torch.distributed.get_rank(group)
+    return slice(r * (L // W), (r + 1) * (L // W)), True
+
+
 def mm_shared(K, jitter):
     """Channel-independent part of the M x M stage: (K + jI)^-1, its log-det and inverse Cholesky factor (:318-319)."""
     M = K.shape[-1]
@@ -142,15 +165,22 @@ class _SVGPStep(torch.autograd.Function):
             b_total = float(count.item())
         c = N_train / b_total
 
-        lc = mm_chunk_channels(L, M, y32.device, cfg.get("mm_chunk"))
         tri = cfg.get("tri", True)
         K64 = Kmm.double()
-        if lc >= L:
+        own, sharded = _own_channels(L, group, cfg.get("shard_k3", True))
+        lc = mm_chunk_channels(own.stop - own.start, M, y32.device, cfg.get("mm_chunk"))
+        one_chunk = lc >= own.stop - own.start
+        if sharded and not one_chunk:            # the chunked stage is replicated (not sharded yet)
+            own, sharded = slice(0, L), False
+            lc = mm_chunk_channels(L, M, y32.device, cfg.get("mm_chunk"))
+        if one_chunk:
             with torch.enable_grad():
-                leaves = [t.detach().requires_grad_(True) for t in (A, V, sums, K64)]
+                leaves = [t.detach().requires_grad_(True) for t in (A[own], V[own], sums[:, own].contiguous(), K64)]
                 mm = mm_stage(leaves[0], leaves[1], leaves[2], leaves[3], jitter, c, b_total)
             # pass B
             S, w, Kinv, Linv = mm["S"].detach(), mm["w"].detach(), mm["Kinv"].detach(), mm["Linv"]
+            if sharded:                      # every rank needs all channels' S_l, w_l and factors for ITS rows
+                S, w, Linv = _allgather0(S, group), _allgather0(w, group), _allgather0(Linv, group)
             # quadratic forms through the Cholesky factors: |R^-1 k|^2 is a sum of squares (half the MMA work and
             # no cancellation between the large entries of S_l / Kinv)
             if tri:
@@ -161,6 +191,10 @@ class _SVGPStep(torch.autograd.Function):
                 q1 = be.rowquad(kop, S)
             recon, kl, ce0 = mm["recon"].detach().clone(), mm["kl"].detach().clone(), mm["ce"].detach()
             mu_hat, A_hat = mm["mu_hat"].detach(), mm["A_hat"].detach()
+            if sharded:
+                recon, kl, ce0, mu_hat = (_allgather0(t, group) for t in (recon, kl, ce0, mu_hat))
+                A_hat = _allgather0(A_hat, group) if cfg.get("return_A_hat", True) else None
+            del Linv
         else:
             # chunked M x M stage: no graph in the forward (the backward re-materialises it chunk by chunk); S is
             # the only (L, M, M) result that stays (pass D reads it), the factors feed the row quads chunk by chunk
@@ -192,6 +226,7 @@ class _SVGPStep(torch.autograd.Function):
             ce = ce - 0.5 * clipsum
 
         ctx.cfg, ctx.kop, ctx.mm, ctx.leaves, ctx.lc = cfg, kop, mm, leaves, lc
+        ctx.own, ctx.sharded, ctx.one_chunk = own, sharded, one_chunk
         ctx.b_total, ctx.c = b_total, c
         ctx.save_for_backward(Fx32, Fz32, hyp32, y32, n32, p, kappa, h, pv, q1 if clip else pv, mask if clip else pv, S, w, Kinv)
         ctx.in_dtypes = (Fx.dtype, Fz.dtype, hyp.dtype, y.dtype, noise.dtype)
@@ -248,11 +283,18 @@ class _SVGPStep(torch.autograd.Function):
         # ---- adjoint of the replicated M x M stage -----------------------------------------------
         A_, V_, sums_, K_ = ctx.leaves
         lc = ctx.lc
-        if lc >= L:
+        own, sharded = ctx.own, ctx.sharded
+        if ctx.one_chunk:
+            # (channel-sharded K3: this rank differentiates its own channels; dKinv likewise is its channels' share)
             gA, gV, gsums, gK = torch.autograd.grad(
                 [mm["S"], mm["w"], mm["Kinv"], mm["recon"], mm["kl"], mm["ce"]], [A_, V_, sums_, K_],
-                grad_outputs=[G_S, G_w, G_Kinv, g_recon, g_kl, g_ce], allow_unused=True)
+                grad_outputs=[G_S[own], G_w[own], -G_S[own].sum(0, keepdim=True), g_recon[own], g_kl[own], g_ce[own]],
+                allow_unused=True)
             gsums = torch.zeros_like(sums_) if gsums is None else gsums
+            if sharded:
+                gA, gV = _allgather0(gA, group), _allgather0(gV, group)
+                gsums = _allgather0(gsums.t().contiguous(), group).t().contiguous()
+                _allreduce(gK, group)
             # ---- pass D: back to the rows --------------------------------------------------------
             # dK_nm and k^T (dA + dA^T) k from ONE pass over the products K G_s: stacked matrices
             # [dA + dA^T ; S - Kinv] with per-row weights [p | 2 dq1] applied in the epilogue.  p_v = kappa - k^T (Kinv - S_l) k:
@@ -342,7 +384,7 @@ class _SVGPStep(torch.autograd.Function):
 
 
 def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, group=None, tc=None, tri=True,
-              chunk_rows=0, mm_chunk=None, return_A_hat=True):
+              chunk_rows=0, mm_chunk=None, return_A_hat=True, shard_k3=True):
     """All-channel SVGP step on one shard of datapoints.
 
     Fx (N, d) data features, Fz (M, d) inducing features, hyp (4,) kernel hypers, y / noise (N, L)
@@ -351,13 +393,15 @@ def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, gro
 
     Returns dict(p_m, p_v (N, L); recon_l, kl_l, ce_l (L,) float64 -- GLOBAL sums, identical on all
     ranks; mu_hat (L, M), A_hat (L, M, M) float64, detached).
+    ``shard_k3``: with a group of W ranks and L % W == 0, every rank runs the float64 M x M stage for L / W channels and
+    the results are all-gathered (default); False keeps the stage replicated.
     ``mm_chunk``: channels per chunk of the float64 M x M stage (default: one chunk while its state fits, see
     mm_chunk_channels); ``return_A_hat=False`` skips the (L, M, M) A_hat output on the chunked path.
     Gradient convention when sharded: make each rank's loss ``local terms + global terms / world``;
     gradients of replicated parameters then come out as per-rank partial sums (sum them).
     """
     cfg = dict(spec=spec, N_train=float(N_train), jitter=float(jitter), clip_pv=clip_pv, group=group, tc=tc, tri=tri,
-               chunk_rows=chunk_rows, mm_chunk=mm_chunk, return_A_hat=return_A_hat)
+               chunk_rows=chunk_rows, mm_chunk=mm_chunk, return_A_hat=return_A_hat, shard_k3=shard_k3)
     pm, pv, recon, kl, ce, mu_hat, A_hat = _SVGPStep.apply(Fx, Fz, hyp, y, noise, cfg)
     return dict(p_m=pm, p_v=pv, recon_l=recon, kl_l=kl, ce_l=ce, mu_hat=mu_hat, A_hat=A_hat)
 

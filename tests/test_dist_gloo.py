@@ -47,14 +47,16 @@ def _worker(rank, world, port, kind, cfg, clip, out):
     Jt = J.detach().clone()
     dist.all_reduce(Jt)
     out[rank] = dict(p_m=res["p_m"].detach(), p_v=res["p_v"].detach(), KL_term=float(res["KL_term"]), J=float(Jt),
-                     gy=grads[0], gn=grads[1], pg=pg)
+                     gy=grads[0], gn=grads[1], pg=pg, mu_hat=res["mu_hat"], A_hat=res["A_hat"])
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,clip", [("mnist", False), ("sprites", True)])
-def test_sharded_step_matches_single_process(oracle_backend, kind, clip):
+@pytest.mark.parametrize("kind,clip,L", [("mnist", False, 3), ("sprites", True, 3), ("mnist", False, 4), ("sprites", True, 4)])
+def test_sharded_step_matches_single_process(oracle_backend, kind, clip, L):
+    """L = 3: the float64 M x M stage stays replicated (3 % 2 != 0); L = 4: it is channel-sharded (two channels per rank,
+    results all-gathered, dK_mm all-reduced)."""
     from conftest import MNIST_FIXTURE, rel_err
-    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=3) if kind == "mnist" else configs.sprites_inputs(M=72, L=3, normalize=False)
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=L) if kind == "mnist" else configs.sprites_inputs(M=72, L=L, normalize=False)
     _, s, _, sp = refs.make_pair(kind, cfg, "cpu")
     r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=clip)
     world = 2
@@ -69,6 +71,7 @@ def test_sharded_step_matches_single_process(oracle_backend, kind, clip):
         assert rel_err(o["p_m"], r1["p_m"][sl]) < tol and rel_err(o["p_v"], r1["p_v"][sl]) < tol
         assert abs(o["KL_term"] - float(r1["KL_term"])) < tol * abs(float(r1["KL_term"]))
         assert abs(o["J"] - float(J1)) < tol * abs(float(J1))
+        assert rel_err(o["mu_hat"], r1["mu_hat"]) < tol and rel_err(o["A_hat"], r1["A_hat"]) < tol
         assert rel_err(o["gy"], g1[0][sl]) < 1e-5 and rel_err(o["gn"], g1[1][sl]) < 1e-5
         for a, b in zip(o["pg"], g1[2:]):
             if b.abs().max() > 0:
