@@ -196,9 +196,19 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep NCCL's version banner off stdout (ONE JSON line)
-        dist.init_process_group("nccl", device_id=dev)
-        group = dist.group.WORLD
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            group = dist.group.WORLD
+            dist.all_reduce(torch.zeros(1, device=dev), group=group)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     be = backend.get_backend()
     N, M, L = args.n, args.m, args.l
     n_total = N * world
