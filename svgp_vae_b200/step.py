@@ -300,7 +300,17 @@ class _SVGPStep(torch.autograd.Function):
             # [dA + dA^T ; S - Kinv] with per-row weights [p | 2 dq1] applied in the epilogue.  p_v = kappa - k^T (Kinv - S_l) k:
             # the difference is formed in float64 BEFORE the fp16 split, so the 1 / jitter-sized components that
             # Kinv and S_l share never enter the tensor-core products
-            Gstack = torch.cat([gA + gA.transpose(-1, -2), S - Kinv], dim=0).contiguous()
+            if kop.tc:
+                # operand planes filled in pieces of 16 channels: no (2L, M, M) float64 copy next to gA and S
+                hi = torch.empty((2 * L, M, M), dtype=torch.float16, device=dev)
+                lo = torch.empty_like(hi)
+                inv = torch.empty(2 * L, dtype=torch.float32, device=dev)
+                for l0 in range(0, L, 16):
+                    be.planes_into(gA[l0:l0 + 16] + gA[l0:l0 + 16].transpose(-1, -2), hi, lo, inv, l0)
+                    be.planes_into(S[l0:l0 + 16] - Kinv, hi, lo, inv, L + l0)
+                Gstack = Planes(hi, lo, inv)
+            else:
+                Gstack = torch.cat([gA + gA.transpose(-1, -2), S - Kinv], dim=0).contiguous()
             del gA
         else:
             # re-materialise the stage chunk by chunk; every chunk's dA_l + dA_l^T goes straight into the operand
