@@ -529,6 +529,84 @@ __global__ void __launch_bounds__(THREADS) kernel_bwd_kernel(
   }
 }
 
+// Z pass specialised for the product of two 4-feature SE factors (the SWEEP kernel; the generic pass above spends
+// ~20 ns per 1000 entries on run-time factor dispatch, a second distance evaluation and four double adds per entry).
+// With c = g k:  dz_f = (sum_i c x_if - z_f sum_i c) / l^2,  dl = sum c r2 / l^3,  damp = 2 sum c / amp  per block --
+// a thread owns one inducing point (features in registers) and 16 of the 64 datapoints of a tile, the datapoint
+// features are broadcast float4 loads, g is read in coalesced 128-byte rows; one float partial per tile, folded into
+// double per thread (the hyper-parameter sums cancel heavily), one double atomic per (column, feature) per block.
+__global__ void __launch_bounds__(THREADS) kernel_bwd_z_se44_kernel(
+    const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz, int64_t M,
+    const float* __restrict__ hyp, const float* __restrict__ G, int64_t ldg, double* __restrict__ dFz,
+    double* __restrict__ dhyp) {
+  __shared__ __align__(16) float xs[TILE * 8];
+  __shared__ double red[4][TILE][11];            // per row group: 8 feature sums, sum c, sum c r2a, sum c r2b
+  const Hyp h = load_hyp(hyp);
+  const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;
+  const int64_t ntr = (N + TILE - 1) / TILE;
+  const int64_t col0 = (int64_t)blockIdx.x * TILE, gc = col0 + c;
+  float z[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) z[f] = gc < M ? Fz[gc * ldz + f] : 0.f;
+  const float LOG2E = 1.4426950408889634f;
+  const float ca = -0.5f * LOG2E / (h.len_a * h.len_a), cb = -0.5f * LOG2E / (h.len_b * h.len_b);
+  const float amp2 = h.amp_a * h.amp_a * h.amp_b * h.amp_b;
+  double acc[11];
+#pragma unroll
+  for (int q = 0; q < 11; ++q) acc[q] = 0.0;
+  for (int64_t rt = blockIdx.y; rt < ntr; rt += gridDim.y) {
+    const int64_t row0 = rt * TILE;
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < TILE * 8; idx += THREADS) {
+      const int64_t gr = row0 + (idx >> 3);
+      xs[idx] = gr < N ? Fx[gr * ldx + (idx & 7)] : 0.f;
+    }
+    __syncthreads();
+    float t[11];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) t[q] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < TILE / 4; ++j) {
+      const int r = rg + 4 * j;
+      const int64_t gr = row0 + r;
+      const float g = (gr < N && gc < M) ? __ldg(G + gr * ldg + gc) : 0.f;
+      const float4 xa = *reinterpret_cast<const float4*>(xs + r * 8);
+      const float4 xb = *reinterpret_cast<const float4*>(xs + r * 8 + 4);
+      float d0 = xa.x - z[0], d1 = xa.y - z[1], d2 = xa.z - z[2], d3 = xa.w - z[3];
+      float e0 = xb.x - z[4], e1 = xb.y - z[5], e2 = xb.z - z[6], e3 = xb.w - z[7];
+      const float ra = fmaf(d3, d3, fmaf(d2, d2, fmaf(d1, d1, d0 * d0)));
+      const float rb = fmaf(e3, e3, fmaf(e2, e2, fmaf(e1, e1, e0 * e0)));
+      const float ck = g * amp2 * exp2f(fmaf(ca, ra, cb * rb));
+      t[0] = fmaf(ck, xa.x, t[0]); t[1] = fmaf(ck, xa.y, t[1]); t[2] = fmaf(ck, xa.z, t[2]); t[3] = fmaf(ck, xa.w, t[3]);
+      t[4] = fmaf(ck, xb.x, t[4]); t[5] = fmaf(ck, xb.y, t[5]); t[6] = fmaf(ck, xb.z, t[6]); t[7] = fmaf(ck, xb.w, t[7]);
+      t[8] += ck; t[9] = fmaf(ck, ra, t[9]); t[10] = fmaf(ck, rb, t[10]);
+    }
+#pragma unroll
+    for (int q = 0; q < 11; ++q) acc[q] += (double)t[q];
+  }
+#pragma unroll
+  for (int q = 0; q < 11; ++q) red[rg][c][q] = acc[q];
+  __syncthreads();
+  if (rg == 0 && gc < M) {
+    double s[11];
+#pragma unroll
+    for (int q = 0; q < 11; ++q) s[q] = red[0][c][q] + red[1][c][q] + red[2][c][q] + red[3][c][q];
+    const double ila = 1.0 / ((double)h.len_a * h.len_a), ilb = 1.0 / ((double)h.len_b * h.len_b);
+#pragma unroll
+    for (int f = 0; f < 8; ++f) atomicAdd(&dFz[gc * 8 + f], (s[f] - (double)z[f] * s[8]) * (f < 4 ? ila : ilb));
+    red[0][c][0] = 2.0 * s[8] / h.amp_a; red[0][c][1] = s[9] * ila / h.len_a;
+    red[0][c][2] = 2.0 * s[8] / h.amp_b; red[0][c][3] = s[10] * ilb / h.len_b;
+  } else if (rg == 0) {
+    red[0][c][0] = red[0][c][1] = red[0][c][2] = red[0][c][3] = 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    double s = 0.0;
+    for (int k = 0; k < TILE; ++k) s += red[0][k][threadIdx.x];
+    atomicAdd(&dhyp[threadIdx.x], s);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // element-wise apply (diag_only=True)
 // ------------------------------------------------------------------------------------------
@@ -736,7 +814,12 @@ int svgp_kernel_bwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, in
     if (gy > ntr) gy = ntr;
     if (gy < 1) gy = 1;
     dim3 grid((unsigned)(ntc < 65535 ? ntc : 65535), (unsigned)gy);
-    kernel_bwd_kernel<false><<<grid, THREADS, sm, st>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, G, ldg, nullptr, dFz, dhyp);
+    const bool se44 = type_a == SVGP_K_SE && type_b == SVGP_K_SE && dim_a == 4 && dim_b == 4 && ntc <= 65535 &&
+                      !getenv("SVGP_K1_BWD_GENERIC");
+    if (se44)
+      kernel_bwd_z_se44_kernel<<<grid, THREADS, 0, st>>>(Fx, ldx, N, Fz, ldz, M, hyp, G, ldg, dFz, dhyp);
+    else
+      kernel_bwd_kernel<false><<<grid, THREADS, sm, st>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, G, ldg, nullptr, dFz, dhyp);
     int rc = check_launch("svgp_kernel_bwd(z)");
     if (rc) return rc;
   }
