@@ -1093,11 +1093,13 @@ bool tc_shape_ok(const svgp_kop* kop) {
   return kop->M >= 128 && kop->N >= 2048 && (kop->ldkh % 8) == 0 && (kop->ldkt % 8) == 0;
 }
 
-// super-chunk length: the K^T slice of one super-chunk (M rows x sc datapoints x hi/lo fp16) should occupy well under
-// half of the 126 MB L2, because items of two consecutive super-chunks are in flight around a boundary
+// super-chunk length: the K^T slice of one super-chunk (M rows x sc datapoints x hi/lo fp16) is what the CTAs in flight
+// stream out of L2, and every item ends with a float64 read-modify-write of its tile (55 GB of DRAM traffic per call
+// at 12288-row super-chunks).  Measured at (1e6, 1024, 64) (profiles/r01_syrk_superchunk_sweep.jsonl): 212 / 201 / 199 /
+// 203 / 215 ms at 16384 / 24576 / 28672 / 32768 / 40960 rows -- the optimum is a slice of about the L2 size (112 MB).
 static int64_t syrk_superchunk_rows(int64_t M, int64_t chunk) {
   const char* e = getenv("SVGP_SYRK_SC");
-  int64_t sc = (e && atoll(e) > 0) ? atoll(e) : (48LL << 20) / (M * 4);
+  int64_t sc = (e && atoll(e) > 0) ? atoll(e) : (112LL << 20) / (M * 4);
   sc = sc / chunk * chunk;
   return sc < chunk ? chunk : sc;
 }
