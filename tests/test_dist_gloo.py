@@ -22,7 +22,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, kind, cfg, clip, out):
+def _worker(rank, world, port, kind, cfg, clip, out, mm_chunk=None):
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
@@ -36,7 +36,7 @@ def _worker(rank, world, port, kind, cfg, clip, out):
     sl = slice(rank * n, (rank + 1) * n)
     y = cfg["y"][sl].clone().requires_grad_(True)
     nz = cfg["noise"][sl].clone().requires_grad_(True)
-    res = s.elbo_step(cfg["aux"][sl], y, nz, clip_pv=clip, group=dist.group.WORLD)
+    res = s.elbo_step(cfg["aux"][sl], y, nz, clip_pv=clip, group=dist.group.WORLD, mm_chunk=mm_chunk)
     gm, gv = refs.upstream(tuple(cfg["y"].shape))
     J = (gm[sl].to(res["p_m"].dtype) * res["p_m"]).sum().double() + (gv[sl].to(res["p_v"].dtype) * res["p_v"]).sum().double() \
         + res["KL_term"] / world
@@ -51,10 +51,11 @@ def _worker(rank, world, port, kind, cfg, clip, out):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,clip,L", [("mnist", False, 3), ("sprites", True, 3), ("mnist", False, 4), ("sprites", True, 4)])
-def test_sharded_step_matches_single_process(oracle_backend, kind, clip, L):
+@pytest.mark.parametrize("kind,clip,L,mm_chunk", [("mnist", False, 3, None), ("sprites", True, 3, None), ("mnist", False, 4, None),
+                                                  ("sprites", True, 4, None), ("mnist", False, 4, 1)])
+def test_sharded_step_matches_single_process(oracle_backend, kind, clip, L, mm_chunk):
     """L = 3: the float64 M x M stage stays replicated (3 % 2 != 0); L = 4: it is channel-sharded (two channels per rank,
-    results all-gathered, dK_mm all-reduced)."""
+    results all-gathered, dK_mm all-reduced); mm_chunk = 1: the channel-chunked stage under a group (replicated)."""
     from conftest import MNIST_FIXTURE, rel_err
     cfg = configs.mnist_inputs(MNIST_FIXTURE, L=L) if kind == "mnist" else configs.sprites_inputs(M=72, L=L, normalize=False)
     _, s, _, sp = refs.make_pair(kind, cfg, "cpu")
@@ -62,7 +63,7 @@ def test_sharded_step_matches_single_process(oracle_backend, kind, clip, L):
     world = 2
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, _free_port(), kind, cfg, clip, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), kind, cfg, clip, out, mm_chunk), nprocs=world, join=True)
     n = cfg["aux"].shape[0] // world
     tol = 2e-6
     for r in range(world):
