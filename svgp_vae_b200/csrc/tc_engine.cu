@@ -1096,10 +1096,13 @@ bool tc_shape_ok(const svgp_kop* kop) {
 // super-chunk length: the K^T slice of one super-chunk (M rows x sc datapoints x hi/lo fp16) is what the CTAs in flight
 // stream out of L2, and every item ends with a float64 read-modify-write of its tile (55 GB of DRAM traffic per call
 // at 12288-row super-chunks).  Measured at (1e6, 1024, 64) (profiles/r01_syrk_superchunk_sweep.jsonl): 212 / 201 / 199 /
-// 203 / 215 ms at 16384 / 24576 / 28672 / 32768 / 40960 rows -- the optimum is a slice of about the L2 size (112 MB).
+// 203 / 215 ms at 16384 / 24576 / 28672 / 32768 / 40960 rows (204 at 20480) -- the speed optimum is a slice of about
+// the L2 size.  The chunk partial sums of an item are folded in fp32 registers, though, and the forward A_l feeds an
+// ill-conditioned inverse: p_m against the float64 oracle went 4.7e-5 -> 8.1e-5 between 24 and 56 partials per item
+// (M = 1024).  80 MB (20480 rows, 40 partials) keeps most of the speed and the accuracy margin.
 static int64_t syrk_superchunk_rows(int64_t M, int64_t chunk) {
   const char* e = getenv("SVGP_SYRK_SC");
-  int64_t sc = (e && atoll(e) > 0) ? atoll(e) : (112LL << 20) / (M * 4);
+  int64_t sc = (e && atoll(e) > 0) ? atoll(e) : (80LL << 20) / (M * 4);
   sc = sc / chunk * chunk;
   return sc < chunk ? chunk : sc;
 }
