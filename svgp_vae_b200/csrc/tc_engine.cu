@@ -1174,7 +1174,8 @@ int tc_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const fl
   P.tri = tri; P.K_hi = (const __half*)kop->Kh; P.K_lo = (const __half*)kop->Kl; P.ldkh = kop->ldkh; P.q = q; P.ldq = ldq;
   // channels whose factor planes (2 * M*M*2 bytes each) share ~half of the 126 MB L2
   int64_t per = 2 * kop->M * kop->M * 2;
-  int64_t g = (64LL << 20) / (per > 0 ? per : 1);
+  const char* eg = getenv("SVGP_QUAD_L2MB");
+  int64_t g = ((eg && atoll(eg) > 0 ? atoll(eg) : 64LL) << 20) / (per > 0 ? per : 1);
   if (g < 1) g = 1;
   if (g > L) g = L;
   while (L % g) --g;                       // keep groups uniform

@@ -40,11 +40,16 @@ def main():
     Lt = torch.tril(S).contiguous()
     tag = os.environ.get("SVGP_TC_BK", "default")
     flush = os.environ.get("SVGP_SYRK_FLUSH", "default")
-    for chunk in (128, 256, 512, 1024, 2048):
+    for chunk in ((128, 256, 512, 1024, 2048) if only != "quad" else ()):
         t = timeit(lambda: be.syrk(kop, W, chunk_rows=chunk))
         print(json.dumps(dict(op="syrk_tc", bk=tag, flush=flush, chunk=chunk, N=N, M=M, L=L, ms=t,
                               alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
     if only == "syrk":
+        return
+    if only == "quad":
+        Ltpl = be.planes(Lt)
+        t = timeit(lambda: be.rowquad(kop, Ltpl, tri=True))
+        print(json.dumps(dict(op="rowquad_tc_tri", N=N, M=M, L=L, ms=t, alg_TFLOPs=N * M * M * L / t / 1e9)), flush=True)
         return
     Spl, Ltpl = be.planes(S), be.planes(Lt)
     t = timeit(lambda: be.planes(S))
