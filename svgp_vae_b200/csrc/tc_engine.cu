@@ -1100,9 +1100,12 @@ bool tc_shape_ok(const svgp_kop* kop) {
 // the L2 size.  The chunk partial sums of an item are folded in fp32 registers, though, and the forward A_l feeds an
 // ill-conditioned inverse: p_m against the float64 oracle went 4.7e-5 -> 8.1e-5 between 24 and 56 partials per item
 // (M = 1024).  80 MB (20480 rows, 40 partials) keeps most of the speed and the accuracy margin.
-static int64_t syrk_superchunk_rows(int64_t M, int64_t chunk) {
+static int64_t syrk_superchunk_rows(int64_t N, int64_t M, int64_t chunk) {
   const char* e = getenv("SVGP_SYRK_SC");
   int64_t sc = (e && atoll(e) > 0) ? atoll(e) : (80LL << 20) / (M * 4);
+  // small problems: at least 8 items per tile, i.e. fewer fp32 partial sums per float64 write-back -- the write-back
+  // traffic is irrelevant there and the few items do not average the fp32 rounding of long register sums
+  if (!(e && atoll(e) > 0) && sc > N / 8) sc = N / 8 > 4 * chunk ? N / 8 : 4 * chunk;
   sc = sc / chunk * chunk;
   return sc < chunk ? chunk : sc;
 }
@@ -1131,7 +1134,7 @@ int tc_syrk(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* win
   int64_t chunk = chunk_rows > 0 ? chunk_rows : 512;
   chunk = (chunk + 63) / 64 * 64;
   P.chunk_rows = chunk;
-  P.sc_rows = syrk_superchunk_rows(kop->M, chunk);
+  P.sc_rows = syrk_superchunk_rows(kop->N, kop->M, chunk);
   P.nsc = (int)ceil_div(kop->N, P.sc_rows);
   P.ntile = syrk_tile_count(kop->M, BN);
   P.flush_every = syrk_flush_every(chunk);
