@@ -170,9 +170,6 @@ class _SVGPStep(torch.autograd.Function):
         own, sharded = _own_channels(L, group, cfg.get("shard_k3", True))
         lc = mm_chunk_channels(own.stop - own.start, M, y32.device, cfg.get("mm_chunk"))
         one_chunk = lc >= own.stop - own.start
-        if sharded and not one_chunk:            # the chunked stage is replicated (not sharded yet)
-            own, sharded = slice(0, L), False
-            lc = mm_chunk_channels(L, M, y32.device, cfg.get("mm_chunk"))
         if one_chunk:
             with torch.enable_grad():
                 leaves = [t.detach().requires_grad_(True) for t in (A[own], V[own], sums[:, own].contiguous(), K64)]
@@ -206,18 +203,35 @@ class _SVGPStep(torch.autograd.Function):
             mu_hat = torch.empty_like(V)
             recon, kl, ce0 = (torch.empty(L, dtype=torch.float64, device=A.device) for _ in range(3))
             q1 = torch.empty((N, L), dtype=torch.float32, device=A.device)
+            W_, L_own = _world(group) if sharded else 1, own.stop - own.start
             with torch.no_grad():
                 Kinv, ldK, LinvK = mm_shared(K64, jitter)
                 h = (be.rowquad(kop, LinvK, tri=True) if tri else be.rowquad(kop, Kinv)).squeeze(1)
-                for l0 in range(0, L, lc):
-                    sl = slice(l0, min(L, l0 + lc))
+                for l0 in range(own.start, own.stop, lc):
+                    sl = slice(l0, min(own.stop, l0 + lc))
                     mc = mm_channels(A[sl], V[sl], sums[:, sl].contiguous(), K64, Kinv, ldK, jitter, c, b_total)
                     S[sl], w[sl], mu_hat[sl] = mc["S"], mc["w"], mc["mu_hat"]
                     recon[sl], kl[sl], ce0[sl] = mc["recon"], mc["kl"], mc["ce"]
                     if want_Ahat:
                         A_hat[sl] = mc["A_hat"]
-                    be.rowquad(kop, mc["Linv"] if tri else mc["S"], tri=tri, out=q1[:, sl])
-                    del mc
+                    F = mc["Linv"] if tri else mc["S"]
+                    if sharded:
+                        # every rank needs every channel's factor for the quadratic forms of ITS rows: gather this
+                        # chunk of all ranks (same chunking everywhere) and scatter the pieces to their columns
+                        n, off = sl.stop - sl.start, sl.start - own.start
+                        Fall = _allgather0(F, group)
+                        for r in range(W_):
+                            be.rowquad(kop, Fall[r * n:(r + 1) * n], tri=tri, out=q1[:, r * L_own + off:r * L_own + off + n])
+                        del Fall
+                    else:
+                        be.rowquad(kop, F, tri=tri, out=q1[:, sl])
+                    del mc, F
+                if sharded:
+                    S = _allgather0(S[own], group)
+                    w, mu_hat = _allgather0(w[own], group), _allgather0(mu_hat[own], group)
+                    recon, kl, ce0 = (_allgather0(t[own], group) for t in (recon, kl, ce0))
+                    if want_Ahat:
+                        A_hat = _allgather0(A_hat[own], group)
         pm = be.gemm_nn(kop, w.float().contiguous())
         pv, clipsum, mask = be.predictive(kappa, h, q1, p, clip)
         ce = ce0.clone()
@@ -277,8 +291,7 @@ class _SVGPStep(torch.autograd.Function):
         # d/d Kinv of h_i = k_i^T Kinv k_i is sum_i (-G_kappa_i) k_i k_i^T = -sum_l G_S,l.  Taking it from G_S (instead
         # of a separate single-channel SYRK) is not only free: both adjoints are amplified by the squared inverses
         # downstream (-Kinv G Kinv and -S_l G S_l, |Kinv|, |S_l| ~ 1 / jitter in the directions the data does not
-        # see) and only cancel there if they carry the SAME rounding noise.
-        G_Kinv = -G_S.sum(0, keepdim=True)
+        # see) and only cancel there if they carry the SAME rounding noise.  (Formed below from this rank's channels.)
 
         # ---- adjoint of the replicated M x M stage -----------------------------------------------
         A_, V_, sums_, K_ = ctx.leaves
@@ -331,10 +344,10 @@ class _SVGPStep(torch.autograd.Function):
                 K_leaf = K_.detach().requires_grad_(True)
                 Kinv_g, ldK_g, _ = mm_shared(K_leaf, jitter)
             gK = torch.zeros_like(K_)
-            gKinv = G_Kinv.clone()
+            gKinv = -G_S[own].sum(0, keepdim=True)          # this rank's channels' share of dKinv (all of it when not sharded)
             gldK = torch.zeros_like(ldK_g)
-            for l0 in range(0, L, lc):
-                sl = slice(l0, min(L, l0 + lc))
+            for l0 in range(own.start, own.stop, lc):
+                sl = slice(l0, min(own.stop, l0 + lc))
                 with torch.enable_grad():
                     lv = [t.detach().requires_grad_(True) for t in (A_[sl], V_[sl], sums_[:, sl].contiguous(), K_, Kinv_g, ldK_g)]
                     mc = mm_channels(*lv, jitter, c, b_total)
@@ -351,6 +364,17 @@ class _SVGPStep(torch.autograd.Function):
             (gK_sh,) = torch.autograd.grad([Kinv_g, ldK_g], [K_leaf], grad_outputs=[gKinv, gldK])
             gK += gK_sh
             del G_S, gKinv
+            if sharded:
+                # the other ranks' dA_l + dA_l^T (operand planes / float64), dv_l and row-sum adjoints; dK_mm summed
+                if kop.tc:
+                    hi[:L] = _allgather0(hi[own], group)
+                    lo[:L] = _allgather0(lo[own], group)
+                    inv[:L] = _allgather0(inv[own], group)
+                else:
+                    G64[:L] = _allgather0(G64[own], group)
+                gV = _allgather0(gV[own], group)
+                gsums = _allgather0(gsums[:, own].t().contiguous(), group).t().contiguous()
+                _allreduce(gK, group)
             for l0 in range(0, L, lc):
                 put(S[l0:l0 + lc] - Kinv, L + l0)
             Gstack = Planes(hi, lo, inv) if kop.tc else G64
