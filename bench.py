@@ -36,9 +36,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=N_PER_GPU, help="datapoints per GPU (default: the named workload)")
-    ap.add_argument("--m", type=int, default=M_IND)
-    ap.add_argument("--l", type=int, default=L_CH)
+    # (--rows / --inducing / --channels: spellings that torchrun's own option abbreviations do not swallow)
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=N_PER_GPU, help="datapoints per GPU (default: the named workload)")
+    ap.add_argument("--m", "--inducing", dest="m", type=int, default=M_IND)
+    ap.add_argument("--l", "--channels", dest="l", type=int, default=L_CH)
     ap.add_argument("--mm-chunk", type=int, default=0, help="channels per chunk of the float64 M x M stage (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=1024)
