@@ -16,7 +16,7 @@ Everything is torch-CPU float64 so that gradients of any output can be taken wit
 torch autograd (the reference uses tf.gradients, MNIST_experiment.py:202-208).
 Parameters are plain tensors; set ``requires_grad_`` on the ones to differentiate.
 
-PARITY UNPINNED (see oracle/__init__.py).
+Pinned to the reference source under the TF shim; unpinned w.r.t. TensorFlow itself (see oracle/__init__.py).
 """
 import math
 

@@ -16,7 +16,7 @@ organised the way the CUDA path computes it (DESIGN.md "collaps
     from the un-jittered K, mu_hat = c K S v and A_hat = K S K use the un-jittered K,
     a_l = Kinv mu_hat uses the jittered inverse (SVGPVAE_model.py:319,328,331,339-341).
 
-float64 torch-CPU; differentiable.  PARITY UNPINNED (see oracle/__init__.py).
+float64 torch (CPU, or CUDA for the full-size probes); differentiable.  Pinning: see oracle/__init__.py.
 """
 import math
 
