@@ -273,3 +273,19 @@ def test_svigp_hensman_against_reference_source(oracle_backend, normalize, batch
     gold = np.load(os.path.join(GOLDEN, "svigp_golden.npz"))
     s, aux, gm = refs.svigp_case(normalize, "cpu", MNIST_FIXTURE)
     refs.svigp_check(s, aux, gm, gold, "svigp_norm" if normalize else "svigp", TOL, rel_err, batched=batched)
+
+
+def test_mm_stage_memory_plan_and_channel_ownership():
+    """Pure host logic: how many channels of the float64 M x M stage run per chunk and which
+    channels a rank owns when the stage is sharded (section 6)."""
+    from svgp_vae_b200 import step
+    dev = torch.device("cpu")
+    assert step.mm_chunk_channels(64, 1024, dev) == 64                      # 8.6 GB of state: one chunk
+    assert step.mm_chunk_channels(64, 2048, dev) == 64                      # 34 GB: still one chunk
+    lc = step.mm_chunk_channels(128, 4096, dev)                             # configs[4]: 275 GB of state -> chunks
+    assert 1 <= lc < 128 and 16 * 8.0 * 4096 * 4096 * lc <= 48e9
+    n = -(-128 // lc)
+    assert -(-128 // n) == lc                                               # chunks are balanced
+    assert step.mm_chunk_channels(16, 4096, dev) == 16                      # an 8-way shard of configs[4] fits one chunk
+    assert step.mm_chunk_channels(64, 1024, dev, override=5) == 5 and step.mm_chunk_channels(3, 8, dev, override=99) == 3
+    assert step._own_channels(64, None) == (slice(0, 64), False)           # single process: everything, not sharded
