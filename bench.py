@@ -21,7 +21,12 @@ import sys
 import threading
 import time
 
-import torch
+# torchrun exports OMP_NUM_THREADS=1 to every worker; the reference arm is a CPU run that should use all host threads
+# (rank 0 alone does any work there), so drop that default before torch / MKL read it
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1" and "RANK" in os.environ:
+    del os.environ["OMP_NUM_THREADS"]
+
+import torch  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
