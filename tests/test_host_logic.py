@@ -289,3 +289,15 @@ def test_mm_stage_memory_plan_and_channel_ownership():
     assert step.mm_chunk_channels(16, 4096, dev) == 16                      # an 8-way shard of configs[4] fits one chunk
     assert step.mm_chunk_channels(64, 1024, dev, override=5) == 5 and step.mm_chunk_channels(3, 8, dev, override=99) == 3
     assert step._own_channels(64, None) == (slice(0, 64), False)           # single process: everything, not sharded
+
+
+def test_graphed_step_rejects_what_it_cannot_capture(oracle_backend):
+    """GraphedElboStep refuses the configurations whose step synchronises with the host (before touching CUDA)."""
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=2)
+    ctor = dict(cfg["ctor"], titsias=True)
+    s = pkg.mnistSVGP(name="t", **ctor)
+    with pytest.raises(ValueError):
+        pkg.GraphedElboStep(s, cfg["aux"], cfg["y"], cfg["noise"])
+    s2 = pkg.mnistSVGP(name="u", **cfg["ctor"])
+    with pytest.raises(ValueError):
+        pkg.GraphedElboStep(s2, cfg["aux"], cfg["y"], cfg["noise"], group=object())
