@@ -46,6 +46,8 @@ extern "C" {
 #define SVGP_IMPL_AUTO 0
 #define SVGP_IMPL_SIMT 1 /* fp32 CUDA-core tiles, any shape                                   */
 #define SVGP_IMPL_TC 2   /* tcgen05 / TMEM / TMA, fp32-emulating 3 x FP16 split operands          */
+#define SVGP_IMPL_TC_I8 3 /* tcgen05 kind::i8 on base-256 digit planes: exact int32 accumulation (svgp_syrk only;
+                             the scaled GEMM has its own entry point svgp_scaled_gemm_i8)            */
 
 int svgp_version(void);
 const char* svgp_last_error(void); /* host string, thread-local */
@@ -107,7 +109,29 @@ typedef struct svgp_kop {
   const void* Ktl;     /* fp16 lo plane, same layout                                                */
   const float* kscale; /* device float[8]: {scale, 1/scale, feature norms..., [6] = 1 if K >= 0 element-wise} */
   int64_t N, M, ldk, ldkh, ldkt;
+  /* int8 digit planes of svgp_kplanes_i8 (all NULL / 0 when absent): the operands of the exact integer products     */
+  const void* Kr;       /* [3][N][ldkr] balanced base-256 digits of rint(K[i, m] / rscale[i]), most significant first */
+  const float* rscale;  /* [N]                                                                                        */
+  const void* Kc;       /* [3][ceil(N/128)][M][128]: digits of rint(K[n, m] / cscale[m]) at [n / 128][m][n % 128]       */
+  const float* cscale;  /* [M]                                                                                        */
+  int64_t ldkr;         /* row pitch of Kr in bytes, multiple of 16, >= M                                             */
 } svgp_kop;
+
+/* int8 digit planes of K_nm for the exact-accumulation tensor-core products (tcgen05.mma.kind::i8, int32 accumulators):
+ * every entry becomes a 24-bit fixed-point integer against the largest |entry| of its row (Kr: products that reduce
+ * over the inducing points) / of its column (Kc: the SYRK, which reduces over the datapoints), written as three
+ * balanced base-256 digits in three int8 planes.  Derived from the fp16 planes of `kop` (Kh, Kl, Kth, Ktl, kscale).
+ * scratch: float[N + M].  Rows n >= N of the last 128-datapoint block of Kc and columns >= M of Kr are zero.
+ * replaces nothing in the reference: operand format of svgp_syrk(impl = SVGP_IMPL_TC_I8) and svgp_scaled_gemm_i8.     */
+int64_t svgp_i8_ldkr(int64_t M);  /* (M + 15) / 16 * 16 */
+int64_t svgp_i8_nblk(int64_t N);  /* (N + 127) / 128    */
+int svgp_kplanes_i8(const svgp_kop* kop, void* Kr, int64_t ldkr, float* rscale, void* Kc, float* cscale, float* scratch,
+                    void* stream);
+
+/* nslices (3 or 4) digit planes of a float64 matrix with one scale per ROW: x[r, c] ~= scale[r] * sum_s d_s[r, c] 256^(S-1-s);
+ * planes[s][r][c] (row pitch ldp bytes, multiple of 16; columns >= cols zeroed).  A batch of matrices is its row-stack. */
+int svgp_split_i8(const double* x, int64_t nrows, int64_t cols, int64_t ldx, int nslices, void* planes, int64_t ldp,
+                  float* scale, void* stream);
 
 /* per-matrix fp16 operand planes of a (nb x rows x cols) float64 batch:  x * s_b = hi + lo with
  * s_b = 2^(14 - e_b), max|x_b| = m 2^e_b (m in [0.5,1));  inv_scale: device float[2*nb] =
@@ -128,6 +152,11 @@ int svgp_split_f16(const double* x, int64_t nb, int64_t count, void* hi, void* l
  * known relative loss of 0.666 n 2^-24 (n MMAs per chain, measured) added back per chunk.
  * replaces: K_mn (K_nm * 1/sigma^2) SVGPVAE_model.py:328-330 (:160 for the ball) and, as the
  * adjoint of svgp_rowquad, the (b,m,m) trace pattern :286-294.                               */
+/* impl = SVGP_IMPL_TC_I8 (needs kop->Kc, cscale): the weighted operand w[n, l] K[n, a] is rebuilt per channel in shared
+ * memory as a 32-bit fixed-point integer (4 digit planes) against the 24-bit K^T planes, the 9 digit-plane pairs of
+ * order <= 3 run as integer MMAs over windows of <= 16384 datapoints and the exactly recombined window sums are added
+ * into A with double atomics: no rounding inside the contraction (the summation ORDER of the window sums in float64 is
+ * not fixed).  Same workspace size function.                                                                        */
 int64_t svgp_syrk_ws_floats(int64_t N, int64_t M, int64_t L);
 int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, int impl,
               int64_t chunk_rows, float* ws, void* stream);
@@ -162,6 +191,16 @@ int svgp_rowquad(const svgp_kop* kop, const void* S_hi, const void* S_lo, const 
 int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_hi, const void* G_lo,
                      const float* G_inv, int64_t L, float* out, int64_t ldo, int accumulate, float* dots,
                      int64_t lddots, int64_t ndot, int impl, void* stream);
+
+/* svgp_scaled_gemm on the integer tensor-core path: G as the 4 digit planes + per-row scales of
+ * svgp_split_i8(G viewed as (L * Mc) x M, nslices = 4, ldp = ldg) -- the matrices must be symmetric or given
+ * transposed (row c of G_l multiplies k_i into output column c); K_nm as kop->Kr / rscale.  Mc = rows of each G_l
+ * (M for the dK_nm product; any value for a skinny product such as K_nm Wm^T with L = 1).  Exact integer accumulation
+ * of the 9 digit-plane pairs of order <= 3, one fp32 rounding when an accumulator tile leaves TMEM, fp32 running sums over
+ * the L matrices.                                                                                                    */
+int svgp_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_planes, int64_t ldg,
+                        const float* G_scale, int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate,
+                        float* dots, int64_t lddots, int64_t ndot, void* stream);
 
 /* out (N x M) (+)= W (N x L) @ V (L x M), all fp32 -- rank-L part of dK_nm (p_m, mean terms)  */
 int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t lda, const float* B,

@@ -12,14 +12,15 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvgp_b200.so")
 
 SVGP_K_NONE, SVGP_K_SE, SVGP_K_EXPSIN, SVGP_K_LINEAR, SVGP_K_COSINE = 0, 1, 2, 3, 4
-IMPL_AUTO, IMPL_SIMT, IMPL_TC = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8 = 0, 1, 2, 3
 
 
 class KopStruct(ctypes.Structure):
     """struct svgp_kop (include/svgp_b200.h)."""
     _fields_ = [("K", c_void_p), ("Kh", c_void_p), ("Kl", c_void_p), ("Kth", c_void_p), ("Ktl", c_void_p),
                 ("kscale", c_void_p), ("N", c_int64), ("M", c_int64), ("ldk", c_int64), ("ldkh", c_int64),
-                ("ldkt", c_int64)]
+                ("ldkt", c_int64), ("Kr", c_void_p), ("rscale", c_void_p), ("Kc", c_void_p), ("cscale", c_void_p),
+                ("ldkr", c_int64)]
 
 
 class SvgpLibraryError(RuntimeError):
@@ -50,6 +51,12 @@ SIGNATURES = {
                          c_int, _P],
     "svgp_gemm_f32": [c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _P],
     "svgp_split_f16": [_P, c_int64, c_int64, _P, _P, _P, _P],
+    "svgp_i8_ldkr": [c_int64],
+    "svgp_i8_nblk": [c_int64],
+    "svgp_kplanes_i8": [POINTER(KopStruct), _P, c_int64, _P, _P, _P, _P, _P],
+    "svgp_split_i8": [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, _P, _P],
+    "svgp_scaled_gemm_i8": [POINTER(KopStruct), _P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64,
+                            c_int64, _P],
     "svgp_chol_f64": [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P],
     "svgp_trinv_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P],
     "svgp_ltl_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P],
@@ -58,7 +65,7 @@ SIGNATURES = {
     "svgp_rowstats_fwd": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_predictive_fwd": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P],
 }
-_RESTYPE = {"svgp_last_error": c_char_p, "svgp_syrk_ws_floats": c_int64}
+_RESTYPE = {"svgp_last_error": c_char_p, "svgp_syrk_ws_floats": c_int64, "svgp_i8_ldkr": c_int64, "svgp_i8_nblk": c_int64}
 
 _lib = None
 

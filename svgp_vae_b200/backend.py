@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, KopStruct
+from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8, KopStruct
 
 
 class Kop:
@@ -28,10 +28,26 @@ class Kop:
         ref = K if K is not None else Kh
         self.N = ref.shape[0] if N is None else N
         self.M = ref.shape[1] if M is None else M
+        # int8 digit planes of the exact integer tensor-core products (svgp_kplanes_i8): Kr (3, N, ldkr) row-scaled,
+        # Kc (3, ceil(N / 128), M, 128) column-scaled and datapoint-blocked, with their scales
+        self.Kr = self.rscale = self.Kc = self.cscale = None
 
     @property
     def tc(self):
         return self.Kh is not None
+
+    @property
+    def i8(self):
+        return self.Kr is not None
+
+    def value_i8(self, which="r"):
+        """K_nm reassembled from the digit planes (float64): which = "r" row-scaled planes, "c" column-scaled ones."""
+        if which == "r":
+            d = self.Kr.double()
+            return ((d[0] * 65536.0 + d[1] * 256.0 + d[2]) * self.rscale.double()[:, None])[:, : self.M]
+        d = self.Kc.double()                                             # (3, nblk, M, 128)
+        v = (d[0] * 65536.0 + d[1] * 256.0 + d[2]) * self.cscale.double()[None, :, None]
+        return v.permute(0, 2, 1).reshape(-1, self.M)[: self.N]
 
     @property
     def device(self):
@@ -59,6 +75,11 @@ class Kop:
         s.ldk = self.K.stride(0) if self.K is not None else 0
         s.ldkh = self.Kh.stride(0) if self.Kh is not None else 0
         s.ldkt = self.Kth.stride(0) if self.Kth is not None else 0
+        s.Kr = self.Kr.data_ptr() if self.Kr is not None else None
+        s.rscale = self.rscale.data_ptr() if self.rscale is not None else None
+        s.Kc = self.Kc.data_ptr() if self.Kc is not None else None
+        s.cscale = self.cscale.data_ptr() if self.cscale is not None else None
+        s.ldkr = self.Kr.stride(1) if self.Kr is not None else 0
         return s
 
 
@@ -67,6 +88,20 @@ class Planes:
 
     def __init__(self, hi, lo, inv):
         self.hi, self.lo, self.inv = hi, lo, inv
+
+
+class PlanesI8:
+    """int8 digit planes of a (B, R, C) float64 batch with one scale per row (svgp_split_i8): planes (S, B * R, ldp),
+    scale (B * R,); x[b, r, c] ~= scale[b R + r] * sum_s planes[s, b R + r, c] 256^(S - 1 - s)."""
+
+    def __init__(self, planes, scale, B, R, C):
+        self.planes, self.scale, self.B, self.R, self.C = planes, scale, B, R, C
+
+    def value(self):
+        S = self.planes.shape[0]
+        d = self.planes.double()
+        v = sum(d[s] * 256.0 ** (S - 1 - s) for s in range(S)) * self.scale.double()[:, None]
+        return v[:, : self.C].reshape(self.B, self.R, self.C)
 
 
 _PROFILE = None
@@ -116,7 +151,8 @@ class CudaBackend:
         if not _lib.load().svgp_device_ok():
             raise _lib.SvgpLibraryError("svgp_vae_b200 kernels are built for sm_100a only (B200)")
         self.launches = 0          # kernels launched through this backend (bench reports it)
-        self.tc_min_rows = int(os.environ.get("SVGP_TC_MIN_ROWS", "2048"))
+        self.tc_min_rows = max(2048, int(os.environ.get("SVGP_TC_MIN_ROWS", "2048")))    # the library needs N >= 2048 (tc_shape_ok)
+        self.use_i8 = os.environ.get("SVGP_TC_I8", "1") != "0"
 
     def start_profile(self):
         global _PROFILE
@@ -140,7 +176,11 @@ class CudaBackend:
     def want_tc(self, N, M):
         return N >= self.tc_min_rows and M >= 128
 
-    def kernel_fwd(self, spec, Fx, Fz, hyp, tc=False):
+    def want_i8(self, N, M):
+        """Exact integer tensor-core products (SYRK, dA + dA^T part of the scaled GEMM) for tensor-core sized problems."""
+        return self.use_i8 and self.want_tc(N, M)
+
+    def kernel_fwd(self, spec, Fx, Fz, hyp, tc=False, i8=None):
         Fx, Fz, hyp = _f32c(Fx), _f32c(Fz), _f32c(hyp)
         N, M = Fx.shape[0], Fz.shape[0]
         ta, da, tb, db = spec
@@ -159,12 +199,32 @@ class CudaBackend:
             kop = Kop(None, Kh, Kl, Kth, Ktl, kscale, N, M)
             _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
                   None, 0, _ptr(Kh), _ptr(Kl), ldkh, _ptr(Kth), _ptr(Ktl), ldkt, _ptr(kscale), _stream())
+            if i8 is None:
+                i8 = self.want_i8(N, M)
+            if i8:
+                self.kplanes_i8(kop)
         else:
             K = torch.empty((N, M), device=dev, dtype=torch.float32)
             kop = Kop(K)
             _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
                   _ptr(K), K.stride(0), None, None, 0, None, None, 0, None, _stream())
         self.launches += 1
+        return kop
+
+    def kplanes_i8(self, kop):
+        """Attach the int8 digit planes of K_nm (svgp_kplanes_i8) to a kop that carries the fp16 planes."""
+        N, M, dev = kop.N, kop.M, kop.device
+        ldkr = _pad(M, 16)
+        nblk = (N + 127) // 128
+        kop.Kr = torch.empty((3, N, ldkr), device=dev, dtype=torch.int8)
+        kop.rscale = torch.empty(N, device=dev, dtype=torch.float32)
+        kop.Kc = torch.empty((3, nblk, M, 128), device=dev, dtype=torch.int8)
+        kop.cscale = torch.empty(M, device=dev, dtype=torch.float32)
+        scratch = torch.empty(N + M, device=dev, dtype=torch.float32)
+        s = kop.struct()
+        _call("svgp_kplanes_i8", ctypes.byref(s), _ptr(kop.Kr), ldkr, _ptr(kop.rscale), _ptr(kop.Kc), _ptr(kop.cscale), _ptr(scratch),
+              _stream())
+        self.launches += 4
         return kop
 
     def kernel_bwd(self, spec, Fx, Fz, hyp, G, need_x=True, need_z=True):
@@ -236,17 +296,64 @@ class CudaBackend:
         inv[at:at + nb] = tmp[:nb]
         self.launches += 2
 
+    def planes_i8(self, X64, nslices=4):
+        """(B, R, C) float64 -> int8 digit planes with one scale per row (svgp_split_i8)."""
+        X64 = _f64c(X64 if X64.is_contiguous() else X64.contiguous())
+        B, R, C = X64.shape
+        ldp = _pad(C, 16)
+        planes = torch.empty((nslices, B * R, ldp), device=X64.device, dtype=torch.int8)
+        scale = torch.empty(B * R, device=X64.device, dtype=torch.float32)
+        _call("svgp_split_i8", _ptr(X64), B * R, C, C, nslices, _ptr(planes), ldp, _ptr(scale), _stream())
+        self.launches += 1
+        return PlanesI8(planes, scale, B, R, C)
+
+    def planes_i8_alloc(self, B, R, C, device, nslices=4):
+        ldp = _pad(C, 16)
+        return PlanesI8(torch.empty((nslices, B * R, ldp), device=device, dtype=torch.int8),
+                        torch.empty(B * R, device=device, dtype=torch.float32), B, R, C)
+
+    def planes_i8_into(self, X64, P, at):
+        """svgp_split_i8 of a (b, R, C) float64 batch into matrices [at, at + b) of the preallocated PlanesI8 ``P``."""
+        X64 = _f64c(X64 if X64.is_contiguous() else X64.contiguous())
+        b, R, C = X64.shape
+        assert R == P.R and C == P.C and at + b <= P.B
+        S, _, ldp = P.planes.shape
+        # the planes of a row range are not contiguous across digit planes: the library takes the base of plane 0 and
+        # the plane stride is implied by nrows -- so split plane by plane range through a temporary of the piece
+        tmp = torch.empty((S, b * R, ldp), device=X64.device, dtype=torch.int8)
+        _call("svgp_split_i8", _ptr(X64), b * R, C, C, S, _ptr(tmp), ldp, _ptr(P.scale[at * R:(at + b) * R]), _stream())
+        P.planes[:, at * R:(at + b) * R] = tmp
+        self.launches += 2
+
+    def scaled_gemm_i8(self, kop, W, G, out=None, ndot=0):
+        """scaled_gemm on the integer tensor-core path; G: PlanesI8 of L stacked (Mc, M) matrices (4 digit planes)."""
+        assert kop.i8 and isinstance(G, PlanesI8) and G.planes.shape[0] == 4 and G.C == kop.M
+        L, Mc = G.B, G.R
+        if W is not None:
+            W = _f32c(W)
+            assert W.shape == (kop.N, L)
+        accumulate = out is not None
+        if out is None:
+            out = torch.empty((kop.N, Mc), device=kop.device, dtype=torch.float32)
+        dots = torch.zeros((kop.N, ndot), device=kop.device, dtype=torch.float32) if ndot else None
+        s = kop.struct()
+        _call("svgp_scaled_gemm_i8", ctypes.byref(s), _ptr(W), W.stride(0) if W is not None else 0, _ptr(G.planes), G.planes.stride(1),
+              _ptr(G.scale), L, Mc, _ptr(out), out.stride(0), int(accumulate), _ptr(dots), ndot, ndot, _stream())
+        self.launches += 1
+        return (out, dots) if ndot else out
+
     def syrk(self, kop, W, impl=IMPL_AUTO, chunk_rows=0):
         W = _f32c(W)
         L = W.shape[1]
         A = torch.zeros((L, kop.M, kop.M), device=W.device, dtype=torch.float64)
         use_tc = kop.tc and impl != IMPL_SIMT
+        use_i8 = use_tc and kop.i8 and impl in (IMPL_AUTO, IMPL_TC_I8)
         ws = None
         if use_tc:
             ws = torch.empty(int(_lib.load().svgp_syrk_ws_floats(kop.N, kop.M, L)), device=W.device, dtype=torch.float32)
         s = kop.struct()
-        _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), L, _ptr(A), IMPL_TC if use_tc else IMPL_SIMT, chunk_rows,
-              _ptr(ws), _stream())
+        _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), L, _ptr(A),
+              IMPL_TC_I8 if use_i8 else (IMPL_TC if use_tc else IMPL_SIMT), chunk_rows, _ptr(ws), _stream())
         self.launches += 4 if use_tc else 1
         return A
 

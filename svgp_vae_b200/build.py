@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsvgp_b200.so")
-SOURCES = ["kernel_matrix.cu", "simt_gemm.cu", "linalg_f64.cu", "rowterms.cu", "tc_engine.cu"]
+SOURCES = ["kernel_matrix.cu", "simt_gemm.cu", "linalg_f64.cu", "rowterms.cu", "tc_engine.cu", "i8_planes.cu", "tc_i8_engine.cu"]
 # NOT -arch=sm_100a: that also emits generic compute_100 PTX, on which tcgen05.* does not assemble
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-shared",
               "-Xcompiler", "-fPIC"]

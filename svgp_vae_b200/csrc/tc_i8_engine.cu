@@ -1,0 +1,644 @@
+// Exact-accumulation tensor-core products for the two contractions whose rounding the SVGP step cannot absorb
+// (sm_100a: tcgen05.mma.kind::i8, int32 accumulators in TMEM, TMA-fed digit planes -- see i8_planes.cu for the format).
+//
+//   svgp_syrk (forward A_l = sum_i p_il k_i k_i^T and its adjoint twin)   SVGPVAE_model.py:328-330, :286-294
+//   svgp_scaled_gemm for the dA_l + dA_l^T family (dObjective/dK_nm and k^T dA k)   tf.gradients through :328-337
+//
+// Why integers.  tcgen05.mma.kind::f16 adds into fp32 TMEM with truncation; on these two products the loss (~n 2^-24 per
+// chain of n MMAs, relative to the largest partial sum) is amplified by cond(Sigma_l) / by the cancellation in
+// K (dA + dA^T) and ends up as 3e-4 .. 3e-3 in the inducing-point gradient (round 1).  Integer MMAs do not round at all:
+// operands are cut into balanced base-256 digits, digit planes are multiplied pairwise, every pair (t, u) with
+// t + u <= 3 is kept (9 MMAs per k-step) and the four orders o = t + u accumulate in four int32 TMEM accumulators that
+// the epilogue recombines exactly (acc_0 2^24 + acc_1 2^16 + acc_2 2^8 + acc_3).  What is dropped is below 2^-32 of
+// (row maximum x column maximum); what remains of the operand quantisation is a CONSISTENT perturbation of K_nm
+// (tools/numerics/sim_parity.py measures both).  kind::i8 runs at twice the MAC rate of kind::f16
+// (profiles/r02_i8_mma_probe.jsonl: 8192 MAC / clk / SM), so 9 integer MMAs cost 4.5 fp16 MMAs against 3 before.
+//
+// Tile: 128 x 128 outputs, k-blocks of 128 reduction elements (one 128-byte swizzle row per operand row and digit plane),
+// two shared-memory stages of 7 planes x 16 KB; the four accumulators fill TMEM (4 x 128 columns), so the epilogue of one
+// chain does not overlap the MMAs of the next -- the SYRK chains are a whole window of datapoints long (irrelevant), the
+// scaled GEMM pays ~15 % at M = 1024 (less as M grows).
+#include "tc_ptx.cuh"
+
+namespace svgp {
+
+constexpr int I8_T = 128;                         // tile rows = tile columns = reduction elements per k-block
+constexpr int I8_PLANE = I8_T * I8_T;             // bytes of one digit plane of one operand tile
+constexpr int I8_NPL = 7;                         // planes per stage: 4 of the finer operand + 3 of the coarser one
+constexpr int I8_STAGE = I8_NPL * I8_PLANE;
+constexpr int I8_STAGES = 2;
+constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 + 256;
+static_assert(I8_SMEM <= 227 * 1024, "shared memory budget");
+
+// D (s32) += A (s8) * B (s8), M = 128, N = 128, K = 32
+constexpr uint32_t I8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_T >> 3) << 17) | ((uint32_t)(I8_T >> 4) << 24);
+
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {        // K-major, 128-byte swizzle rows, 8-row groups 1024 B apart
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// 16 consecutive columns of this warp's 32 TMEM lanes (no wait: the caller batches several loads)
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, int (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {     // generic mode: selector bit 3 = replicate sign
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+
+// One k-block of MMAs: planes F_0..F_3 (fine operand, 4 digits) and C_0..C_2 (coarse operand, 3 digits) of the stage at
+// `st`; FINE_IS_A says which of them is the A (M-side) operand.  first = this is the first k-block of the chain.
+template <bool FINE_IS_A>
+__device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_base, bool first) {
+  uint64_t fine[4], coarse[3];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) fine[t] = i8_desc(st + t * I8_PLANE);
+#pragma unroll
+  for (int u = 0; u < 3; ++u) coarse[u] = i8_desc(st + (4 + u) * I8_PLANE);
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+    const bool f = first && ks == 0;
+    // order 0
+    { const uint64_t a = (FINE_IS_A ? fine[0] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[0]) + adv; umma_i8(tmem_base + 0 * I8_T, a, b, f ? 0u : 1u); }
+    // order 1: (0,1), (1,0)
+    { const uint64_t a = (FINE_IS_A ? fine[0] : coarse[1]) + adv, b = (FINE_IS_A ? coarse[1] : fine[0]) + adv; umma_i8(tmem_base + 1 * I8_T, a, b, f ? 0u : 1u); }
+    { const uint64_t a = (FINE_IS_A ? fine[1] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[1]) + adv; umma_i8(tmem_base + 1 * I8_T, a, b, 1u); }
+    // order 2: (0,2), (1,1), (2,0)
+    { const uint64_t a = (FINE_IS_A ? fine[0] : coarse[2]) + adv, b = (FINE_IS_A ? coarse[2] : fine[0]) + adv; umma_i8(tmem_base + 2 * I8_T, a, b, f ? 0u : 1u); }
+    { const uint64_t a = (FINE_IS_A ? fine[1] : coarse[1]) + adv, b = (FINE_IS_A ? coarse[1] : fine[1]) + adv; umma_i8(tmem_base + 2 * I8_T, a, b, 1u); }
+    { const uint64_t a = (FINE_IS_A ? fine[2] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[2]) + adv; umma_i8(tmem_base + 2 * I8_T, a, b, 1u); }
+    // order 3: (1,2), (2,1), (3,0)
+    { const uint64_t a = (FINE_IS_A ? fine[1] : coarse[2]) + adv, b = (FINE_IS_A ? coarse[2] : fine[1]) + adv; umma_i8(tmem_base + 3 * I8_T, a, b, f ? 0u : 1u); }
+    { const uint64_t a = (FINE_IS_A ? fine[2] : coarse[1]) + adv, b = (FINE_IS_A ? coarse[1] : fine[2]) + adv; umma_i8(tmem_base + 3 * I8_T, a, b, 1u); }
+    { const uint64_t a = (FINE_IS_A ? fine[3] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[3]) + adv; umma_i8(tmem_base + 3 * I8_T, a, b, 1u); }
+  }
+}
+
+// shared prologue: barriers + TMEM.  Barrier slots: full[s], ready[s], empty[s] (s < I8_STAGES), fullB[s], tmem_full, tmem_empty.
+struct I8Smem {
+  uint32_t base, bars, tmem_ptr;
+  __device__ uint32_t stage(int s) const { return base + s * I8_STAGE; }
+  __device__ uint32_t full(int s) const { return bars + 8u * s; }
+  __device__ uint32_t ready(int s) const { return bars + 8u * (I8_STAGES + s); }
+  __device__ uint32_t empty(int s) const { return bars + 8u * (2 * I8_STAGES + s); }
+  __device__ uint32_t fullB(int s) const { return bars + 8u * (3 * I8_STAGES + s); }
+  __device__ uint32_t tmem_full() const { return bars + 8u * (4 * I8_STAGES); }
+  __device__ uint32_t tmem_empty() const { return bars + 8u * (4 * I8_STAGES + 1); }
+};
+__device__ __forceinline__ I8Smem i8_setup(uint8_t* smem_raw, int ready_count, int epi_warps, uint32_t& tmem_base) {
+  I8Smem S;
+  S.base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  S.bars = S.base + I8_STAGES * I8_STAGE;
+  S.tmem_ptr = S.bars + 8u * (4 * I8_STAGES + 2);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < I8_STAGES; ++s) {
+      mbar_init(S.full(s), 1);
+      mbar_init(S.fullB(s), 1);
+      mbar_init(S.ready(s), ready_count > 0 ? ready_count : 1);
+      mbar_init(S.empty(s), 1);
+    }
+    mbar_init(S.tmem_full(), 1);
+    mbar_init(S.tmem_empty(), epi_warps);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(S.tmem_ptr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(S.tmem_ptr));
+  return S;
+}
+__device__ __forceinline__ void i8_teardown(uint32_t tmem_base) {
+  tc_fence_before();
+  __syncthreads();
+  if ((threadIdx.x >> 5) == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// =============================================================================================================
+// SYRK   A_l[a, b] += sum_n (w[n, l] K[n, a]) K[n, b]       (lower-triangle tiles; double atomics into A)
+// =============================================================================================================
+struct SyrkI8Params {
+  int64_t N, M, L;
+  const float* Wt;          // (L, ldwt) channel-major weights, w / wmax_l * 256, zero padded to whole 128-datapoint blocks
+  int64_t ldwt;
+  const float* wmax;        // [L]
+  const float* cscale;      // [M] value of one unit of the column-scaled integer K
+  double* A;                // (L, M, M)
+  int64_t win_rows;         // datapoints per chain (multiple of 128): one item = (window, tile pair, channel)
+  int nwin, ntile;
+  int64_t n_items;
+};
+
+constexpr int SYRK8_THREADS = 512;       // warp 0 TMA, warp 1 MMA, warps 4-11 operand transform, warps 12-15 epilogue
+constexpr int SYRK8_XF_WARP0 = 4, SYRK8_XF_WARPS = 8, SYRK8_EPI_WARP0 = 12;
+
+__global__ void __launch_bounds__(SYRK8_THREADS, 1)
+syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint32_t tmem_base;
+  const I8Smem S = i8_setup(smem_raw, SYRK8_XF_WARPS, 4, tmem_base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) prefetch_tmap(&mapKc);
+
+  struct Item { int64_t l, n0, n1; int ta, tb, nkb; };
+  auto decode = [&](int64_t item) -> Item {
+    Item it;
+    const int64_t per_win = (int64_t)P.ntile * P.L;
+    const int64_t win = item / per_win, rem = item - win * per_win;
+    it.l = rem % P.L;
+    const int tile = (int)(rem / P.L);
+    int ta = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+    while ((ta + 1) * (ta + 2) / 2 <= tile) ++ta;
+    while (ta * (ta + 1) / 2 > tile) --ta;
+    it.ta = ta; it.tb = tile - ta * (ta + 1) / 2;
+    it.n0 = win * P.win_rows;
+    it.n1 = it.n0 + P.win_rows < P.N ? it.n0 + P.win_rows : P.N;
+    it.nkb = (int)((it.n1 - it.n0 + I8_T - 1) / I8_T);
+    return it;
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        const Item it = decode(item);
+        const int32_t blk0 = (int32_t)(it.n0 / I8_T);
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(S.empty(stage), phase ^ 1);
+          const uint32_t st = S.stage(stage);
+          // the weighted operand's raw planes first (the transform warps work on them while the others land)
+          mbar_expect_tx(S.full(stage), 3 * I8_PLANE);
+#pragma unroll
+          for (int s = 0; s < 3; ++s) tma_load_4d(st + s * I8_PLANE, &mapKc, S.full(stage), 0, it.ta * I8_T, blk0 + kb, s);
+          mbar_expect_tx(S.fullB(stage), 3 * I8_PLANE);
+#pragma unroll
+          for (int s = 0; s < 3; ++s) tma_load_4d(st + (4 + s) * I8_PLANE, &mapKc, S.fullB(stage), 0, it.tb * I8_T, blk0 + kb, s);
+          if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ==================================================
+    int stage = 0; uint32_t phase = 0, tphase = 0;
+    for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      mbar_wait(S.tmem_empty(), tphase ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < it.nkb; ++kb) {
+        mbar_wait(S.fullB(stage), phase);
+        mbar_wait(S.ready(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          issue_kblock<true>(S.stage(stage), tmem_base, kb == 0);
+          umma_commit(S.empty(stage));
+          if (kb == it.nkb - 1) umma_commit(S.tmem_full());
+        }
+        __syncwarp();
+        if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+      }
+      tphase ^= 1;
+    }
+  } else if (warp >= SYRK8_XF_WARP0 && warp < SYRK8_XF_WARP0 + SYRK8_XF_WARPS) {
+    // =============================== operand transform ============================================
+    // V[n, a] = w[n] K[n, a]: the three raw digit planes of the A tile (rows a, 128 datapoints n) are recombined to the
+    // 24-bit integer, multiplied by the channel's weight in fp32 (24 significant bits: a per-entry RELATIVE rounding,
+    // i.e. a perturbation of the weights, harmless), rounded to a 32-bit fixed-point integer against the channel's
+    // largest weight and cut into four digit planes, in place.  A thread owns one logical 16-byte chunk (16 datapoints:
+    // its 16 weights are loaded once per k-block) of 4 rows; the swizzled physical chunk is the same for all of them.
+    const int t = threadIdx.x - SYRK8_XF_WARP0 * 32;          // 0..255
+    const int lchunk = t & 7, rbase = t >> 3;                  // rows rbase + 32 j
+    const int pchunk = lchunk ^ (rbase & 7);
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      for (int kb = 0; kb < it.nkb; ++kb) {
+        const int64_t n = it.n0 + (int64_t)kb * I8_T + lchunk * 16;
+        float w[16];
+        {
+          const float4* wp = reinterpret_cast<const float4*>(P.Wt + it.l * P.ldwt + n);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 v = __ldg(wp + g);
+            w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
+          }
+        }
+        mbar_wait(S.full(stage), phase);
+        const uint32_t p0 = S.stage(stage) + rbase * 128 + pchunk * 16;
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t a = p0 + j * 32 * 128;
+          const uint4 k0 = lds128(a), k1 = lds128(a + I8_PLANE), k2 = lds128(a + 2 * I8_PLANE);
+          const uint32_t k0w[4] = {k0.x, k0.y, k0.z, k0.w}, k1w[4] = {k1.x, k1.y, k1.z, k1.w}, k2w[4] = {k2.x, k2.y, k2.z, k2.w};
+          uint32_t o[4][4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t e[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              // bytes [d2, d1, d0, sign(d0)] of element b -> integer
+              const uint32_t lo = prmt(k2w[g], k1w[g], (uint32_t)(b | ((4 + b) << 4)));
+              const uint32_t d = prmt(lo, k0w[g], 0x0010u | ((uint32_t)(4 + b) << 8) | ((uint32_t)(0xC + b) << 12));
+              const int kint = (int)((d ^ 0x00008080u) - 0x00008080u);
+              const int v = __float2int_rn(__int2float_rn(kint) * w[4 * g + b]);
+              e[b] = ((uint32_t)v + 0x00808080u) ^ 0x00808080u;
+            }
+            const uint32_t x01 = __byte_perm(e[0], e[1], 0x7362), y01 = __byte_perm(e[0], e[1], 0x5140);
+            const uint32_t x23 = __byte_perm(e[2], e[3], 0x7362), y23 = __byte_perm(e[2], e[3], 0x5140);
+            o[0][g] = __byte_perm(x01, x23, 0x7632);
+            o[1][g] = __byte_perm(x01, x23, 0x5410);
+            o[2][g] = __byte_perm(y01, y23, 0x7632);
+            o[3][g] = __byte_perm(y01, y23, 0x5410);
+          }
+#pragma unroll
+          for (int s = 0; s < 4; ++s) sts128(a + s * I8_PLANE, make_uint4(o[s][0], o[s][1], o[s][2], o[s][3]));
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(S.ready(stage));
+        if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= SYRK8_EPI_WARP0) {
+    // =============================== epilogue ====================================================
+    const int qd = warp & 3;
+    uint32_t tphase = 0;
+    for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const Item it = decode(item);
+      const int64_t r = (int64_t)it.ta * I8_T + qd * 32 + lane;           // output row a
+      const int64_t rmax_w = (int64_t)it.ta * I8_T + qd * 32 + 31;
+      const double rs = (r < P.M) ? 256.0 * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
+      mbar_wait(S.tmem_full(), tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+      for (int c16 = 0; c16 < I8_T / 16; ++c16) {
+        const int64_t c0 = (int64_t)it.tb * I8_T + c16 * 16;
+        if (c0 > rmax_w || c0 >= P.M) break;                              // warp-uniform: nothing of the lower triangle left
+        int a0[16], a1[16], a2[16], a3[16];
+        tmem_ld16_nowait(taddr + 0 * I8_T + c16 * 16, a0);
+        tmem_ld16_nowait(taddr + 1 * I8_T + c16 * 16, a1);
+        tmem_ld16_nowait(taddr + 2 * I8_T + c16 * 16, a2);
+        tmem_ld16_nowait(taddr + 3 * I8_T + c16 * 16, a3);
+        tmem_ld_wait();
+        double* dst = P.A + (it.l * P.M + r) * P.M + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t c = c0 + j;
+          if (r < P.M && c <= r) {
+            const long long i64 = ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
+            atomicAdd(dst + j, (double)i64 * rs * (double)__ldg(P.cscale + c));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(S.tmem_empty());
+      tphase ^= 1;
+    }
+  }
+  i8_teardown(tmem_base);
+}
+
+// =============================================================================================================
+// scaled GEMM   out[i, c] (+)= sum_s w[i, s] T_s[i, c],   dots[i, s] += sum_c T_s[i, c] K[i, c],   T_s = K G_s
+// =============================================================================================================
+struct ScaledI8Params {
+  int64_t N, M, L, Mc;          // L stacked matrices of Mc rows (output columns) x M
+  const float* rscale;          // [N] value of one unit of the row-scaled integer K
+  const float* gscale;          // [L * Mc] value of one unit of row c of matrix s
+  const float* W;               // (N, ldw) or null (all ones)
+  int64_t ldw;
+  float* out;
+  int64_t ldo;
+  int accumulate;
+  float* dots;                  // (N, lddots) or null
+  int64_t lddots, ndot;
+  const int8_t* Kr;             // digit planes of K_nm for the k-dot: [3][N][ldkr]
+  int64_t ldkr;
+  int nct;                      // column tiles
+  int64_t n_items;
+};
+
+constexpr int SCALED8_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 4-11 epilogue (two per TMEM lane quarter)
+constexpr int SCALED8_EPI_WARP0 = 4;
+
+__global__ void __launch_bounds__(SCALED8_THREADS, 1)
+scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapG, const ScaledI8Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint32_t tmem_base;
+  const I8Smem S = i8_setup(smem_raw, 0, 8, tmem_base);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { prefetch_tmap(&mapK); prefetch_tmap(&mapG); }
+  const int nkb = (int)((P.M + I8_T - 1) / I8_T);
+
+  if ((warp >> 2) == 0) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0) {
+      // =============================== TMA producer ===============================================
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+          const int32_t row0 = (int32_t)((item / P.nct) * I8_T), col0 = (int32_t)((item % P.nct) * I8_T);
+          for (int64_t s = 0; s < P.L; ++s) {
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(S.empty(stage), phase ^ 1);
+              const uint32_t st = S.stage(stage);
+              mbar_expect_tx(S.full(stage), I8_NPL * I8_PLANE);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) tma_load_3d(st + u * I8_PLANE, &mapG, S.full(stage), kb * I8_T, (int32_t)(s * P.Mc) + col0, u);
+#pragma unroll
+              for (int t = 0; t < 3; ++t) tma_load_3d(st + (4 + t) * I8_PLANE, &mapK, S.full(stage), kb * I8_T, row0, t);
+              if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // =============================== MMA issuer ==================================================
+      int stage = 0; uint32_t phase = 0, tphase = 0;
+      for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+        for (int64_t s = 0; s < P.L; ++s) {
+          mbar_wait(S.tmem_empty(), tphase ^ 1);
+          tc_fence_after();
+          for (int kb = 0; kb < nkb; ++kb) {
+            mbar_wait(S.full(stage), phase);
+            tc_fence_after();
+            if (lane == 0) {
+              issue_kblock<false>(S.stage(stage), tmem_base, kb == 0);     // A = K rows (3 digits), B = G rows (4 digits)
+              umma_commit(S.empty(stage));
+              if (kb == nkb - 1) umma_commit(S.tmem_full());
+            }
+            __syncwarp();
+            if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+          }
+          tphase ^= 1;
+        }
+      }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    // =============================== epilogue ====================================================
+    const int qd = warp & 3, half = (warp - SCALED8_EPI_WARP0) >> 2;       // TMEM lane quarter, column half
+    uint32_t tphase = 0;
+    const bool has_dots = P.dots != nullptr && P.ndot > 0;
+    for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      const int64_t i = (item / P.nct) * I8_T + qd * 32 + lane;
+      const int64_t cw0 = (item % P.nct) * I8_T + half * 64;               // first column of this warp
+      const bool live = i < P.N;
+      const float rs = live ? P.rscale[i] : 0.f;
+      float run[64], kv[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) run[j] = 0.f;
+      if (has_dots) {
+        // this row's K entries of the tile's columns as integers (fp32 holds 24 bits exactly)
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, d2 = d0;
+          if (live && cw0 + g * 16 < P.ldkr) {
+            const int8_t* base = P.Kr + i * P.ldkr + cw0 + g * 16;
+            d0 = __ldg(reinterpret_cast<const uint4*>(base));
+            d1 = __ldg(reinterpret_cast<const uint4*>(base + P.N * P.ldkr));
+            d2 = __ldg(reinterpret_cast<const uint4*>(base + 2 * P.N * P.ldkr));
+          }
+          const uint32_t w0[4] = {d0.x, d0.y, d0.z, d0.w}, w1[4] = {d1.x, d1.y, d1.z, d1.w}, w2[4] = {d2.x, d2.y, d2.z, d2.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t lo = prmt(w2[q], w1[q], (uint32_t)(b | ((4 + b) << 4)));
+              const uint32_t d = prmt(lo, w0[q], 0x0010u | ((uint32_t)(4 + b) << 8) | ((uint32_t)(0xC + b) << 12));
+              kv[g * 16 + q * 4 + b] = __int2float_rn((int)((d ^ 0x00008080u) - 0x00008080u));
+            }
+        }
+      }
+      for (int64_t s = 0; s < P.L; ++s) {
+        const float wgt = live ? (P.W ? P.W[i * P.ldw + s] : 1.f) * rs * 65536.f : 0.f;
+        const bool want_dot = has_dots && s < P.ndot;                      // warp-uniform
+        float dsum = 0.f;
+        const float* gs = P.gscale + s * P.Mc;
+        mbar_wait(S.tmem_full(), tphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 64);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          const int64_t c0 = cw0 + c16 * 16;
+          if (c0 < P.Mc) {                                                 // warp-uniform
+            int a0[16], a1[16], a2[16], a3[16];
+            tmem_ld16_nowait(taddr + 0 * I8_T + c16 * 16, a0);
+            tmem_ld16_nowait(taddr + 1 * I8_T + c16 * 16, a1);
+            tmem_ld16_nowait(taddr + 2 * I8_T + c16 * 16, a2);
+            tmem_ld16_nowait(taddr + 3 * I8_T + c16 * 16, a3);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float g = (c0 + j < P.Mc) ? __ldg(gs + c0 + j) : 0.f;
+              // |acc_o| < 2^24 for M <= 1024 (exact conversions); beyond that the fp32 rounding of an order's sum is 2^-24 relative
+              float tv = fmaf(__int2float_rn(a2[j]), 256.f, __int2float_rn(a3[j]));
+              tv = fmaf(__int2float_rn(a1[j]), 65536.f, tv);
+              tv = fmaf(__int2float_rn(a0[j]), 16777216.f, tv);
+              tv *= g;
+              run[c16 * 16 + j] = fmaf(wgt, tv, run[c16 * 16 + j]);
+              if (want_dot) dsum = fmaf(tv, kv[c16 * 16 + j], dsum);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(S.tmem_empty());
+        tphase ^= 1;
+        if (want_dot && live) atomicAdd(&P.dots[i * P.lddots + s], dsum * rs * rs * 65536.f);
+      }
+      if (live) {
+        float* o = P.out + i * P.ldo + cw0;
+#pragma unroll
+        for (int j = 0; j < 64; ++j)
+          if (cw0 + j < P.Mc) o[j] = P.accumulate ? o[j] + run[j] : run[j];
+      }
+    }
+  }
+  i8_teardown(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int encode_i8(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SVGP_ERR_CUDA; }
+  if ((uintptr_t)base & 15) { set_error("TMA operand needs a 16-byte aligned base"); return SVGP_ERR_ARG; }
+  for (int d = 0; d < rank - 1; ++d)
+    if (strides_bytes[d] % 16) { set_error("TMA operand needs 16-byte pitches"); return SVGP_ERR_ARG; }
+  cuuint32_t box[4] = {(cuuint32_t)I8_T, (cuuint32_t)I8_T, 1, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (i8) failed (%d)", (int)r); return SVGP_ERR_CUDA; }
+  return SVGP_OK;
+}
+
+// window of datapoints per SYRK chain: bounded by the int32 accumulators (3 digit pairs of up to 2^14 each per datapoint:
+// 43690 datapoints), by the L2-resident slice of the K^T planes (3 bytes x M per datapoint, ~64 MB), and small enough
+// to give every SM several items
+int64_t i8_syrk_window(int64_t N, int64_t M, int64_t L) {
+  int64_t w = (64LL << 20) / (3 * M);
+  if (w > 16384) w = 16384;
+  const int64_t T = (M + I8_T - 1) / I8_T, ntile = T * (T + 1) / 2;
+  // at least ~2 items per SM when the problem allows it
+  while (w > 1024 && ((N + w - 1) / w) * ntile * L < 2 * num_sms()) w /= 2;
+  w = w / I8_T * I8_T;
+  return w < I8_T ? I8_T : w;
+}
+
+int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, int64_t L, double* A, cudaStream_t st) {
+  if (!kop->Kc || !kop->cscale) { set_error("tc_syrk_i8: int8 transposed planes missing (svgp_kplanes_i8)"); return SVGP_ERR_ARG; }
+  if (((uintptr_t)Wt & 15) || (ldwt % I8_T)) { set_error("tc_syrk_i8: weights need whole zero-padded 128-datapoint blocks"); return SVGP_ERR_ARG; }
+  const int64_t N = kop->N, M = kop->M, nblk = (N + I8_T - 1) / I8_T;
+  CUtensorMap map;
+  const cuuint64_t dims[4] = {(cuuint64_t)I8_T, (cuuint64_t)M, (cuuint64_t)nblk, 3};
+  const cuuint64_t strides[3] = {(cuuint64_t)I8_T, (cuuint64_t)(M * I8_T), (cuuint64_t)(nblk * M * I8_T)};
+  int rc = encode_i8(&map, kop->Kc, 4, dims, strides);
+  if (rc) return rc;
+  SyrkI8Params P{};
+  P.N = N; P.M = M; P.L = L; P.Wt = Wt; P.ldwt = ldwt; P.wmax = wmax; P.cscale = kop->cscale; P.A = A;
+  P.win_rows = i8_syrk_window(N, M, L);
+  P.nwin = (int)ceil_div(N, P.win_rows);
+  const int64_t T = ceil_div(M, I8_T);
+  P.ntile = (int)(T * (T + 1) / 2);
+  P.n_items = (int64_t)P.nwin * P.ntile * L;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(syrk_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_syrk(i8 attr)");
+    attr_done = true;
+  }
+  int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
+  if (grid <= 0) return SVGP_OK;
+  syrk_i8_kernel<<<(unsigned)grid, SYRK8_THREADS, I8_SMEM, st>>>(map, P);
+  return check_launch("svgp_syrk(i8)");
+}
+
+int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* Gp, int64_t ldg, const float* gscale, int64_t L,
+                      int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, cudaStream_t st) {
+  if (!kop->Kr || !kop->rscale) { set_error("tc_scaled_gemm_i8: int8 planes of K_nm missing (svgp_kplanes_i8)"); return SVGP_ERR_ARG; }
+  if (dots && Mc != kop->M) { set_error("tc_scaled_gemm_i8: the k-dots need square M x M matrices"); return SVGP_ERR_ARG; }
+  const int64_t N = kop->N, M = kop->M;
+  CUtensorMap mapK, mapG;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)kop->ldkr, (cuuint64_t)N, 3};
+    const cuuint64_t strides[2] = {(cuuint64_t)kop->ldkr, (cuuint64_t)(N * kop->ldkr)};
+    int rc = encode_i8(&mapK, kop->Kr, 3, dims, strides);
+    if (rc) return rc;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)ldg, (cuuint64_t)(L * Mc), 4};
+    const cuuint64_t strides[2] = {(cuuint64_t)ldg, (cuuint64_t)(L * Mc * ldg)};
+    int rc = encode_i8(&mapG, Gp, 3, dims, strides);
+    if (rc) return rc;
+  }
+  ScaledI8Params P{};
+  P.N = N; P.M = M; P.L = L; P.Mc = Mc; P.rscale = kop->rscale; P.gscale = gscale; P.W = W; P.ldw = ldw;
+  P.out = out; P.ldo = ldo; P.accumulate = accumulate; P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
+  P.Kr = (const int8_t*)kop->Kr; P.ldkr = kop->ldkr;
+  P.nct = (int)ceil_div(Mc, I8_T);
+  P.n_items = ceil_div(N, I8_T) * P.nct;
+  static bool attr_done = false;
+  if (!attr_done) {
+    if (cudaFuncSetAttribute(scaled_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
+    attr_done = true;
+  }
+  int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
+  if (grid <= 0) return SVGP_OK;
+  scaled_i8_kernel<<<(unsigned)grid, SCALED8_THREADS, I8_SMEM, st>>>(mapK, mapG, P);
+  return check_launch("svgp_scaled_gemm(i8)");
+}
+
+// ---- SYRK weights: per-channel max |w|, then the channel-major copy scaled to |w| <= 256, zero padded to whole blocks ----
+__global__ void i8_wabsmax_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t L, float* __restrict__ mx) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  for (int64_t l0 = 0; l0 < L; l0 += 32) {
+    const int64_t l = l0 + lane;
+    float m = 0.f;
+    if (l < L)
+      for (int64_t i = (int64_t)blockIdx.x * nwarp + warp; i < N; i += (int64_t)gridDim.x * nwarp) m = fmaxf(m, fabsf(W[i * ldw + l]));
+    if (l < L && m > 0.f) atomicMax(reinterpret_cast<int*>(mx + l), __float_as_int(m));
+  }
+}
+__global__ void i8_wprep_kernel(const float* __restrict__ W, int64_t ldw, int64_t N, int64_t L, const float* __restrict__ mx,
+                                float* __restrict__ Wt, int64_t ldwt) {
+  __shared__ float tile[32][33];
+  const int64_t n0 = (int64_t)blockIdx.x * 32, l0 = (int64_t)blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t n = n0 + r, l = l0 + tx;
+    tile[r][tx] = (n < N && l < L) ? W[n * ldw + l] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t l = l0 + r, n = n0 + tx;
+    if (l < L && n < ldwt) {
+      const float m = mx[l];
+      Wt[l * ldwt + n] = m > 0.f ? tile[tx][r] * (256.0f / m) : 0.f;
+    }
+  }
+}
+
+int launch_mirror_lower(double* A, int64_t M, int64_t L, cudaStream_t st);      // tc_engine.cu
+
+int64_t i8_syrk_ws_floats(int64_t N, int64_t L) { return L * ((N + I8_T - 1) / I8_T * I8_T) + L; }
+
+// W (N x L) -> workspace [Wt (L x ldwt) | wmax (L)], then the SYRK
+int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st) {
+  const int64_t N = kop->N, ldwt = (N + I8_T - 1) / I8_T * I8_T;
+  float* Wt = ws;
+  float* mx = ws + L * ldwt;
+  if (cudaMemsetAsync(mx, 0, L * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(i8 memset)");
+  int64_t blocks = ceil_div(N, 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  i8_wabsmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(W, ldw, N, L, mx);
+  dim3 grid((unsigned)ceil_div(ldwt, 32), (unsigned)ceil_div(L, 32));
+  i8_wprep_kernel<<<grid, 256, 0, st>>>(W, ldw, N, L, mx, Wt, ldwt);
+  int rc = check_launch("svgp_syrk(i8 prep)");
+  if (rc) return rc;
+  rc = tc_syrk_i8(kop, Wt, ldwt, mx, L, A, st);
+  if (rc) return rc;
+  return launch_mirror_lower(A, kop->M, L, st);          // the tiles cover the lower triangle only
+}
+
+}  // namespace svgp

@@ -1,0 +1,4 @@
+set -x
+python -m pytest tests/test_gpu_i8_engine.py -q 2>&1 | tail -5
+python tests/probes/parity_probe.py 16384,256,4 32768,512,4 32768,1024,2 32768,2048,2 > gpurun_out/r02_parity_i8_v1.jsonl 2>gpurun_out/r02_parity_i8_v1.err; tail -3 gpurun_out/r02_parity_i8_v1.err; cat gpurun_out/r02_parity_i8_v1.jsonl
+python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/r02_bench_i8_v1.json 2>gpurun_out/r02_bench_i8_v1.err; tail -3 gpurun_out/r02_bench_i8_v1.err; cat gpurun_out/r02_bench_i8_v1.json
