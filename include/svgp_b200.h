@@ -109,24 +109,32 @@ typedef struct svgp_kop {
   const void* Ktl;     /* fp16 lo plane, same layout                                                */
   const float* kscale; /* device float[8]: {scale, 1/scale, feature norms..., [6] = 1 if K >= 0 element-wise} */
   int64_t N, M, ldk, ldkh, ldkt;
-  /* int8 digit planes of svgp_kplanes_i8 (all NULL / 0 when absent): the operands of the exact integer products     */
-  const void* Kr;       /* [3][N][ldkr] balanced base-256 digits of rint(K[i, m] / rscale[i]), most significant first */
+  /* int8 digit planes of svgp_kernel_fwd_i8 (all NULL / 0 when absent): the operands of the exact integer products  */
+  const void* Kr;       /* [4][N][ldkr] balanced base-256 digits of rint(K[i, m] / rscale[i]), most significant first */
   const float* rscale;  /* [N]                                                                                        */
-  const void* Kc;       /* [3][ceil(N/128)][M][128]: digits of rint(K[n, m] / cscale[m]) at [n / 128][m][n % 128]       */
+  const void* Kc;       /* [4][ceil(N/128)][M][128]: digits of rint(K[n, m] / cscale[m]) at [n / 128][m][n % 128]       */
   const float* cscale;  /* [M]                                                                                        */
   int64_t ldkr;         /* row pitch of Kr in bytes, multiple of 16, >= M                                             */
 } svgp_kop;
 
-/* int8 digit planes of K_nm for the exact-accumulation tensor-core products (tcgen05.mma.kind::i8, int32 accumulators):
- * every entry becomes a 24-bit fixed-point integer against the largest |entry| of its row (Kr: products that reduce
- * over the inducing points) / of its column (Kc: the SYRK, which reduces over the datapoints), written as three
- * balanced base-256 digits in three int8 planes.  Derived from the fp16 planes of `kop` (Kh, Kl, Kth, Ktl, kscale).
- * scratch: float[N + M].  Rows n >= N of the last 128-datapoint block of Kc and columns >= M of Kr are zero.
- * replaces nothing in the reference: operand format of svgp_syrk(impl = SVGP_IMPL_TC_I8) and svgp_scaled_gemm_i8.     */
+/* the same kernel matrix in float64 arithmetic and storage (fp32 features): K_mm of the float64 M x M stage.  An fp32
+ * evaluation carries ~5e-7 of relative error per entry (rounding of the exponent's argument); the ill-conditioned
+ * M x M stage amplifies that into 1e-4 of the inducing-point gradient at M = 2048.                                   */
+int svgp_kernel_fwd_f64(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a,
+                        int dim_a, int type_b, int dim_b, const float* hyp, double* K, int64_t ldk, void* stream);
+
+/* K1 for the exact-accumulation tensor-core products (tcgen05.mma.kind::i8, int32 accumulators): every entry of K_nm
+ * becomes a 32-bit fixed-point integer against the largest |entry| of its row (Kr: products that reduce over the inducing
+ * points) / of its column (Kc: the SYRK, which reduces over the datapoints), written as four balanced base-256 digits in
+ * four int8 planes, from kernel values evaluated in float64 and rounded once to fp32; plus the fp16 hi/lo row planes and kscale of svgp_kernel_fwd
+ * for the remaining fp16 consumers (no transposed fp16 planes).  Two passes over the tiles (maxima, then write).
+ * scratch: float[N + M].  Rows n >= N of the last 128-datapoint block of Kc and the pad columns of Kr / Kh / Kl are zero.
+ * replaces: the same reference lines as svgp_kernel_fwd.                                                              */
 int64_t svgp_i8_ldkr(int64_t M);  /* (M + 15) / 16 * 16 */
 int64_t svgp_i8_nblk(int64_t N);  /* (N + 127) / 128    */
-int svgp_kplanes_i8(const svgp_kop* kop, void* Kr, int64_t ldkr, float* rscale, void* Kc, float* cscale, float* scratch,
-                    void* stream);
+int svgp_kernel_fwd_i8(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a,
+                       int dim_a, int type_b, int dim_b, const float* hyp, void* Kh, void* Kl, int64_t ldkh, void* Kr,
+                       int64_t ldkr, float* rscale, void* Kc, float* cscale, float* scratch, float* kscale, void* stream);
 
 /* nslices (3 or 4) digit planes of a float64 matrix with one scale per ROW: x[r, c] ~= scale[r] * sum_s d_s[r, c] 256^(S-1-s);
  * planes[s][r][c] (row pitch ldp bytes, multiple of 16; columns >= cols zeroed).  A batch of matrices is its row-stack. */
@@ -153,7 +161,7 @@ int svgp_split_f16(const double* x, int64_t nb, int64_t count, void* hi, void* l
  * replaces: K_mn (K_nm * 1/sigma^2) SVGPVAE_model.py:328-330 (:160 for the ball) and, as the
  * adjoint of svgp_rowquad, the (b,m,m) trace pattern :286-294.                               */
 /* impl = SVGP_IMPL_TC_I8 (needs kop->Kc, cscale): the weighted operand w[n, l] K[n, a] is rebuilt per channel in shared
- * memory as a 32-bit fixed-point integer (4 digit planes) against the 24-bit K^T planes, the 9 digit-plane pairs of
+ * memory as a 32-bit fixed-point integer (4 digit planes) against the 32-bit K^T planes, the 10 digit-plane pairs of
  * order <= 3 run as integer MMAs over windows of <= 16384 datapoints and the exactly recombined window sums are added
  * into A with double atomics: no rounding inside the contraction (the summation ORDER of the window sums in float64 is
  * not fixed).  Same workspace size function.                                                                        */
@@ -195,8 +203,8 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
 /* svgp_scaled_gemm on the integer tensor-core path: G as the 4 digit planes + per-row scales of
  * svgp_split_i8(G viewed as (L * Mc) x M, nslices = 4, ldp = ldg) -- the matrices must be symmetric or given
  * transposed (row c of G_l multiplies k_i into output column c); K_nm as kop->Kr / rscale.  Mc = rows of each G_l
- * (M for the dK_nm product; any value for a skinny product such as K_nm Wm^T with L = 1).  Exact integer accumulation
- * of the 9 digit-plane pairs of order <= 3, one fp32 rounding when an accumulator tile leaves TMEM, fp32 running sums over
+ * (M for the dK_nm product; any value for a skinny product such as K_nm Wm^T with L = 1, W = NULL).  Exact integer accumulation
+ * of the 10 digit-plane pairs of order <= 3, one fp32 rounding when an accumulator tile leaves TMEM, fp32 running sums over
  * the L matrices.                                                                                                    */
 int svgp_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_planes, int64_t ldg,
                         const float* G_scale, int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate,

@@ -53,7 +53,9 @@ SIGNATURES = {
     "svgp_split_f16": [_P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_i8_ldkr": [c_int64],
     "svgp_i8_nblk": [c_int64],
-    "svgp_kplanes_i8": [POINTER(KopStruct), _P, c_int64, _P, _P, _P, _P, _P],
+    "svgp_kernel_fwd_f64": [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_int64, _P],
+    "svgp_kernel_fwd_i8": [_P, c_int64, c_int64, _P, c_int64, c_int64, c_int, c_int, c_int, c_int, _P,
+                           _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P],
     "svgp_split_i8": [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, _P, _P],
     "svgp_scaled_gemm_i8": [POINTER(KopStruct), _P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64,
                             c_int64, _P],

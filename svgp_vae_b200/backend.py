@@ -28,8 +28,8 @@ class Kop:
         ref = K if K is not None else Kh
         self.N = ref.shape[0] if N is None else N
         self.M = ref.shape[1] if M is None else M
-        # int8 digit planes of the exact integer tensor-core products (svgp_kplanes_i8): Kr (3, N, ldkr) row-scaled,
-        # Kc (3, ceil(N / 128), M, 128) column-scaled and datapoint-blocked, with their scales
+        # int8 digit planes of the exact integer tensor-core products (svgp_kernel_fwd_i8): Kr (4, N, ldkr) row-scaled,
+        # Kc (4, ceil(N / 128), M, 128) column-scaled and datapoint-blocked, with their scales
         self.Kr = self.rscale = self.Kc = self.cscale = None
 
     @property
@@ -44,9 +44,9 @@ class Kop:
         """K_nm reassembled from the digit planes (float64): which = "r" row-scaled planes, "c" column-scaled ones."""
         if which == "r":
             d = self.Kr.double()
-            return ((d[0] * 65536.0 + d[1] * 256.0 + d[2]) * self.rscale.double()[:, None])[:, : self.M]
-        d = self.Kc.double()                                             # (3, nblk, M, 128)
-        v = (d[0] * 65536.0 + d[1] * 256.0 + d[2]) * self.cscale.double()[None, :, None]
+            return ((((d[0] * 256.0 + d[1]) * 256.0 + d[2]) * 256.0 + d[3]) * self.rscale.double()[:, None])[:, : self.M]
+        d = self.Kc.double()                                             # (4, nblk, M, 128)
+        v = (((d[0] * 256.0 + d[1]) * 256.0 + d[2]) * 256.0 + d[3]) * self.cscale.double()[None, :, None]
         return v.permute(0, 2, 1).reshape(-1, self.M)[: self.N]
 
     @property
@@ -185,7 +185,25 @@ class CudaBackend:
         N, M = Fx.shape[0], Fz.shape[0]
         ta, da, tb, db = spec
         dev = Fx.device
-        if tc:
+        if i8 is None:
+            i8 = bool(tc) and self.want_i8(N, M)
+        if tc and i8:
+            # fp16 hi/lo row planes + the int8 digit planes of the integer tensor-core products, straight from fp32 values
+            ldkh, ldkr, nblk = _pad(M, 8), _pad(M, 16), (N + 127) // 128
+            Kh = torch.empty((N, ldkh), device=dev, dtype=torch.float16)
+            Kl = torch.empty((N, ldkh), device=dev, dtype=torch.float16)
+            kscale = torch.empty(8, device=dev, dtype=torch.float32)
+            kop = Kop(None, Kh, Kl, None, None, kscale, N, M)
+            kop.Kr = torch.empty((4, N, ldkr), device=dev, dtype=torch.int8)
+            kop.rscale = torch.empty(N, device=dev, dtype=torch.float32)
+            kop.Kc = torch.empty((4, nblk, M, 128), device=dev, dtype=torch.int8)
+            kop.cscale = torch.empty(M, device=dev, dtype=torch.float32)
+            scratch = torch.empty(N + M, device=dev, dtype=torch.float32)
+            _call("svgp_kernel_fwd_i8", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
+                  _ptr(Kh), _ptr(Kl), ldkh, _ptr(kop.Kr), ldkr, _ptr(kop.rscale), _ptr(kop.Kc), _ptr(kop.cscale), _ptr(scratch),
+                  _ptr(kscale), _stream())
+            self.launches += 2
+        elif tc:
             ldkh = _pad(M, 8)
             alloc = torch.zeros if (ldkh != M) else torch.empty
             Kh = alloc((N, ldkh), device=dev, dtype=torch.float16)
@@ -199,10 +217,6 @@ class CudaBackend:
             kop = Kop(None, Kh, Kl, Kth, Ktl, kscale, N, M)
             _call("svgp_kernel_fwd", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp),
                   None, 0, _ptr(Kh), _ptr(Kl), ldkh, _ptr(Kth), _ptr(Ktl), ldkt, _ptr(kscale), _stream())
-            if i8 is None:
-                i8 = self.want_i8(N, M)
-            if i8:
-                self.kplanes_i8(kop)
         else:
             K = torch.empty((N, M), device=dev, dtype=torch.float32)
             kop = Kop(K)
@@ -211,21 +225,15 @@ class CudaBackend:
         self.launches += 1
         return kop
 
-    def kplanes_i8(self, kop):
-        """Attach the int8 digit planes of K_nm (svgp_kplanes_i8) to a kop that carries the fp16 planes."""
-        N, M, dev = kop.N, kop.M, kop.device
-        ldkr = _pad(M, 16)
-        nblk = (N + 127) // 128
-        kop.Kr = torch.empty((3, N, ldkr), device=dev, dtype=torch.int8)
-        kop.rscale = torch.empty(N, device=dev, dtype=torch.float32)
-        kop.Kc = torch.empty((3, nblk, M, 128), device=dev, dtype=torch.int8)
-        kop.cscale = torch.empty(M, device=dev, dtype=torch.float32)
-        scratch = torch.empty(N + M, device=dev, dtype=torch.float32)
-        s = kop.struct()
-        _call("svgp_kplanes_i8", ctypes.byref(s), _ptr(kop.Kr), ldkr, _ptr(kop.rscale), _ptr(kop.Kc), _ptr(kop.cscale), _ptr(scratch),
-              _stream())
-        self.launches += 4
-        return kop
+    def kernel_fwd_f64(self, spec, Fx, Fz, hyp):
+        """K(Fx, Fz) evaluated and stored in float64 (fp32 features): K_mm of the M x M stage."""
+        Fx, Fz, hyp = _f32c(Fx), _f32c(Fz), _f32c(hyp)
+        N, M = Fx.shape[0], Fz.shape[0]
+        ta, da, tb, db = spec
+        K = torch.empty((N, M), device=Fx.device, dtype=torch.float64)
+        _call("svgp_kernel_fwd_f64", _ptr(Fx), Fx.stride(0), N, _ptr(Fz), Fz.stride(0), M, ta, da, tb, db, _ptr(hyp), _ptr(K), M, _stream())
+        self.launches += 1
+        return K
 
     def kernel_bwd(self, spec, Fx, Fz, hyp, G, need_x=True, need_z=True):
         Fx, Fz, hyp, G = _f32c(Fx), _f32c(Fz), _f32c(hyp), _f32c(G)
@@ -370,6 +378,9 @@ class CudaBackend:
         L = Wm.shape[0]
         out = torch.empty((kop.N, L), device=Wm.device, dtype=torch.float32)
         s = kop.struct()
+        if kop.i8 and impl in (IMPL_AUTO, IMPL_TC_I8):
+            # exact integer products: K_nm w_l cancels heavily at large M (p_m, dy at M = 2048)
+            return self.scaled_gemm_i8(kop, None, self.planes_i8(Wm.double().contiguous().unsqueeze(0)))
         if kop.tc and impl != IMPL_SIMT and kop.M >= 128 and kop.N >= self.tc_min_rows:
             pl = self.planes(Wm.double().contiguous().unsqueeze(0))          # (1, L, M) -> one scale for the whole matrix
             _call("svgp_gemm_nn_tc", ctypes.byref(s), _ptr(pl.hi), _ptr(pl.lo), _ptr(pl.inv), L, _ptr(out), out.stride(0), _stream())

@@ -71,6 +71,33 @@ __device__ __forceinline__ float factor_value(int type, const float* x, const fl
   return dot;
 }
 
+// the same in float64 arithmetic on the fp32 features (the integer tensor-core operands and the M x M stage's K_mm:
+// an fp32 evaluation carries ~|exponent| 2^-24 ~ 5e-7 of relative error per entry, which the ill-conditioned M x M
+// stage turns into 1e-4 of the inducing-point gradient at M = 2048 -- tools/numerics/sim_parity.py, SIM_KNOISE)
+__device__ __forceinline__ double factor_value_f64(int type, const float* x, const float* z, int d, double amp,
+                                                   double len, double nx, double nz) {
+  if (type == SVGP_K_NONE) return 1.0;
+  if (type == SVGP_K_SE) {
+    double r2 = 0.0;
+    for (int f = 0; f < d; ++f) { const double t = (double)x[f] - (double)z[f]; r2 = fma(t, t, r2); }
+    return amp * amp * exp(-0.5 * r2 / (len * len));
+  }
+  if (type == SVGP_K_EXPSIN) {
+    double u = 0.0;
+    for (int f = 0; f < d; ++f) { const double s = sin(0.5 * fabs((double)x[f] - (double)z[f])); u = fma(s, s, u); }
+    return amp * amp * exp(-2.0 * u / (len * len));
+  }
+  double dot = 0.0;
+  for (int f = 0; f < d; ++f) dot = fma((double)x[f], (double)z[f], dot);
+  if (type == SVGP_K_COSINE) dot = dot / (nx * nz);
+  return dot;
+}
+__device__ __forceinline__ double block_norm_f64(const float* v, int d) {
+  double s = 0.0;
+  for (int f = 0; f < d; ++f) s = fma((double)v[f], (double)v[f], s);
+  return sqrt(s);
+}
+
 // adjoint coefficients of one factor for one (row, col) pair, given gk = g * (other factor):
 //   d/dz_f = c1 * x_f + c2z * z_f (+ e for EXPSIN on its single feature, sign + for z, - for x)
 //   d/dx_f = c1 * z_f + c2x * x_f
@@ -386,6 +413,228 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_planes_kernel(
       }
     }
     __syncthreads();
+  }
+}
+
+// float64 kernel matrix (fp32 features, float64 arithmetic and output): K_mm of the M x M stage
+__global__ void kernel_fwd_f64_kernel(const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz,
+                                      int64_t M, Spec sp, const float* __restrict__ hyp, double* __restrict__ K, int64_t ldk) {
+  const Hyp h = load_hyp(hyp);
+  const int64_t total = N * M;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / M, j = idx - i * M;
+    const float* x = Fx + i * ldx;
+    const float* z = Fz + j * ldz;
+    const double ka = factor_value_f64(sp.ta, x, z, sp.da, h.amp_a, h.len_a, sp.ta == SVGP_K_COSINE ? block_norm_f64(x, sp.da) : 1.0,
+                                       sp.ta == SVGP_K_COSINE ? block_norm_f64(z, sp.da) : 1.0);
+    const double kb = factor_value_f64(sp.tb, x + sp.da, z + sp.da, sp.db, h.amp_b, h.len_b,
+                                       sp.tb == SVGP_K_COSINE ? block_norm_f64(x + sp.da, sp.db) : 1.0,
+                                       sp.tb == SVGP_K_COSINE ? block_norm_f64(z + sp.da, sp.db) : 1.0);
+    K[i * ldk + j] = ka * kb;
+  }
+}
+
+// Builder of the integer tensor-core operand format (tc_i8_engine.cu, i8_planes.cu): every entry of K_nm as a 32-bit
+// fixed-point integer against the largest entry of its ROW (Kr: products that reduce over the inducing points) and of
+// its COLUMN (Kc, datapoint-blocked transpose: the SYRK), cut into four balanced base-256 digit planes each -- written
+// straight from the fp32 kernel values, so the planes carry fp32 accuracy (a plane derived from the fp16 hi/lo pair
+// would stop at 22 bits; the M = 2048 sweep point needs more: tools/numerics/sim_parity.py) -- plus the fp16 hi/lo row
+// planes the remaining fp16 consumers read.  Two passes over the same tiles: MAXPASS = true only reduces the row and
+// column maxima (float bits, atomicMax), MAXPASS = false writes.
+template <bool SE44, bool MAXPASS>
+__global__ void __launch_bounds__(THREADS) kernel_fwd_i8_kernel(
+    const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz, int64_t M,
+    Spec sp, const float* __restrict__ hyp, __half* __restrict__ Kh, __half* __restrict__ Kl, int64_t ldkh,
+    int8_t* __restrict__ Kr, int64_t ldkr, float* __restrict__ rscale, int8_t* __restrict__ Kc, float* __restrict__ cscale,
+    float* __restrict__ rmax, float* __restrict__ cmax, float* __restrict__ kscale) {
+  extern __shared__ float smem[];
+  const int d = sp.da + sp.db;
+  const int dpx = SE44 ? 8 : (d | 1), dpz = d | 1;
+  float* xs = smem;
+  float* zs = xs + TILE * (SE44 ? 8 : dpz);
+  float* tile = zs + TILE * dpz;                      // [TILE][TILE + 1] kernel values (fp32)
+  float* nxa = tile + TILE * (TILE + 1);
+  float* nxb = nxa + TILE;
+  float* nza = nxb + TILE;
+  float* nzb = nza + TILE;
+  constexpr int P = TILE + 1;
+  constexpr float XMAX4F = 2130706432.0f;             // 127 * 2^24
+  const Hyp h = load_hyp(hyp);
+  const int64_t col0 = (int64_t)blockIdx.x * TILE;
+  const int64_t ntiles_r = (N + TILE - 1) / TILE;
+  const float scale = plane_scale(sp, h, kscale);
+  if (!MAXPASS && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    kscale[0] = scale; kscale[1] = 1.0f / scale; kscale[6] = kernel_nonneg(sp) ? 1.0f : 0.0f;
+  }
+  load_features(Fz, ldz, col0, M, d, dpz, sp, zs, nza, nzb);
+  const int c = threadIdx.x % TILE, rg = threadIdx.x / TILE;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k4 = lane & 3, sub = lane >> 2;
+  float zr[8];
+  float ca = 0.f, cb = 0.f, amp2 = 0.f;
+  if (SE44) {
+#pragma unroll
+    for (int f = 0; f < 8; ++f) zr[f] = zs[c * dpz + f];
+    const float LOG2E = 1.4426950408889634f;
+    ca = -0.5f * LOG2E / (h.len_a * h.len_a);
+    cb = -0.5f * LOG2E / (h.len_b * h.len_b);
+    amp2 = h.amp_a * h.amp_a * h.amp_b * h.amp_b;
+  }
+  const double LOG2E_D = 1.4426950408889634;
+  const double cad = -0.5 * LOG2E_D / ((double)h.len_a * (double)h.len_a), cbd = -0.5 * LOG2E_D / ((double)h.len_b * (double)h.len_b);
+  const double amp2d = (double)h.amp_a * (double)h.amp_a * (double)h.amp_b * (double)h.amp_b;
+  const int64_t nb128 = (N + 127) / 128;
+  const int64_t rplane = N * ldkr, cplane = nb128 * M * 128;
+  float colmax = 0.f;                                 // MAXPASS: this thread's column over all its row tiles
+  float qc = 0.f;                                     // write pass: quantisation factor of the read-out column
+  if (!MAXPASS) {
+    const int64_t gc = col0 + warp * 8 + sub;
+    const float m = gc < M ? cmax[gc] : 0.f;
+    qc = m > 0.f ? XMAX4F / m : 0.f;
+    if (blockIdx.y == 0 && k4 == 0 && gc < M) cscale[gc] = m > 0.f ? m / XMAX4F : 0.f;
+  }
+
+  for (int64_t rt = blockIdx.y; rt < ntiles_r; rt += gridDim.y) {
+    const int64_t row0 = rt * TILE;
+    load_features(Fx, ldx, row0, N, d, dpx, sp, xs, nxa, nxb);
+#pragma unroll 4
+    for (int j = 0; j < TILE / 4; ++j) {
+      const int r = rg + 4 * j;
+      float v;
+      if (SE44 && MAXPASS) {
+        const float4 xa = *reinterpret_cast<const float4*>(xs + r * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + r * 8 + 4);
+        float t, ra, rb;
+        t = xa.x - zr[0]; ra = t * t;
+        t = xa.y - zr[1]; ra = fmaf(t, t, ra);
+        t = xa.z - zr[2]; ra = fmaf(t, t, ra);
+        t = xa.w - zr[3]; ra = fmaf(t, t, ra);
+        t = xb.x - zr[4]; rb = t * t;
+        t = xb.y - zr[5]; rb = fmaf(t, t, rb);
+        t = xb.z - zr[6]; rb = fmaf(t, t, rb);
+        t = xb.w - zr[7]; rb = fmaf(t, t, rb);
+        v = amp2 * exp2f(fmaf(ca, ra, cb * rb));
+      } else if (SE44) {
+        // write pass: float64 evaluation (the maxima above only position the fixed-point grid)
+        const float4 xa = *reinterpret_cast<const float4*>(xs + r * 8);
+        const float4 xb = *reinterpret_cast<const float4*>(xs + r * 8 + 4);
+        double t, ra, rb;
+        t = (double)xa.x - (double)zr[0]; ra = t * t;
+        t = (double)xa.y - (double)zr[1]; ra = fma(t, t, ra);
+        t = (double)xa.z - (double)zr[2]; ra = fma(t, t, ra);
+        t = (double)xa.w - (double)zr[3]; ra = fma(t, t, ra);
+        t = (double)xb.x - (double)zr[4]; rb = t * t;
+        t = (double)xb.y - (double)zr[5]; rb = fma(t, t, rb);
+        t = (double)xb.z - (double)zr[6]; rb = fma(t, t, rb);
+        t = (double)xb.w - (double)zr[7]; rb = fma(t, t, rb);
+        v = (float)(amp2d * exp2(fma(cad, ra, cbd * rb)));
+      } else if (MAXPASS) {
+        const float ka = factor_value(sp.ta, xs + r * dpx, zs + c * dpz, sp.da, h.amp_a, h.len_a, nxa[r], nza[c]);
+        const float kb = factor_value(sp.tb, xs + r * dpx + sp.da, zs + c * dpz + sp.da, sp.db, h.amp_b, h.len_b, nxb[r], nzb[c]);
+        v = ka * kb;
+      } else {
+        const double ka = factor_value_f64(sp.ta, xs + r * dpx, zs + c * dpz, sp.da, h.amp_a, h.len_a,
+                                           sp.ta == SVGP_K_COSINE ? block_norm_f64(xs + r * dpx, sp.da) : 1.0,
+                                           sp.ta == SVGP_K_COSINE ? block_norm_f64(zs + c * dpz, sp.da) : 1.0);
+        const double kb = factor_value_f64(sp.tb, xs + r * dpx + sp.da, zs + c * dpz + sp.da, sp.db, h.amp_b, h.len_b,
+                                           sp.tb == SVGP_K_COSINE ? block_norm_f64(xs + r * dpx + sp.da, sp.db) : 1.0,
+                                           sp.tb == SVGP_K_COSINE ? block_norm_f64(zs + c * dpz + sp.da, sp.db) : 1.0);
+        v = (float)(ka * kb);
+      }
+      if (row0 + r >= N || col0 + c >= M) v = 0.f;
+      if (MAXPASS) colmax = fmaxf(colmax, fabsf(v));
+      tile[r * P + c] = v;
+    }
+    __syncthreads();
+    if (MAXPASS) {
+      // row maxima of this tile: a warp covers 8 rows x 64 columns (4 lanes x 16 entries per row)
+      const int r = warp * 8 + sub;
+      float m = 0.f;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) m = fmaxf(m, fabsf(tile[r * P + k4 * 16 + i]));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+      if (k4 == 0 && row0 + r < N && m > 0.f) atomicMax(reinterpret_cast<int*>(rmax + row0 + r), __float_as_int(m));
+    } else {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        {   // row r, columns e0 .. e0 + 7: fp16 hi / lo planes and the row-scaled digits
+          const int r = warp * 8 + sub, e0 = half * 32 + k4 * 8;
+          const int64_t gr = row0 + r, gc = col0 + e0;
+          if (gr < N && gc < M) {
+            const float mr = rmax[gr];
+            const float qr = mr > 0.f ? XMAX4F / mr : 0.f;
+            if (blockIdx.x == 0 && e0 == 0) rscale[gr] = mr > 0.f ? mr / XMAX4F : 0.f;
+            uint32_t hw[4], lw[4], e[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+              const float v0 = tile[r * P + e0 + i], v1 = tile[r * P + e0 + i + 1];
+              const __half2 hi = __floats2half2_rn(v0 * scale, v1 * scale);
+              const float2 hf = __half22float2(hi);
+              const __half2 lo = __floats2half2_rn(v0 * scale - hf.x, v1 * scale - hf.y);
+              hw[i >> 1] = *reinterpret_cast<const uint32_t*>(&hi);
+              lw[i >> 1] = *reinterpret_cast<const uint32_t*>(&lo);
+              e[i] = ((uint32_t)__float2int_rn(v0 * qr) + 0x00808080u) ^ 0x00808080u;
+              e[i + 1] = ((uint32_t)__float2int_rn(v1 * qr) + 0x00808080u) ^ 0x00808080u;
+            }
+            // (columns >= M inside this run are zero in the tile: zero digits)
+            *reinterpret_cast<uint4*>(Kh + gr * ldkh + gc) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(Kl + gr * ldkh + gc) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+            uint32_t w0[4], w1[4];
+            {
+              const uint32_t x01 = __byte_perm(e[0], e[1], 0x7362), y01 = __byte_perm(e[0], e[1], 0x5140);
+              const uint32_t x23 = __byte_perm(e[2], e[3], 0x7362), y23 = __byte_perm(e[2], e[3], 0x5140);
+              w0[0] = __byte_perm(x01, x23, 0x7632); w0[1] = __byte_perm(x01, x23, 0x5410);
+              w0[2] = __byte_perm(y01, y23, 0x7632); w0[3] = __byte_perm(y01, y23, 0x5410);
+            }
+            {
+              const uint32_t x01 = __byte_perm(e[4], e[5], 0x7362), y01 = __byte_perm(e[4], e[5], 0x5140);
+              const uint32_t x23 = __byte_perm(e[6], e[7], 0x7362), y23 = __byte_perm(e[6], e[7], 0x5140);
+              w1[0] = __byte_perm(x01, x23, 0x7632); w1[1] = __byte_perm(x01, x23, 0x5410);
+              w1[2] = __byte_perm(y01, y23, 0x7632); w1[3] = __byte_perm(y01, y23, 0x5410);
+            }
+#pragma unroll
+            for (int s = 0; s < 4; ++s) *reinterpret_cast<uint2*>(Kr + s * rplane + gr * ldkr + gc) = make_uint2(w0[s], w1[s]);
+          }
+        }
+        {   // column cc, datapoints e0 .. e0 + 7 of this 64-datapoint half block: column-scaled digits, blocked by 128
+          const int cc = warp * 8 + sub, e0 = half * 32 + k4 * 8;
+          const int64_t gc = col0 + cc;
+          if (gc < M) {
+            uint32_t e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) e[i] = ((uint32_t)__float2int_rn(tile[(e0 + i) * P + cc] * qc) + 0x00808080u) ^ 0x00808080u;
+            uint32_t w0[4], w1[4];
+            {
+              const uint32_t x01 = __byte_perm(e[0], e[1], 0x7362), y01 = __byte_perm(e[0], e[1], 0x5140);
+              const uint32_t x23 = __byte_perm(e[2], e[3], 0x7362), y23 = __byte_perm(e[2], e[3], 0x5140);
+              w0[0] = __byte_perm(x01, x23, 0x7632); w0[1] = __byte_perm(x01, x23, 0x5410);
+              w0[2] = __byte_perm(y01, y23, 0x7632); w0[3] = __byte_perm(y01, y23, 0x5410);
+            }
+            {
+              const uint32_t x01 = __byte_perm(e[4], e[5], 0x7362), y01 = __byte_perm(e[4], e[5], 0x5140);
+              const uint32_t x23 = __byte_perm(e[6], e[7], 0x7362), y23 = __byte_perm(e[6], e[7], 0x5140);
+              w1[0] = __byte_perm(x01, x23, 0x7632); w1[1] = __byte_perm(x01, x23, 0x5410);
+              w1[2] = __byte_perm(y01, y23, 0x7632); w1[3] = __byte_perm(y01, y23, 0x5410);
+            }
+            const int64_t o = ((row0 >> 7) * M + gc) * 128 + (row0 & 127) + e0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) *reinterpret_cast<uint2*>(Kc + s * cplane + o) = make_uint2(w0[s], w1[s]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (MAXPASS) {
+    // fold the four row groups of every column, then one atomic per column and block
+    __syncthreads();
+    tile[rg * P + c] = colmax;
+    __syncthreads();
+    if (rg == 0) {
+      const float m = fmaxf(fmaxf(tile[c], tile[P + c]), fmaxf(tile[2 * P + c], tile[3 * P + c]));
+      if (col0 + c < M && m > 0.f) atomicMax(reinterpret_cast<int*>(cmax + col0 + c), __float_as_int(m));
+    }
   }
 }
 
@@ -790,6 +1039,70 @@ int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, in
   kernel_fwd_kernel<<<grid, THREADS, fwd_smem(dim_a + dim_b), st>>>(
       Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
   return check_launch("svgp_kernel_fwd");
+}
+
+int svgp_kernel_fwd_f64(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a, int dim_a,
+                        int type_b, int dim_b, const float* hyp, double* K, int64_t ldk, void* stream) {
+  SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
+  SVGP_REQUIRE(Fx && Fz && hyp && K && N >= 0 && M >= 0 && ldk >= M, "bad argument");
+  if (N == 0 || M == 0) return SVGP_OK;
+  Spec sp{type_a, dim_a, type_b, dim_b};
+  int64_t blocks = ceil_div(N * M, 256);
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  kernel_fwd_f64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk);
+  return check_launch("svgp_kernel_fwd_f64");
+}
+
+int svgp_kernel_fwd_i8(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a, int dim_a,
+                       int type_b, int dim_b, const float* hyp, void* Kh, void* Kl, int64_t ldkh, void* Kr, int64_t ldkr,
+                       float* rscale, void* Kc, float* cscale, float* scratch, float* kscale, void* stream) {
+  SVGP_REQUIRE(check_spec(type_a, dim_a, type_b, dim_b), "bad kernel spec");
+  SVGP_REQUIRE(Fx && Fz && hyp && Kh && Kl && Kr && rscale && Kc && cscale && scratch && kscale && N >= 0 && M >= 0, "null argument");
+  SVGP_REQUIRE(ldkh % 8 == 0 && ldkh >= (M + 7) / 8 * 8 && ldkr % 16 == 0 && ldkr >= (M + 7) / 8 * 8, "row pitches: ldkh multiple of 8, ldkr multiple of 16, both >= M rounded up to 8");
+  SVGP_REQUIRE((((uintptr_t)Kh | (uintptr_t)Kl | (uintptr_t)Kr | (uintptr_t)Kc) & 15) == 0, "planes need 16-byte alignment");
+  if (N == 0 || M == 0) return SVGP_OK;
+  Spec sp{type_a, dim_a, type_b, dim_b};
+  cudaStream_t st = (cudaStream_t)stream;
+  float* rmax = scratch;
+  float* cmax = scratch + N;
+  if (cudaMemsetAsync(kscale, 0, 8 * sizeof(float), st) != cudaSuccess) return check_launch("svgp_kernel_fwd_i8(memset)");
+  if (cudaMemsetAsync(scratch, 0, (N + M) * sizeof(float), st) != cudaSuccess) return check_launch("svgp_kernel_fwd_i8(memset)");
+  // the last 128-datapoint block of Kc and the pad columns of Kr / Kh / Kl must be zeros (TMA boxes read them)
+  const int64_t nb128 = (N + 127) / 128;
+  if (N % 128) {
+    for (int s = 0; s < 4; ++s)
+      if (cudaMemsetAsync((int8_t*)Kc + (s * nb128 + (nb128 - 1)) * M * 128, 0, M * 128, st) != cudaSuccess) return check_launch("svgp_kernel_fwd_i8(memset)");
+  }
+  if (ldkr != M && cudaMemsetAsync(Kr, 0, 4 * N * ldkr, st) != cudaSuccess) return check_launch("svgp_kernel_fwd_i8(memset)");
+  if (ldkh != M) {
+    if (cudaMemsetAsync(Kh, 0, N * ldkh * 2, st) != cudaSuccess || cudaMemsetAsync(Kl, 0, N * ldkh * 2, st) != cudaSuccess)
+      return check_launch("svgp_kernel_fwd_i8(memset)");
+  }
+  if (type_a == SVGP_K_LINEAR || type_b == SVGP_K_LINEAR) {
+    int64_t bx = ceil_div(N, 256), bz = ceil_div(M, 256);
+    if (bx > 148 * 8) bx = 148 * 8;
+    if (bz > 148 * 8) bz = 148 * 8;
+    feature_norm_kernel<<<(unsigned)bx, 256, 0, st>>>(Fx, ldx, N, sp, kscale, 2);
+    feature_norm_kernel<<<(unsigned)bz, 256, 0, st>>>(Fz, ldz, M, sp, kscale, 4);
+    int rc = check_launch("svgp_kernel_fwd_i8(norms)");
+    if (rc) return rc;
+  }
+  int64_t ntc = ceil_div(M, TILE), ntr = ceil_div(N, TILE);
+  int64_t gy = ntr;
+  int64_t cap = (148 * 16 + ntc - 1) / ntc;
+  if (gy > cap) gy = cap;
+  if (gy < 1) gy = 1;
+  if (gy > 65535) gy = 65535;
+  dim3 grid((unsigned)ntc, (unsigned)gy);
+  const bool se44 = type_a == SVGP_K_SE && type_b == SVGP_K_SE && dim_a == 4 && dim_b == 4;
+  const size_t sm = fwd_smem(dim_a + dim_b);
+#define SVGP_LAUNCH_I8(SE, MX)                                                                                                    \
+  kernel_fwd_i8_kernel<SE, MX><<<grid, THREADS, sm, st>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, (__half*)Kh, (__half*)Kl, ldkh, (int8_t*)Kr, \
+                                                          ldkr, rscale, (int8_t*)Kc, cscale, rmax, cmax, kscale)
+  if (se44) { SVGP_LAUNCH_I8(true, true); SVGP_LAUNCH_I8(true, false); }
+  else { SVGP_LAUNCH_I8(false, true); SVGP_LAUNCH_I8(false, false); }
+#undef SVGP_LAUNCH_I8
+  return check_launch("svgp_kernel_fwd_i8");
 }
 
 int svgp_kernel_bwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, int64_t ldz, int64_t M, int type_a,

@@ -344,7 +344,7 @@ using namespace svgp;
 static bool use_tc(const svgp_kop* kop, int impl) {
   if (impl == SVGP_IMPL_SIMT) return false;
   if (impl == SVGP_IMPL_TC) return true;
-  return kop->Kh && kop->Kl && kop->Kth && kop->Ktl && kop->kscale && tc_shape_ok(kop);
+  return kop->Kh && kop->Kl && kop->kscale && tc_shape_ok(kop);     // (the fp16 SYRK additionally needs the transposed planes)
 }
 
 extern "C" {
@@ -359,9 +359,9 @@ int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, doubl
   SVGP_REQUIRE(kop && W && A && L >= 1, "null argument");
   if (kop->N == 0 || kop->M == 0) return SVGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == SVGP_IMPL_TC_I8) {
+  if (impl == SVGP_IMPL_TC_I8 || (impl == SVGP_IMPL_AUTO && kop->Kc && kop->cscale && tc_shape_ok(kop))) {
     SVGP_REQUIRE(ws != nullptr, "TC path needs the workspace (svgp_syrk_ws_floats)");
-    SVGP_REQUIRE(kop->Kc && kop->cscale && kop->M >= 128 && kop->N >= 128, "integer path needs the int8 planes (svgp_kplanes_i8) and M, N >= 128");
+    SVGP_REQUIRE(kop->Kc && kop->cscale && kop->M >= 128 && kop->N >= 128, "integer path needs the int8 planes (svgp_kernel_fwd_i8) and M, N >= 128");
     return tc_syrk_i8_prep_run(kop, W, ldw, L, A, ws, st);
   }
   if (use_tc(kop, impl)) {
@@ -481,7 +481,7 @@ int svgp_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const 
                         void* stream) {
   SVGP_REQUIRE(kop && G_planes && G_scale && out && L >= 1 && Mc >= 1, "null argument");
   SVGP_REQUIRE(!dots || (ndot >= 0 && ndot <= L && lddots >= ndot), "bad dots argument");
-  SVGP_REQUIRE(kop->Kr && kop->rscale && kop->M >= 128 && kop->N >= 128, "integer path needs the int8 planes (svgp_kplanes_i8) and M, N >= 128");
+  SVGP_REQUIRE(kop->Kr && kop->rscale && kop->M >= 128 && kop->N >= 128, "integer path needs the int8 planes (svgp_kernel_fwd_i8) and M, N >= 128");
   SVGP_REQUIRE(ldg % 16 == 0 && ldg >= kop->M && ldo >= Mc, "bad pitch");
   if (kop->N == 0) return SVGP_OK;
   return tc_scaled_gemm_i8(kop, W, ldw, G_planes, ldg, G_scale, L, Mc, out, ldo, accumulate, dots, lddots, ndot, (cudaStream_t)stream);

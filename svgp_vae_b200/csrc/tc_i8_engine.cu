@@ -1,32 +1,35 @@
-// Exact-accumulation tensor-core products for the two contractions whose rounding the SVGP step cannot absorb
+// Exact-accumulation tensor-core products for the contractions whose rounding the SVGP step cannot absorb
 // (sm_100a: tcgen05.mma.kind::i8, int32 accumulators in TMEM, TMA-fed digit planes -- see i8_planes.cu for the format).
 //
 //   svgp_syrk (forward A_l = sum_i p_il k_i k_i^T and its adjoint twin)   SVGPVAE_model.py:328-330, :286-294
-//   svgp_scaled_gemm for the dA_l + dA_l^T family (dObjective/dK_nm and k^T dA k)   tf.gradients through :328-337
+//   svgp_scaled_gemm_i8: the dA_l + dA_l^T family (dObjective/dK_nm and k^T dA k) and the skinny products K_nm Wm^T
+//                                                                         tf.gradients through :328-337; :332-334
 //
-// Why integers.  tcgen05.mma.kind::f16 adds into fp32 TMEM with truncation; on these two products the loss (~n 2^-24 per
+// Why integers.  tcgen05.mma.kind::f16 adds into fp32 TMEM with truncation; on these products the loss (~n 2^-24 per
 // chain of n MMAs, relative to the largest partial sum) is amplified by cond(Sigma_l) / by the cancellation in
 // K (dA + dA^T) and ends up as 3e-4 .. 3e-3 in the inducing-point gradient (round 1).  Integer MMAs do not round at all:
-// operands are cut into balanced base-256 digits, digit planes are multiplied pairwise, every pair (t, u) with
-// t + u <= 3 is kept (9 MMAs per k-step) and the four orders o = t + u accumulate in four int32 TMEM accumulators that
-// the epilogue recombines exactly (acc_0 2^24 + acc_1 2^16 + acc_2 2^8 + acc_3).  What is dropped is below 2^-32 of
-// (row maximum x column maximum); what remains of the operand quantisation is a CONSISTENT perturbation of K_nm
-// (tools/numerics/sim_parity.py measures both).  kind::i8 runs at twice the MAC rate of kind::f16
-// (profiles/r02_i8_mma_probe.jsonl: 8192 MAC / clk / SM), so 9 integer MMAs cost 4.5 fp16 MMAs against 3 before.
+// both operands are 32-bit fixed-point integers cut into four balanced base-256 digits, digit planes are multiplied
+// pairwise, every pair (t, u) with t + u <= 3 is kept (10 MMAs per k-step) and the four orders o = t + u accumulate in
+// four int32 TMEM accumulators that the epilogue recombines exactly (acc_0 2^24 + acc_1 2^16 + acc_2 2^8 + acc_3).
+// What is dropped is below 2^-32 of (row maximum x column maximum) per term; what remains of the operand quantisation
+// is a CONSISTENT perturbation of K_nm at fp32 level (tools/numerics/sim_parity.py measures both, and shows that
+// 24-bit operands or 9 pairs are NOT enough at M = 2048).  kind::i8 runs at twice the MAC rate of kind::f16
+// (profiles/r02_i8_mma_probe.jsonl: 8192 MAC / clk / SM), so 10 integer MMAs cost 5 fp16 MMAs against 3 before.
 //
-// Tile: 128 x 128 outputs, k-blocks of 128 reduction elements (one 128-byte swizzle row per operand row and digit plane),
-// two shared-memory stages of 7 planes x 16 KB; the four accumulators fill TMEM (4 x 128 columns), so the epilogue of one
-// chain does not overlap the MMAs of the next -- the SYRK chains are a whole window of datapoints long (irrelevant), the
-// scaled GEMM pays ~15 % at M = 1024 (less as M grows).
+// Tile: 128 x 128 outputs, k-blocks of 64 reduction elements (one 64-byte swizzle row per operand row and digit plane),
+// three shared-memory stages of 8 planes x 8 KB; the four accumulators fill TMEM (4 x 128 columns), so the epilogue of
+// one chain does not overlap the MMAs of the next -- the SYRK chains are a whole window of datapoints long (irrelevant),
+// the scaled GEMM pays ~15 % at M = 1024 (less as M grows).
 #include "tc_ptx.cuh"
 
 namespace svgp {
 
-constexpr int I8_T = 128;                         // tile rows = tile columns = reduction elements per k-block
-constexpr int I8_PLANE = I8_T * I8_T;             // bytes of one digit plane of one operand tile
-constexpr int I8_NPL = 7;                         // planes per stage: 4 of the finer operand + 3 of the coarser one
+constexpr int I8_T = 128;                         // tile rows = tile columns
+constexpr int I8_KB = 64;                         // reduction elements (= bytes per operand row) per k-block
+constexpr int I8_PLANE = I8_T * I8_KB;            // bytes of one digit plane of one operand tile
+constexpr int I8_NPL = 8;                         // planes per stage: 4 digits of the A operand + 4 of the B operand
 constexpr int I8_STAGE = I8_NPL * I8_PLANE;
-constexpr int I8_STAGES = 2;
+constexpr int I8_STAGES = 3;
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 + 256;
 static_assert(I8_SMEM <= 227 * 1024, "shared memory budget");
 
@@ -43,13 +46,13 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
       "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accum)
       : "memory");
 }
-__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {        // K-major, 128-byte swizzle rows, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {        // K-major, 64-byte swizzle rows, 8-row groups 512 B apart
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * I8_KB) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)4 << 61;                                            // SWIZZLE_64B
   return d;
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
@@ -74,32 +77,20 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
   return d;
 }
 
-// One k-block of MMAs: planes F_0..F_3 (fine operand, 4 digits) and C_0..C_2 (coarse operand, 3 digits) of the stage at
-// `st`; FINE_IS_A says which of them is the A (M-side) operand.  first = this is the first k-block of the chain.
-template <bool FINE_IS_A>
+// One k-block of MMAs: digit planes A_0..A_3 (slots 0-3 of the stage at `st`) against B_0..B_3 (slots 4-7), the ten pairs
+// t + u <= 3 into the accumulator of their order.  first = first k-block of the chain (the accumulators start from zero).
 __device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_base, bool first) {
-  uint64_t fine[4], coarse[3];
+  uint64_t a[4], b[4];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) fine[t] = i8_desc(st + t * I8_PLANE);
+  for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + t * I8_PLANE); b[t] = i8_desc(st + (4 + t) * I8_PLANE); }
 #pragma unroll
-  for (int u = 0; u < 3; ++u) coarse[u] = i8_desc(st + (4 + u) * I8_PLANE);
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
+  for (int ks = 0; ks < I8_KB / 32; ++ks) {
     const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-    const bool f = first && ks == 0;
-    // order 0
-    { const uint64_t a = (FINE_IS_A ? fine[0] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[0]) + adv; umma_i8(tmem_base + 0 * I8_T, a, b, f ? 0u : 1u); }
-    // order 1: (0,1), (1,0)
-    { const uint64_t a = (FINE_IS_A ? fine[0] : coarse[1]) + adv, b = (FINE_IS_A ? coarse[1] : fine[0]) + adv; umma_i8(tmem_base + 1 * I8_T, a, b, f ? 0u : 1u); }
-    { const uint64_t a = (FINE_IS_A ? fine[1] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[1]) + adv; umma_i8(tmem_base + 1 * I8_T, a, b, 1u); }
-    // order 2: (0,2), (1,1), (2,0)
-    { const uint64_t a = (FINE_IS_A ? fine[0] : coarse[2]) + adv, b = (FINE_IS_A ? coarse[2] : fine[0]) + adv; umma_i8(tmem_base + 2 * I8_T, a, b, f ? 0u : 1u); }
-    { const uint64_t a = (FINE_IS_A ? fine[1] : coarse[1]) + adv, b = (FINE_IS_A ? coarse[1] : fine[1]) + adv; umma_i8(tmem_base + 2 * I8_T, a, b, 1u); }
-    { const uint64_t a = (FINE_IS_A ? fine[2] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[2]) + adv; umma_i8(tmem_base + 2 * I8_T, a, b, 1u); }
-    // order 3: (1,2), (2,1), (3,0)
-    { const uint64_t a = (FINE_IS_A ? fine[1] : coarse[2]) + adv, b = (FINE_IS_A ? coarse[2] : fine[1]) + adv; umma_i8(tmem_base + 3 * I8_T, a, b, f ? 0u : 1u); }
-    { const uint64_t a = (FINE_IS_A ? fine[2] : coarse[1]) + adv, b = (FINE_IS_A ? coarse[1] : fine[2]) + adv; umma_i8(tmem_base + 3 * I8_T, a, b, 1u); }
-    { const uint64_t a = (FINE_IS_A ? fine[3] : coarse[0]) + adv, b = (FINE_IS_A ? coarse[0] : fine[3]) + adv; umma_i8(tmem_base + 3 * I8_T, a, b, 1u); }
+    const uint32_t f = (first && ks == 0) ? 0u : 1u;
+#pragma unroll
+    for (int o = 0; o < 4; ++o)
+#pragma unroll
+      for (int t = 0; t <= o; ++t) umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, t == 0 ? f : 1u);
   }
 }
 
@@ -155,7 +146,7 @@ __device__ __forceinline__ void i8_teardown(uint32_t tmem_base) {
 // =============================================================================================================
 struct SyrkI8Params {
   int64_t N, M, L;
-  const float* Wt;          // (L, ldwt) channel-major weights, w / wmax_l * 256, zero padded to whole 128-datapoint blocks
+  const float* Wt;          // (L, ldwt) channel-major weights, w / wmax_l, zero padded to whole 128-datapoint blocks
   int64_t ldwt;
   const float* wmax;        // [L]
   const float* cscale;      // [M] value of one unit of the column-scaled integer K
@@ -189,7 +180,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
     it.ta = ta; it.tb = tile - ta * (ta + 1) / 2;
     it.n0 = win * P.win_rows;
     it.n1 = it.n0 + P.win_rows < P.N ? it.n0 + P.win_rows : P.N;
-    it.nkb = (int)((it.n1 - it.n0 + I8_T - 1) / I8_T);
+    it.nkb = (int)((it.n1 - it.n0 + I8_KB - 1) / I8_KB);
     return it;
   };
 
@@ -199,17 +190,18 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode(item);
-        const int32_t blk0 = (int32_t)(it.n0 / I8_T);
         for (int kb = 0; kb < it.nkb; ++kb) {
           mbar_wait(S.empty(stage), phase ^ 1);
           const uint32_t st = S.stage(stage);
+          const int64_t n = it.n0 + (int64_t)kb * I8_KB;                 // first datapoint of this k-block
+          const int32_t blk = (int32_t)(n >> 7), off = (int32_t)(n & 127);
           // the weighted operand's raw planes first (the transform warps work on them while the others land)
-          mbar_expect_tx(S.full(stage), 3 * I8_PLANE);
+          mbar_expect_tx(S.full(stage), 4 * I8_PLANE);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) tma_load_4d(st + s * I8_PLANE, &mapKc, S.full(stage), 0, it.ta * I8_T, blk0 + kb, s);
-          mbar_expect_tx(S.fullB(stage), 3 * I8_PLANE);
+          for (int s = 0; s < 4; ++s) tma_load_4d(st + s * I8_PLANE, &mapKc, S.full(stage), off, it.ta * I8_T, blk, s);
+          mbar_expect_tx(S.fullB(stage), 4 * I8_PLANE);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) tma_load_4d(st + (4 + s) * I8_PLANE, &mapKc, S.fullB(stage), 0, it.tb * I8_T, blk0 + kb, s);
+          for (int s = 0; s < 4; ++s) tma_load_4d(st + (4 + s) * I8_PLANE, &mapKc, S.fullB(stage), off, it.tb * I8_T, blk, s);
           if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -226,7 +218,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
         mbar_wait(S.ready(stage), phase);
         tc_fence_after();
         if (lane == 0) {
-          issue_kblock<true>(S.stage(stage), tmem_base, kb == 0);
+          issue_kblock(S.stage(stage), tmem_base, kb == 0);
           umma_commit(S.empty(stage));
           if (kb == it.nkb - 1) umma_commit(S.tmem_full());
         }
@@ -237,19 +229,19 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
     }
   } else if (warp >= SYRK8_XF_WARP0 && warp < SYRK8_XF_WARP0 + SYRK8_XF_WARPS) {
     // =============================== operand transform ============================================
-    // V[n, a] = w[n] K[n, a]: the three raw digit planes of the A tile (rows a, 128 datapoints n) are recombined to the
-    // 24-bit integer, multiplied by the channel's weight in fp32 (24 significant bits: a per-entry RELATIVE rounding,
+    // V[n, a] = w[n] K[n, a]: the four raw digit planes of the A tile (rows a, 64 datapoints n) are recombined to the
+    // 32-bit integer, multiplied by the channel's weight in fp32 (24 significant bits: a per-entry RELATIVE rounding,
     // i.e. a perturbation of the weights, harmless), rounded to a 32-bit fixed-point integer against the channel's
-    // largest weight and cut into four digit planes, in place.  A thread owns one logical 16-byte chunk (16 datapoints:
-    // its 16 weights are loaded once per k-block) of 4 rows; the swizzled physical chunk is the same for all of them.
+    // largest weight and cut into four digit planes again, in place.  A thread owns one logical 16-byte chunk (16
+    // datapoints: its 16 weights are loaded once per k-block) of 2 rows; the swizzled physical chunk is the same for both.
     const int t = threadIdx.x - SYRK8_XF_WARP0 * 32;          // 0..255
-    const int lchunk = t & 7, rbase = t >> 3;                  // rows rbase + 32 j
-    const int pchunk = lchunk ^ (rbase & 7);
+    const int lchunk = t & 3, rbase = t >> 2;                  // rows rbase, rbase + 64
+    const int pchunk = lchunk ^ ((rbase >> 1) & 3);
     int stage = 0; uint32_t phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
       for (int kb = 0; kb < it.nkb; ++kb) {
-        const int64_t n = it.n0 + (int64_t)kb * I8_T + lchunk * 16;
+        const int64_t n = it.n0 + (int64_t)kb * I8_KB + lchunk * 16;
         float w[16];
         {
           const float4* wp = reinterpret_cast<const float4*>(P.Wt + it.l * P.ldwt + n);
@@ -260,22 +252,23 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
           }
         }
         mbar_wait(S.full(stage), phase);
-        const uint32_t p0 = S.stage(stage) + rbase * 128 + pchunk * 16;
+        const uint32_t p0 = S.stage(stage) + rbase * I8_KB + pchunk * 16;
 #pragma unroll 1
-        for (int j = 0; j < 4; ++j) {
-          const uint32_t a = p0 + j * 32 * 128;
-          const uint4 k0 = lds128(a), k1 = lds128(a + I8_PLANE), k2 = lds128(a + 2 * I8_PLANE);
-          const uint32_t k0w[4] = {k0.x, k0.y, k0.z, k0.w}, k1w[4] = {k1.x, k1.y, k1.z, k1.w}, k2w[4] = {k2.x, k2.y, k2.z, k2.w};
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t a = p0 + j * 64 * I8_KB;
+          const uint4 k0 = lds128(a), k1 = lds128(a + I8_PLANE), k2 = lds128(a + 2 * I8_PLANE), k3 = lds128(a + 3 * I8_PLANE);
+          const uint32_t k0w[4] = {k0.x, k0.y, k0.z, k0.w}, k1w[4] = {k1.x, k1.y, k1.z, k1.w};
+          const uint32_t k2w[4] = {k2.x, k2.y, k2.z, k2.w}, k3w[4] = {k3.x, k3.y, k3.z, k3.w};
           uint32_t o[4][4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t e[4];
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              // bytes [d2, d1, d0, sign(d0)] of element b -> integer
-              const uint32_t lo = prmt(k2w[g], k1w[g], (uint32_t)(b | ((4 + b) << 4)));
-              const uint32_t d = prmt(lo, k0w[g], 0x0010u | ((uint32_t)(4 + b) << 8) | ((uint32_t)(0xC + b) << 12));
-              const int kint = (int)((d ^ 0x00008080u) - 0x00008080u);
+              // bytes [d3, d2, d1, d0] of element b -> two's-complement integer
+              const uint32_t sel = (uint32_t)(b | ((4 + b) << 4));
+              const uint32_t d = __byte_perm(__byte_perm(k3w[g], k2w[g], sel), __byte_perm(k1w[g], k0w[g], sel), 0x5410);
+              const int kint = (int)((d ^ 0x00808080u) - 0x00808080u);
               const int v = __float2int_rn(__int2float_rn(kint) * w[4 * g + b]);
               e[b] = ((uint32_t)v + 0x00808080u) ^ 0x00808080u;
             }
@@ -303,7 +296,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
       const Item it = decode(item);
       const int64_t r = (int64_t)it.ta * I8_T + qd * 32 + lane;           // output row a
       const int64_t rmax_w = (int64_t)it.ta * I8_T + qd * 32 + 31;
-      const double rs = (r < P.M) ? 256.0 * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
+      const double rs = (r < P.M) ? 16777216.0 * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
       mbar_wait(S.tmem_full(), tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
@@ -350,7 +343,7 @@ struct ScaledI8Params {
   int accumulate;
   float* dots;                  // (N, lddots) or null
   int64_t lddots, ndot;
-  const int8_t* Kr;             // digit planes of K_nm for the k-dot: [3][N][ldkr]
+  const int8_t* Kr;             // digit planes of K_nm for the k-dot: [4][N][ldkr]
   int64_t ldkr;
   int nct;                      // column tiles
   int64_t n_items;
@@ -366,7 +359,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
   const I8Smem S = i8_setup(smem_raw, 0, 8, tmem_base);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) { prefetch_tmap(&mapK); prefetch_tmap(&mapG); }
-  const int nkb = (int)((P.M + I8_T - 1) / I8_T);
+  const int nkb = (int)((P.M + I8_KB - 1) / I8_KB);
 
   if ((warp >> 2) == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -382,9 +375,9 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
               const uint32_t st = S.stage(stage);
               mbar_expect_tx(S.full(stage), I8_NPL * I8_PLANE);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) tma_load_3d(st + u * I8_PLANE, &mapG, S.full(stage), kb * I8_T, (int32_t)(s * P.Mc) + col0, u);
+              for (int t = 0; t < 4; ++t) tma_load_3d(st + t * I8_PLANE, &mapK, S.full(stage), kb * I8_KB, row0, t);
 #pragma unroll
-              for (int t = 0; t < 3; ++t) tma_load_3d(st + (4 + t) * I8_PLANE, &mapK, S.full(stage), kb * I8_T, row0, t);
+              for (int u = 0; u < 4; ++u) tma_load_3d(st + (4 + u) * I8_PLANE, &mapG, S.full(stage), kb * I8_KB, (int32_t)(s * P.Mc) + col0, u);
               if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -401,7 +394,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             mbar_wait(S.full(stage), phase);
             tc_fence_after();
             if (lane == 0) {
-              issue_kblock<false>(S.stage(stage), tmem_base, kb == 0);     // A = K rows (3 digits), B = G rows (4 digits)
+              issue_kblock(S.stage(stage), tmem_base, kb == 0);     // A = K rows, B = G rows (output columns)
               umma_commit(S.empty(stage));
               if (kb == nkb - 1) umma_commit(S.tmem_full());
             }
@@ -427,29 +420,32 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
 #pragma unroll
       for (int j = 0; j < 64; ++j) run[j] = 0.f;
       if (has_dots) {
-        // this row's K entries of the tile's columns as integers (fp32 holds 24 bits exactly)
+        // this row's K entries of the tile's columns as integers (rounded to fp32: the dot's operand)
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, d2 = d0;
+          uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, d2 = d0, d3 = d0;
           if (live && cw0 + g * 16 < P.ldkr) {
             const int8_t* base = P.Kr + i * P.ldkr + cw0 + g * 16;
+            const int64_t pl = P.N * P.ldkr;
             d0 = __ldg(reinterpret_cast<const uint4*>(base));
-            d1 = __ldg(reinterpret_cast<const uint4*>(base + P.N * P.ldkr));
-            d2 = __ldg(reinterpret_cast<const uint4*>(base + 2 * P.N * P.ldkr));
+            d1 = __ldg(reinterpret_cast<const uint4*>(base + pl));
+            d2 = __ldg(reinterpret_cast<const uint4*>(base + 2 * pl));
+            d3 = __ldg(reinterpret_cast<const uint4*>(base + 3 * pl));
           }
-          const uint32_t w0[4] = {d0.x, d0.y, d0.z, d0.w}, w1[4] = {d1.x, d1.y, d1.z, d1.w}, w2[4] = {d2.x, d2.y, d2.z, d2.w};
+          const uint32_t w0[4] = {d0.x, d0.y, d0.z, d0.w}, w1[4] = {d1.x, d1.y, d1.z, d1.w};
+          const uint32_t w2[4] = {d2.x, d2.y, d2.z, d2.w}, w3[4] = {d3.x, d3.y, d3.z, d3.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-              const uint32_t lo = prmt(w2[q], w1[q], (uint32_t)(b | ((4 + b) << 4)));
-              const uint32_t d = prmt(lo, w0[q], 0x0010u | ((uint32_t)(4 + b) << 8) | ((uint32_t)(0xC + b) << 12));
-              kv[g * 16 + q * 4 + b] = __int2float_rn((int)((d ^ 0x00008080u) - 0x00008080u));
+              const uint32_t sel = (uint32_t)(b | ((4 + b) << 4));
+              const uint32_t d = __byte_perm(__byte_perm(w3[q], w2[q], sel), __byte_perm(w1[q], w0[q], sel), 0x5410);
+              kv[g * 16 + q * 4 + b] = __int2float_rn((int)((d ^ 0x00808080u) - 0x00808080u));
             }
         }
       }
       for (int64_t s = 0; s < P.L; ++s) {
-        const float wgt = live ? (P.W ? P.W[i * P.ldw + s] : 1.f) * rs * 65536.f : 0.f;
+        const float wgt = live ? (P.W ? P.W[i * P.ldw + s] : 1.f) * rs * 16777216.f : 0.f;
         const bool want_dot = has_dots && s < P.ndot;                      // warp-uniform
         float dsum = 0.f;
         const float* gs = P.gscale + s * P.Mc;
@@ -483,7 +479,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(S.tmem_empty());
         tphase ^= 1;
-        if (want_dot && live) atomicAdd(&P.dots[i * P.lddots + s], dsum * rs * rs * 65536.f);
+        if (want_dot && live) atomicAdd(&P.dots[i * P.lddots + s], dsum * rs * rs * 16777216.f);
       }
       if (live) {
         float* o = P.out + i * P.ldo + cw0;
@@ -505,35 +501,35 @@ static int encode_i8(CUtensorMap* map, const void* base, int rank, const cuuint6
   if ((uintptr_t)base & 15) { set_error("TMA operand needs a 16-byte aligned base"); return SVGP_ERR_ARG; }
   for (int d = 0; d < rank - 1; ++d)
     if (strides_bytes[d] % 16) { set_error("TMA operand needs 16-byte pitches"); return SVGP_ERR_ARG; }
-  cuuint32_t box[4] = {(cuuint32_t)I8_T, (cuuint32_t)I8_T, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)I8_KB, (cuuint32_t)I8_T, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (i8) failed (%d)", (int)r); return SVGP_ERR_CUDA; }
   return SVGP_OK;
 }
 
-// window of datapoints per SYRK chain: bounded by the int32 accumulators (3 digit pairs of up to 2^14 each per datapoint:
-// 43690 datapoints), by the L2-resident slice of the K^T planes (3 bytes x M per datapoint, ~64 MB), and small enough
+// window of datapoints per SYRK chain: bounded by the int32 accumulators (4 digit pairs of up to 2^14 each per datapoint:
+// 32768 datapoints), by the L2-resident slice of the K^T planes (4 bytes x M per datapoint, ~64 MB), and small enough
 // to give every SM several items
 int64_t i8_syrk_window(int64_t N, int64_t M, int64_t L) {
-  int64_t w = (64LL << 20) / (3 * M);
+  int64_t w = (64LL << 20) / (4 * M);
   if (w > 16384) w = 16384;
   const int64_t T = (M + I8_T - 1) / I8_T, ntile = T * (T + 1) / 2;
   // at least ~2 items per SM when the problem allows it
   while (w > 1024 && ((N + w - 1) / w) * ntile * L < 2 * num_sms()) w /= 2;
-  w = w / I8_T * I8_T;
-  return w < I8_T ? I8_T : w;
+  w = w / 128 * 128;
+  return w < 128 ? 128 : w;
 }
 
 int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, int64_t L, double* A, cudaStream_t st) {
-  if (!kop->Kc || !kop->cscale) { set_error("tc_syrk_i8: int8 transposed planes missing (svgp_kplanes_i8)"); return SVGP_ERR_ARG; }
-  if (((uintptr_t)Wt & 15) || (ldwt % I8_T)) { set_error("tc_syrk_i8: weights need whole zero-padded 128-datapoint blocks"); return SVGP_ERR_ARG; }
-  const int64_t N = kop->N, M = kop->M, nblk = (N + I8_T - 1) / I8_T;
+  if (!kop->Kc || !kop->cscale) { set_error("tc_syrk_i8: int8 transposed planes missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
+  if (((uintptr_t)Wt & 15) || (ldwt % 128)) { set_error("tc_syrk_i8: weights need whole zero-padded 128-datapoint blocks"); return SVGP_ERR_ARG; }
+  const int64_t N = kop->N, M = kop->M, nblk = (N + 127) / 128;
   CUtensorMap map;
-  const cuuint64_t dims[4] = {(cuuint64_t)I8_T, (cuuint64_t)M, (cuuint64_t)nblk, 3};
-  const cuuint64_t strides[3] = {(cuuint64_t)I8_T, (cuuint64_t)(M * I8_T), (cuuint64_t)(nblk * M * I8_T)};
+  const cuuint64_t dims[4] = {128, (cuuint64_t)M, (cuuint64_t)nblk, 4};
+  const cuuint64_t strides[3] = {128, (cuuint64_t)(M * 128), (cuuint64_t)(nblk * M * 128)};
   int rc = encode_i8(&map, kop->Kc, 4, dims, strides);
   if (rc) return rc;
   SyrkI8Params P{};
@@ -556,12 +552,12 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
 
 int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* Gp, int64_t ldg, const float* gscale, int64_t L,
                       int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, cudaStream_t st) {
-  if (!kop->Kr || !kop->rscale) { set_error("tc_scaled_gemm_i8: int8 planes of K_nm missing (svgp_kplanes_i8)"); return SVGP_ERR_ARG; }
+  if (!kop->Kr || !kop->rscale) { set_error("tc_scaled_gemm_i8: int8 planes of K_nm missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (dots && Mc != kop->M) { set_error("tc_scaled_gemm_i8: the k-dots need square M x M matrices"); return SVGP_ERR_ARG; }
   const int64_t N = kop->N, M = kop->M;
   CUtensorMap mapK, mapG;
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)kop->ldkr, (cuuint64_t)N, 3};
+    const cuuint64_t dims[3] = {(cuuint64_t)kop->ldkr, (cuuint64_t)N, 4};
     const cuuint64_t strides[2] = {(cuuint64_t)kop->ldkr, (cuuint64_t)(N * kop->ldkr)};
     int rc = encode_i8(&mapK, kop->Kr, 3, dims, strides);
     if (rc) return rc;
@@ -614,18 +610,18 @@ __global__ void i8_wprep_kernel(const float* __restrict__ W, int64_t ldw, int64_
     const int64_t l = l0 + r, n = n0 + tx;
     if (l < L && n < ldwt) {
       const float m = mx[l];
-      Wt[l * ldwt + n] = m > 0.f ? tile[tx][r] * (256.0f / m) : 0.f;
+      Wt[l * ldwt + n] = m > 0.f ? tile[tx][r] / m : 0.f;
     }
   }
 }
 
 int launch_mirror_lower(double* A, int64_t M, int64_t L, cudaStream_t st);      // tc_engine.cu
 
-int64_t i8_syrk_ws_floats(int64_t N, int64_t L) { return L * ((N + I8_T - 1) / I8_T * I8_T) + L; }
+int64_t i8_syrk_ws_floats(int64_t N, int64_t L) { return L * ((N + 127) / 128 * 128) + L; }
 
 // W (N x L) -> workspace [Wt (L x ldwt) | wmax (L)], then the SYRK
 int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st) {
-  const int64_t N = kop->N, ldwt = (N + I8_T - 1) / I8_T * I8_T;
+  const int64_t N = kop->N, ldwt = (N + 127) / 128 * 128;
   float* Wt = ws;
   float* mx = ws + L * ldwt;
   if (cudaMemsetAsync(mx, 0, L * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(i8 memset)");

@@ -152,7 +152,8 @@ class _SVGPStep(torch.autograd.Function):
 
         # pass A
         kop = be.kernel_fwd(spec, Fx32, Fz32, hyp32, tc=tc)
-        Kmm = be.kernel_fwd(spec, Fz32, Fz32, hyp32, tc=False).K
+        # K_mm in float64 arithmetic: the M x M stage amplifies its entries' errors by cond(K + J) and more
+        K64 = be.kernel_fwd_f64(spec, Fz32, Fz32, hyp32)
         kappa = be.kernel_diag_fwd(spec, Fx32, Fx32, hyp32)
         p, py, sums = be.rowstats(y32, n32, kappa)
         A = be.syrk(kop, p, chunk_rows=cfg.get("chunk_rows", 0))
@@ -166,7 +167,6 @@ class _SVGPStep(torch.autograd.Function):
         c = N_train / b_total
 
         tri = cfg.get("tri", True)
-        K64 = Kmm.double()
         own, sharded = _own_channels(L, group, cfg.get("shard_k3", True))
         lc = mm_chunk_channels(own.stop - own.start, M, y32.device, cfg.get("mm_chunk"))
         one_chunk = lc >= own.stop - own.start

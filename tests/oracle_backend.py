@@ -54,6 +54,9 @@ class OracleBackend:
     def kernel_fwd(self, spec, Fx, Fz, hyp, tc=False):
         return Kop(kernel_value(spec, Fx, Fz, hyp).float())
 
+    def kernel_fwd_f64(self, spec, Fx, Fz, hyp):
+        return kernel_value(spec, Fx, Fz, hyp)
+
     def kernel_bwd(self, spec, Fx, Fz, hyp, G, need_x=True, need_z=True):
         with torch.enable_grad():
             Fx_, Fz_, h_ = (t.detach().to(F64).requires_grad_(True) for t in (Fx, Fz, hyp))

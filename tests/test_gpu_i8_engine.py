@@ -1,13 +1,14 @@
 """Integer tensor-core path (tcgen05.mma.kind::i8, csrc/tc_i8_engine.cu + i8_planes.cu) against a digit-exact emulation.
 
 The integer MMAs do not round, so the checks are much sharper than 1e-4: the digit planes must reassemble to the
-operand within half a unit of their fixed-point grid, the SYRK must equal the sum of the nine kept digit-plane pairs
+operand within half a unit of their fixed-point grid, the SYRK must equal the sum of the ten kept digit-plane pairs
 computed in float64 from THE SAME planes to ~1e-13, and the scaled GEMM (one fp32 rounding per accumulator tile) to 1e-6.
 """
 import pytest
 import torch
 
 from conftest import rel_err
+from oracle_backend import kernel_value
 from svgp_vae_b200 import configs
 
 pytestmark = pytest.mark.gpu
@@ -19,7 +20,13 @@ def _kop(be, N, M, L=2):
     Z = torch.from_numpy(cfg["ctor"]["initial_inducing_points"]).float().cuda()
     hyp = torch.ones(4, device="cuda")
     kop = be.kernel_fwd((1, 4, 1, 4), cfg["aux"].float().contiguous(), Z.contiguous(), hyp, tc=True, i8=True)
+    kop.K64 = kernel_value((1, 4, 1, 4), cfg["aux"], Z, hyp)                # float64 kernel values (oracle formulas)
     return cfg, kop
+
+
+def _ints(planes):
+    d = _digits(planes)
+    return ((d[0] * 256 + d[1]) * 256 + d[2]) * 256 + d[3]
 
 
 def _digits(planes):
@@ -42,13 +49,17 @@ def _balanced_digits4(V):
 def test_kplanes_reassemble(cuda_backend, N, M):
     be = cuda_backend
     _, kop = _kop(be, N, M)
-    K = ((kop.Kh.double() + kop.Kl.double()) * kop.kscale[1].double())[:N, :M]
+    K = kop.K64
     Kr, Kc = kop.value_i8("r"), kop.value_i8("c")
-    # half a unit of the 24-bit grid relative to the row / column maximum + the fp32 rounding of the stored scale
-    # (a uniform relative factor of the row / column: up to another half unit on its largest entries)
-    assert ((Kr - K).abs().amax(1) <= 1.02 * K.abs().amax(1) / 8323072.0 + 1e-30).all()
-    assert ((Kc - K).abs().amax(0) <= 1.02 * K.abs().amax(0) / 8323072.0 + 1e-30).all()
+    # fp32 kernel arithmetic (a few ulp of the entry) + one unit of the 32-bit grid relative to the row / column maximum
+    unit_r, unit_c = K.abs().amax(1, keepdim=True) / 2130706432.0, K.abs().amax(0, keepdim=True) / 2130706432.0
+    assert ((Kr - K).abs() <= 4e-6 * K.abs() + 1.1 * unit_r).all()
+    assert ((Kc - K).abs() <= 4e-6 * K.abs() + 1.1 * unit_c).all()
     assert kop.Kr[0].int().abs().max() <= 127 and kop.Kc[0].int().abs().max() <= 127
+    # the fp16 hi / lo row planes of the same call
+    assert rel_err(kop.value(), K) < 2e-6
+    # pad columns / the ragged last block are zeros (TMA boxes read them)
+    assert (kop.Kr[:, :, M:] == 0).all() and (kop.Kc.permute(0, 1, 3, 2).reshape(4, -1, M)[:, N:] == 0).all()
 
 
 @pytest.mark.parametrize("R,C,S", [(300, 256, 4), (64, 1000, 4), (128, 384, 3)])
@@ -71,29 +82,28 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L):
     g = torch.Generator(device="cuda").manual_seed(2)
     W = torch.randn(N, L, generator=g, device="cuda") * torch.exp(torch.randn(N, L, generator=g, device="cuda"))
     A = be.syrk(kop, W.contiguous())
-    # emulation from the same planes: weighted operand = rn(float(Kint) * (w / wmax * 256)) as a 32-bit integer
+    # emulation from the same planes: weighted operand = rn(float(Kint) * (w / wmax)) as a 32-bit integer
     k = _digits(kop.Kc)                                                   # (nblk, M, 128) each
-    Kint = (k[0] * 65536 + k[1] * 256 + k[2]).permute(0, 2, 1).reshape(-1, M)[:N]          # (N, M)
+    Kint = _ints(kop.Kc).permute(0, 2, 1).reshape(-1, M)[:N]              # (N, M)
     kd = [x.permute(0, 2, 1).reshape(-1, M)[:N] for x in k]
     cs = kop.cscale.double()
     ref = torch.empty_like(A)
     for l in range(L):
         wmax = W[:, l].abs().max()
-        wt = (W[:, l] * (256.0 / wmax)).float()
-        V = torch.round(Kint.float() * wt[:, None]).to(torch.int64)
+        wt = W[:, l] / wmax
+        V = torch.round(Kint.to(torch.int64).float() * wt[:, None]).to(torch.int64)
         v = _balanced_digits4(V)
         acc = [torch.zeros(M, M, dtype=F64, device="cuda") for _ in range(4)]
         for t in range(4):
-            for u in range(3):
+            for u in range(4):
                 if t + u <= 3:
                     acc[t + u] += v[t].t() @ kd[u]                        # exact: |sum| < 2^53
         i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
-        ref[l] = i64.double() * (256.0 * wmax.double()) * cs[:, None] * cs[None, :]
+        ref[l] = i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :]
     ref = torch.tril(ref) + torch.tril(ref, -1).transpose(-1, -2)
     assert rel_err(A, ref) < 1e-12
-    # and against the plain float64 contraction of the fp16 planes: the quantisation is at the 2^-24 level
-    K = kop.value().double()
-    full = torch.einsum('il,ia,ib->lab', W.double(), K, K)
+    # and against the plain float64 contraction of the float64 kernel values: fp32 kernel arithmetic is what is left
+    full = torch.einsum('il,ia,ib->lab', W.double(), kop.K64, kop.K64)
     assert rel_err(A, full) < 1e-6
 
 
@@ -113,27 +123,37 @@ def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot):
     kd = [x[:, :M] for x in _digits(kop.Kr)]
     gd = [x.reshape(L, M, -1)[:, :, :M] for x in _digits(P.planes)]
     rs, gs = kop.rscale.double(), P.scale.double().reshape(L, M)
-    Kint = kd[0] * 65536 + kd[1] * 256 + kd[2]
+    Kint = _ints(kop.Kr)[:, :M]
     ref = torch.zeros(N, M, dtype=F64, device="cuda")
     dref = torch.zeros(N, max(ndot, 1), dtype=F64, device="cuda")
     for s in range(L):
         T = torch.zeros(N, M, dtype=F64, device="cuda")
-        for t in range(3):
+        for t in range(4):
             for u in range(4):
                 if t + u <= 3:
                     T += (kd[t] @ gd[u][s].t()) * 256.0 ** (3 - t - u)
         T = T * gs[s][None, :]                                            # plane units of the kernel's `tv`
-        ref += W[:, s:s + 1].double() * rs[:, None] * 65536.0 * T
+        ref += W[:, s:s + 1].double() * rs[:, None] * 16777216.0 * T
         if s < ndot:
-            dref[:, s] = (T * Kint).sum(1) * rs * rs * 65536.0
+            dref[:, s] = (T * Kint).sum(1) * rs * rs * 16777216.0
     assert rel_err(out, ref) < 2e-6
     if ndot:
         assert rel_err(dots, dref[:, :ndot]) < 2e-6
     # against the float64 product of the un-quantised operands
-    K = kop.value().double()
-    full = torch.einsum('il,ia,lac->ic', W.double(), K, G)
+    full = torch.einsum('il,ia,lac->ic', W.double(), kop.K64, G)
     assert rel_err(out, full) < 1e-5
     # accumulate flag
     base = torch.ones_like(out)
     out2 = be.scaled_gemm_i8(kop, W.contiguous(), P, out=base.clone())
     assert rel_err(out2 - 1.0, ref) < 5e-6
+
+
+def test_gemm_nn_i8(cuda_backend):
+    be = cuda_backend
+    N, M, L = 4096, 384, 5
+    _, kop = _kop(be, N, M, L)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    Wm = torch.randn(L, M, generator=g, device="cuda", dtype=F64) * torch.exp(2 * torch.randn(L, M, generator=g, device="cuda", dtype=F64))
+    out = be.gemm_nn(kop, Wm)
+    assert out.shape == (N, L)
+    assert rel_err(out, kop.K64 @ Wm.t()) < 2e-6

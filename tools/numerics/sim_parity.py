@@ -132,7 +132,17 @@ class SimBackend(OracleBackend):
         return True
 
     def kernel_fwd(self, spec, Fx, Fz, hyp, tc=False):
-        kop = Kop(kernel_value(spec, Fx, Fz, hyp).float())
+        K = kernel_value(spec, Fx, Fz, hyp)
+        noise = float(os.environ.get("SIM_KNOISE", "0"))      # relative error of the fp32 kernel evaluation (exp argument rounding)
+        mmnoise = float(os.environ.get("SIM_KMMNOISE", "0"))  # the same for the fp32 K_mm
+        if not tc and mmnoise > 0 and K.shape[0] == K.shape[1]:
+            g = torch.Generator().manual_seed(12)
+            E = torch.randn(K.shape, generator=g, dtype=F64)
+            K = K * (1.0 + mmnoise * 0.5 * (E + E.t()))
+        if tc and noise > 0:
+            g = torch.Generator().manual_seed(11)
+            K = K * (1.0 + noise * torch.randn(K.shape, generator=g, dtype=F64))
+        kop = Kop(K.float())
         kop.sim = bool(tc)
         kop.cache = {}
         return kop
