@@ -27,9 +27,17 @@ def aux_data_SVGPVAE_sprites(data_batch, repr_nn, segment_ids, repeats):
 
 def forward_pass_SVGPVAE(data_batch, beta, vae, svgp, C_ma, lagrange_mult, alpha, kappa, clipping_qs=False, GECO=False,
                          repr_NN=None, segment_ids=None, repeats=None, bias_analysis=False, epsilon=None, group=None):
-    """SVGPVAE_model.py:823-936.  ``epsilon`` (optional, (b, L)) fixes the reparametrisation noise of :901;
-    ``group`` shards the batch over a torch.distributed group (see mainSVGP.elbo_step)."""
+    """SVGPVAE_model.py:823-936.  ``epsilon`` (optional, (b, L)) fixes the reparametrisation noise of :901.
+
+    ``group`` shards the batch over a torch.distributed group (see mainSVGP.elbo_step).  Convention when sharded: the
+    scalars of the SVGP step (KL_term, inside_elbo, ce_term ...) are GLOBAL and identical on every rank; the returned
+    ``elbo`` is this rank's SHARE of the global objective -- local reconstruction term + global terms / world size -- so
+    that the sum of the ranks' elbo values is the reference's elbo of the whole batch and back-propagating each rank's
+    share gives per-rank partial gradients of the replicated parameters (all-reduce-sum them).  ``recon_loss`` is the
+    local share as well; ``C_ma`` / ``lagrange_mult`` (GECO) are computed from the all-reduced reconstruction loss and
+    are identical on all ranks."""
     images, aux_data = data_batch
+    world = 1 if group is None else torch.distributed.get_world_size(group)
     _, w, h, c = images.shape                                                             # :850 (NHWC like the reference)
     K = float(w * h * c)
     b = float(images.shape[0])
@@ -56,13 +64,19 @@ def forward_pass_SVGPVAE(data_batch, beta, vae, svgp, C_ma, lagrange_mult, alpha
     if GECO:                                                                              # :908-915
         recon_loss = ((images - recon_images_logits) ** 2).mean(dim=(1, 2, 3))
         recon_loss = (recon_loss - kappa ** 2).sum()
-        C_ma = alpha * C_ma + (1 - alpha) * recon_loss / b
-        elbo = -KL_term + lagrange_mult * (recon_loss / b + (C_ma - recon_loss / b).detach())
+        recon_all, b_all = recon_loss.detach().clone(), b
+        if group is not None:                              # the moving average and the multiplier see the WHOLE batch
+            count = torch.tensor([b], dtype=recon_all.dtype, device=recon_all.device)
+            torch.distributed.all_reduce(recon_all, group=group)
+            torch.distributed.all_reduce(count, group=group)
+            b_all = float(count.item())
+        C_ma = alpha * C_ma + (1 - alpha) * recon_all / b_all
+        elbo = -KL_term / world + lagrange_mult * (recon_loss / b_all + (C_ma - recon_all / b_all).detach() / world)
         lagrange_mult = lagrange_mult * torch.exp(torch.as_tensor(C_ma))
     else:                                                                                 # :917-925
         recon_loss = ((images - recon_images_logits) ** 2).sum()
         recon_loss = recon_loss / K
-        elbo = -recon_loss + (beta / L) * KL_term
+        elbo = -recon_loss + (beta / L) * KL_term / world
 
     if bias_analysis:                                                                     # :928-931
         mean_vectors = [svgp.mean_vector_bias_analysis(aux_data, qnet_mu[:, l], qnet_var[:, l]) for l in range(qnet_mu.shape[1])]

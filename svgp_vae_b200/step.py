@@ -242,6 +242,7 @@ class _SVGPStep(torch.autograd.Function):
         ctx.cfg, ctx.kop, ctx.mm, ctx.leaves, ctx.lc = cfg, kop, mm, leaves, lc
         ctx.own, ctx.sharded, ctx.one_chunk = own, sharded, one_chunk
         ctx.b_total, ctx.c = b_total, c
+        cfg["_b_total"] = b_total                      # read back by svgp_step (a host number, not a tensor)
         ctx.save_for_backward(Fx32, Fz32, hyp32, y32, n32, p, kappa, h, pv, q1 if clip else pv, mask if clip else pv, S, w, Kinv)
         ctx.in_dtypes = (Fx.dtype, Fz.dtype, hyp.dtype, y.dtype, noise.dtype)
         out_dt = y.dtype
@@ -462,7 +463,7 @@ def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, gro
     sharded (None = single process); A_l, v_l and the scalar sums are all-reduced over it.
 
     Returns dict(p_m, p_v (N, L); recon_l, kl_l, ce_l (L,) float64 -- GLOBAL sums, identical on all
-    ranks; mu_hat (L, M), A_hat (L, M, M) float64, detached).
+    ranks; mu_hat (L, M), A_hat (L, M, M) float64, detached; b_total = the all-reduced number of datapoints).
     ``shard_k3``: with a group of W ranks and L % W == 0, every rank runs the float64 M x M stage for L / W channels and
     the results are all-gathered (default); False keeps the stage replicated.
     ``mm_chunk``: channels per chunk of the float64 M x M stage (default: one chunk while its state fits, see
@@ -473,7 +474,7 @@ def svgp_step(spec, Fx, Fz, hyp, y, noise, *, N_train, jitter, clip_pv=None, gro
     cfg = dict(spec=spec, N_train=float(N_train), jitter=float(jitter), clip_pv=clip_pv, group=group, tc=tc, tri=tri,
                chunk_rows=chunk_rows, mm_chunk=mm_chunk, return_A_hat=return_A_hat, shard_k3=shard_k3)
     pm, pv, recon, kl, ce, mu_hat, A_hat = _SVGPStep.apply(Fx, Fz, hyp, y, noise, cfg)
-    return dict(p_m=pm, p_v=pv, recon_l=recon, kl_l=kl, ce_l=ce, mu_hat=mu_hat, A_hat=A_hat)
+    return dict(p_m=pm, p_v=pv, recon_l=recon, kl_l=kl, ce_l=ce, mu_hat=mu_hat, A_hat=A_hat, b_total=cfg["_b_total"])
 
 
 def elbo_terms(res, b, N_train):

@@ -187,10 +187,7 @@ class mainSVGP(_KernelBase):
         Fz = self._features(self.inducing_index_points, True)
         res = svgp_step(self._spec(), Fx, Fz, self._hyp(), qnet_mu, qnet_var, N_train=self.N_train,
                         jitter=self.jitter, clip_pv=(1e-4, 100.0) if clip_pv else None, group=group, **kw)
-        b = float(aux_data.shape[0])
-        if group is not None:
-            b = b * torch.distributed.get_world_size(group)      # equal shards
-        res.update(elbo_terms(res, b, self.N_train))
+        res.update(elbo_terms(res, res["b_total"], self.N_train))      # the all-reduced batch size (shards may be unequal)
         return res
 
 

@@ -77,3 +77,78 @@ def test_sharded_step_matches_single_process(oracle_backend, kind, clip, L, mm_c
         for a, b in zip(o["pg"], g1[2:]):
             if b.abs().max() > 0:
                 assert rel_err(a, b) < 1e-5
+
+
+# ---- forward_pass_SVGPVAE under a group: per-rank elbo shares sum to the single-process elbo, gradients likewise -----
+class _ShardVAE:
+    dtype = torch.float64
+
+    def __init__(self, mu, var):
+        self.mu, self.var = mu, var
+
+    def encode(self, images):
+        return self.mu, self.var
+
+    def decode(self, z):
+        base = torch.linspace(-1.0, 1.0, 28 * 28, dtype=z.dtype).reshape(1, 28, 28, 1)
+        return torch.tanh(z.sum(1)).reshape(-1, 1, 1, 1) * base + 0.1 * z[:, :1].reshape(-1, 1, 1, 1)
+
+
+def _shard_images(b):
+    i = torch.arange(b, dtype=torch.float64).reshape(-1, 1, 1, 1)
+    return torch.sin(0.1 * i + 3.0 * torch.linspace(0.0, 1.0, 28 * 28, dtype=torch.float64).reshape(1, 28, 28, 1))
+
+
+def _glue_worker(rank, world, port, cfg, geco, eps, out):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root); sys.path.insert(0, os.path.join(root, "tests"))
+    from oracle_backend import OracleBackend
+    import svgp_vae_b200 as pkg
+    from svgp_vae_b200 import backend
+    backend.set_backend_for_tests(OracleBackend())
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    _, s, _, sp = refs.make_pair("mnist", cfg, "cpu")
+    n = cfg["aux"].shape[0] // world
+    sl = slice(rank * n, (rank + 1) * n)
+    mu, var = cfg["y"][sl].clone().requires_grad_(True), cfg["noise"][sl].clone().requires_grad_(True)
+    r = pkg.forward_pass_SVGPVAE((_shard_images(cfg["aux"].shape[0])[sl], cfg["aux"][sl]), beta=0.7, vae=_ShardVAE(mu, var), svgp=s,
+                                 C_ma=0.3, lagrange_mult=1.5, alpha=0.99, kappa=0.02, clipping_qs=True, GECO=geco, epsilon=eps[sl],
+                                 group=dist.group.WORLD)
+    g = torch.autograd.grad(r[0], [mu, var] + list(sp))
+    pg = [t.double().clone() for t in g[2:]]
+    for t in pg:
+        dist.all_reduce(t)
+    e = r[0].detach().clone()
+    dist.all_reduce(e)
+    out[rank] = dict(elbo=float(e), C_ma=float(r[13]), lm=float(r[14]), gmu=g[0], gvar=g[1], pg=pg)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("geco", [False, True])
+def test_glue_sharded_matches_single_process(oracle_backend, geco):
+    """the global KL_term must enter each rank's elbo share divided by the world size (GECO: the moving average
+    and the multiplier from the all-reduced reconstruction loss)."""
+    from conftest import MNIST_FIXTURE, rel_err
+    import svgp_vae_b200 as pkg
+    cfg = configs.mnist_inputs(MNIST_FIXTURE, L=4)
+    b = cfg["aux"].shape[0]
+    eps = torch.randn(b, 4, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    _, s, _, sp = refs.make_pair("mnist", cfg, "cpu")
+    mu, var = cfg["y"].clone().requires_grad_(True), cfg["noise"].clone().requires_grad_(True)
+    r1 = pkg.forward_pass_SVGPVAE((_shard_images(b), cfg["aux"]), beta=0.7, vae=_ShardVAE(mu, var), svgp=s, C_ma=0.3, lagrange_mult=1.5,
+                                  alpha=0.99, kappa=0.02, clipping_qs=True, GECO=geco, epsilon=eps)
+    g1 = torch.autograd.grad(r1[0], [mu, var] + list(sp))
+    world = 2
+    out = mp.Manager().dict()
+    mp.spawn(_glue_worker, args=(world, _free_port(), cfg, geco, eps, out), nprocs=world, join=True)
+    n = b // world
+    for r in range(world):
+        o, sl = out[r], slice(r * n, (r + 1) * n)
+        assert abs(o["elbo"] - float(r1[0])) < 1e-8 * abs(float(r1[0]))
+        assert abs(o["C_ma"] - float(r1[13])) < 1e-10 * abs(float(r1[13])) and abs(o["lm"] - float(r1[14])) < 1e-10 * abs(float(r1[14]))
+        assert rel_err(o["gmu"], g1[0][sl]) < 1e-6 and rel_err(o["gvar"], g1[1][sl]) < 1e-6
+        for a, c in zip(o["pg"], g1[2:]):
+            if c.abs().max() > 0:
+                assert rel_err(a, c) < 1e-6
