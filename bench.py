@@ -47,7 +47,6 @@ def parse():
     ap.add_argument("--l", "--channels", dest="l", type=int, default=L_CH)
     ap.add_argument("--mm-chunk", type=int, default=0, help="channels per chunk of the float64 M x M stage (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", type=int, default=1024)
     return ap.parse_args()
 
 
@@ -95,19 +94,23 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 # CPU restatement (the "reference arm" and the cpu_baseline leg): oracle/ is only touched here
 # --------------------------------------------------------------------------------------------------
-def cpu_reference_step(n_sample, M, L, threads=None):
-    """fwd + bwd of the streamlined float64 restatement on `n_sample` rows; returns (t_rows, t_mm) seconds:
-    the part proportional to the number of rows and the row-independent M x M part."""
+def workload_name(args, world):
+    """The one workload string both arms print (the driver compares the `config` of the two lines)."""
+    return "SWEEP N=%d per GPU x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3])" % (args.n, world, args.m, args.l)
+
+
+def cpu_reference_timer(max_rows, M, L):
+    """-> full(rows): seconds of one fwd + bwd of the streamlined float64 restatement on `rows` rows of the workload."""
     from oracle import svgp_streamlined as st
     from oracle import tfp_kernels as tfk
     from svgp_vae_b200 import configs
-    cfg = configs.sweep_inputs(n_sample, M, L, device="cpu", N_train=n_sample)
+    cfg = configs.sweep_inputs(max_rows, M, L, device="cpu", N_train=max_rows)
     X, y, nz = cfg["aux"].double(), cfg["y"].double().requires_grad_(True), cfg["noise"].double().requires_grad_(True)
     Z = torch.as_tensor(cfg["ctor"]["initial_inducing_points"]).double().requires_grad_(True)
     one = torch.ones((), dtype=torch.float64)
     kern = lambda a, b: tfk.ExponentiatedQuadratic(one, one).matrix(a[:, :4], b[:, :4]) * tfk.ExponentiatedQuadratic(one, one).matrix(a[:, 4:], b[:, 4:])
     g = torch.Generator().manual_seed(0)
-    gm, gv = torch.randn(n_sample, L, generator=g, dtype=torch.float64), torch.randn(n_sample, L, generator=g, dtype=torch.float64)
+    gm, gv = torch.randn(max_rows, L, generator=g, dtype=torch.float64), torch.randn(max_rows, L, generator=g, dtype=torch.float64)
 
     def full(rows):
         t0 = time.perf_counter()
@@ -118,51 +121,104 @@ def cpu_reference_step(n_sample, M, L, threads=None):
         J = gl["KL_term"] + (gm[:rows] * t["p_m"]).sum() + (gv[:rows] * t["p_v"]).sum()
         torch.autograd.grad(J, [y, nz, Z])
         return time.perf_counter() - t0
+    return full
 
-    t_full = full(n_sample)
-    t_half = full(n_sample // 2)
-    t_rows = max(2.0 * (t_full - t_half), 1e-9)          # seconds for n_sample rows, row-proportional part
-    t_mm = max(t_full - t_rows, 0.0)
-    return t_rows, t_mm, t_full
+
+def fit_rows(samples):
+    """Least-squares line t = intercept + slope * rows through (rows, seconds) samples -> (slope, intercept, max relative residual).
+    The step costs a row-independent float64 M x M part (intercept) plus a part proportional to the datapoints (slope)."""
+    n = len(samples)
+    mx = sum(r for r, _ in samples) / n
+    my = sum(t for _, t in samples) / n
+    sxx = sum((r - mx) ** 2 for r, _ in samples)
+    if sxx == 0:                       # one size only: no separation possible, charge everything to the rows (pessimistic for the CPU)
+        return my / mx, 0.0, None
+    slope = sum((r - mx) * (t - my) for r, t in samples) / sxx
+    slope = max(slope, 1e-12)
+    icpt = max(my - slope * mx, 0.0)
+    resid = max(abs(icpt + slope * r - t) / t for r, t in samples)
+    return slope, icpt, resid
+
+
+def literal_small_configs():
+    """fwd + bwd of the LITERAL restatement (per-channel loop, explicit inverses, the (b, m, m) tensor: what the reference's
+    graph does) on the reference's own shapes, median of 3 -- BASELINE.md section 4."""
+    out = {}
+    try:
+        from oracle import svgp_literal as lit
+        from svgp_vae_b200 import configs
+        fix = os.path.join(ROOT, "tests", "golden", "mnist_aux.npz")
+        cases = {"mnist_b256_m32_L16": ("mnist", configs.mnist_inputs(fix, L=16)), "sprites_b500_M72_L64": ("sprites", configs.sprites_inputs(M=72, L=64))}
+        for name, (kind, cfg) in cases.items():
+            o = (lit.MnistSVGP if kind == "mnist" else lit.SpritesSVGP)(name="o", **cfg["ctor"])
+            ts = []
+            for _ in range(3):
+                y = cfg["y"].double().clone().requires_grad_(True)
+                nz = cfg["noise"].double().clone().requires_grad_(True)
+                t0 = time.perf_counter()
+                res = lit.minibatch_glue(o, cfg["aux"].double(), y, nz, clip_pv=(kind == "sprites"))
+                torch.autograd.grad(res["KL_term"] + res["p_m"].sum() + res["p_v"].sum(), [y, nz])
+                ts.append(time.perf_counter() - t0)
+            out[name] = {"ms_per_step": 1e3 * sorted(ts)[1], "datapoints_per_s": cfg["aux"].shape[0] / sorted(ts)[1]}
+    except Exception as e:  # noqa: BLE001
+        out["error"] = repr(e)
+    return out
 
 
 def cpu_baseline(args, n_total):
+    """The cpu_baseline leg of the GPU arm (rank 0, one GPU): two sizes, ~10-30 s of CPU work on a many-core host."""
     threads = torch.get_num_threads()     # (torch.set_num_threads breaks MKL's batched LU in this image: leave the default)
-    t_rows, t_mm, t_full = cpu_reference_step(args.cpu_sample, args.m, args.l)
-    t_total = t_rows * (n_total / args.cpu_sample) + t_mm
-    return {"value": n_total / t_total, "unit": "datapoints/s", "cores": threads, "kind": "port",
-            "sample": "streamlined float64 restatement (oracle/svgp_streamlined.py, torch-CPU/MKL; TensorFlow 1.15 is not installable) "
-                      "fwd+bwd on %d and %d rows of the same workload (M=%d, L=%d): row-proportional part %.2f s per %d rows, "
-                      "M x M part %.2f s; extrapolated linearly in rows to N=%d" % (args.cpu_sample, args.cpu_sample // 2, args.m, args.l,
-                                                                                   t_rows, args.cpu_sample, t_mm, n_total),
-            "seconds_measured": t_full}
+    full = cpu_reference_timer(4096, args.m, args.l)
+    full(256)                             # warm-up (thread pools, allocator)
+    samples = [(r, full(r)) for r in (1024, 4096)]
+    slope, icpt, resid = fit_rows(samples)
+    t_total = slope * n_total + icpt
+    return {"value": n_total / t_total, "unit": "datapoints/s", "cores": threads, "kind": "port", "extrapolated": True,
+            "sample_rows": [r for r, _ in samples], "sample_seconds": [round(t, 3) for _, t in samples],
+            "fit": {"seconds_per_row": slope, "row_independent_seconds": icpt},
+            "sample": "streamlined float64 restatement (oracle/svgp_streamlined.py, torch-CPU/MKL, %d threads; TensorFlow 1.15 is not installable) "
+                      "fwd+bwd on 1024 and 4096 rows of the same workload (M=%d, L=%d); t = %.2f s + %.3g s/row extrapolated linearly in "
+                      "rows to N=%d" % (threads, args.m, args.l, icpt, slope, n_total),
+            "literal_small_configs": literal_small_configs()}
 
 
 def run_reference(args):
+    """Reference arm: the CPU restatement of the reference path on the host cores.  Each step = one fwd + bwd on a bounded
+    sample of the workload (sizes cycle through 8192 / 2048 / 4096 rows so that the row-proportional cost and the
+    row-independent M x M cost separate by a line fit over the timed steps); the whole run is time-boxed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = torch.get_num_threads()
     n_total = args.n * args.gpus
-    vals = []
-    for i in range(args.warmup + args.steps):
-        t_rows, t_mm, t_full = cpu_reference_step(args.cpu_sample, args.m, args.l)
-        if i >= args.warmup:
-            vals.append((t_rows, t_mm, t_full))
-        if i == 0 and t_full * (args.warmup + args.steps) > 240:      # keep the whole run within minutes
-            vals.append((t_rows, t_mm, t_full))
+    sizes = [8192, 2048, 4096]
+    full = cpu_reference_timer(max(sizes), args.m, args.l)
+    t_start = time.perf_counter()
+    for _ in range(max(1, min(args.warmup, 2))):
+        full(512)                                               # untimed warm-up steps (small: the budget goes to the timed ones)
+    samples = []
+    for i in range(max(args.steps, 3)):
+        samples.append((sizes[i % 3], full(sizes[i % 3])))
+        if len(samples) >= 3 and time.perf_counter() - t_start > 200:      # keep the whole run within minutes
             break
-    t_rows = sorted(v[0] for v in vals)[len(vals) // 2]
-    t_mm = sorted(v[1] for v in vals)[len(vals) // 2]
-    t_total = t_rows * (n_total / args.cpu_sample) + t_mm
+    slope, icpt, resid = fit_rows(samples)
+    # spread of the row cost over the repeats of the largest size (the extrapolation's dominant term)
+    big = sorted(t for r, t in samples if r == sizes[0])
+    t_total = slope * n_total + icpt
     value = n_total / t_total
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "datapoints/s", "n_gpus": args.gpus, "steps": len(vals),
+    world = args.gpus
+    cb = {"value": value, "unit": "datapoints/s", "cores": threads, "kind": "port", "extrapolated": True,
+          "sample_rows": [r for r, _ in samples], "sample_seconds": [round(t, 3) for _, t in samples],
+          "fit": {"seconds_per_row": slope, "row_independent_seconds": icpt, "max_rel_residual": resid,
+                  "largest_size_seconds_min_max": [big[0], big[-1]] if big else None},
+          "sample": "each step = fwd+bwd of the streamlined float64 restatement (oracle/svgp_streamlined.py, torch-CPU/MKL, %d threads) on "
+                    "8192 / 2048 / 4096 rows in turn; line fit t = %.2f s + %.3g s/row over %d timed steps, extrapolated linearly in rows to "
+                    "N=%d; TensorFlow 1.15 / TFP 0.8 cannot be installed here" % (threads, icpt, slope, len(samples), n_total)}
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "datapoints/s", "n_gpus": args.gpus, "steps": len(samples),
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "SWEEP N=%d x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2" % (args.n, args.gpus, args.m, args.l)},
-            "cpu_baseline": {"value": value, "unit": "datapoints/s", "cores": threads, "kind": "port",
-                             "sample": "each step = fwd+bwd of the streamlined float64 restatement on %d (+%d) rows, extrapolated linearly in rows "
-                                       "to N=%d; TensorFlow 1.15 / TFP 0.8 cannot be installed here" % (args.cpu_sample, args.cpu_sample // 2, n_total)},
+            "dtype": "f64", "data": "synthetic", "extrapolated": True,
+            "config": {"workload": workload_name(args, world)},
+            "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

@@ -458,7 +458,19 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_i8_kernel(
   float* nza = nxb + TILE;
   float* nzb = nza + TILE;
   constexpr int P = TILE + 1;
-  constexpr float XMAX4F = 2130706432.0f;             // 127 * 2^24
+  // POWER-OF-TWO fixed-point grids: max = m 2^e (m in [0.5, 1)) -> integer = value * 2^(31 - e) (2^(30 - e) when m > 0.99).  The
+  // product with a power of two is exact in fp32 and a 24-bit mantissa within 2^-7 of the maximum fits the grid whole, so
+  // the row-scaled and the column-scaled planes hold THE SAME number wherever it matters.  (With max / (127 2^24) as the
+  // unit the two grids rounded every entry independently at the 2^-24 level; that inconsistency between the K_nm of the
+  // SYRK and the K_nm of everything else alone cost 1e-4 of the inducing-point gradient at M = 2048.)
+  auto pow2_q = [](float m) -> float {
+    if (!(m > 0.f)) return 0.f;
+    int e;
+    const float f = frexpf(m, &e);                      // m = f 2^e, f in [0.5, 1)
+    e = (f <= 0.99f ? 31 : 30) - e;                     // largest integer <= 127 2^24 = 0.992 2^31 (the top digit is signed)
+    e = e > 120 ? 120 : (e < -120 ? -120 : e);
+    return ldexpf(1.0f, e);
+  };
   const Hyp h = load_hyp(hyp);
   const int64_t col0 = (int64_t)blockIdx.x * TILE;
   const int64_t ntiles_r = (N + TILE - 1) / TILE;
@@ -490,8 +502,8 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_i8_kernel(
   if (!MAXPASS) {
     const int64_t gc = col0 + warp * 8 + sub;
     const float m = gc < M ? cmax[gc] : 0.f;
-    qc = m > 0.f ? XMAX4F / m : 0.f;
-    if (blockIdx.y == 0 && k4 == 0 && gc < M) cscale[gc] = m > 0.f ? m / XMAX4F : 0.f;
+    qc = pow2_q(m);
+    if (blockIdx.y == 0 && k4 == 0 && gc < M) cscale[gc] = qc > 0.f ? 1.0f / qc : 0.f;
   }
 
   for (int64_t rt = blockIdx.y; rt < ntiles_r; rt += gridDim.y) {
@@ -562,9 +574,8 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_i8_kernel(
           const int r = warp * 8 + sub, e0 = half * 32 + k4 * 8;
           const int64_t gr = row0 + r, gc = col0 + e0;
           if (gr < N && gc < M) {
-            const float mr = rmax[gr];
-            const float qr = mr > 0.f ? XMAX4F / mr : 0.f;
-            if (blockIdx.x == 0 && e0 == 0) rscale[gr] = mr > 0.f ? mr / XMAX4F : 0.f;
+            const float qr = pow2_q(rmax[gr]);
+            if (blockIdx.x == 0 && e0 == 0) rscale[gr] = qr > 0.f ? 1.0f / qr : 0.f;
             uint32_t hw[4], lw[4], e[8];
 #pragma unroll
             for (int i = 0; i < 8; i += 2) {

@@ -326,7 +326,7 @@ int tc_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const void*
                    cudaStream_t st);
 bool tc_shape_ok(const svgp_kop* kop);
 // entry points of the integer tcgen05 implementation (tc_i8_engine.cu)
-int64_t i8_syrk_ws_floats(int64_t N, int64_t L);
+int64_t i8_syrk_ws_floats(int64_t N, int64_t M, int64_t L);
 int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st);
 int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* Gp, int64_t ldg, const float* gscale, int64_t L,
                       int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, cudaStream_t st);
@@ -350,7 +350,7 @@ static bool use_tc(const svgp_kop* kop, int impl) {
 extern "C" {
 
 int64_t svgp_syrk_ws_floats(int64_t N, int64_t M, int64_t L) {
-  const int64_t a = L * pad8(N) + 3 * L + tc_syrk_lock_words(M, L), b = i8_syrk_ws_floats(N, L);
+  const int64_t a = L * pad8(N) + 3 * L + tc_syrk_lock_words(M, L), b = i8_syrk_ws_floats(N, M, L);
   return a > b ? a : b;
 }
 

@@ -149,12 +149,70 @@ struct SyrkI8Params {
   const float* Wt;          // (L, ldwt) channel-major weights, w / wmax_l, zero padded to whole 128-datapoint blocks
   int64_t ldwt;
   const float* wmax;        // [L]
+  const float* vmax;        // (L, M): max_n |float(Kint[n, a]) * Wt[l, n]| -- positions the fixed-point grid of the weighted operand
   const float* cscale;      // [M] value of one unit of the column-scaled integer K
   double* A;                // (L, M, M)
   int64_t win_rows;         // datapoints per chain (multiple of 128): one item = (window, tile pair, channel)
   int nwin, ntile;
   int64_t n_items;
 };
+
+// quantisation factor of the weighted operand of row a: |float(Kint) * wn * q| <= 127 2^24 (two fp32 roundings of headroom)
+__host__ __device__ __forceinline__ float syrk_vq(float u) { return u > 0.f ? 2130706432.0f * 0.99999f / u : 0.f; }
+
+// vmax[l, a] = max_n |float(Kint[n, a]) * Wt[l, n]|: the exact fp32 products the operand transform forms, so the bound is
+// sharp and never exceeded.  One thread per inducing point a, LG channels per pass (their running maxima in registers),
+// the |weights| of a 128-datapoint block staged in shared memory ([datapoint][channel]: 4 channels per 16-byte read).
+template <int LG>
+__global__ void __launch_bounds__(128) syrk_vmax_kernel(const int8_t* __restrict__ Kc, int64_t N, int64_t M, int64_t nblk,
+                                                        const float* __restrict__ Wt, int64_t ldwt, int64_t L, float* __restrict__ vmax) {
+  __shared__ __align__(16) float ws[128][LG];
+  const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
+  const int64_t plane = nblk * M * 128;
+  for (int64_t l0 = 0; l0 < L; l0 += LG) {
+    float um[LG];
+#pragma unroll
+    for (int l = 0; l < LG; ++l) um[l] = 0.f;
+    for (int64_t blk = blockIdx.y; blk < nblk; blk += gridDim.y) {
+      __syncthreads();
+      for (int l = 0; l < LG; ++l) ws[threadIdx.x][l] = (l0 + l < L) ? fabsf(Wt[(l0 + l) * ldwt + blk * 128 + threadIdx.x]) : 0.f;
+      __syncthreads();
+      if (m < M) {
+        const int8_t* base = Kc + (blk * M + m) * 128;
+#pragma unroll 1
+        for (int ch = 0; ch < 8; ++ch) {
+          const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(base + ch * 16));
+          const uint4 d1 = __ldg(reinterpret_cast<const uint4*>(base + plane + ch * 16));
+          const uint4 d2 = __ldg(reinterpret_cast<const uint4*>(base + 2 * plane + ch * 16));
+          const uint4 d3 = __ldg(reinterpret_cast<const uint4*>(base + 3 * plane + ch * 16));
+          const uint32_t w0[4] = {d0.x, d0.y, d0.z, d0.w}, w1[4] = {d1.x, d1.y, d1.z, d1.w};
+          const uint32_t w2[4] = {d2.x, d2.y, d2.z, d2.w}, w3[4] = {d3.x, d3.y, d3.z, d3.w};
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+              const uint32_t sel = (uint32_t)(b | ((4 + b) << 4));
+              const uint32_t d = __byte_perm(__byte_perm(w3[g], w2[g], sel), __byte_perm(w1[g], w0[g], sel), 0x5410);
+              const float kf = fabsf(__int2float_rn((int)((d ^ 0x00808080u) - 0x00808080u)));
+              const float4* wr = reinterpret_cast<const float4*>(ws[ch * 16 + g * 4 + b]);
+#pragma unroll
+              for (int l4 = 0; l4 < LG / 4; ++l4) {
+                const float4 w = wr[l4];
+                um[4 * l4] = fmaxf(um[4 * l4], kf * w.x);
+                um[4 * l4 + 1] = fmaxf(um[4 * l4 + 1], kf * w.y);
+                um[4 * l4 + 2] = fmaxf(um[4 * l4 + 2], kf * w.z);
+                um[4 * l4 + 3] = fmaxf(um[4 * l4 + 3], kf * w.w);
+              }
+            }
+        }
+      }
+    }
+    if (m < M)
+#pragma unroll
+      for (int l = 0; l < LG; ++l)
+        if (l0 + l < L && um[l] > 0.f) atomicMax(reinterpret_cast<int*>(vmax + (l0 + l) * M + m), __float_as_int(um[l]));
+  }
+}
 
 constexpr int SYRK8_THREADS = 512;       // warp 0 TMA, warp 1 MMA, warps 4-11 operand transform, warps 12-15 epilogue
 constexpr int SYRK8_XF_WARP0 = 4, SYRK8_XF_WARPS = 8, SYRK8_EPI_WARP0 = 12;
@@ -240,6 +298,16 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
     int stage = 0; uint32_t phase = 0;
     for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(item);
+      // grid of the weighted operand: per (channel, row a) against the largest |w K| of that row (syrk_vmax_kernel) -- with
+      // the channel's largest weight times the column maximum instead, the grid is ~10x coarser than the entries need
+      // (the datapoint with the largest weight is rarely the one next to inducing point a) and the forward A_l loses 3-4 bits
+      float q[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int64_t r = (int64_t)it.ta * I8_T + rbase + 64 * j;
+        const float u = r < P.M ? __ldg(P.vmax + it.l * P.M + r) : 0.f;
+        q[j] = syrk_vq(u);
+      }
       for (int kb = 0; kb < it.nkb; ++kb) {
         const int64_t n = it.n0 + (int64_t)kb * I8_KB + lchunk * 16;
         float w[16];
@@ -269,7 +337,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
               const uint32_t sel = (uint32_t)(b | ((4 + b) << 4));
               const uint32_t d = __byte_perm(__byte_perm(k3w[g], k2w[g], sel), __byte_perm(k1w[g], k0w[g], sel), 0x5410);
               const int kint = (int)((d ^ 0x00808080u) - 0x00808080u);
-              const int v = __float2int_rn(__int2float_rn(kint) * w[4 * g + b]);
+              const int v = __float2int_rn(__int2float_rn(kint) * w[4 * g + b] * q[j]);
               e[b] = ((uint32_t)v + 0x00808080u) ^ 0x00808080u;
             }
             const uint32_t x01 = __byte_perm(e[0], e[1], 0x7362), y01 = __byte_perm(e[0], e[1], 0x5140);
@@ -296,7 +364,8 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
       const Item it = decode(item);
       const int64_t r = (int64_t)it.ta * I8_T + qd * 32 + lane;           // output row a
       const int64_t rmax_w = (int64_t)it.ta * I8_T + qd * 32 + 31;
-      const double rs = (r < P.M) ? 16777216.0 * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
+      const float qv = r < P.M ? syrk_vq(__ldg(P.vmax + it.l * P.M + r)) : 0.f;
+      const double rs = (qv > 0.f) ? 16777216.0 * (double)P.wmax[it.l] * (double)P.cscale[r] / (double)qv : 0.0;
       mbar_wait(S.tmem_full(), tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
@@ -523,7 +592,7 @@ int64_t i8_syrk_window(int64_t N, int64_t M, int64_t L) {
   return w < 128 ? 128 : w;
 }
 
-int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, int64_t L, double* A, cudaStream_t st) {
+int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, float* vmax, int64_t L, double* A, cudaStream_t st) {
   if (!kop->Kc || !kop->cscale) { set_error("tc_syrk_i8: int8 transposed planes missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (((uintptr_t)Wt & 15) || (ldwt % 128)) { set_error("tc_syrk_i8: weights need whole zero-padded 128-datapoint blocks"); return SVGP_ERR_ARG; }
   const int64_t N = kop->N, M = kop->M, nblk = (N + 127) / 128;
@@ -532,8 +601,18 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   const cuuint64_t strides[3] = {128, (cuuint64_t)(M * 128), (cuuint64_t)(nblk * M * 128)};
   int rc = encode_i8(&map, kop->Kc, 4, dims, strides);
   if (rc) return rc;
+  {
+    // grid of the weighted operand (see the transform): one pass over the K^T planes per 32 channels
+    if (cudaMemsetAsync(vmax, 0, L * M * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(i8 vmax memset)");
+    int64_t gy = nblk < 64 ? nblk : 64;
+    while (gy * 2 <= nblk && ceil_div(M, 128) * gy * 2 <= 148 * 8) gy *= 2;
+    dim3 grid((unsigned)ceil_div(M, 128), (unsigned)gy);
+    syrk_vmax_kernel<32><<<grid, 128, 0, st>>>((const int8_t*)kop->Kc, N, M, nblk, Wt, ldwt, L, vmax);
+    rc = check_launch("svgp_syrk(i8 vmax)");
+    if (rc) return rc;
+  }
   SyrkI8Params P{};
-  P.N = N; P.M = M; P.L = L; P.Wt = Wt; P.ldwt = ldwt; P.wmax = wmax; P.cscale = kop->cscale; P.A = A;
+  P.N = N; P.M = M; P.L = L; P.Wt = Wt; P.ldwt = ldwt; P.wmax = wmax; P.vmax = vmax; P.cscale = kop->cscale; P.A = A;
   P.win_rows = i8_syrk_window(N, M, L);
   P.nwin = (int)ceil_div(N, P.win_rows);
   const int64_t T = ceil_div(M, I8_T);
@@ -617,7 +696,7 @@ __global__ void i8_wprep_kernel(const float* __restrict__ W, int64_t ldw, int64_
 
 int launch_mirror_lower(double* A, int64_t M, int64_t L, cudaStream_t st);      // tc_engine.cu
 
-int64_t i8_syrk_ws_floats(int64_t N, int64_t L) { return L * ((N + 127) / 128 * 128) + L; }
+int64_t i8_syrk_ws_floats(int64_t N, int64_t M, int64_t L) { return L * ((N + 127) / 128 * 128) + L + L * M; }
 
 // W (N x L) -> workspace [Wt (L x ldwt) | wmax (L)], then the SYRK
 int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st) {
@@ -632,7 +711,7 @@ int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_
   i8_wprep_kernel<<<grid, 256, 0, st>>>(W, ldw, N, L, mx, Wt, ldwt);
   int rc = check_launch("svgp_syrk(i8 prep)");
   if (rc) return rc;
-  rc = tc_syrk_i8(kop, Wt, ldwt, mx, L, A, st);
+  rc = tc_syrk_i8(kop, Wt, ldwt, mx, mx + L, L, A, st);
   if (rc) return rc;
   return launch_mirror_lower(A, kop->M, L, st);          // the tiles cover the lower triangle only
 }

@@ -43,8 +43,45 @@ def main():
     orig = dict(scaled=be.scaled_gemm, tn=be.gemm_tn, quad=be.rowquad, nn=be.gemm_nn, f32=be.gemm_f32, kbwd=be.kernel_bwd)
     state = {"which": ()}
 
-    def Kval(kop):
-        return kop.value_i8("r") if kop.i8 else kop.value().double()
+    from oracle_backend import kernel_value
+    Ktrue = {}
+
+    def Kval(kop, which="r"):
+        if "ktrue" in state["which"]:                        # the float64 kernel values themselves instead of the operand planes
+            if "K" not in Ktrue:
+                Ktrue["K"] = kernel_value((1, 4, 1, 4), cfg["aux"].cuda(), torch.as_tensor(cfg["ctor"]["initial_inducing_points"]).cuda(),
+                                          torch.ones(4, device="cuda"))
+            return Ktrue["K"]
+        return kop.value_i8(which) if kop.i8 else kop.value().double()
+
+    orig_syrk, orig_si8 = be.syrk, be.scaled_gemm_i8
+
+    def x_syrk(kop, W, impl=0, chunk_rows=0):
+        if "syrk" not in state["which"]:
+            return orig_syrk(kop, W, impl=impl, chunk_rows=chunk_rows)
+        K = Kval(kop, "r" if "kr" in state["which"] else "c")      # "kr": the SAME dequantised K as every other product
+        return torch.stack([(K * W[:, l:l + 1].double()).t() @ K for l in range(W.shape[1])])
+
+    def x_si8(kop, W, G, out=None, ndot=0):
+        if "scaledA" not in state["which"]:
+            return orig_si8(kop, W, G, out=out, ndot=ndot)
+        K = Kval(kop)
+        Gv = G.value()
+        r = torch.zeros(K.shape[0], G.R, dtype=F64, device=K.device)
+        dots = torch.zeros(K.shape[0], max(ndot, 1), dtype=F64, device=K.device)
+        for t in range(G.B):
+            T = K @ Gv[t].t()
+            r += T if W is None else W[:, t:t + 1].double() * T
+            if t < ndot:
+                dots[:, t] = (T * K).sum(1)
+        if out is not None:
+            out += r.float()
+            r = out
+        else:
+            r = r.float()
+        return (r, dots[:, :ndot].float()) if ndot else r
+
+    be.syrk, be.scaled_gemm_i8 = x_syrk, x_si8
 
     def x_scaled(kop, W, G64, out=None, ndot=0, impl=0):
         if "scaledS" not in state["which"] or ndot:

@@ -52,10 +52,14 @@ def test_kplanes_reassemble(cuda_backend, N, M):
     K = kop.K64
     Kr, Kc = kop.value_i8("r"), kop.value_i8("c")
     # fp32 kernel arithmetic (a few ulp of the entry) + one unit of the 32-bit grid relative to the row / column maximum
-    unit_r, unit_c = K.abs().amax(1, keepdim=True) / 2130706432.0, K.abs().amax(0, keepdim=True) / 2130706432.0
-    assert ((Kr - K).abs() <= 4e-6 * K.abs() + 1.1 * unit_r).all()
-    assert ((Kc - K).abs() <= 4e-6 * K.abs() + 1.1 * unit_c).all()
+    # power-of-two grids of 2^-30 of the (rounded-up) row / column maximum; the evaluation is float64 rounded once to fp32
+    unit_r, unit_c = K.abs().amax(1, keepdim=True) / 2.0 ** 29, K.abs().amax(0, keepdim=True) / 2.0 ** 29
+    assert ((Kr - K).abs() <= 1e-7 * K.abs() + 0.51 * unit_r).all()
+    assert ((Kc - K).abs() <= 1e-7 * K.abs() + 0.51 * unit_c).all()
     assert kop.Kr[0].int().abs().max() <= 127 and kop.Kc[0].int().abs().max() <= 127
+    # the two sets of planes hold the same fp32 number wherever it fits both grids (entries within 2^-6 of both maxima)
+    big = (K.abs() * 64 >= K.abs().amax(1, keepdim=True)) & (K.abs() * 64 >= K.abs().amax(0, keepdim=True))
+    assert big.any() and (Kr[big] == Kc[big]).all()
     # the fp16 hi / lo row planes of the same call
     assert rel_err(kop.value(), K) < 2e-6
     # pad columns / the ragged last block are zeros (TMA boxes read them)
@@ -82,7 +86,8 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L):
     g = torch.Generator(device="cuda").manual_seed(2)
     W = torch.randn(N, L, generator=g, device="cuda") * torch.exp(torch.randn(N, L, generator=g, device="cuda"))
     A = be.syrk(kop, W.contiguous())
-    # emulation from the same planes: weighted operand = rn(float(Kint) * (w / wmax)) as a 32-bit integer
+    # emulation from the same planes: weighted operand = rn(float(Kint) * (w / wmax) * q_a) as a 32-bit integer, q_a from
+    # the largest |float(Kint) * (w / wmax)| of row a
     k = _digits(kop.Kc)                                                   # (nblk, M, 128) each
     Kint = _ints(kop.Kc).permute(0, 2, 1).reshape(-1, M)[:N]              # (N, M)
     kd = [x.permute(0, 2, 1).reshape(-1, M)[:N] for x in k]
@@ -91,7 +96,9 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L):
     for l in range(L):
         wmax = W[:, l].abs().max()
         wt = W[:, l] / wmax
-        V = torch.round(Kint.to(torch.int64).float() * wt[:, None]).to(torch.int64)
+        prod = Kint.to(torch.int64).float() * wt[:, None]
+        qa = (torch.tensor(2130706432.0, device="cuda") * torch.tensor(0.99999, device="cuda")) / prod.abs().amax(0)
+        V = torch.round(prod * qa[None, :]).to(torch.int64)
         v = _balanced_digits4(V)
         acc = [torch.zeros(M, M, dtype=F64, device="cuda") for _ in range(4)]
         for t in range(4):
@@ -99,7 +106,7 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L):
                 if t + u <= 3:
                     acc[t + u] += v[t].t() @ kd[u]                        # exact: |sum| < 2^53
         i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
-        ref[l] = i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :]
+        ref[l] = i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / qa.double()[:, None]
     ref = torch.tril(ref) + torch.tril(ref, -1).transpose(-1, -2)
     assert rel_err(A, ref) < 1e-12
     # and against the plain float64 contraction of the float64 kernel values: fp32 kernel arithmetic is what is left

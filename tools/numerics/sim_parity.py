@@ -97,6 +97,10 @@ class Model:
         if self.kind in ("sym", "symf"):          # SYRK of ONE quantised operand sqrt(w) K against itself, all slice pairs
             self.bits, self.sa = int(p[1]), int(p[2])
             self.sb, self.cut = self.sa, (int(p[3]) if len(p) > 3 else 99)
+        if self.kind == "e8":                     # ONE two-sided equilibrated integer K (power-of-two row and column scales)
+            self.bits = int(p[1])
+            self.sa, self.sb = (int(x) for x in p[2].split("x"))
+            self.cut = int(p[3])
         if self.kind == "i8":
             self.bits = int(p[1])
             self.sa, self.sb = (int(x) for x in p[2].split("x"))
@@ -155,6 +159,19 @@ class SimBackend(OracleBackend):
         return kop.cache[key]
 
     @staticmethod
+    def _kequil(kop, m):
+        """-> (Kint float64 integers, r (N,1), c (1,M)) with K ~= Kint r c 2^-b, r / c powers of two, |Kint| <= 2^b."""
+        key = ("equil", m.bits)
+        if key not in kop.cache:
+            K = kop.K.double()
+            b = m.bits if m.bits else 30
+            r = 2.0 ** torch.ceil(torch.log2(K.abs().amax(1, keepdim=True).clamp_min(1e-300)))
+            c = 2.0 ** torch.ceil(torch.log2((K / r).abs().amax(0, keepdim=True).clamp_min(1e-300)))
+            Kint = torch.round(K / (r * c) * 2.0 ** b)
+            kop.cache[key] = (Kint, r, c, b)
+        return kop.cache[key]
+
+    @staticmethod
     def _khl(kop):
         if "hl" not in kop.cache:
             kop.cache["hl"] = f16hl(kop.K.double())
@@ -163,6 +180,9 @@ class SimBackend(OracleBackend):
     def _kval(self, kop, m, axis=1):
         if not getattr(kop, "sim", False) or m.kind == "exact":
             return kop.K.double()
+        if m.kind == "e8":
+            Kint, r, c, b = self._kequil(kop, m)
+            return Kint * r * c * 2.0 ** -b
         return self._khl(kop) if m.kind == "f16hl" else self._kfixed(kop, m, axis).value()
 
     # ---- reductions over datapoints ---------------------------------------------------------------------------
@@ -175,6 +195,19 @@ class SimBackend(OracleBackend):
             K = self._khl(kop)
             return torch.stack([(f16hl((W[:, l:l + 1].float() * K.float()).double())).t() @ K for l in range(W.shape[1])])
         out = []
+        if m.kind == "e8":
+            Kint, r, c, b = self._kequil(kop, m)
+            Kf = Fixed.__new__(Fixed)
+            Kf.bits, Kf.ns, Kf.Xi, Kf.scale = 31, m.sb, Kint * 2.0, None          # digits of the shared integer (31-bit container)
+            for l in range(W.shape[1]):
+                wp = (W[:, l:l + 1].double() * r * r)                               # w r^2 per datapoint
+                wn = (wp / wp.abs().max()).float()
+                V = (wn * Kint.float()).double()                                    # fp32 product, |V| <= 2^b
+                Vf = Fixed.__new__(Fixed)
+                Vf.bits, Vf.ns, Vf.Xi, Vf.scale = 31, m.sa, torch.round(V * 2.0), None
+                rr = sliced_matmul(Vf, Kf, m.cut, lambda a_, b_: a_.t() @ b_) / 4.0
+                out.append(rr * wp.abs().max() * (c.t() * c) * 2.0 ** (-2 * b))
+            return torch.stack(out)
         if m.kind in ("sym", "symf"):
             K = kop.K.double()
             for l in range(W.shape[1]):
@@ -217,6 +250,14 @@ class SimBackend(OracleBackend):
             return kop.K.double() @ G
         if m.kind == "f16hl":
             return self._khl(kop) @ f16hl(G)
+        if m.kind == "e8":
+            Kint, r, c, b = self._kequil(kop, m)
+            Gp = G * c.t()                                             # rows of G scaled by the column scales of K
+            Gf = Fixed(Gp, 0, 8 * m.sb - 1, m.sb)
+            Kf = Fixed.__new__(Fixed)
+            Kf.bits, Kf.ns, Kf.Xi, Kf.scale = 31, m.sa, Kint * 2.0, None
+            rr = sliced_matmul(Kf, Gf, m.cut, lambda a_, b_: a_ @ b_) / 2.0
+            return rr * r * 2.0 ** -b * Gf.scale
         Gf = m.fixed(G, 0, "b")                                        # scale per output column
         Kr = self._kfixed(kop, m, 1)
         r = sliced_matmul(Kr, Gf, m.cut, lambda a, b: a @ b)
