@@ -24,7 +24,7 @@ import math
 import torch
 
 from . import ops
-from .backend import Planes, get_backend
+from .backend import Planes, PlanesI8, get_backend
 
 LOG_2PI = 1.8378770664093453      # utils.py:498
 LOG_2PI_RT = math.log(2.0 * math.pi)
@@ -315,17 +315,14 @@ class _SVGPStep(torch.autograd.Function):
             # the difference is formed in float64 BEFORE the fp16 split, so the 1 / jitter-sized components that
             # Kinv and S_l share never enter the tensor-core products
             if kop.tc and getattr(kop, "i8", False):
-                # dA + dA^T as four int8 digit planes for the exact integer products (K (dA + dA^T) cancels by 10^2..10^3
-                # against the entries of dA: the truncating fp16 accumulation of round 1 left 3e-4 in dZ here);
-                # S - Kinv stays on the fp16 path, whose rounding it tolerates
-                GA = be.planes_i8_alloc(L, M, M, dev)
-                hi = torch.empty((L, M, M), dtype=torch.float16, device=dev)
-                lo = torch.empty_like(hi)
-                inv = torch.empty(L, dtype=torch.float32, device=dev)
+                # both families as four int8 digit planes each for the exact integer products: K (dA + dA^T) cancels by
+                # 10^2..10^3 against the entries of dA (the truncating fp16 accumulation of round 1 left 3e-4 in dZ at
+                # M = 1024), and at M = 2048 the S - Kinv family does not tolerate it either (6e-5 of dZ, measured with
+                # tests/probes/ablate_i8_probe.py)
+                Gstack = be.planes_i8_alloc(2 * L, M, M, dev)
                 for l0 in range(0, L, 16):
-                    be.planes_i8_into(gA[l0:l0 + 16] + gA[l0:l0 + 16].transpose(-1, -2), GA, l0)
-                    be.planes_into(S[l0:l0 + 16] - Kinv, hi, lo, inv, l0)
-                Gstack = (GA, Planes(hi, lo, inv))
+                    be.planes_i8_into(gA[l0:l0 + 16] + gA[l0:l0 + 16].transpose(-1, -2), Gstack, l0)
+                    be.planes_i8_into(S[l0:l0 + 16] - Kinv, Gstack, L + l0)
             elif kop.tc:
                 # operand planes filled in pieces of 16 channels: no (2L, M, M) float64 copy next to gA and S
                 hi = torch.empty((2 * L, M, M), dtype=torch.float16, device=dev)
@@ -344,16 +341,8 @@ class _SVGPStep(torch.autograd.Function):
             jitter, c, b_total = cfg["jitter"], ctx.c, ctx.b_total
             use_i8 = kop.tc and getattr(kop, "i8", False)
             if use_i8:
-                GA = be.planes_i8_alloc(L, M, M, dev)
-                hi = torch.empty((L, M, M), dtype=torch.float16, device=dev)
-                lo = torch.empty_like(hi)
-                inv = torch.empty(L, dtype=torch.float32, device=dev)
-
-                def put(X, at):                               # at < L: dA + dA^T (digit planes); at >= L: S - Kinv (fp16 planes)
-                    if at < L:
-                        be.planes_i8_into(X, GA, at)
-                    else:
-                        be.planes_into(X, hi, lo, inv, at - L)
+                GA = be.planes_i8_alloc(2 * L, M, M, dev)
+                put = lambda X, at: be.planes_i8_into(X, GA, at)
             elif kop.tc:
                 hi = torch.empty((2 * L, M, M), dtype=torch.float16, device=dev)
                 lo = torch.empty_like(hi)
@@ -392,10 +381,10 @@ class _SVGPStep(torch.autograd.Function):
             if sharded:
                 # the other ranks' dA_l + dA_l^T (operand planes / float64), dv_l and row-sum adjoints; dK_mm summed
                 if use_i8:
-                    pl = GA.planes.view(GA.planes.shape[0], L, M, -1)
+                    pl = GA.planes.view(GA.planes.shape[0], 2 * L, M, -1)
                     for d in range(pl.shape[0]):
-                        pl[d] = _allgather0(pl[d][own], group)
-                    GA.scale.view(L, M)[:] = _allgather0(GA.scale.view(L, M)[own], group)
+                        pl[d][:L] = _allgather0(pl[d][own], group)
+                    GA.scale.view(2 * L, M)[:L] = _allgather0(GA.scale.view(2 * L, M)[own], group)
                 elif kop.tc:
                     hi[:L] = _allgather0(hi[own], group)
                     lo[:L] = _allgather0(lo[own], group)
@@ -407,17 +396,13 @@ class _SVGPStep(torch.autograd.Function):
                 _allreduce(gK, group)
             for l0 in range(0, L, lc):
                 put(S[l0:l0 + lc] - Kinv, L + l0)
-            Gstack = (GA, Planes(hi, lo, inv)) if use_i8 else (Planes(hi, lo, inv) if kop.tc else G64)
-        if isinstance(Gstack, tuple):
-            GA, GS = Gstack
-            G_K, kGk = be.scaled_gemm_i8(kop, p, GA, ndot=L)
-            be.scaled_gemm(kop, (2.0 * G_q1).contiguous(), GS, out=G_K)
-            del GA, GS
+            Gstack = GA if use_i8 else (Planes(hi, lo, inv) if kop.tc else G64)
+        Wstack = torch.cat([p, 2.0 * G_q1], dim=1).contiguous()
+        if isinstance(Gstack, PlanesI8):
+            G_K, kGk = be.scaled_gemm_i8(kop, Wstack, Gstack, ndot=L)
         else:
-            Wstack = torch.cat([p, 2.0 * G_q1], dim=1).contiguous()
             G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
-            del Wstack
-        del Gstack
+        del Wstack, Gstack
         py = p * y
         # rank-2L part of dK_nm in one pass over it: [p*y | g_pm] (N, 2L) @ [dV ; w] (2L, M)   (via v_l and via p_m)
         be.gemm_f32(torch.cat([py, g_pm], dim=1), torch.cat([gV.float(), w.float()], dim=0).contiguous(), out=G_K)
