@@ -365,10 +365,8 @@ def test_cuda_graph_step_matches_eager(cuda_backend, kind):
 
 def test_sweep_ragged_shapes_on_the_tensor_core_path(cuda_backend):
     """N, M not multiples of the tile sizes (30000 rows, 1000 inducing points -> padded planes, ragged last row / column
-    tiles, ragged SYRK chunk) and an odd channel count (single-CTA SYRK instead of the two-CTA cluster) on the tcgen05
-    path against the streamlined float64 oracle.  Tolerances: the measured M = 1000 level of DESIGN.md section 7 (the
-    forward moments sit at 1e-4, the gradients at 1-5e-4 -- M = 1000 is where the truncating accumulation starts to
-    show), doubled."""
+    tiles, ragged SYRK window) and an odd channel count on the tensor-core path against the streamlined float64 oracle:
+    every quantity at 1e-4 (round 1 needed 2e-4 .. 1e-3 here; the integer path accumulates exactly)."""
     cfg = configs.sweep_inputs(30000, 1000, 3)
     o, s, op, sp = refs.make_pair("sweep", cfg, "cuda")
     X, y, nz = cfg["aux"].double(), cfg["y"].double().requires_grad_(True), cfg["noise"].double().requires_grad_(True)
@@ -382,7 +380,7 @@ def test_sweep_ragged_shapes_on_the_tensor_core_path(cuda_backend):
     J0 = g0["KL_term"] + (gm * t0["p_m"]).sum() + (gv * t0["p_v"]).sum()
     gr0 = torch.autograd.grad(J0, [y, nz] + op)
     r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"].cuda(), cfg["y"].cuda(), cfg["noise"].cuda(), tc=True)
-    assert rel_err(r1["p_m"], t0["p_m"]) < 2e-4 and rel_err(r1["p_v"], t0["p_v"]) < TOL
+    assert rel_err(r1["p_m"], t0["p_m"]) < TOL and rel_err(r1["p_v"], t0["p_v"]) < TOL
     _cmp_scalars(r1, g0)
-    for name, a, b, tol in zip(["dy", "dnoise", "dZ", "dhyp"], gr0, g1, [2e-4, 2e-4, 1e-3, 1e-4]):
-        assert rel_err(b, a) < tol, name
+    for name, a, b in zip(["dy", "dnoise", "dZ", "dhyp"], gr0, g1):
+        assert rel_err(b, a) < TOL, name

@@ -47,7 +47,7 @@ def test_syrk_shard_additivity_permutation_and_channel_slices(big):
     perm = torch.randperm(N, generator=g, device="cuda")
     kop_p = be.kernel_fwd(SPEC, Fx[perm].contiguous(), Fz, hyp, tc=True)
     assert rel_err(be.syrk(kop_p, W[perm].contiguous()), A) < 2e-6
-    # one channel on its own (odd L: single-CTA kernel) vs its slice of the batched call (cluster kernel)
+    # one channel on its own vs its slice of the batched call
     assert rel_err(be.syrk(kop, W[:, 2:3].contiguous())[0], A[2]) < 2e-6
     # a sub-block against float64 on the reassembled K_nm
     K64 = kop.value()[:, 256:512].double()
@@ -90,23 +90,22 @@ def test_full_step_invariants(cuda_backend):
     assert torch.isfinite(res2["KL_term"]) and res2["p_m"].shape == (half, L)
 
 
-def test_step_against_float64_oracle_on_the_gpu(cuda_backend):
-    """The whole step at M = 1024 and N = 262144 rows against the streamlined float64 ORACLE evaluated on the GPU
-    (tests/probes/parity_fullsize.py: oracle/svgp_streamlined.py is device-agnostic torch float64; the kernel matrix is
-    restated with the squared-distance expansion in float64 and checked there against oracle/tfp_kernels).
+@pytest.mark.parametrize("n,m,l", [(262144, 1024, 8), (32768, 2048, 2)])
+def test_step_against_float64_oracle_on_the_gpu(cuda_backend, n, m, l):
+    """The whole step at the headline M = 1024 (262144 rows, 8 channels) and at the M = 2048 sweep point against the
+    streamlined float64 ORACLE evaluated on the GPU (tests/probes/parity_fullsize.py: oracle/svgp_streamlined.py is
+    device-agnostic torch float64; the kernel matrix is restated with the squared-distance expansion in float64 and
+    checked there against oracle/tfp_kernels).
 
-    Tolerance 1e-4 of max|oracle tensor| (north_star) for the posterior moments, the ELBO sums, the cancelling
-    KL_term and the gradients w.r.t. y, noise and the kernel hyper-parameters.  The inducing-point gradient is what
-    is left of a ~60-fold cancellation between its K_nm and K_mm paths; on the tensor-core path its K_nm part carries
-    the truncation bias of the fp32 TMEM accumulation (profiles/r01_ablation_M1024.jsonl): it is
-    required to 5e-3 here and measured at 1-2e-3; the float64-accumulating SIMT path reaches 4e-6 on the same inputs
-    (profiles/r01_parity_simt_path.jsonl)."""
+    Tolerance 1e-4 of max|oracle tensor| (north_star) for ALL TEN quantities: posterior moments, the three ELBO sums, the
+    cancelling KL_term and the gradients w.r.t. y, noise, the kernel hyper-parameters and the inducing points.  (Round 1
+    held dZ to 5e-3 here: the truncating fp32 TMEM accumulation of the fp16 tensor-core path left 3e-4 .. 3e-3; the
+    integer tensor-core path accumulates exactly -- DESIGN.md section 7.)"""
     import os
     import sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "probes"))
     import parity_fullsize
-    o = parity_fullsize.run(262144, 1024, 2)
+    o = parity_fullsize.run(n, m, l)
     print(o)
-    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "KL_term", "dy", "dnoise", "dhyp"):
+    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "KL_term", "dy", "dnoise", "dhyp", "dZ"):
         assert o[k] < 1e-4, (k, o)
-    assert o["dZ"] < 5e-3, o

@@ -14,7 +14,7 @@ def _setup(be, N, M, L, seed=0):
     Fx = torch.randn(N, 8, generator=g, device="cuda")
     Fz = torch.randn(M, 8, generator=g, device="cuda")
     hyp = torch.ones(4, device="cuda")
-    kop = be.kernel_fwd(SPEC, Fx, Fz, hyp, tc=True)
+    kop = be.kernel_fwd(SPEC, Fx, Fz, hyp, tc=True, i8=False)
     K64 = kop.value().double()
     W = torch.randn(N, L, generator=g, device="cuda")
     return kop, K64, W, g

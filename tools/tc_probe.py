@@ -30,11 +30,11 @@ def main():
     hyp = torch.ones(4, device="cuda")
     spec = (1, 4, 1, 4)
     if not only:
-        t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=True))
+        t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=True, i8=False))
         print(json.dumps(dict(op="kernel_fwd_planes", N=N, M=M, ms=t, GBs=4 * N * M * 2 / t / 1e6)), flush=True)
         t = timeit(lambda: be.kernel_fwd(spec, Fx, Fz, hyp, tc=False))
         print(json.dumps(dict(op="kernel_fwd_f32", N=N, M=M, ms=t, GBs=N * M * 4 / t / 1e6)), flush=True)
-    kop = be.kernel_fwd(spec, Fx, Fz, hyp, tc=True)
+    kop = be.kernel_fwd(spec, Fx, Fz, hyp, tc=True, i8=False)
     W = torch.randn(N, L, generator=g, device="cuda")
     S = torch.randn(L, M, M, generator=g, device="cuda", dtype=torch.float64); S = (S + S.transpose(1, 2)).contiguous()
     Lt = torch.tril(S).contiguous()
