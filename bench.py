@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--l", "--channels", dest="l", type=int, default=L_CH)
     ap.add_argument("--mm-chunk", type=int, default=0, help="channels per chunk of the float64 M x M stage (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL number of datapoints, split over the GPUs")
     return ap.parse_args()
 
 
@@ -273,6 +274,8 @@ def run_gpu(args):
             os.close(saved)
     be = backend.get_backend()
     N, M, L = args.n, args.m, args.l
+    if args.strong:                                # configs[3] read as a strong-scaling sweep: the N = 1e6 problem split over the ranks
+        N = (args.n + world - 1) // world
     n_total = N * world
 
     cfg = configs.sweep_inputs(N, M, L, device=dev, rank=rank, N_train=n_total)
@@ -322,9 +325,13 @@ def run_gpu(args):
     launches = (be.launches - l0) // max(args.steps, 1)
 
     # per-kernel device times of one more step (CUDA events on the launch stream)
+    from svgp_vae_b200 import step as step_mod
     be.start_profile()
+    if world > 1:
+        step_mod.start_coll_profile()
     dev_step()
     prof = be.stop_profile()
+    coll = step_mod.stop_coll_profile() if world > 1 else {}
 
     # e2e: pinned host buffers in, results out, every step
     h_aux, h_y, h_nz = (t.detach().cpu().pin_memory() for t in (aux, y, noise))
@@ -357,11 +364,13 @@ def run_gpu(args):
         # dominant kernel of the step = the entry point with the largest total device time; its launch = the longest call
         top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else ("", {"ms": float("nan"), "calls": 0, "max_ms": float("nan")})
         top_name, top_ms = top[0], top[1]["max_ms"]
-        # algorithmic FLOPs of that launch (2 x MACs): scaled_gemm = 2L full N x M x M products; syrk = lower triangle
-        # of L products N x M x M; rowquad (triangular factor) = half of L full products
-        kern_alg = {"svgp_scaled_gemm": 2.0 * N * M * M * (2 * L), "svgp_syrk": 1.0 * N * M * M * L,
-                    "svgp_rowquad": 1.0 * N * M * M * L}
-        top_flops = kern_alg.get(top_name, float("nan"))
+        # algorithmic FLOPs of one launch (2 x MACs) and the MMAs issued per algorithmic MAC in bf16-equivalents: the integer
+        # path issues 10 kind::i8 MMAs (digit-plane pairs) per MAC at twice the kind::f16 rate (profiles/r02_i8_mma_probe.jsonl)
+        # = 5 bf16-equivalents; the fp16 path issues 3.  scaled_gemm = 2L full N x M x M products; syrk = lower triangle of
+        # L products; rowquad (triangular factor) = half of L full products
+        kern_alg = {"svgp_scaled_gemm_i8": (2.0 * N * M * M * (2 * L), 5.0), "svgp_scaled_gemm": (2.0 * N * M * M * (2 * L), 3.0),
+                    "svgp_syrk": (1.0 * N * M * M * L, 5.0 if be.use_i8 else 3.0), "svgp_rowquad": (1.0 * N * M * M * L, 3.0)}
+        top_flops, top_e = kern_alg.get(top_name, (float("nan"), float("nan")))
         # DRAM bytes of one launch of that kernel from the committed ncu capture of this exact workload (else null)
         traffic = None
         try:
@@ -370,35 +379,39 @@ def run_gpu(args):
                 traffic = tr.get(top_name)
         except Exception:  # noqa: BLE001
             pass
-        achieved = 3.0 * top_flops / (top_ms * 1e-3) / 1e12
-        # K1 (the kernel-matrix builder) is the HBM-bound kernel of the path: 4 fp16 planes of N x M written once
-        k1_ms = prof.get("svgp_kernel_fwd", {}).get("max_ms")
+        achieved = top_e * top_flops / (top_ms * 1e-3) / 1e12
+        # what the tensor kernels of this implementation really issue per step, in bf16-equivalent FLOPs: 2 SYRKs (N M^2 L each,
+        # x5) + 1 triangular row quad (N M^2 L, x3) + the 2L-matrix product of pass D (2 N M^2 2L, x5)
+        launched = (2 * 5.0 + 3.0 + 4 * 5.0) * L * N * M * M if be.use_i8 else 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M
+        # K1 (the kernel-matrix builder) is the HBM-bound kernel of the path: fp16 hi/lo row planes + 4 + 4 int8 digit planes
+        k1_name = "svgp_kernel_fwd_i8" if "svgp_kernel_fwd_i8" in prof else "svgp_kernel_fwd"
+        k1_ms = prof.get(k1_name, {}).get("max_ms")
+        k1_bytes = (12.0 if k1_name.endswith("i8") else 8.0) * N * M + N * 8 * 4
         hbm_peak = peaks.get("hbm_gbs")
         k1 = None
         if k1_ms:
-            k1_gbs = (4.0 * N * M * 2 + N * 8 * 4) / (k1_ms * 1e-3) / 1e9
-            k1 = {"bound": "hbm", "kernel": "svgp_kernel_fwd (planes builder)", "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s",
-                  "frac": k1_gbs / hbm_peak if hbm_peak else None, "kernel_ms": k1_ms,
-                  "algorithmic_bytes": 4.0 * N * M * 2 + N * 8 * 4}
+            k1_gbs = k1_bytes / (k1_ms * 1e-3) / 1e9
+            k1 = {"bound": "hbm", "kernel": k1_name + " (operand-plane builder: maxima pass + write pass, float64 kernel evaluation)",
+                  "achieved": k1_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": k1_gbs / hbm_peak if hbm_peak else None, "kernel_ms": k1_ms,
+                  "algorithmic_bytes": k1_bytes}
         line = {
             "metric": METRIC, "value": n_total / t_s, "unit": "datapoints/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 emulated as 3 x FP16 split on tcgen05 (fp32 TMEM accumulate) + f64 MxM stage", "data": "synthetic",
-            "config": {"workload": "SWEEP N=%d per GPU x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3])" % (N, world, M, L),
-                       "l2": "inputs_exceed_l2 (K_nm fp16 hi/lo planes + transpose = %.1f GB per GPU)" % (4 * N * M * 2 / 1e9),
-                       "parallelism": "N-sharded x%d, all-reduce of A_l/v_l and their adjoints" % world},
-            "roofline": {"bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "dtype": "int8 digit planes on tcgen05 kind::i8 with exact int32 TMEM accumulation (SYRK, scaled GEMM: fp32-accurate operands, "
+                     "no accumulation rounding) + 3 x FP16 split (row quads) + f64 MxM stage", "data": "synthetic",
+            "config": {"workload": workload_name(args, world) if not args.strong else
+                       "SWEEP N=%d TOTAL split over %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3], strong scaling)" % (n_total, world, M, L),
+                       "l2": "inputs_exceed_l2 (K_nm operand planes: fp16 hi/lo + 2 x 4 int8 digit planes = %.1f GB per GPU)" % (12.0 * N * M / 1e9),
+                       "parallelism": "N-sharded x%d, all-reduce of A_l/v_l and their adjoints, channel-sharded f64 MxM stage" % world},
+            "roofline": {"bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s (bf16-equivalent)",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "note": "achieved = e x algorithmic FLOPs of the kernel's launch / its CUDA-event duration inside the step, e = 3 FP16 MMAs "
-                                 "per algorithmic MAC (fp32-emulating split); peak = %s; fp16 cuBLAS 8192^3 timed in this run: %.1f TFLOP/s"
-                                 % (peak_src, f16_run),
-                         "kernel_ms": top_ms, "kernel_algorithmic_tflops": top_flops / (top_ms * 1e-3) / 1e12,
-                         "step_algorithmic_tflops": f_alg / t_s / 1e12, "step_issued_tflops": 3 * f_alg / t_s / 1e12,
-                         "step_frac_of_peak": 3 * f_alg / t_s / 1e12 / peak if peak else None, "e": 3,
-                         # what the tensor kernels of this implementation really issue per step: 2 SYRKs + 1 triangular row quad
-                         # (N M^2 L FLOP each) + the 2L-matrix product of pass D, times e
-                         "step_tensor_flops_launched": 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M,
-                         "step_tensor_tflops_launched": 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M / t_s / 1e12,
+                         "note": "achieved = e x algorithmic FLOPs of the kernel's launch / its CUDA-event duration inside the step; e = MMAs issued "
+                                 "per algorithmic MAC in bf16-equivalents: 10 kind::i8 digit-plane MMAs at twice the bf16 rate = 5 (integer path), "
+                                 "3 (fp16 split path); peak = %s; fp16 cuBLAS 8192^3 timed in this run: %.1f TFLOP/s" % (peak_src, f16_run),
+                         "kernel_ms": top_ms, "kernel_algorithmic_tflops": top_flops / (top_ms * 1e-3) / 1e12, "e": top_e,
+                         "step_algorithmic_tflops": f_alg / t_s / 1e12,
+                         "step_tensor_flops_launched": launched, "step_tensor_tflops_launched": launched / t_s / 1e12,
+                         "step_frac_of_peak": launched / t_s / 1e12 / peak if peak else None,
                          "f16_cublas_tflops_in_run": f16_run},
             "roofline_k1": k1,
             "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
@@ -407,6 +420,10 @@ def run_gpu(args):
                     "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
+        line["max_mem_gb"] = round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)
+        line["k3_ms"] = round(sum(v["ms"] for k, v in prof.items() if k in ("svgp_gemm_f64", "svgp_trinv_f64", "svgp_chol_f64", "svgp_ltl_f64")), 3)
+        if world > 1:
+            line["collectives"] = {k: {"ms": round(v["ms"], 3), "calls": v["calls"], "bytes": v["bytes"]} for k, v in coll.items()}
         if not args.no_cpu_baseline and world == 1:           # CPU leg: rank 0 of the single-GPU run only
             line["cpu_baseline"] = cpu_baseline(args, n_total)
         print(json.dumps(line), flush=True)

@@ -34,7 +34,7 @@ class Kop:
 
     @property
     def tc(self):
-        return self.Kh is not None
+        return self.Kh is not None or self.Kr is not None
 
     @property
     def i8(self):
@@ -51,7 +51,7 @@ class Kop:
 
     @property
     def device(self):
-        return (self.K if self.K is not None else self.Kh).device
+        return (self.K if self.K is not None else (self.Kh if self.Kh is not None else self.Kr)).device
 
     def value(self):
         if self.K is not None:

@@ -30,9 +30,48 @@ LOG_2PI = 1.8378770664093453      # utils.py:498
 LOG_2PI_RT = math.log(2.0 * math.pi)
 
 
+_COLL = None        # bench.py: [(kind, bytes, start event, end event)] while a collective profile is running
+
+
+def start_coll_profile():
+    global _COLL
+    _COLL = []
+
+
+def stop_coll_profile():
+    """-> {"all_reduce" / "all_gather": {"ms", "calls", "bytes"}} (CUDA events on the launch stream around every collective)."""
+    global _COLL
+    torch.cuda.synchronize()
+    out = {}
+    for kind, nbytes, e0, e1 in _COLL or []:
+        d = out.setdefault(kind, {"ms": 0.0, "calls": 0, "bytes": 0})
+        d["ms"] += e0.elapsed_time(e1)
+        d["calls"] += 1
+        d["bytes"] += nbytes
+    _COLL = None
+    return out
+
+
+class _timed_coll:
+    def __init__(self, kind, t):
+        self.kind, self.nbytes = kind, t.numel() * t.element_size()
+
+    def __enter__(self):
+        if _COLL is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+
+    def __exit__(self, *a):
+        if _COLL is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            _COLL.append((self.kind, self.nbytes, self.e0, e1))
+
+
 def _allreduce(t, group):
     if group is not None:
-        torch.distributed.all_reduce(t, group=group)
+        with _timed_coll("all_reduce", t):
+            torch.distributed.all_reduce(t, group=group)
     return t
 
 
@@ -45,10 +84,11 @@ def _allgather0(t, group):
     t = t.contiguous()
     W = _world(group)
     out = torch.empty((W * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    try:
-        torch.distributed.all_gather_into_tensor(out, t, group=group)
-    except (RuntimeError, NotImplementedError):          # backends without the flat variant
-        torch.distributed.all_gather(list(out.chunk(W, 0)), t, group=group)
+    with _timed_coll("all_gather", out):
+        try:
+            torch.distributed.all_gather_into_tensor(out, t, group=group)
+        except (RuntimeError, NotImplementedError):          # backends without the flat variant
+            torch.distributed.all_gather(list(out.chunk(W, 0)), t, group=group)
     return out
 
 
@@ -289,6 +329,10 @@ class _SVGPStep(torch.autograd.Function):
         G_w = be.gemm_tn(kop, g_pm)
         for t in (G_S, G_w):
             _allreduce(t, group)
+        if getattr(kop, "i8", False):
+            # last use of the column-scaled K^T planes and of the fp16 row planes: pass D reads the row-scaled digit planes
+            # only (configs[4]: 33 GB per GPU at N = 1e6, M = 4096 returned before the adjoint of the M x M stage allocates)
+            kop.Kc = kop.cscale = kop.Kh = kop.Kl = None
         # d/d Kinv of h_i = k_i^T Kinv k_i is sum_i (-G_kappa_i) k_i k_i^T = -sum_l G_S,l.  Taking it from G_S (instead
         # of a separate single-channel SYRK) is not only free: both adjoints are amplified by the squared inverses
         # downstream (-Kinv G Kinv and -S_l G S_l, |Kinv|, |S_l| ~ 1 / jitter in the directions the data does not
@@ -305,6 +349,9 @@ class _SVGPStep(torch.autograd.Function):
                 grad_outputs=[G_S[own], G_w[own], -G_S[own].sum(0, keepdim=True), g_recon[own], g_kl[own], g_ce[own]],
                 allow_unused=True)
             gsums = torch.zeros_like(sums_) if gsums is None else gsums
+            # the autograd state of the stage, A_l and dS_l are dead from here on (17 GB each at M = 4096, L = 128)
+            mm = ctx.mm = ctx.leaves = None
+            del A_, G_S
             if sharded:
                 gA, gV = _allgather0(gA, group), _allgather0(gV, group)
                 gsums = _allgather0(gsums.t().contiguous(), group).t().contiguous()
