@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--l", "--channels", dest="l", type=int, default=L_CH)
     ap.add_argument("--mm-chunk", type=int, default=0, help="channels per chunk of the float64 M x M stage (0 = automatic)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lean", action="store_true", help="big configurations on a GPU budget: no extra profiling step (the per-kernel / collective "
+                    "profile is taken on the last timed step's twin run only when not lean: here on the first warm-up step) and no e2e loop")
     ap.add_argument("--strong", action="store_true", help="strong scaling: --n is the TOTAL number of datapoints, split over the GPUs")
     return ap.parse_args()
 
@@ -317,25 +319,36 @@ def run_gpu(args):
         return float(t.item()) / steps
 
     dev_step = lambda: step(aux, y.detach(), noise.detach())
-    for _ in range(args.warmup):
+    from svgp_vae_b200 import step as step_mod
+    prof, coll = None, {}
+    for w in range(args.warmup):
+        if args.lean and w == args.warmup - 1:
+            be.start_profile()
+            if world > 1:
+                step_mod.start_coll_profile()
         dev_step()
+        if args.lean and w == args.warmup - 1:
+            prof = be.stop_profile()
+            coll = step_mod.stop_coll_profile() if world > 1 else {}
     l0 = be.launches
     with ClockSampler(local) as clocks:
         ms = timed(dev_step, args.steps)
     launches = (be.launches - l0) // max(args.steps, 1)
 
     # per-kernel device times of one more step (CUDA events on the launch stream)
-    from svgp_vae_b200 import step as step_mod
-    be.start_profile()
-    if world > 1:
-        step_mod.start_coll_profile()
-    dev_step()
-    prof = be.stop_profile()
-    coll = step_mod.stop_coll_profile() if world > 1 else {}
+    if prof is None:
+        be.start_profile()
+        if world > 1:
+            step_mod.start_coll_profile()
+        dev_step()
+        prof = be.stop_profile()
+        coll = step_mod.stop_coll_profile() if world > 1 else {}
 
     # e2e: pinned host buffers in, results out, every step
-    h_aux, h_y, h_nz = (t.detach().cpu().pin_memory() for t in (aux, y, noise))
-    h_out = [torch.empty((N, L), dtype=torch.float32).pin_memory() for _ in range(4)]
+    if args.lean:
+        ms_e2e, h2d, d2h = float("nan"), 0, 0
+    h_aux, h_y, h_nz = ((t.detach().cpu().pin_memory() for t in (aux, y, noise)) if not args.lean else (None, None, None))
+    h_out = [torch.empty((N, L), dtype=torch.float32).pin_memory() for _ in range(4)] if not args.lean else []
 
     def e2e_step():
         a = h_aux.to(dev, non_blocking=True); yy = h_y.to(dev, non_blocking=True); nn = h_nz.to(dev, non_blocking=True)
@@ -343,10 +356,11 @@ def run_gpu(args):
         for dst, src in zip(h_out, (res["p_m"], res["p_v"], gy, gn)):
             dst.copy_(src.detach(), non_blocking=True)
         float(res["KL_term"])                                     # scalar read-back (syncs)
-    e2e_step()
-    ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
-    h2d = sum(t.numel() * t.element_size() for t in (h_aux, h_y, h_nz))
-    d2h = sum(t.numel() * t.element_size() for t in h_out) + 8
+    if not args.lean:
+        e2e_step()
+        ms_e2e = timed(e2e_step, max(1, min(args.steps, 3)))
+        h2d = sum(t.numel() * t.element_size() for t in (h_aux, h_y, h_nz))
+        d2h = sum(t.numel() * t.element_size() for t in h_out) + 8
 
     if rank == 0:
         peaks = {}
@@ -416,8 +430,8 @@ def run_gpu(args):
             "roofline_k1": k1,
             "kernels_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
             "kernels_calls": {k: v["calls"] for k, v in prof.items()},
-            "e2e": {"value": n_total / (ms_e2e * 1e-3), "unit": "datapoints/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
+            "e2e": ({"value": n_total / (ms_e2e * 1e-3), "unit": "datapoints/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h} if not args.lean else None),
             "gpu_launches": int(launches), "clocks": clocks.summary(),
         }
         line["max_mem_gb"] = round(torch.cuda.max_memory_allocated(dev) / 1e9, 2)

@@ -10,7 +10,8 @@ CPU fallback -- importing is cheap, the first kernel call raises if the library 
 from .svgp import (SVGP, _add_diagonal_jitter, gauss_cross_entropy, mainSVGP, mnistSVGP, productSVGP,  # noqa: F401
                    reciprocal_no_nan, spritesSVGP)
 from .step import elbo_terms, svgp_step  # noqa: F401
-from .glue import aux_data_SVGPVAE_sprites, forward_pass_SVGPVAE  # noqa: F401
+from .glue import (GraphedBallStep, aux_data_SVGPVAE_sprites, ball_svgp_terms, build_SVGPVAE_elbo_graph,  # noqa: F401
+                   forward_pass_SVGPVAE)
 from .svigp import SVIGP_Hensman, forward_pass_deep_SVIGP_Hensman  # noqa: F401
 from .graphed import GraphedElboStep  # noqa: F401
 from .predict import posterior_predict, precompute_GP_params_SVGPVAE, predict_from_precomputed  # noqa: F401

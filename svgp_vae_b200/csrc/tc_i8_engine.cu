@@ -418,17 +418,94 @@ struct ScaledI8Params {
   int64_t n_items;
 };
 
-constexpr int SCALED8_THREADS = 384;     // warp 0 TMA, warp 1 MMA, warps 4-11 epilogue (two per TMEM lane quarter)
+constexpr int SCALED8_THREADS = 384;     // warp 0 TMA, warp 1 MMA (pair: the peer's warp 1 forwards its "stage full"), warps 4-11 epilogue
 constexpr int SCALED8_EPI_WARP0 = 4;
 
+__device__ __forceinline__ void umma_i8_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {          // arrives on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {   // arrive on the barrier at the same offset in CTA `cta`
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // barrier with arrivals from the peer CTA
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+// PAIR = two CTAs of a cluster on one 256 x 128 output tile with tcgen05.mma.cta_group::2: each CTA feeds its 128 rows of K_nm
+// (A) and ITS HALF of the 128 G rows (B), the leader issues, both hold their 128 rows of the four accumulators.  Per MMA a
+// CTA's shared memory serves 4 KB of A + 2 KB of B instead of 4 + 4: the single-CTA kernel is bound by exactly that traffic
+// (20 MMAs x 8 KB + 64 KB of TMA writes per 1280 MMA-cycles = 175 B / clk against the 128 B / clk port).
+template <bool PAIR>
 __global__ void __launch_bounds__(SCALED8_THREADS, 1)
 scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapG, const ScaledI8Params P) {
+  constexpr int STAGES = PAIR ? 4 : 3;
+  constexpr int BPL = PAIR ? I8_PLANE / 2 : I8_PLANE;            // bytes of one digit plane of this CTA's part of the B tile
+  constexpr int STAGE = 4 * I8_PLANE + 4 * BPL;
+  constexpr int ROWS = PAIR ? 2 * I8_T : I8_T;                    // datapoints per item
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_T >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+  static_assert(STAGES * STAGE + 1024 + 256 <= I8_SMEM, "shared memory budget");
   extern __shared__ uint8_t smem_raw[];
-  uint32_t tmem_base;
-  const I8Smem S = i8_setup(smem_raw, 0, 8, tmem_base);
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE;
+  auto full = [&](int s) { return bars + 8u * s; };
+  auto empty = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto pfull = [&](int s) { return bars + 8u * (2 * STAGES + s); };    // leader: the peer's stage s has landed
+  const uint32_t tfull = bars + 8u * (3 * STAGES), tempty = tfull + 8u, tmem_ptr = tfull + 16u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full(s), 1); mbar_init(empty(s), 1); mbar_init(pfull(s), 1); }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, PAIR ? 16 : 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   if (warp == 0 && lane == 0) { prefetch_tmap(&mapK); prefetch_tmap(&mapG); }
+  if (warp == 1) {
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr));
+
   const int nkb = (int)((P.M + I8_KB - 1) / I8_KB);
+  const int64_t unit = PAIR ? blockIdx.x / 2 : blockIdx.x, nunits = PAIR ? gridDim.x / 2 : gridDim.x;
 
   if ((warp >> 2) == 0) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -436,42 +513,71 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
       // =============================== TMA producer ===============================================
       if (lane == 0) {
         int stage = 0; uint32_t phase = 0;
-        for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-          const int32_t row0 = (int32_t)((item / P.nct) * I8_T), col0 = (int32_t)((item % P.nct) * I8_T);
+        for (int64_t item = unit; item < P.n_items; item += nunits) {
+          const int32_t row0 = (int32_t)((item / P.nct) * ROWS + crank * I8_T);
+          const int32_t col0 = (int32_t)((item % P.nct) * I8_T + (PAIR ? crank * (I8_T / 2) : 0));
           for (int64_t s = 0; s < P.L; ++s) {
             for (int kb = 0; kb < nkb; ++kb) {
-              mbar_wait(S.empty(stage), phase ^ 1);
-              const uint32_t st = S.stage(stage);
-              mbar_expect_tx(S.full(stage), I8_NPL * I8_PLANE);
+              mbar_wait(empty(stage), phase ^ 1);
+              const uint32_t st = base + stage * STAGE;
+              mbar_expect_tx(full(stage), STAGE);
 #pragma unroll
-              for (int t = 0; t < 4; ++t) tma_load_3d(st + t * I8_PLANE, &mapK, S.full(stage), kb * I8_KB, row0, t);
+              for (int t = 0; t < 4; ++t) tma_load_3d(st + t * I8_PLANE, &mapK, full(stage), kb * I8_KB, row0, t);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) tma_load_3d(st + (4 + u) * I8_PLANE, &mapG, S.full(stage), kb * I8_KB, (int32_t)(s * P.Mc) + col0, u);
-              if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+              for (int u = 0; u < 4; ++u) tma_load_3d(st + 4 * I8_PLANE + u * BPL, &mapG, full(stage), kb * I8_KB, (int32_t)(s * P.Mc) + col0, u);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
-    } else if (warp == 1) {
+    } else if (warp == 1 && crank == 0) {
       // =============================== MMA issuer ==================================================
       int stage = 0; uint32_t phase = 0, tphase = 0;
-      for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
+      for (int64_t item = unit; item < P.n_items; item += nunits) {
         for (int64_t s = 0; s < P.L; ++s) {
-          mbar_wait(S.tmem_empty(), tphase ^ 1);
+          if (PAIR) mbar_wait_cluster(tempty, tphase ^ 1); else mbar_wait(tempty, tphase ^ 1);
           tc_fence_after();
           for (int kb = 0; kb < nkb; ++kb) {
-            mbar_wait(S.full(stage), phase);
+            mbar_wait(full(stage), phase);
+            if (PAIR) mbar_wait_cluster(pfull(stage), phase);
             tc_fence_after();
             if (lane == 0) {
-              issue_kblock(S.stage(stage), tmem_base, kb == 0);     // A = K rows, B = G rows (output columns)
-              umma_commit(S.empty(stage));
-              if (kb == nkb - 1) umma_commit(S.tmem_full());
+              const uint32_t st = base + stage * STAGE;
+              uint64_t a[4], b[4];
+#pragma unroll
+              for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + t * I8_PLANE); b[t] = i8_desc(st + 4 * I8_PLANE + t * BPL); }
+#pragma unroll
+              for (int ks = 0; ks < I8_KB / 32; ++ks) {
+                const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
+#pragma unroll
+                for (int o = 0; o < 4; ++o)
+#pragma unroll
+                  for (int t = 0; t <= o; ++t) {
+                    if (PAIR) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, t == 0 ? f : 1u);
+                    else umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, t == 0 ? f : 1u);
+                  }
+              }
+              if (PAIR) { umma_commit_cg2(empty(stage)); if (kb == nkb - 1) umma_commit_cg2(tfull); }
+              else { umma_commit(empty(stage)); if (kb == nkb - 1) umma_commit(tfull); }
             }
             __syncwarp();
-            if (++stage == I8_STAGES) { stage = 0; phase ^= 1; }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
           tphase ^= 1;
         }
+      }
+    } else if (PAIR && warp == 1) {
+      // =============================== peer: tell the leader when this CTA's stage has landed ======
+      if (lane == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t item = unit; item < P.n_items; item += nunits)
+          for (int64_t s = 0; s < P.L; ++s)
+            for (int kb = 0; kb < nkb; ++kb) {
+              mbar_wait(full(stage), phase);
+              mbar_arrive_remote(pfull(stage), 0);
+              if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
       }
     }
   } else {
@@ -480,8 +586,8 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     const int qd = warp & 3, half = (warp - SCALED8_EPI_WARP0) >> 2;       // TMEM lane quarter, column half
     uint32_t tphase = 0;
     const bool has_dots = P.dots != nullptr && P.ndot > 0;
-    for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
-      const int64_t i = (item / P.nct) * I8_T + qd * 32 + lane;
+    for (int64_t item = unit; item < P.n_items; item += nunits) {
+      const int64_t i = (item / P.nct) * ROWS + crank * I8_T + qd * 32 + lane;
       const int64_t cw0 = (item % P.nct) * I8_T + half * 64;               // first column of this warp
       const bool live = i < P.N;
       const float rs = live ? P.rscale[i] : 0.f;
@@ -494,12 +600,12 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         for (int g = 0; g < 4; ++g) {
           uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0, d2 = d0, d3 = d0;
           if (live && cw0 + g * 16 < P.ldkr) {
-            const int8_t* base = P.Kr + i * P.ldkr + cw0 + g * 16;
+            const int8_t* bp = P.Kr + i * P.ldkr + cw0 + g * 16;
             const int64_t pl = P.N * P.ldkr;
-            d0 = __ldg(reinterpret_cast<const uint4*>(base));
-            d1 = __ldg(reinterpret_cast<const uint4*>(base + pl));
-            d2 = __ldg(reinterpret_cast<const uint4*>(base + 2 * pl));
-            d3 = __ldg(reinterpret_cast<const uint4*>(base + 3 * pl));
+            d0 = __ldg(reinterpret_cast<const uint4*>(bp));
+            d1 = __ldg(reinterpret_cast<const uint4*>(bp + pl));
+            d2 = __ldg(reinterpret_cast<const uint4*>(bp + 2 * pl));
+            d3 = __ldg(reinterpret_cast<const uint4*>(bp + 3 * pl));
           }
           const uint32_t w0[4] = {d0.x, d0.y, d0.z, d0.w}, w1[4] = {d1.x, d1.y, d1.z, d1.w};
           const uint32_t w2[4] = {d2.x, d2.y, d2.z, d2.w}, w3[4] = {d3.x, d3.y, d3.z, d3.w};
@@ -518,7 +624,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         const bool want_dot = has_dots && s < P.ndot;                      // warp-uniform
         float dsum = 0.f;
         const float* gs = P.gscale + s * P.Mc;
-        mbar_wait(S.tmem_full(), tphase);
+        mbar_wait(tfull, tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 64);
 #pragma unroll
@@ -546,7 +652,9 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(S.tmem_empty());
+        if (lane == 0) {
+          if (PAIR && crank != 0) mbar_arrive_remote(tempty, 0); else mbar_arrive(tempty);
+        }
         tphase ^= 1;
         if (want_dot && live) atomicAdd(&P.dots[i * P.lddots + s], dsum * rs * rs * 16777216.f);
       }
@@ -558,19 +666,26 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
       }
     }
   }
-  i8_teardown(tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  if (PAIR) cluster_sync_all();       // nobody leaves while the peer may still signal this CTA / read its shared memory
+  if (warp == 1) {
+    tc_fence_after();
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int encode_i8(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes) {
+static int encode_i8(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, int box_rows = I8_T) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SVGP_ERR_CUDA; }
   if ((uintptr_t)base & 15) { set_error("TMA operand needs a 16-byte aligned base"); return SVGP_ERR_ARG; }
   for (int d = 0; d < rank - 1; ++d)
     if (strides_bytes[d] % 16) { set_error("TMA operand needs 16-byte pitches"); return SVGP_ERR_ARG; }
-  cuuint32_t box[4] = {(cuuint32_t)I8_KB, (cuuint32_t)I8_T, 1, 1};
+  cuuint32_t box[4] = {(cuuint32_t)I8_KB, (cuuint32_t)box_rows, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -634,7 +749,7 @@ int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const vo
   if (!kop->Kr || !kop->rscale) { set_error("tc_scaled_gemm_i8: int8 planes of K_nm missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (dots && Mc != kop->M) { set_error("tc_scaled_gemm_i8: the k-dots need square M x M matrices"); return SVGP_ERR_ARG; }
   const int64_t N = kop->N, M = kop->M;
-  CUtensorMap mapK, mapG;
+  CUtensorMap mapK, mapG, mapG64;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)kop->ldkr, (cuuint64_t)N, 4};
     const cuuint64_t strides[2] = {(cuuint64_t)kop->ldkr, (cuuint64_t)(N * kop->ldkr)};
@@ -646,21 +761,53 @@ int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const vo
     const cuuint64_t strides[2] = {(cuuint64_t)ldg, (cuuint64_t)(L * Mc * ldg)};
     int rc = encode_i8(&mapG, Gp, 3, dims, strides);
     if (rc) return rc;
+    rc = encode_i8(&mapG64, Gp, 3, dims, strides, I8_T / 2);       // CTA pairs: each CTA loads its half of the G rows
+    if (rc) return rc;
   }
   ScaledI8Params P{};
   P.N = N; P.M = M; P.L = L; P.Mc = Mc; P.rscale = kop->rscale; P.gscale = gscale; P.W = W; P.ldw = ldw;
   P.out = out; P.ldo = ldo; P.accumulate = accumulate; P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
   P.Kr = (const int8_t*)kop->Kr; P.ldkr = kop->ldkr;
   P.nct = (int)ceil_div(Mc, I8_T);
+  // CTA pairs (tcgen05.mma.cta_group::2) when there are at least as many 256-row items as clusters; SVGP_I8_PAIR=0 forces
+  // the single-CTA kernel
+  static int pair_clusters = -1;       // co-resident clusters of two CTAs (0: unavailable)
+  const char* ep = getenv("SVGP_I8_PAIR");
+  bool pair = !(ep && atoi(ep) == 0) && N >= 2 * I8_T * 4;
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  cfg.blockDim = dim3(SCALED8_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = I8_SMEM;
+  cfg.stream = st;
+  if (pair && pair_clusters < 0) {
+    if (cudaFuncSetAttribute(scaled_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3(num_sms() / 2 * 2, 1, 1);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, scaled_i8_kernel<true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    pair_clusters = n;
+  }
+  if (pair && pair_clusters > 0) {
+    P.n_items = ceil_div(N, 2 * I8_T) * P.nct;
+    int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+    if (cudaLaunchKernelEx(&cfg, scaled_i8_kernel<true>, mapK, mapG64, P) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 pair)");
+    return check_launch("svgp_scaled_gemm(i8 pair)");
+  }
   P.n_items = ceil_div(N, I8_T) * P.nct;
   static bool attr_done = false;
   if (!attr_done) {
-    if (cudaFuncSetAttribute(scaled_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
+    if (cudaFuncSetAttribute(scaled_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
     attr_done = true;
   }
   int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
   if (grid <= 0) return SVGP_OK;
-  scaled_i8_kernel<<<(unsigned)grid, SCALED8_THREADS, I8_SMEM, st>>>(mapK, mapG, P);
+  scaled_i8_kernel<false><<<(unsigned)grid, SCALED8_THREADS, I8_SMEM, st>>>(mapK, mapG, P);
   return check_launch("svgp_scaled_gemm(i8)");
 }
 

@@ -84,3 +84,83 @@ def forward_pass_SVGPVAE(data_batch, beta, vae, svgp, C_ma, lagrange_mult, alpha
         mean_vectors = torch.tensor(1.0)
     return (elbo, recon_loss, KL_term, inside_elbo, ce_term, p_m, p_v, qnet_mu, qnet_var, recon_images, inside_elbo_recon,
             inside_elbo_kl, latent_samples, C_ma, lagrange_mult, mean_vectors)
+
+
+def ball_svgp_terms(svgp_x, svgp_y, qnet_mu, qnet_var):
+    """The SVGP part of ``build_SVGPVAE_elbo_graph`` (SVGPVAE_model.py:663-664, 674-697): both latent objects of the
+    moving-ball model on the time grid 1..tmax.  qnet_mu / qnet_var (batch, tmax, 2) ->
+    dict(full_p_mu, full_p_var (batch, tmax, 2), inside_elbo_recon, inside_elbo_kl, inside_elbo, ce_term, KL_term (batch,),
+         p_v_x, p_v_y (batch, tmax, tmax) full posterior covariances, mu_hat_*, A_hat_*)."""
+    from .svgp import gauss_cross_entropy
+    batch, tmax, _ = qnet_mu.shape
+    T = torch.arange(tmax, dtype=qnet_mu.dtype, device=qnet_mu.device) + 1.0            # :663  (1..tmax, not 0..tmax-1)
+    batch_T = T.reshape(1, tmax).repeat(batch, 1)                                       # :664
+    p_m_x, p_v_x, mu_hat_x, A_hat_x = svgp_x.approximate_posterior_params(batch_T, y=qnet_mu[:, :, 0], noise=qnet_var[:, :, 0])   # :674
+    p_m_y, p_v_y, mu_hat_y, A_hat_y = svgp_y.approximate_posterior_params(batch_T, y=qnet_mu[:, :, 1], noise=qnet_var[:, :, 1])   # :676
+    rec_x, kl_x = svgp_x.variational_loss(batch_T, qnet_mu[:, :, 0], qnet_var[:, :, 0], mu_hat=mu_hat_x, A_hat=A_hat_x)           # :680
+    rec_y, kl_y = svgp_y.variational_loss(batch_T, qnet_mu[:, :, 1], qnet_var[:, :, 1], mu_hat=mu_hat_y, A_hat=A_hat_y)           # :682
+    inside_elbo_recon = rec_x + rec_y                                                   # :684
+    inside_elbo_kl = kl_x + kl_y
+    inside_elbo = inside_elbo_recon - inside_elbo_kl                                    # :686 (no b / N_train factor: per-video GPs)
+    full_p_mu = torch.stack([p_m_x, p_m_y], dim=2)                                      # :692
+    full_p_var = torch.stack([torch.diagonal(p_v_x, dim1=-2, dim2=-1), torch.diagonal(p_v_y, dim1=-2, dim2=-1)], dim=2)       # :693
+    ce_term = -gauss_cross_entropy(full_p_mu, full_p_var, qnet_mu, qnet_var).sum((1, 2))   # :696-697 (note the sign)
+    KL_term = ce_term + inside_elbo                                                     # :709
+    return dict(full_p_mu=full_p_mu, full_p_var=full_p_var, inside_elbo_recon=inside_elbo_recon, inside_elbo_kl=inside_elbo_kl,
+                inside_elbo=inside_elbo, ce_term=ce_term, KL_term=KL_term, p_v_x=p_v_x, p_v_y=p_v_y, mu_hat_x=mu_hat_x,
+                A_hat_x=A_hat_x, mu_hat_y=mu_hat_y, A_hat_y=A_hat_y)
+
+
+def build_SVGPVAE_elbo_graph(vid_batch, beta, svgp_x, svgp_y, clipping_qs=False, encoder=None, decoder=None, epsilon=None):
+    """SVGPVAE_model.py:638-716 for the moving-ball model.  The reference builds its MLP encoder / decoder inside
+    (VAE_utils.build_MLP_inference_graph / build_MLP_decoder_graph, out of the graft); here they are the caller's modules:
+    ``encoder(vid_batch) -> (qnet_mu, qnet_var)`` (batch, tmax, 2) each, ``decoder(latent_samples) -> logits``
+    (batch, tmax, px, py).  ``epsilon`` (batch, tmax, 2) fixes the reparametrisation noise of :700.
+    Returns the reference's tuple (the trailing ``globals()`` entry is None)."""
+    qnet_mu, qnet_var = encoder(vid_batch)                                              # :667
+    if clipping_qs:
+        qnet_var = torch.clamp(qnet_var, 1e-6, 1e3)                                     # :671
+    t = ball_svgp_terms(svgp_x, svgp_y, qnet_mu, qnet_var)
+    full_p_mu, full_p_var = t["full_p_mu"], t["full_p_var"]
+    if epsilon is None:
+        epsilon = torch.randn_like(full_p_mu)                                           # :700
+    latent_samples = full_p_mu + epsilon * torch.sqrt(torch.clamp(full_p_var, 1e-4, 1000))   # :701
+    logits = decoder(latent_samples)                                                    # :704
+    pred_vid = torch.sigmoid(logits)
+    recon_term = -torch.nn.functional.binary_cross_entropy_with_logits(logits, vid_batch, reduction="none").sum((1, 2, 3))   # :706-707
+    CPH_elbo = recon_term + beta * t["KL_term"]                                         # :710
+    return (CPH_elbo, recon_term, t["KL_term"], t["inside_elbo"], t["ce_term"], full_p_mu, full_p_var, qnet_mu, qnet_var, pred_vid,
+            svgp_x.l_GP, svgp_y.l_GP, t["inside_elbo_recon"], t["inside_elbo_kl"], svgp_x.inducing_index_points,
+            svgp_y.inducing_index_points, t["p_v_x"].mean(0), t["p_v_y"].mean(0), None)
+
+
+class GraphedBallStep:
+    """``ball_svgp_terms`` captured as CUDA graphs (forward and backward; the encoder / decoder run between them as ordinary
+    PyTorch).  The ball configuration is ~500 launches of a few microseconds: launch-bound, so graphs are the lever.
+    Call with (qnet_mu, qnet_var) of the captured shape -> (full_p_mu, full_p_var, KL_term)."""
+
+    def __init__(self, svgp_x, svgp_y, batch, tmax, device="cuda", dtype=torch.float32):
+        self.svgp_x, self.svgp_y = svgp_x, svgp_y
+        mu = torch.zeros(batch, tmax, 2, device=device, dtype=dtype, requires_grad=True)
+        var = torch.ones(batch, tmax, 2, device=device, dtype=dtype, requires_grad=True)
+
+        class _M(torch.nn.Module):
+            def __init__(self, sx, sy):
+                super().__init__()
+                self.sx, self.sy = sx, sy
+
+            def forward(self, m, v):
+                t = ball_svgp_terms(self.sx, self.sy, m, v)
+                return t["full_p_mu"], t["full_p_var"], t["KL_term"]
+        from . import ops
+        ops.pd_flag(mu.device)                      # static device word the captured Cholesky calls report a bad pivot into
+        self._fn = torch.cuda.make_graphed_callables(_M(svgp_x, svgp_y), (mu, var), num_warmup_iters=3, allow_unused_input=True)
+        self._device = mu.device
+
+    def __call__(self, qnet_mu, qnet_var):
+        return self._fn(qnet_mu, qnet_var)
+
+    def check(self):
+        """Raise ops.NotPositiveDefinite if any Cholesky factorisation of a replayed step met a non-positive pivot."""
+        from . import ops
+        ops.pd_flag_check(self._device)

@@ -71,9 +71,35 @@ class NotPositiveDefinite(RuntimeError):
     """Raised when a Cholesky pivot is <= 0 (the reference raises InvalidArgumentError at sess.run)."""
 
 
+_PD_FLAGS = {}
+
+
+def pd_flag(device):
+    """Static device word (int32[1]) into which Cholesky calls captured in a CUDA graph write their worst status: no host
+    synchronisation is possible under capture, so the bad pivot is recorded on the device and read later (pd_flag_check).
+    Create it BEFORE capturing."""
+    key = torch.device(device)
+    if key not in _PD_FLAGS:
+        _PD_FLAGS[key] = torch.zeros(1, dtype=torch.int32, device=key)
+    return _PD_FLAGS[key]
+
+
+def pd_flag_check(device):
+    """Read (and clear) the device word: raises NotPositiveDefinite if a replayed graph met a non-positive pivot."""
+    f = _PD_FLAGS.get(torch.device(device))
+    if f is not None and int(f.item()) != 0:
+        piv = int(f.item()) - 1
+        f.zero_()
+        raise NotPositiveDefinite("a CUDA-graph replay met a non-positive Cholesky pivot (column %d)" % piv)
+
+
 def _check_status(status, what):
     if status.is_cuda and torch.cuda.is_current_stream_capturing():
-        return                      # no host synchronisation inside a CUDA graph (graphed.py): the caller checks eagerly
+        # no host synchronisation inside a CUDA graph (graphed.py): record the worst status in the static device word
+        f = _PD_FLAGS.get(status.device)
+        if f is not None:
+            f.copy_(torch.maximum(f, status.max().reshape(1).to(torch.int32)))
+        return
     bad = torch.nonzero(status)
     if bad.numel():
         b = int(bad[0, 0])

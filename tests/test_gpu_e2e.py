@@ -384,3 +384,29 @@ def test_sweep_ragged_shapes_on_the_tensor_core_path(cuda_backend):
     _cmp_scalars(r1, g0)
     for name, a, b in zip(["dy", "dnoise", "dZ", "dhyp"], gr0, g1):
         assert rel_err(b, a) < TOL, name
+
+
+def test_ball_glue_graphed_matches_eager(cuda_backend):
+    """glue.GraphedBallStep (forward and backward of ball_svgp_terms as CUDA graphs) == the eager product code; the
+    captured Cholesky calls report into the static device word instead of being skipped."""
+    cfg = configs.ball_inputs()
+    sx, sy = pkg.SVGP(name="x", **cfg["ctor"]).cuda(), pkg.SVGP(name="y", **cfg["ctor"]).cuda()
+    y, nz = cfg["y"].cuda().requires_grad_(True), cfg["noise"].cuda().requires_grad_(True)
+    t = pkg.ball_svgp_terms(sx, sy, y, nz)
+    gm, gv = refs.upstream((35, 30, 2), "cuda")
+    J = t["KL_term"].sum() + (gm.float() * t["full_p_mu"]).sum() + (gv.float() * t["full_p_var"]).sum()
+    g0 = torch.autograd.grad(J, [y, nz])
+    step = pkg.GraphedBallStep(sx, sy, 35, 30)
+    for _ in range(2):                                   # replay twice: static buffers are reused correctly
+        y2, n2 = cfg["y"].cuda().requires_grad_(True), cfg["noise"].cuda().requires_grad_(True)
+        pm, pv, kl = step(y2, n2)
+        J2 = kl.sum() + (gm.float() * pm).sum() + (gv.float() * pv).sum()
+        g1 = torch.autograd.grad(J2, [y2, n2])
+        assert rel_err(pm, t["full_p_mu"]) < 1e-6 and rel_err(pv, t["full_p_var"]) < 1e-6 and rel_err(kl, t["KL_term"]) < 1e-6
+        assert rel_err(g1[0], g0[0]) < 1e-5 and rel_err(g1[1], g0[1]) < 1e-5
+    step.check()                                         # no bad pivot recorded
+    # a non-positive-definite replay is reported, not silently NaN
+    bad = torch.full_like(n2, -1.0)
+    step(y2.detach(), bad)
+    with pytest.raises(pkg.ops.NotPositiveDefinite):
+        step.check()

@@ -301,3 +301,30 @@ def test_graphed_step_rejects_what_it_cannot_capture(oracle_backend):
     s2 = pkg.mnistSVGP(name="u", **cfg["ctor"])
     with pytest.raises(ValueError):
         pkg.GraphedElboStep(s2, cfg["aux"], cfg["y"], cfg["noise"], group=object())
+
+
+def test_ball_glue_product_code_against_reference_source(oracle_backend):
+    """glue.ball_svgp_terms / build_SVGPVAE_elbo_graph (SVGPVAE_model.py:638-716) vs the reference source's own outputs for
+    the ball configuration (tests/golden/make_reference_golden.py::ball_case)."""
+    gold = np.load(os.path.join(GOLDEN, "reference_golden.npz"))
+    cfg = configs.ball_inputs()
+    sx, sy = pkg.SVGP(name="x", **cfg["ctor"]), pkg.SVGP(name="y", **cfg["ctor"])
+    y, nz = cfg["y"].clone().requires_grad_(True), cfg["noise"].clone().requires_grad_(True)
+    t = pkg.ball_svgp_terms(sx, sy, y, nz)
+    g = lambda k: torch.from_numpy(gold["ball/" + k])
+    assert rel_err(t["full_p_mu"], g("p_m")) < TOL and rel_err(t["full_p_var"], g("p_v")) < TOL
+    assert rel_err(t["p_v_x"], g("B_x")) < TOL and rel_err(t["mu_hat_x"], g("mu_hat_x")) < TOL and rel_err(t["A_hat_x"], g("A_hat_x")) < TOL
+    assert rel_err(t["KL_term"], g("KL_term")) < TOL and rel_err(t["inside_elbo_recon"], g("recon")) < TOL
+    assert rel_err(t["inside_elbo_kl"], g("kl")) < TOL
+    gm, gv = refs.upstream((35, 30, 2))
+    J = t["KL_term"].sum() + (gm.float() * t["full_p_mu"]).sum() + (gv.float() * t["full_p_var"]).sum()
+    gy, gn = torch.autograd.grad(J, [y, nz])
+    assert rel_err(gy, g("grad_y")) < TOL and rel_err(gn, g("grad_noise")) < TOL
+    # the full call-site function with the caller's encoder / decoder
+    vid = (torch.rand(35, 30, 8, 8, generator=torch.Generator().manual_seed(1)) > 0.5).float()
+    enc = lambda v: (cfg["y"], cfg["noise"])
+    dec = lambda z: z.sum(-1)[:, :, None, None] * torch.linspace(-1, 1, 64).reshape(1, 1, 8, 8)
+    eps = torch.randn(35, 30, 2, generator=torch.Generator().manual_seed(2))
+    out = pkg.build_SVGPVAE_elbo_graph(vid, 0.5, sx, sy, clipping_qs=True, encoder=enc, decoder=dec, epsilon=eps)
+    assert len(out) == 19 and out[0].shape == (35,) and out[9].shape == vid.shape and out[16].shape == (30, 30)
+    assert rel_err(out[0], out[1] + 0.5 * out[2]) < 1e-6 and rel_err(out[2], g("KL_term")) < TOL
