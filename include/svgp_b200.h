@@ -249,6 +249,22 @@ int svgp_predictive_fwd(const float* kappa, const float* h, float* q1_pv, const 
                         int64_t L, int clip, float clip_lo, float clip_hi, double* clipsum,
                         unsigned char* clipmask, void* stream);
 
+/* Backward of the row terms, fused (one pass over the N x L tensors each).
+ * pre  (before the adjoint SYRK): G_q1 = dObjective/dq1 (g_pv; on clipped entries 0.5 gce p, SVGPVAE_model.py:891-892),
+ *      the stacked row weights of the adjoint products Wst = [p | 2 G_q1] and PYst = [p y | g_pm] (N x 2L each),
+ *      G_p_clip = -0.5 gce (pv - pv_raw) when clipping, G_kappa[i] = sum_l G_q1.  clipmask == NULL: no clip branch
+ *      (pv, kappa, h, q1raw, gce, G_p_clip unused); g_pv may be NULL (zero upstream).
+ * post (after the adjoint products): G_y, G_noise (through p = reciprocal_no_nan(noise) and log noise) and
+ *      G_kappa[i] += sum_l p gs0 from kGk = k^T (dA + dA^T) k, G_py = K_nm dV and gsums (3 x L, double) = the adjoints
+ *      of the three row sums of svgp_rowstats_fwd.
+ * replaces: tf.gradients through SVGPVAE_model.py:282-299, :332-337 and utils.py:498-502 (row-local part).            */
+int svgp_rowterms_bwd_pre(const float* g_pv, const float* g_pm, const float* p, const float* y, const unsigned char* clipmask,
+                          const float* pv, const float* kappa, const float* h, const float* q1raw, const float* gce, int64_t N,
+                          int64_t L, float* G_q1, float* Wst, float* PYst, float* G_p_clip, float* G_kappa, void* stream);
+int svgp_rowterms_bwd_post(const float* y, const float* noise, const float* p, const float* kappa, const float* kGk,
+                           const float* G_py, const double* gsums, const float* G_p_clip, int64_t N, int64_t L, float* G_y,
+                           float* G_noise, float* G_kappa, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

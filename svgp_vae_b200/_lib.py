@@ -66,6 +66,8 @@ SIGNATURES = {
                       c_int64, c_double, _P, c_int64, c_int64, c_int64, _P],
     "svgp_rowstats_fwd": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_predictive_fwd": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P],
+    "svgp_rowterms_bwd_pre": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P],
+    "svgp_rowterms_bwd_post": [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P],
 }
 _RESTYPE = {"svgp_last_error": c_char_p, "svgp_syrk_ws_floats": c_int64, "svgp_i8_ldkr": c_int64, "svgp_i8_nblk": c_int64}
 

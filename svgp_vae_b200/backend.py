@@ -514,6 +514,34 @@ class CudaBackend:
         return pv, clipsum, mask
 
 
+    def rowterms_bwd_pre(self, g_pv, g_pm, p, y, clip=None):
+        """-> G_q1 (N, L), Wst = [p | 2 G_q1], PYst = [p y | g_pm] (N, 2L), G_p_clip (N, L) or None, G_kappa (N,).
+        clip = (mask uint8, pv, kappa, h, q1raw, gce (L,) fp32) on the SPRITES clip branch."""
+        g_pm, p, y = _f32c(g_pm), _f32c(p), _f32c(y)
+        N, L = y.shape
+        dev = y.device
+        G_q1 = torch.empty((N, L), device=dev, dtype=torch.float32)
+        Wst = torch.empty((N, 2 * L), device=dev, dtype=torch.float32)
+        PYst = torch.empty((N, 2 * L), device=dev, dtype=torch.float32)
+        G_kappa = torch.empty(N, device=dev, dtype=torch.float32)
+        G_p_clip = torch.empty((N, L), device=dev, dtype=torch.float32) if clip else None
+        mask, pv, kappa, h, q1raw, gce = clip if clip else (None,) * 6
+        _call("svgp_rowterms_bwd_pre", _ptr(None if g_pv is None else _f32c(g_pv)), _ptr(g_pm), _ptr(p), _ptr(y), _ptr(mask),
+              _ptr(pv), _ptr(kappa), _ptr(h), _ptr(q1raw), _ptr(gce), N, L, _ptr(G_q1), _ptr(Wst), _ptr(PYst), _ptr(G_p_clip),
+              _ptr(G_kappa), _stream())
+        self.launches += 1
+        return G_q1, Wst, PYst, G_p_clip, G_kappa
+
+    def rowterms_bwd_post(self, y, noise, p, kappa, kGk, G_py, gsums, G_p_clip, G_kappa):
+        """-> G_y, G_noise (N, L); G_kappa (N,) is updated in place."""
+        N, L = y.shape
+        G_y, G_noise = torch.empty_like(y), torch.empty_like(y)
+        _call("svgp_rowterms_bwd_post", _ptr(_f32c(y)), _ptr(_f32c(noise)), _ptr(_f32c(p)), _ptr(_f32c(kappa)), _ptr(_f32c(kGk)),
+              _ptr(_f32c(G_py)), _ptr(_f64c(gsums)), _ptr(G_p_clip), N, L, _ptr(G_y), _ptr(G_noise), _ptr(G_kappa), _stream())
+        self.launches += 1
+        return G_y, G_noise, G_kappa
+
+
 _BACKEND = None
 
 

@@ -88,6 +88,69 @@ __global__ void __launch_bounds__(RT_THREADS) predictive_kernel(const float* __r
   }
 }
 
+// ---- backward of the row terms (pass C / pass D of step.py), one warp per datapoint, lanes over the channels ----------
+// pre: adjoints of the predictive moments -> the SYRK weights G_q1, the stacked row weights [p | 2 G_q1] and [p y | g_pm]
+// of pass D (written side by side: no concatenation afterwards), the clip correction of d/dp, and sum_l G_q1 (= d/d kappa).
+__global__ void __launch_bounds__(RT_THREADS) rowterms_bwd_pre_kernel(
+    const float* __restrict__ g_pv, const float* __restrict__ g_pm, const float* __restrict__ p, const float* __restrict__ y,
+    const unsigned char* __restrict__ mask, const float* __restrict__ pv, const float* __restrict__ kappa, const float* __restrict__ h,
+    const float* __restrict__ q1raw, const float* __restrict__ gce, int64_t N, int64_t L, float* __restrict__ G_q1,
+    float* __restrict__ Wst, float* __restrict__ PYst, float* __restrict__ G_p_clip, float* __restrict__ G_kappa) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < N; i += nwarp) {
+    float ks = 0.f;
+    const float kh = mask ? kappa[i] - h[i] : 0.f;
+    for (int64_t l = lane; l < L; l += 32) {
+      const int64_t o = i * L + l;
+      const float pp = p[o];
+      float gq = g_pv ? g_pv[o] : 0.f;
+      if (mask) {
+        // d/d pv_raw: unclipped entries pass g_pv; clipped ones only see the clip correction of the collapsed CE sum
+        const float gc = gce[l];
+        if (mask[o]) gq = 0.5f * gc * pp;
+        G_p_clip[o] = -0.5f * gc * (pv[o] - (kh + q1raw[o]));
+      }
+      G_q1[o] = gq;
+      Wst[i * 2 * L + l] = pp;
+      Wst[i * 2 * L + L + l] = 2.0f * gq;
+      PYst[i * 2 * L + l] = pp * y[o];
+      PYst[i * 2 * L + L + l] = g_pm[o];
+      ks += gq;
+    }
+    ks = warp_sum(ks);
+    if (lane == 0) G_kappa[i] = ks;
+  }
+}
+// post: dObjective/dy, dObjective/dnoise and the rest of d/d kappa from the products of pass D
+//   G_p     = kGk / 2 + y G_py + kappa gs0 + y^2 gs1 (+ clip correction)
+//   G_y     = p G_py + 2 p y gs1
+//   G_noise = -p^2 G_p (0 where noise == 0: reciprocal_no_nan) + gs2 / noise
+//   G_kappa += sum_l p gs0
+__global__ void __launch_bounds__(RT_THREADS) rowterms_bwd_post_kernel(
+    const float* __restrict__ y, const float* __restrict__ noise, const float* __restrict__ p, const float* __restrict__ kappa,
+    const float* __restrict__ kGk, const float* __restrict__ G_py, const double* __restrict__ gs, const float* __restrict__ G_p_clip,
+    int64_t N, int64_t L, float* __restrict__ G_y, float* __restrict__ G_noise, float* __restrict__ G_kappa) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t i = warp; i < N; i += nwarp) {
+    const float kap = kappa[i];
+    float ks = 0.f;
+    for (int64_t l = lane; l < L; l += 32) {
+      const int64_t o = i * L + l;
+      const float g0 = (float)gs[l], g1 = (float)gs[L + l], g2 = (float)gs[2 * L + l];
+      const float pp = p[o], yy = y[o], nn = noise[o], gpy = G_py[o];
+      float gp = 0.5f * kGk[o] + yy * gpy + kap * g0 + yy * yy * g1;
+      if (G_p_clip) gp += G_p_clip[o];
+      G_y[o] = pp * gpy + 2.0f * pp * yy * g1;
+      G_noise[o] = (nn != 0.f) ? (-pp * pp * gp + g2 / nn) : g2;
+      ks += pp * g0;
+    }
+    ks = warp_sum(ks);
+    if (lane == 0) G_kappa[i] += ks;
+  }
+}
+
 }  // namespace svgp
 
 using namespace svgp;
@@ -122,6 +185,33 @@ int svgp_predictive_fwd(const float* kappa, const float* h, float* q1_pv, const 
   predictive_kernel<<<grid, RT_THREADS, 0, (cudaStream_t)stream>>>(kappa, h, q1_pv, p, N, L, clip, clip_lo, clip_hi, clipsum,
                                                                    clipmask);
   return check_launch("svgp_predictive_fwd");
+}
+
+static unsigned rows_grid(int64_t N) {
+  int64_t g = ceil_div(N, RT_THREADS / 32);
+  if (g > 148 * 16) g = 148 * 16;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+int svgp_rowterms_bwd_pre(const float* g_pv, const float* g_pm, const float* p, const float* y, const unsigned char* clipmask,
+                          const float* pv, const float* kappa, const float* h, const float* q1raw, const float* gce, int64_t N,
+                          int64_t L, float* G_q1, float* Wst, float* PYst, float* G_p_clip, float* G_kappa, void* stream) {
+  SVGP_REQUIRE(g_pm && p && y && G_q1 && Wst && PYst && G_kappa && N >= 0 && L >= 1, "bad argument");
+  SVGP_REQUIRE(!clipmask || (pv && kappa && h && q1raw && gce && G_p_clip), "the clip branch needs pv, kappa, h, q1raw, gce and G_p_clip");
+  if (N == 0) return SVGP_OK;
+  rowterms_bwd_pre_kernel<<<rows_grid(N), RT_THREADS, 0, (cudaStream_t)stream>>>(g_pv, g_pm, p, y, clipmask, pv, kappa, h, q1raw, gce, N, L,
+                                                                                 G_q1, Wst, PYst, G_p_clip, G_kappa);
+  return check_launch("svgp_rowterms_bwd_pre");
+}
+
+int svgp_rowterms_bwd_post(const float* y, const float* noise, const float* p, const float* kappa, const float* kGk,
+                           const float* G_py, const double* gsums, const float* G_p_clip, int64_t N, int64_t L, float* G_y,
+                           float* G_noise, float* G_kappa, void* stream) {
+  SVGP_REQUIRE(y && noise && p && kappa && kGk && G_py && gsums && G_y && G_noise && G_kappa && N >= 0 && L >= 1, "bad argument");
+  if (N == 0) return SVGP_OK;
+  rowterms_bwd_post_kernel<<<rows_grid(N), RT_THREADS, 0, (cudaStream_t)stream>>>(y, noise, p, kappa, kGk, G_py, gsums, G_p_clip, N, L,
+                                                                                  G_y, G_noise, G_kappa);
+  return check_launch("svgp_rowterms_bwd_post");
 }
 
 }  // extern "C"

@@ -306,25 +306,17 @@ class _SVGPStep(torch.autograd.Function):
         g_kl = zeros_L if g_kl is None else g_kl.double()
         g_ce = zeros_L if g_ce is None else g_ce.double()
         g_pm = torch.zeros_like(y) if g_pm is None else g_pm.float().contiguous()
-        g_pv = torch.zeros_like(y) if g_pv is None else g_pv.float()
+        g_pv = torch.zeros_like(y) if g_pv is None else g_pv.float().contiguous()
         # scalar adjoints are per-rank shares of the same global scalars: total = sum over ranks
         sc = torch.stack([g_recon, g_kl, g_ce])
         _allreduce(sc, group)
         g_recon, g_kl, g_ce = sc[0], sc[1], sc[2]
 
         # ---- pass C: row-local adjoints of the predictive moments --------------------------------
-        gce32 = g_ce.float()
-        if clip:
-            m = mask.bool()
-            pv_raw = kappa[:, None] - h[:, None] + q1raw
-            # d/d pv_raw: unclipped rows pass g_pv; clipped rows only see the clip correction of the collapsed CE sum
-            G_q1 = torch.where(m, 0.5 * gce32[None, :] * p, g_pv)
-            G_p_clip = -0.5 * gce32[None, :] * (pv - pv_raw)
-        else:
-            G_q1 = g_pv
-            G_p_clip = None
-        G_q1 = G_q1.contiguous()
-        G_kappa = G_q1.sum(1)                                    # d/d kappa_i  (and -d/d h_i)
+        # one fused pass (svgp_rowterms_bwd_pre): dObjective/dq1 (clipped entries only see the clip correction of the
+        # collapsed CE sum), the stacked row weights [p | 2 dq1] and [p y | g_pm] of pass D, sum_l dq1 = d/d kappa_i (= -d/d h_i)
+        clip_args = (mask, pv, kappa, h, q1raw, g_ce.float().contiguous()) if clip else None
+        G_q1, Wstack, PYstack, G_p_clip, G_kappa = be.rowterms_bwd_pre(g_pv if g_pv is not None else None, g_pm, p, y, clip_args)
         G_S = be.syrk(kop, G_q1, chunk_rows=cfg.get("chunk_rows", 0))
         G_w = be.gemm_tn(kop, g_pm)
         for t in (G_S, G_w):
@@ -444,27 +436,17 @@ class _SVGPStep(torch.autograd.Function):
             for l0 in range(0, L, lc):
                 put(S[l0:l0 + lc] - Kinv, L + l0)
             Gstack = GA if use_i8 else (Planes(hi, lo, inv) if kop.tc else G64)
-        Wstack = torch.cat([p, 2.0 * G_q1], dim=1).contiguous()
         if isinstance(Gstack, PlanesI8):
             G_K, kGk = be.scaled_gemm_i8(kop, Wstack, Gstack, ndot=L)
         else:
             G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
         del Wstack, Gstack
-        py = p * y
         # rank-2L part of dK_nm in one pass over it: [p*y | g_pm] (N, 2L) @ [dV ; w] (2L, M)   (via v_l and via p_m)
-        be.gemm_f32(torch.cat([py, g_pm], dim=1), torch.cat([gV.float(), w.float()], dim=0).contiguous(), out=G_K)
-        # dp, dy, dnoise
-        G_p = 0.5 * kGk                                                          # k^T dA k
+        be.gemm_f32(PYstack, torch.cat([gV.float(), w.float()], dim=0).contiguous(), out=G_K)
+        del PYstack
+        # dy, dnoise and the rest of d/d kappa, fused (svgp_rowterms_bwd_post): kGk / 2 = k^T dA k
         G_py = be.gemm_nn(kop, gV.float().contiguous())
-        gs = gsums.float()
-        G_p = G_p + y * G_py + kappa[:, None] * gs[0][None, :] + (y * y) * gs[1][None, :]
-        if G_p_clip is not None:
-            G_p = G_p + G_p_clip
-        G_y = p * G_py + 2.0 * py * gs[1][None, :]
-        nz = noise != 0
-        safe = torch.where(nz, noise, torch.ones_like(noise))
-        G_noise = torch.where(nz, -p * p * G_p, torch.zeros_like(p)) + gs[2][None, :] / safe
-        G_kappa = G_kappa + (p * gs[0][None, :]).sum(1)
+        G_y, G_noise, G_kappa = be.rowterms_bwd_post(y, noise, p, kappa, kGk, G_py, gsums.contiguous(), G_p_clip, G_kappa)
 
         # ---- K1 adjoint ----------------------------------------------------------------------------
         need_x = ctx.needs_input_grad[0]

@@ -158,3 +158,26 @@ class OracleBackend:
         mask = (pv != raw).to(torch.uint8)
         clipsum = (p.to(F64) * (pv.to(F64) - raw.to(F64))).sum(0)
         return pv, clipsum, mask
+
+    def rowterms_bwd_pre(self, g_pv, g_pm, p, y, clip=None):
+        G_q1 = torch.zeros_like(y) if g_pv is None else g_pv.clone()
+        G_p_clip = None
+        if clip:
+            mask, pv, kappa, h, q1raw, gce = clip
+            m = mask.bool()
+            pv_raw = kappa[:, None] - h[:, None] + q1raw
+            G_q1 = torch.where(m, 0.5 * gce[None, :] * p, G_q1)
+            G_p_clip = -0.5 * gce[None, :] * (pv - pv_raw)
+        return (G_q1.contiguous(), torch.cat([p, 2.0 * G_q1], 1).contiguous(), torch.cat([p * y, g_pm], 1).contiguous(), G_p_clip,
+                G_q1.sum(1))
+
+    def rowterms_bwd_post(self, y, noise, p, kappa, kGk, G_py, gsums, G_p_clip, G_kappa):
+        gs = gsums.float()
+        G_p = 0.5 * kGk + y * G_py + kappa[:, None] * gs[0][None, :] + (y * y) * gs[1][None, :]
+        if G_p_clip is not None:
+            G_p = G_p + G_p_clip
+        G_y = p * G_py + 2.0 * p * y * gs[1][None, :]
+        nz = noise != 0
+        safe = torch.where(nz, noise, torch.ones_like(noise))
+        G_noise = torch.where(nz, -p * p * G_p, torch.zeros_like(p)) + gs[2][None, :] / safe
+        return G_y, G_noise, G_kappa + (p * gs[0][None, :]).sum(1)
