@@ -6,12 +6,13 @@
 
 One step = forward (p_m, p_v, inside_elbo_recon/kl, ce_term) + backward of
 J = KL_term + <g_m, p_m> + <g_v, p_v> to y, noise, inducing points and kernel hypers, on the SWEEP
-workload of SURVEY 8(d): N = 1e6 datapoints per GPU (weak scaling), M = 1024, L = 64, product-SE kernel
-d = 4 + 4, jitter 1e-2.  Prints ONE JSON line (rank 0).  `value` is device-resident throughput; `e2e`
-includes the pinned-host -> device copy of (aux, y, noise) and the device -> host read of p_m, p_v, dy,
-dnoise and the scalars every step.  roofline: tensor-core bound, F_alg = 9 L M^2 per datapoint, e = 3
-FP16 MMAs per algorithmic MAC (3 x FP16 split emulating fp32 products); peak = the driver-measured
-sustained bf16/fp16 dense GEMM rate of MEASURED_PEAKS.json (an fp16 cuBLAS GEMM is also timed in-run).
+workload of SURVEY 8(d): N = 1e6 datapoints per GPU (weak scaling; --strong splits N over the GPUs), M = 1024,
+L = 64, product-SE kernel d = 4 + 4, jitter 1e-2.  Prints ONE JSON line (rank 0).  `value` is device-resident
+throughput; `e2e` includes the pinned-host -> device copy of (aux, y, noise) and the device -> host read of
+p_m, p_v, dy, dnoise and the scalars every step.  roofline: tensor-core bound; the integer tensor-core path issues
+10 tcgen05 kind::i8 MMAs per algorithmic MAC at twice the bf16 rate (= 5 bf16-equivalents; the fp16-split row quads
+issue 3); peak = the driver-measured sustained bf16/fp16 dense GEMM rate of MEASURED_PEAKS.json (an fp16 cuBLAS GEMM
+is also timed in-run).  --impl reference: the CPU restatement of the reference path on the host cores.
 """
 import argparse
 import json

@@ -141,6 +141,44 @@ __device__ __forceinline__ void i8_teardown(uint32_t tmem_base) {
   }
 }
 
+__device__ __forceinline__ void umma_i8_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {          // arrives on `bar` (same offset) in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {   // arrive on the barrier at the same offset in CTA `cta`
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(bar), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // barrier with arrivals from the peer CTA
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
 // =============================================================================================================
 // SYRK   A_l[a, b] += sum_n (w[n, l] K[n, a]) K[n, b]       (lower-triangle tiles; double atomics into A)
 // =============================================================================================================
@@ -398,6 +436,255 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
   i8_teardown(tmem_base);
 }
 
+// ---- the same SYRK on CTA pairs (tcgen05.mma.cta_group::2) ---------------------------------------------------------
+// The single-CTA kernel is bound by its operand transform (8192 elements x ~20 instructions per 1280 MMA-cycles).  A pair
+// works on a 256 x 128 tile: every CTA feeds its 128 RAW rows a (A operand, untouched TMA planes) and ITS 64 rows b of the
+// WEIGHTED operand (B operand): half the transform work, half the B traffic per CTA.  The leader issues; the peer's warp 1
+// forwards "my A has landed and my B half is transformed" to the leader's barrier.
+struct SyrkPairTiles {              // tiles (ta: 256 rows, tb: 128 columns) touching the lower triangle: tb <= 2 ta + 1
+  __host__ __device__ static int count(int64_t M) {
+    const int T2 = (int)((M + 255) / 256), Tb = (int)((M + 127) / 128);
+    int c = 0;
+    for (int ta = 0; ta < T2; ++ta) c += (2 * ta + 2 < Tb ? 2 * ta + 2 : Tb);
+    return c;
+  }
+  __device__ static void decode(int idx, int64_t M, int& ta_out, int& tb_out) {
+    const int T2 = (int)((M + 255) / 256), Tb = (int)((M + 127) / 128);
+    int c = 0;
+    for (int ta = 0; ta < T2; ++ta) {
+      const int n = (2 * ta + 2 < Tb ? 2 * ta + 2 : Tb);
+      if (idx < c + n) { ta_out = ta; tb_out = idx - c; return; }
+      c += n;
+    }
+    ta_out = tb_out = 0;
+  }
+};
+
+__global__ void __launch_bounds__(SYRK8_THREADS, 1)
+syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB64, const SyrkI8Params P) {
+  constexpr int STAGES = 4;
+  constexpr int BPL = I8_PLANE / 2;                                 // one digit plane of this CTA's 64 weighted rows
+  constexpr int STAGE = 4 * I8_PLANE + 4 * BPL;                     // 48 KB
+  constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_T >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+  static_assert(STAGES * STAGE + 1024 + 256 <= I8_SMEM, "shared memory budget");
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = base + STAGES * STAGE;
+  auto fullA = [&](int s) { return bars + 8u * s; };
+  auto fullB = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto ready = [&](int s) { return bars + 8u * (2 * STAGES + s); };
+  auto empty = [&](int s) { return bars + 8u * (3 * STAGES + s); };
+  auto pfull = [&](int s) { return bars + 8u * (4 * STAGES + s); };
+  const uint32_t tfull = bars + 8u * (5 * STAGES), tempty = tfull + 8u, tmem_ptr = tfull + 16u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = cluster_ctarank();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(fullA(s), 1); mbar_init(fullB(s), 1); mbar_init(ready(s), SYRK8_XF_WARPS); mbar_init(empty(s), 1); mbar_init(pfull(s), 1);
+    }
+    mbar_init(tfull, 1);
+    mbar_init(tempty, 8);                                           // 4 epilogue warps of each CTA
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&mapA); prefetch_tmap(&mapB64); }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr));
+
+  struct Item { int64_t l, n0, n1; int ta, tb, nkb; };
+  auto decode = [&](int64_t item) -> Item {
+    Item it;
+    const int64_t per_win = (int64_t)P.ntile * P.L;
+    const int64_t win = item / per_win, rem = item - win * per_win;
+    it.l = rem % P.L;
+    SyrkPairTiles::decode((int)(rem / P.L), P.M, it.ta, it.tb);
+    it.n0 = win * P.win_rows;
+    it.n1 = it.n0 + P.win_rows < P.N ? it.n0 + P.win_rows : P.N;
+    it.nkb = (int)((it.n1 - it.n0 + I8_KB - 1) / I8_KB);
+    return it;
+  };
+  const int64_t unit = blockIdx.x / 2, nunits = gridDim.x / 2;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t item = unit; item < P.n_items; item += nunits) {
+        const Item it = decode(item);
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(empty(stage), phase ^ 1);
+          const uint32_t st = base + stage * STAGE;
+          const int64_t n = it.n0 + (int64_t)kb * I8_KB;
+          const int32_t blk = (int32_t)(n >> 7), off = (int32_t)(n & 127);
+          // this CTA's 64 rows of the weighted operand first (the transform warps work on them while the A planes land)
+          mbar_expect_tx(fullB(stage), 4 * BPL);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) tma_load_4d(st + 4 * I8_PLANE + s * BPL, &mapB64, fullB(stage), off, it.tb * I8_T + (int32_t)crank * 64, blk, s);
+          mbar_expect_tx(fullA(stage), 4 * I8_PLANE);
+#pragma unroll
+          for (int s = 0; s < 4; ++s) tma_load_4d(st + s * I8_PLANE, &mapA, fullA(stage), off, it.ta * 256 + (int32_t)crank * I8_T, blk, s);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && crank == 0) {
+    // =============================== MMA issuer (leader) =========================================
+    int stage = 0; uint32_t phase = 0, tphase = 0;
+    for (int64_t item = unit; item < P.n_items; item += nunits) {
+      const Item it = decode(item);
+      mbar_wait_cluster(tempty, tphase ^ 1);
+      tc_fence_after();
+      for (int kb = 0; kb < it.nkb; ++kb) {
+        mbar_wait(fullA(stage), phase);
+        mbar_wait(ready(stage), phase);
+        mbar_wait_cluster(pfull(stage), phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = base + stage * STAGE;
+          uint64_t a[4], b[4];
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + t * I8_PLANE); b[t] = i8_desc(st + 4 * I8_PLANE + t * BPL); }
+#pragma unroll
+          for (int ks = 0; ks < I8_KB / 32; ++ks) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+            const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
+#pragma unroll
+            for (int o = 0; o < 4; ++o)
+#pragma unroll
+              for (int t = 0; t <= o; ++t) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, t == 0 ? f : 1u);
+          }
+          umma_commit_cg2(empty(stage));
+          if (kb == it.nkb - 1) umma_commit_cg2(tfull);
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      tphase ^= 1;
+    }
+  } else if (warp == 1) {
+    // =============================== peer: forward "A landed, B half transformed" ===============
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t item = unit; item < P.n_items; item += nunits) {
+        const Item it = decode(item);
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(fullA(stage), phase);
+          mbar_wait(ready(stage), phase);
+          mbar_arrive_remote(pfull(stage), 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= SYRK8_XF_WARP0 && warp < SYRK8_XF_WARP0 + SYRK8_XF_WARPS) {
+    // =============================== operand transform (this CTA's 64 weighted rows) =============
+    const int t = threadIdx.x - SYRK8_XF_WARP0 * 32;          // 0..255
+    const int lchunk = t & 3, row = t >> 2;                    // one row of 64 datapoints per 4 threads
+    const int pchunk = lchunk ^ ((row >> 1) & 3);
+    int stage = 0; uint32_t phase = 0;
+    for (int64_t item = unit; item < P.n_items; item += nunits) {
+      const Item it = decode(item);
+      const int64_t r = (int64_t)it.tb * I8_T + crank * 64 + row;      // index b of this weighted row
+      const float q = syrk_vq(r < P.M ? __ldg(P.vmax + it.l * P.M + r) : 0.f);
+      for (int kb = 0; kb < it.nkb; ++kb) {
+        const int64_t n = it.n0 + (int64_t)kb * I8_KB + lchunk * 16;
+        float w[16];
+        {
+          const float4* wp = reinterpret_cast<const float4*>(P.Wt + it.l * P.ldwt + n);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const float4 v = __ldg(wp + g);
+            w[4 * g] = v.x; w[4 * g + 1] = v.y; w[4 * g + 2] = v.z; w[4 * g + 3] = v.w;
+          }
+        }
+        mbar_wait(fullB(stage), phase);
+        const uint32_t a = base + stage * STAGE + 4 * I8_PLANE + row * I8_KB + pchunk * 16;
+        const uint4 k0 = lds128(a), k1 = lds128(a + BPL), k2 = lds128(a + 2 * BPL), k3 = lds128(a + 3 * BPL);
+        const uint32_t k0w[4] = {k0.x, k0.y, k0.z, k0.w}, k1w[4] = {k1.x, k1.y, k1.z, k1.w};
+        const uint32_t k2w[4] = {k2.x, k2.y, k2.z, k2.w}, k3w[4] = {k3.x, k3.y, k3.z, k3.w};
+        uint32_t o[4][4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t e[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t sel = (uint32_t)(b | ((4 + b) << 4));
+            const uint32_t d = __byte_perm(__byte_perm(k3w[g], k2w[g], sel), __byte_perm(k1w[g], k0w[g], sel), 0x5410);
+            const int kint = (int)((d ^ 0x00808080u) - 0x00808080u);
+            const int v = __float2int_rn(__int2float_rn(kint) * w[4 * g + b] * q);      // same rounding order as the single-CTA kernel
+            e[b] = ((uint32_t)v + 0x00808080u) ^ 0x00808080u;
+          }
+          const uint32_t x01 = __byte_perm(e[0], e[1], 0x7362), y01 = __byte_perm(e[0], e[1], 0x5140);
+          const uint32_t x23 = __byte_perm(e[2], e[3], 0x7362), y23 = __byte_perm(e[2], e[3], 0x5140);
+          o[0][g] = __byte_perm(x01, x23, 0x7632);
+          o[1][g] = __byte_perm(x01, x23, 0x5410);
+          o[2][g] = __byte_perm(y01, y23, 0x7632);
+          o[3][g] = __byte_perm(y01, y23, 0x5410);
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s) sts128(a + s * BPL, make_uint4(o[s][0], o[s][1], o[s][2], o[s][3]));
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready(stage));
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp >= SYRK8_EPI_WARP0) {
+    // =============================== epilogue (this CTA's 128 rows a) ============================
+    const int qd = warp & 3;
+    uint32_t tphase = 0;
+    for (int64_t item = unit; item < P.n_items; item += nunits) {
+      const Item it = decode(item);
+      const int64_t r = (int64_t)it.ta * 256 + crank * I8_T + qd * 32 + lane;        // output row a
+      const int64_t rmax_w = (int64_t)it.ta * 256 + crank * I8_T + qd * 32 + 31;
+      const double rs = (r < P.M) ? 16777216.0 * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
+      mbar_wait(tfull, tphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
+#pragma unroll 1
+      for (int c16 = 0; c16 < I8_T / 16; ++c16) {
+        const int64_t c0 = (int64_t)it.tb * I8_T + c16 * 16;
+        if (c0 > rmax_w || c0 >= P.M) break;                              // warp-uniform
+        int a0[16], a1[16], a2[16], a3[16];
+        tmem_ld16_nowait(taddr + 0 * I8_T + c16 * 16, a0);
+        tmem_ld16_nowait(taddr + 1 * I8_T + c16 * 16, a1);
+        tmem_ld16_nowait(taddr + 2 * I8_T + c16 * 16, a2);
+        tmem_ld16_nowait(taddr + 3 * I8_T + c16 * 16, a3);
+        tmem_ld_wait();
+        double* dst = P.A + (it.l * P.M + r) * P.M + c0;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int64_t c = c0 + j;
+          if (r < P.M && c <= r) {
+            const float qc = syrk_vq(__ldg(P.vmax + it.l * P.M + c));
+            if (qc > 0.f) {
+              const long long i64 = ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
+              atomicAdd(dst + j, (double)i64 * rs * ((double)__ldg(P.cscale + c) / (double)qc));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { if (crank != 0) mbar_arrive_remote(tempty, 0); else mbar_arrive(tempty); }
+      tphase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // =============================================================================================================
 // scaled GEMM   out[i, c] (+)= sum_s w[i, s] T_s[i, c],   dots[i, s] += sum_c T_s[i, c] K[i, c],   T_s = K G_s
 // =============================================================================================================
@@ -416,48 +703,11 @@ struct ScaledI8Params {
   int64_t ldkr;
   int nct;                      // column tiles
   int64_t n_items;
+  int debug;                    // experiments (SVGP_I8_DEBUG, wrong results): bit 0 = the epilogue releases TMEM without reading it
 };
 
 constexpr int SCALED8_THREADS = 384;     // warp 0 TMA, warp 1 MMA (pair: the peer's warp 1 forwards its "stage full"), warps 4-11 epilogue
 constexpr int SCALED8_EPI_WARP0 = 4;
-
-__device__ __forceinline__ void umma_i8_cg2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_cg2(uint32_t bar) {          // arrives on `bar` (same offset) in both CTAs of the pair
-  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
-               : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {   // arrive on the barrier at the same offset in CTA `cta`
-  asm volatile(
-      "{\n"
-      ".reg .b32 ra;\n"
-      "mapa.shared::cluster.u32 ra, %0, %1;\n"
-      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
-      "}\n" ::"r"(bar), "r"(cta)
-      : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {  // barrier with arrivals from the peer CTA
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
 
 // PAIR = two CTAs of a cluster on one 256 x 128 output tile with tcgen05.mma.cta_group::2: each CTA feeds its 128 rows of K_nm
 // (A) and ITS HALF of the 128 G rows (B), the leader issues, both hold their 128 rows of the four accumulators.  Per MMA a
@@ -630,7 +880,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
 #pragma unroll
         for (int c16 = 0; c16 < 4; ++c16) {
           const int64_t c0 = cw0 + c16 * 16;
-          if (c0 < P.Mc) {                                                 // warp-uniform
+          if (c0 < P.Mc && !(P.debug & 1)) {                               // warp-uniform
             int a0[16], a1[16], a2[16], a3[16];
             tmem_ld16_nowait(taddr + 0 * I8_T + c16 * 16, a0);
             tmem_ld16_nowait(taddr + 1 * I8_T + c16 * 16, a1);
@@ -730,6 +980,37 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   P.N = N; P.M = M; P.L = L; P.Wt = Wt; P.ldwt = ldwt; P.wmax = wmax; P.vmax = vmax; P.cscale = kop->cscale; P.A = A;
   P.win_rows = i8_syrk_window(N, M, L);
   P.nwin = (int)ceil_div(N, P.win_rows);
+  // CTA pairs (256 x 128 tiles, tcgen05.mma.cta_group::2) unless SVGP_I8_PAIR=0 or no co-resident clusters are available
+  static int pair_clusters = -1;
+  const char* ep = getenv("SVGP_I8_PAIR");
+  const bool want_pair = !(ep && atoi(ep) == 0);
+  cudaLaunchConfig_t cfg = {};
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.blockDim = dim3(SYRK8_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = I8_SMEM;
+  cfg.stream = st;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (want_pair && pair_clusters < 0) {
+    if (cudaFuncSetAttribute(syrk_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_syrk(i8 attr)");
+    cfg.gridDim = dim3(num_sms() / 2 * 2, 1, 1);
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, syrk_i8_pair_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    pair_clusters = n;
+  }
+  if (want_pair && pair_clusters > 0) {
+    CUtensorMap map64;
+    rc = encode_i8(&map64, kop->Kc, 4, dims, strides, I8_T / 2);
+    if (rc) return rc;
+    P.ntile = SyrkPairTiles::count(M);
+    P.n_items = (int64_t)P.nwin * P.ntile * L;
+    const int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
+    if (clusters <= 0) return SVGP_OK;
+    cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+    if (cudaLaunchKernelEx(&cfg, syrk_i8_pair_kernel, map, map64, P) != cudaSuccess) return check_launch("svgp_syrk(i8 pair)");
+    return check_launch("svgp_syrk(i8 pair)");
+  }
   const int64_t T = ceil_div(M, I8_T);
   P.ntile = (int)(T * (T + 1) / 2);
   P.n_items = (int64_t)P.nwin * P.ntile * L;
@@ -769,6 +1050,7 @@ int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const vo
   P.out = out; P.ldo = ldo; P.accumulate = accumulate; P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
   P.Kr = (const int8_t*)kop->Kr; P.ldkr = kop->ldkr;
   P.nct = (int)ceil_div(Mc, I8_T);
+  { const char* e = getenv("SVGP_I8_DEBUG"); P.debug = e ? atoi(e) : 0; }
   // CTA pairs (tcgen05.mma.cta_group::2) when there are at least as many 256-row items as clusters; SVGP_I8_PAIR=0 forces
   // the single-CTA kernel
   static int pair_clusters = -1;       // co-resident clusters of two CTAs (0: unavailable)

@@ -79,8 +79,12 @@ def test_split_i8(cuda_backend, R, C, S):
     assert (P.planes[:, :, C:] == 0).all()
 
 
+@pytest.mark.parametrize("pair", [True, False])
 @pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1)])
-def test_syrk_i8_is_exact(cuda_backend, N, M, L):
+def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, monkeypatch):
+    """pair: the CTA-pair kernel (tcgen05.mma.cta_group::2; the weighted operand is the B side: rows b) / the single-CTA
+    kernel (weighted operand = A side: rows a).  Both must equal the digit-exact emulation of their own operand placement."""
+    monkeypatch.setenv("SVGP_I8_PAIR", "1" if pair else "0")
     be = cuda_backend
     _, kop = _kop(be, N, M, L)
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -104,9 +108,9 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L):
         for t in range(4):
             for u in range(4):
                 if t + u <= 3:
-                    acc[t + u] += v[t].t() @ kd[u]                        # exact: |sum| < 2^53
+                    acc[t + u] += (kd[u].t() @ v[t]) if pair else (v[t].t() @ kd[u])      # exact: |sum| < 2^53
         i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
-        ref[l] = i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / qa.double()[:, None]
+        ref[l] = i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if pair else qa.double()[:, None])
     ref = torch.tril(ref) + torch.tril(ref, -1).transpose(-1, -2)
     assert rel_err(A, ref) < 1e-12
     # and against the plain float64 contraction of the float64 kernel values: fp32 kernel arithmetic is what is left

@@ -294,6 +294,40 @@ static void run(const char* name, int n, int a_fmt, int b_fmt, int reps, int gri
   cudaFree(d_out); cudaFree(d_cyc); cudaFree(d_fail);
 }
 
+template <int KIND>
+static void sustained(const char* name, int grid) {
+  int *d_out, *d_fail;
+  long long* d_cyc;
+  const int n = 256, reps = 100000;                  // 400k MMAs per CTA per launch: ~30 ms
+  CK(cudaMalloc(&d_out, sizeof(int) * 128 * n));
+  CK(cudaMalloc(&d_cyc, sizeof(long long) * grid));
+  CK(cudaMalloc(&d_fail, sizeof(int)));
+  CK(cudaMemset(d_fail, 0, sizeof(int)));
+  Params P{n, KIND == 1 ? 1 : 0, KIND == 1 ? 1 : 0, reps, d_out, d_cyc, d_fail};
+  const int smem = 128 * 128 + 256 * 128 + 64 + 1024;
+  auto kern = probe_kernel<KIND, 1>;
+  CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  kern<<<grid, 128, smem>>>(P);
+  CK(cudaDeviceSynchronize());
+  int launches = 0;
+  float ms = 0;
+  CK(cudaEventRecord(e0));
+  do {
+    for (int i = 0; i < 10; ++i) kern<<<grid, 128, smem>>>(P);
+    launches += 10;
+    CK(cudaEventRecord(e1));
+    CK(cudaEventSynchronize(e1));
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+  } while (ms < 3000.f);
+  const double macs = 4.0 * reps * 128.0 * n * (KIND == 1 ? 32 : 16) * grid * launches;
+  printf("{\"probe\": \"%s\", \"kind\": \"%s\", \"seconds\": %.2f, \"chip_tmacs_sustained\": %.1f, \"tops_sustained\": %.1f}\n", name,
+         KIND == 1 ? "i8" : "f16", ms * 1e-3, macs / (ms * 1e-3) / 1e12, 2.0 * macs / (ms * 1e-3) / 1e12);
+  fflush(stdout);
+  cudaFree(d_out); cudaFree(d_cyc); cudaFree(d_fail);
+}
+
 int main() {
   int dev = 0, sms = 0;
   CK(cudaGetDevice(&dev));
@@ -310,5 +344,9 @@ int main() {
   run<1, 2>("i8_ss_pair_n256", 256, 1, 1, reps, sms);
   run<1, 2>("i8_ss_pair_n128", 128, 1, 1, reps, sms);
   run<0, 2>("f16_pair_n256", 256, 0, 0, reps, sms);
+  // sustained rates under the power cap: the same kernels back to back for ~3 s each (the roofline denominator of a
+  // kernel timed inside a long step; MEASURED_PEAKS.json has the bf16 cuBLAS figure, this is the raw MMA-issue figure)
+  sustained<0>("f16_n256_sustained_3s", sms);
+  sustained<1>("i8_ss_n256_sustained_3s", sms);
   return 0;
 }
