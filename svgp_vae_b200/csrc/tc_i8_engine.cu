@@ -31,7 +31,8 @@ constexpr int I8_NPL = 8;                         // planes per stage: 4 digits 
 constexpr int I8_STAGE = I8_NPL * I8_PLANE;
 constexpr int I8_STAGES = 3;
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE + 1024 + 256;
-static_assert(I8_SMEM <= 227 * 1024, "shared memory budget");
+constexpr int I8_SMEM_WIDE = 4 * (7 * I8_PLANE) + 1024 + 256;   // scaled GEMM on CTA pairs with N = 256 MMAs: 4 stages of 32 + 24 KB
+static_assert(I8_SMEM <= 227 * 1024 && I8_SMEM_WIDE <= 227 * 1024, "shared memory budget");
 
 // D (s32) += A (s8) * B (s8), M = 128, N = 128, K = 32
 constexpr uint32_t I8_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_T >> 3) << 17) | ((uint32_t)(I8_T >> 4) << 24);
@@ -44,6 +45,16 @@ __device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t adesc, uint64_
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(d_tmem),
       "l"(adesc), "l"(bdesc), "r"(I8_IDESC), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_i8_idesc(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
 __device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {        // K-major, 64-byte swizzle rows, 8-row groups 512 B apart
@@ -193,6 +204,7 @@ struct SyrkI8Params {
   int64_t win_rows;         // datapoints per chain (multiple of 128): one item = (window, tile pair, channel)
   int nwin, ntile;
   int64_t n_items;
+  int split;                // pair kernel: leave the tiles tb = 2 ta + 1 out; single-CTA kernel: ONLY the blocks (2 t + 1, 2 t + 1)
 };
 
 // quantisation factor of the weighted operand of row a: |float(Kint) * wn * q| <= 127 2^24 (two fp32 roundings of headroom)
@@ -270,10 +282,14 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
     const int64_t win = item / per_win, rem = item - win * per_win;
     it.l = rem % P.L;
     const int tile = (int)(rem / P.L);
-    int ta = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
-    while ((ta + 1) * (ta + 2) / 2 <= tile) ++ta;
-    while (ta * (ta + 1) / 2 > tile) --ta;
-    it.ta = ta; it.tb = tile - ta * (ta + 1) / 2;
+    if (P.split) {
+      it.ta = it.tb = 2 * tile + 1;
+    } else {
+      int ta = (int)((sqrtf(8.f * (float)tile + 1.f) - 1.f) * 0.5f);
+      while ((ta + 1) * (ta + 2) / 2 <= tile) ++ta;
+      while (ta * (ta + 1) / 2 > tile) --ta;
+      it.ta = ta; it.tb = tile - ta * (ta + 1) / 2;
+    }
     it.n0 = win * P.win_rows;
     it.n1 = it.n0 + P.win_rows < P.N ? it.n0 + P.win_rows : P.N;
     it.nkb = (int)((it.n1 - it.n0 + I8_KB - 1) / I8_KB);
@@ -441,18 +457,21 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
 // works on a 256 x 128 tile: every CTA feeds its 128 RAW rows a (A operand, untouched TMA planes) and ITS 64 rows b of the
 // WEIGHTED operand (B operand): half the transform work, half the B traffic per CTA.  The leader issues; the peer's warp 1
 // forwards "my A has landed and my B half is transformed" to the leader's barrier.
+// Of the tile tb = 2 ta + 1 only the lower CTA's diagonal 128 x 128 block touches the triangle: with `split` those tiles are left
+// out here and their diagonal blocks (2 ta + 1, 2 ta + 1) go to the single-CTA kernel instead (10 % fewer MMAs at M = 1024).
 struct SyrkPairTiles {              // tiles (ta: 256 rows, tb: 128 columns) touching the lower triangle: tb <= 2 ta + 1
-  __host__ __device__ static int count(int64_t M) {
+  __host__ __device__ static int count(int64_t M, int split) {
     const int T2 = (int)((M + 255) / 256), Tb = (int)((M + 127) / 128);
     int c = 0;
-    for (int ta = 0; ta < T2; ++ta) c += (2 * ta + 2 < Tb ? 2 * ta + 2 : Tb);
+    for (int ta = 0; ta < T2; ++ta) c += (2 * ta + 2 - split < Tb ? 2 * ta + 2 - split : Tb);
     return c;
   }
-  __device__ static void decode(int idx, int64_t M, int& ta_out, int& tb_out) {
+  __host__ __device__ static int odd_blocks(int64_t M) { return (int)((M + 127) / 128) / 2; }      // blocks (2 t + 1, 2 t + 1)
+  __device__ static void decode(int idx, int64_t M, int split, int& ta_out, int& tb_out) {
     const int T2 = (int)((M + 255) / 256), Tb = (int)((M + 127) / 128);
     int c = 0;
     for (int ta = 0; ta < T2; ++ta) {
-      const int n = (2 * ta + 2 < Tb ? 2 * ta + 2 : Tb);
+      const int n = (2 * ta + 2 - split < Tb ? 2 * ta + 2 - split : Tb);
       if (idx < c + n) { ta_out = ta; tb_out = idx - c; return; }
       c += n;
     }
@@ -504,7 +523,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int64_t per_win = (int64_t)P.ntile * P.L;
     const int64_t win = item / per_win, rem = item - win * per_win;
     it.l = rem % P.L;
-    SyrkPairTiles::decode((int)(rem / P.L), P.M, it.ta, it.tb);
+    SyrkPairTiles::decode((int)(rem / P.L), P.M, P.split, it.ta, it.tb);
     it.n0 = win * P.win_rows;
     it.n1 = it.n0 + P.win_rows < P.N ? it.n0 + P.win_rows : P.N;
     it.nkb = (int)((it.n1 - it.n0 + I8_KB - 1) / I8_KB);
@@ -713,15 +732,28 @@ constexpr int SCALED8_EPI_WARP0 = 4;
 // (A) and ITS HALF of the 128 G rows (B), the leader issues, both hold their 128 rows of the four accumulators.  Per MMA a
 // CTA's shared memory serves 4 KB of A + 2 KB of B instead of 4 + 4: the single-CTA kernel is bound by exactly that traffic
 // (20 MMAs x 8 KB + 64 KB of TMA writes per 1280 MMA-cycles = 175 B / clk against the 128 B / clk port).
-template <bool PAIR>
+//
+// WIDE = six MMAs per 32-element k-step instead of ten: two digit planes of the B operand that lie behind each other in shared
+// memory are ONE operand of 256 rows, and the accumulators of consecutive orders are neighbours in TMEM, so
+//   A_t x [B_u ; B_u+1]  (N = 256)  adds A_t B_u to acc_(t+u) and A_t B_(u+1) to acc_(t+u+1)
+// with ONE fetch of the A plane: A_0 x [B_0;B_1], A_0 x [B_2;B_3], A_1 x [B_0;B_1], A_2 x [B_0;B_1], A_1 x B_2, A_3 x B_0 -- the same
+// ten digit-plane products, 6 instead of 10 fetches of a 4 KB A plane.  Both kernels are bound by shared-memory operand
+// fetches (tools/micro/i8_mma_probe.cu: the N = 64 probe saturates the 128 B / clk port).  On a CTA pair the B operand of an
+// MMA is split by ROWS between the two CTAs, so for N = 256 CTA 0 holds the first plane of the pair and CTA 1 the second
+// (slots P = planes {0 | 1}, Q = planes {2 | 3}, whole 128-row planes) and for the two N = 128 MMAs each CTA holds its
+// 64-row half (slots R = plane 2, T = plane 0): 24 KB of B per stage and CTA.
+template <bool PAIR, bool WIDE>
 __global__ void __launch_bounds__(SCALED8_THREADS, 1)
-scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapG, const ScaledI8Params P) {
+scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapG64,
+                 const ScaledI8Params P) {
   constexpr int STAGES = PAIR ? 4 : 3;
-  constexpr int BPL = PAIR ? I8_PLANE / 2 : I8_PLANE;            // bytes of one digit plane of this CTA's part of the B tile
-  constexpr int STAGE = 4 * I8_PLANE + 4 * BPL;
+  constexpr int BPL = (PAIR && !WIDE) ? I8_PLANE / 2 : I8_PLANE;  // bytes of one digit plane of this CTA's part of the B tile
+  constexpr int STAGE = 4 * I8_PLANE + ((PAIR && WIDE) ? 3 * I8_PLANE : 4 * BPL);
   constexpr int ROWS = PAIR ? 2 * I8_T : I8_T;                    // datapoints per item
   constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_T >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
-  static_assert(STAGES * STAGE + 1024 + 256 <= I8_SMEM, "shared memory budget");
+  constexpr uint32_t IDESC_W = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * I8_T) >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
+  static_assert(STAGES * STAGE + 1024 + 256 <= I8_SMEM_WIDE, "shared memory budget");
+  static_assert(WIDE || STAGES * STAGE + 1024 + 256 <= I8_SMEM, "shared memory budget");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE;
@@ -737,7 +769,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     mbar_init(tempty, PAIR ? 16 : 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0 && lane == 0) { prefetch_tmap(&mapK); prefetch_tmap(&mapG); }
+  if (warp == 0 && lane == 0) { prefetch_tmap(&mapK); prefetch_tmap(&mapG); prefetch_tmap(&mapG64); }
   if (warp == 1) {
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_ptr), "r"(512));
@@ -765,7 +797,8 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         int stage = 0; uint32_t phase = 0;
         for (int64_t item = unit; item < P.n_items; item += nunits) {
           const int32_t row0 = (int32_t)((item / P.nct) * ROWS + crank * I8_T);
-          const int32_t col0 = (int32_t)((item % P.nct) * I8_T + (PAIR ? crank * (I8_T / 2) : 0));
+          const int32_t colt = (int32_t)((item % P.nct) * I8_T);              // first column of the tile
+          const int32_t col0 = colt + (int32_t)(PAIR ? crank * (I8_T / 2) : 0);  // first column of this CTA's half
           for (int64_t s = 0; s < P.L; ++s) {
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(empty(stage), phase ^ 1);
@@ -773,8 +806,18 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
               mbar_expect_tx(full(stage), STAGE);
 #pragma unroll
               for (int t = 0; t < 4; ++t) tma_load_3d(st + t * I8_PLANE, &mapK, full(stage), kb * I8_KB, row0, t);
+              if (PAIR && WIDE) {
+                const uint32_t sb = st + 4 * I8_PLANE;
+                const int32_t g0 = (int32_t)(s * P.Mc);
+                tma_load_3d(sb, &mapG, full(stage), kb * I8_KB, g0 + colt, (int32_t)crank);                       // P: plane 0 | 1
+                tma_load_3d(sb + I8_PLANE, &mapG, full(stage), kb * I8_KB, g0 + colt, 2 + (int32_t)crank);        // Q: plane 2 | 3
+                tma_load_3d(sb + 2 * I8_PLANE, &mapG64, full(stage), kb * I8_KB, g0 + col0, 2);                   // R: my half of plane 2
+                tma_load_3d(sb + 2 * I8_PLANE + I8_PLANE / 2, &mapG64, full(stage), kb * I8_KB, g0 + col0, 0);    // T: my half of plane 0
+              } else {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) tma_load_3d(st + 4 * I8_PLANE + u * BPL, &mapG, full(stage), kb * I8_KB, (int32_t)(s * P.Mc) + col0, u);
+                for (int u = 0; u < 4; ++u)
+                  tma_load_3d(st + 4 * I8_PLANE + u * BPL, PAIR ? &mapG64 : &mapG, full(stage), kb * I8_KB, (int32_t)(s * P.Mc) + col0, u);
+              }
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
           }
@@ -796,17 +839,45 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
               uint64_t a[4], b[4];
 #pragma unroll
               for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + t * I8_PLANE); b[t] = i8_desc(st + 4 * I8_PLANE + t * BPL); }
+              if (WIDE) {
+                // operands of the six MMAs: pair -> slots P, Q (whole planes), R, T (64-row halves); single CTA -> the four
+                // planes lie behind each other, [B_0;B_1] starts at plane 0 and [B_2;B_3] at plane 2
+                const uint32_t sb = st + 4 * I8_PLANE;
+                const uint64_t b01 = i8_desc(sb), b23 = i8_desc(sb + (PAIR ? I8_PLANE : 2 * I8_PLANE));
+                const uint64_t b2 = i8_desc(sb + 2 * I8_PLANE), b0 = PAIR ? i8_desc(sb + 2 * I8_PLANE + I8_PLANE / 2) : b01;
 #pragma unroll
-              for (int ks = 0; ks < I8_KB / 32; ++ks) {
-                const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-                const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
-#pragma unroll
-                for (int o = 0; o < 4; ++o)
-#pragma unroll
-                  for (int t = 0; t <= o; ++t) {
-                    if (PAIR) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, t == 0 ? f : 1u);
-                    else umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, t == 0 ? f : 1u);
+                for (int ks = 0; ks < I8_KB / 32; ++ks) {
+                  const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                  const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
+                  if (PAIR) {
+                    umma_i8_cg2(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);       // acc0 (+)= A0 B0, acc1 (+)= A0 B1
+                    umma_i8_cg2(tmem_base + 2 * I8_T, a[0] + adv, b23 + adv, IDESC_W, f);       // acc2 (+)= A0 B2, acc3 (+)= A0 B3
+                    umma_i8_cg2(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);      // acc1 += A1 B0, acc2 += A1 B1
+                    umma_i8_cg2(tmem_base + 2 * I8_T, a[2] + adv, b01 + adv, IDESC_W, 1u);      // acc2 += A2 B0, acc3 += A2 B1
+                    umma_i8_cg2(tmem_base + 3 * I8_T, a[1] + adv, b2 + adv, IDESC, 1u);         // acc3 += A1 B2
+                    umma_i8_cg2(tmem_base + 3 * I8_T, a[3] + adv, b0 + adv, IDESC, 1u);         // acc3 += A3 B0
+                  } else {
+                    umma_i8_idesc(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);
+                    umma_i8_idesc(tmem_base + 2 * I8_T, a[0] + adv, b23 + adv, IDESC_W, f);
+                    umma_i8_idesc(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);
+                    umma_i8_idesc(tmem_base + 2 * I8_T, a[2] + adv, b01 + adv, IDESC_W, 1u);
+                    umma_i8_idesc(tmem_base + 3 * I8_T, a[1] + adv, b2 + adv, IDESC, 1u);
+                    umma_i8_idesc(tmem_base + 3 * I8_T, a[3] + adv, b0 + adv, IDESC, 1u);
                   }
+                }
+              } else {
+#pragma unroll
+                for (int ks = 0; ks < I8_KB / 32; ++ks) {
+                  const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                  const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
+#pragma unroll
+                  for (int o = 0; o < 4; ++o)
+#pragma unroll
+                    for (int t = 0; t <= o; ++t) {
+                      if (PAIR) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, t == 0 ? f : 1u);
+                      else umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, t == 0 ? f : 1u);
+                    }
+                }
               }
               if (PAIR) { umma_commit_cg2(empty(stage)); if (kb == nkb - 1) umma_commit_cg2(tfull); }
               else { umma_commit(empty(stage)); if (kb == nkb - 1) umma_commit(tfull); }
@@ -1003,16 +1074,25 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
     CUtensorMap map64;
     rc = encode_i8(&map64, kop->Kc, 4, dims, strides, I8_T / 2);
     if (rc) return rc;
-    P.ntile = SyrkPairTiles::count(M);
+    // SVGP_I8_SYRK_SPLIT=0: all tiles on the pair kernel (the diagonal blocks of the tiles tb = 2 ta + 1 then cost a whole tile)
+    const char* es = getenv("SVGP_I8_SYRK_SPLIT");
+    P.split = !(es && atoi(es) == 0) && SyrkPairTiles::odd_blocks(M) > 0 ? 1 : 0;
+    P.ntile = SyrkPairTiles::count(M, P.split);
     P.n_items = (int64_t)P.nwin * P.ntile * L;
     const int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
-    if (clusters <= 0) return SVGP_OK;
-    cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
-    if (cudaLaunchKernelEx(&cfg, syrk_i8_pair_kernel, map, map64, P) != cudaSuccess) return check_launch("svgp_syrk(i8 pair)");
-    return check_launch("svgp_syrk(i8 pair)");
+    if (clusters > 0) {
+      cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+      if (cudaLaunchKernelEx(&cfg, syrk_i8_pair_kernel, map, map64, P) != cudaSuccess) return check_launch("svgp_syrk(i8 pair)");
+      rc = check_launch("svgp_syrk(i8 pair)");
+      if (rc) return rc;
+    }
+    if (!P.split) return SVGP_OK;
+    P.ntile = SyrkPairTiles::odd_blocks(M);              // the diagonal blocks left out above, on single CTAs
+  } else {
+    const int64_t T = ceil_div(M, I8_T);
+    P.split = 0;
+    P.ntile = (int)(T * (T + 1) / 2);
   }
-  const int64_t T = ceil_div(M, I8_T);
-  P.ntile = (int)(T * (T + 1) / 2);
   P.n_items = (int64_t)P.nwin * P.ntile * L;
   static bool attr_done = false;
   if (!attr_done) {
@@ -1052,44 +1132,49 @@ int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const vo
   P.nct = (int)ceil_div(Mc, I8_T);
   { const char* e = getenv("SVGP_I8_DEBUG"); P.debug = e ? atoi(e) : 0; }
   // CTA pairs (tcgen05.mma.cta_group::2) when there are at least as many 256-row items as clusters; SVGP_I8_PAIR=0 forces
-  // the single-CTA kernel
-  static int pair_clusters = -1;       // co-resident clusters of two CTAs (0: unavailable)
+  // the single-CTA kernel, SVGP_I8_WIDE=0 the ten N = 128 MMAs per k-step instead of the six wide ones
+  static int pair_clusters[2] = {-1, -1};       // co-resident clusters of two CTAs (0: unavailable), per WIDE
   const char* ep = getenv("SVGP_I8_PAIR");
+  const char* ew = getenv("SVGP_I8_WIDE");
+  const int wide = !(ew && atoi(ew) == 0);
   bool pair = !(ep && atoi(ep) == 0) && N >= 2 * I8_T * 4;
+  auto pair_kernel = wide ? scaled_i8_kernel<true, true> : scaled_i8_kernel<true, false>;
+  auto single_kernel = wide ? scaled_i8_kernel<false, true> : scaled_i8_kernel<false, false>;
+  const int pair_smem = wide ? I8_SMEM_WIDE : I8_SMEM;
   cudaLaunchConfig_t cfg = {};
   cudaLaunchAttribute attr[1];
   cfg.blockDim = dim3(SCALED8_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = I8_SMEM;
+  cfg.dynamicSmemBytes = pair_smem;
   cfg.stream = st;
-  if (pair && pair_clusters < 0) {
-    if (cudaFuncSetAttribute(scaled_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
+  if (pair && pair_clusters[wide] < 0) {
+    if (cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.gridDim = dim3(num_sms() / 2 * 2, 1, 1);
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, scaled_i8_kernel<true>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
-    pair_clusters = n;
+    if (cudaOccupancyMaxActiveClusters(&n, pair_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    pair_clusters[wide] = n;
   }
-  if (pair && pair_clusters > 0) {
+  if (pair && pair_clusters[wide] > 0) {
     P.n_items = ceil_div(N, 2 * I8_T) * P.nct;
-    int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
+    int64_t clusters = P.n_items < pair_clusters[wide] ? P.n_items : pair_clusters[wide];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
-    if (cudaLaunchKernelEx(&cfg, scaled_i8_kernel<true>, mapK, mapG64, P) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 pair)");
+    if (cudaLaunchKernelEx(&cfg, pair_kernel, mapK, mapG, mapG64, P) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 pair)");
     return check_launch("svgp_scaled_gemm(i8 pair)");
   }
   P.n_items = ceil_div(N, I8_T) * P.nct;
-  static bool attr_done = false;
-  if (!attr_done) {
-    if (cudaFuncSetAttribute(scaled_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
-    attr_done = true;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[wide]) {
+    if (cudaFuncSetAttribute(single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_scaled_gemm(i8 attr)");
+    attr_done[wide] = true;
   }
   int64_t grid = P.n_items < num_sms() ? P.n_items : num_sms();
   if (grid <= 0) return SVGP_OK;
-  scaled_i8_kernel<false><<<(unsigned)grid, SCALED8_THREADS, I8_SMEM, st>>>(mapK, mapG, P);
+  single_kernel<<<(unsigned)grid, SCALED8_THREADS, I8_SMEM, st>>>(mapK, mapG, mapG64, P);
   return check_launch("svgp_scaled_gemm(i8)");
 }
 

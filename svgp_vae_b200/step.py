@@ -153,6 +153,105 @@ def mm_stage(A, V, sums, K, jitter, c, b_total):
     return mm
 
 
+# ---- the same stage with a hand-written adjoint -------------------------------------------------------------------------
+# mm_channels above is the readable definition (torch autograd chains ops.bmm64 / spd_inverse_logdet / spd_logdet; the
+# per-channel API of svgp.py and the tests use it as the cross-check).  The batched step runs the two functions below
+# instead: no autograd graph, 4 + 8 batched float64 products per step instead of 4 + ~14, and the state kept between the
+# forward and the backward is five (L, M, M) tensors (S, A_hat, its inverse Cholesky factor, Kinv A_hat, Kinv A_hat Kinv)
+# next to A instead of the ~16 the graph holds.
+def mm_channels_fwd(A, V, sums, K, Kinv_b, ldK, jitter, c, b_total):
+    """Values of mm_channels (same formulas, same jitter placement), no graph.  -> (out dict as mm_channels, saved state)."""
+    be = get_backend()
+    L, M, _ = A.shape
+    eye = torch.eye(M, dtype=A.dtype, device=A.device)
+    Kb = K.unsqueeze(0)
+    Lf, status = be.chol((Kb + c * A + jitter * eye).contiguous())
+    ops._check_status(status, "mm_channels_fwd(Sigma)")
+    Linv = be.trinv(Lf)
+    S = be.ltl(Linv)
+    del Lf
+    mv = lambda X, x: be.bmm64(X, x.unsqueeze(-1).contiguous()).squeeze(-1)
+    w = c * mv(S, V)
+    mu_hat = mv(Kb, w)
+    a = mv(Kinv_b, mu_hat)
+    KS = be.bmm64(Kb, S)
+    A_hat = be.bmm64(KS, Kb)
+    del KS
+    LfA, status = be.chol((A_hat + jitter * eye).contiguous())
+    ops._check_status(status, "mm_channels_fwd(A_hat)")
+    ld_Ahat = 2.0 * torch.log(torch.diagonal(LfA, dim1=-2, dim2=-1)).sum(-1)
+    T = be.bmm64(Kinv_b, A_hat)                               # Kinv A_hat
+    tr_KinvAhat = torch.diagonal(T, dim1=-2, dim2=-1).sum(-1)
+    kl = 0.5 * (ldK - ld_Ahat - M + tr_KinvAhat + (mu_hat * a).sum(-1))
+    Wm = be.bmm64(T, Kinv_b)                                  # Kinv A_hat Kinv
+    s_pk, s_pyy, s_log = sums[0], sums[1], sums[2]
+    s_ph = (Kinv_b * A).sum((-1, -2))
+    s_t = (Wm * A).sum((-1, -2))
+    Aa = mv(A, a)
+    recon = -0.5 * (s_pk - s_ph + s_t + s_log + b_total * LOG_2PI_RT + s_pyy - 2.0 * (a * V).sum(-1) + (a * Aa).sum(-1))
+    Aw = mv(A, w)
+    s_ppv = s_pk - s_ph + (S * A).sum((-1, -2))
+    ce = -0.5 * (b_total * LOG_2PI + s_log + s_ppv + (w * Aw).sum(-1) - 2.0 * (w * V).sum(-1) + s_pyy)
+    out = dict(S=S, w=w, Linv=Linv, recon=recon, kl=kl, ce=ce, mu_hat=mu_hat, A_hat=A_hat)
+    saved = dict(A=A, V=V, S=S, w=w, mu_hat=mu_hat, a=a, A_hat=A_hat, LfA=LfA, T=T, Wm=Wm, Aa=Aa, Aw=Aw, c=c)
+    return out, saved
+
+
+def mm_channels_bwd(sv, K, Kinv_b, G_S, G_w, g_recon, g_kl, g_ce):
+    """Adjoint of mm_channels_fwd for the channels in `sv`.  G_S (Lc, M, M) / G_w (Lc, M): adjoints of S_l / w_l; g_recon,
+    g_kl, g_ce (Lc,): adjoints of the three per-channel scalars.  -> dict(gA, gV, gsums (3, Lc), gK (M, M), gKinv (1, M, M),
+    gldK scalar): gK is the DIRECT dependence on K only (Sigma_l, mu_hat, A_hat); what flows through Kinv and ldK is
+    returned as their adjoints (mm_shared_bwd turns the sum over all channels into dK once).
+
+    With r, k, e the three scalar adjoints, bars for adjoints (every matrix below is symmetric or used symmetrised):
+      w_bar   = G_w - e A w + e V + K mu_bar            a_bar = r V - r A a + k/2 mu          mu_bar = k/2 a + Kinv a_bar
+      Ahat_bar = -k/2 (A_hat + jI)^-1 + k/2 Kinv - r/2 Kinv A Kinv
+      S_bar   = G_S - e/2 A + c w_bar V^T + K Ahat_bar K               Sigma_bar = -S sym(S_bar) S
+      A_bar   = (e + r)/2 Kinv - e/2 S - e/2 w w^T - r/2 Wm - r/2 a a^T + c Sigma_bar
+      K_bar   = Ahat_bar K S + (Ahat_bar K S)^T + mu_bar w^T + Sigma_bar
+      Kinv_bar = (e + r)/2 A + k/2 A_hat - r/2 (A T + (A T)^T) + a_bar mu^T,   T = Kinv A_hat"""
+    be = get_backend()
+    A, V, S, w, mu, a, A_hat, T, Wm, c = (sv[k_] for k_ in ("A", "V", "S", "w", "mu_hat", "a", "A_hat", "T", "Wm", "c"))
+    Kb = K.unsqueeze(0)
+    r, k, e = g_recon, g_kl, g_ce
+    r3, k3, e3 = r[:, None, None], k[:, None, None], e[:, None, None]
+    mv = lambda X, x: be.bmm64(X, x.unsqueeze(-1).contiguous()).squeeze(-1)
+    outer = lambda x, y: x.unsqueeze(-1) * y.unsqueeze(-2)
+    # vectors
+    a_bar = r[:, None] * (V - sv["Aa"]) + 0.5 * k[:, None] * mu
+    mu_bar = 0.5 * k[:, None] * a + mv(Kinv_b, a_bar)
+    w_bar = G_w + e[:, None] * (V - sv["Aw"]) + mv(Kb, mu_bar)
+    gV = e[:, None] * w + r[:, None] * a + c * mv(S, w_bar)
+    gsums = (-0.5 * (e + r)).unsqueeze(0).expand(3, -1).contiguous()
+    # adjoint of A_hat
+    AhatInv = be.ltl(be.trinv(sv["LfA"]))
+    KinvA = be.bmm64(Kinv_b, A)
+    Ahat_bar = -0.5 * k3 * AhatInv + 0.5 * k3 * Kinv_b - 0.5 * r3 * be.bmm64(KinvA, Kinv_b)
+    del AhatInv, KinvA
+    # adjoint of Kinv (this chunk's share)
+    Y = be.bmm64(A, T)
+    gKinv = (0.5 * (e3 + r3) * A + 0.5 * k3 * A_hat - 0.5 * r3 * (Y + Y.transpose(-1, -2)) + outer(a_bar, mu)).sum(0, keepdim=True)
+    del Y
+    # through A_hat = K S K
+    Pm = be.bmm64(Ahat_bar, Kb)
+    Q = be.bmm64(Pm, S)
+    S_bar = G_S - 0.5 * e3 * A + c * outer(w_bar, V) + be.bmm64(Kb, Pm)
+    del Pm
+    Sig_bar = -be.bmm64(be.bmm64(S, (0.5 * (S_bar + S_bar.transpose(-1, -2))).contiguous()), S)
+    del S_bar
+    gK = (Q + Q.transpose(-1, -2) + outer(mu_bar, w) + Sig_bar).sum(0)
+    del Q
+    gA = 0.5 * (e3 + r3) * Kinv_b - 0.5 * e3 * (S + outer(w, w)) - 0.5 * r3 * (Wm + outer(a, a)) + c * Sig_bar
+    return dict(gA=gA, gV=gV, gsums=gsums, gK=gK, gKinv=gKinv, gldK=0.5 * k.sum())
+
+
+def mm_shared_bwd(Kinv_b, gKinv, gldK):
+    """dK through Kinv = (K + jI)^-1 and ldK = logdet(K + jI) (adjoint of mm_shared)."""
+    be = get_backend()
+    Gs = (0.5 * (gKinv + gKinv.transpose(-1, -2))).contiguous()
+    return (gldK * Kinv_b - be.bmm64(be.bmm64(Kinv_b, Gs), Kinv_b)).squeeze(0)
+
+
 # autograd state of mm_channels: about this many (M, M) float64 matrices per channel stay alive between its
 # forward and backward (A, Sigma, S, KS, A_hat, its Cholesky factor, Kinv A_hat, Wm, products saved twice ...)
 _MM_LIVE_MATRICES = 16
@@ -211,31 +310,30 @@ class _SVGPStep(torch.autograd.Function):
         lc = mm_chunk_channels(own.stop - own.start, M, y32.device, cfg.get("mm_chunk"))
         one_chunk = lc >= own.stop - own.start
         if one_chunk:
-            with torch.enable_grad():
-                leaves = [t.detach().requires_grad_(True) for t in (A[own], V[own], sums[:, own].contiguous(), K64)]
-                mm = mm_stage(leaves[0], leaves[1], leaves[2], leaves[3], jitter, c, b_total)
+            Kinv, ldK, LinvK = mm_shared(K64, jitter)
+            mm, saved = mm_channels_fwd(A[own].contiguous(), V[own].contiguous(), sums[:, own].contiguous(), K64, Kinv, ldK, jitter, c, b_total)
             # pass B
-            S, w, Kinv, Linv = mm["S"].detach(), mm["w"].detach(), mm["Kinv"].detach(), mm["Linv"]
+            S, w, Linv = mm["S"], mm["w"], mm["Linv"]
             if sharded:                      # every rank needs all channels' S_l, w_l and factors for ITS rows
                 S, w, Linv = _allgather0(S, group), _allgather0(w, group), _allgather0(Linv, group)
             # quadratic forms through the Cholesky factors: |R^-1 k|^2 is a sum of squares (half the MMA work and
             # no cancellation between the large entries of S_l / Kinv)
             if tri:
-                h = be.rowquad(kop, mm["LinvK"], tri=True).squeeze(1)
+                h = be.rowquad(kop, LinvK, tri=True).squeeze(1)
                 q1 = be.rowquad(kop, Linv, tri=True)
             else:
                 h = be.rowquad(kop, Kinv).squeeze(1)
                 q1 = be.rowquad(kop, S)
-            recon, kl, ce0 = mm["recon"].detach().clone(), mm["kl"].detach().clone(), mm["ce"].detach()
-            mu_hat, A_hat = mm["mu_hat"].detach(), mm["A_hat"].detach()
+            recon, kl, ce0 = mm["recon"].clone(), mm["kl"].clone(), mm["ce"]
+            mu_hat, A_hat = mm["mu_hat"], mm["A_hat"]
             if sharded:
                 recon, kl, ce0, mu_hat = (_allgather0(t, group) for t in (recon, kl, ce0, mu_hat))
                 A_hat = _allgather0(A_hat, group) if cfg.get("return_A_hat", True) else None
-            del Linv
+            del Linv, LinvK, mm
         else:
             # chunked M x M stage: no graph in the forward (the backward re-materialises it chunk by chunk); S is
             # the only (L, M, M) result that stays (pass D reads it), the factors feed the row quads chunk by chunk
-            leaves, mm = (A, V, sums, K64), None
+            saved = None
             want_Ahat = cfg.get("return_A_hat", True)
             S = torch.empty_like(A)
             A_hat = torch.empty_like(A) if want_Ahat else None
@@ -249,7 +347,7 @@ class _SVGPStep(torch.autograd.Function):
                 h = (be.rowquad(kop, LinvK, tri=True) if tri else be.rowquad(kop, Kinv)).squeeze(1)
                 for l0 in range(own.start, own.stop, lc):
                     sl = slice(l0, min(own.stop, l0 + lc))
-                    mc = mm_channels(A[sl], V[sl], sums[:, sl].contiguous(), K64, Kinv, ldK, jitter, c, b_total)
+                    mc, _ = mm_channels_fwd(A[sl], V[sl], sums[:, sl].contiguous(), K64, Kinv, ldK, jitter, c, b_total)
                     S[sl], w[sl], mu_hat[sl] = mc["S"], mc["w"], mc["mu_hat"]
                     recon[sl], kl[sl], ce0[sl] = mc["recon"], mc["kl"], mc["ce"]
                     if want_Ahat:
@@ -279,7 +377,8 @@ class _SVGPStep(torch.autograd.Function):
             _allreduce(clipsum, group)
             ce = ce - 0.5 * clipsum
 
-        ctx.cfg, ctx.kop, ctx.mm, ctx.leaves, ctx.lc = cfg, kop, mm, leaves, lc
+        ctx.cfg, ctx.kop, ctx.mm_saved, ctx.lc = cfg, kop, saved, lc
+        ctx.mm_in = (A, V, sums, K64, ldK)
         ctx.own, ctx.sharded, ctx.one_chunk = own, sharded, one_chunk
         ctx.b_total, ctx.c = b_total, c
         cfg["_b_total"] = b_total                      # read back by svgp_step (a host number, not a tensor)
@@ -295,7 +394,7 @@ class _SVGPStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_pm, g_pv, g_recon, g_kl, g_ce, _g_mu, _g_Ahat):
         be = get_backend()
-        cfg, kop, mm = ctx.cfg, ctx.kop, ctx.mm
+        cfg, kop = ctx.cfg, ctx.kop
         spec, group, clip = cfg["spec"], cfg.get("group"), cfg.get("clip_pv")
         Fx, Fz, hyp, y, noise, p, kappa, h, pv, q1raw, mask, S, w, Kinv = ctx.saved_tensors
         N, L = y.shape
@@ -331,19 +430,17 @@ class _SVGPStep(torch.autograd.Function):
         # see) and only cancel there if they carry the SAME rounding noise.  (Formed below from this rank's channels.)
 
         # ---- adjoint of the replicated M x M stage -----------------------------------------------
-        A_, V_, sums_, K_ = ctx.leaves
+        A_, V_, sums_, K_, ldK_ = ctx.mm_in
         lc = ctx.lc
         own, sharded = ctx.own, ctx.sharded
         if ctx.one_chunk:
             # (channel-sharded K3: this rank differentiates its own channels; dKinv likewise is its channels' share)
-            gA, gV, gsums, gK = torch.autograd.grad(
-                [mm["S"], mm["w"], mm["Kinv"], mm["recon"], mm["kl"], mm["ce"]], [A_, V_, sums_, K_],
-                grad_outputs=[G_S[own], G_w[own], -G_S[own].sum(0, keepdim=True), g_recon[own], g_kl[own], g_ce[own]],
-                allow_unused=True)
-            gsums = torch.zeros_like(sums_) if gsums is None else gsums
-            # the autograd state of the stage, A_l and dS_l are dead from here on (17 GB each at M = 4096, L = 128)
-            mm = ctx.mm = ctx.leaves = None
-            del A_, G_S
+            g = mm_channels_bwd(ctx.mm_saved, K_, Kinv, G_S[own], G_w[own], g_recon[own], g_kl[own], g_ce[own])
+            gA, gV, gsums = g["gA"], g["gV"], g["gsums"]
+            gK = g["gK"] + mm_shared_bwd(Kinv, g["gKinv"] - G_S[own].sum(0, keepdim=True), g["gldK"])
+            # the saved state of the stage, A_l and dS_l are dead from here on (17 GB each at M = 4096, L = 128)
+            ctx.mm_saved = ctx.mm_in = None
+            del A_, G_S, g
             if sharded:
                 gA, gV = _allgather0(gA, group), _allgather0(gV, group)
                 gsums = _allgather0(gsums.t().contiguous(), group).t().contiguous()
@@ -393,29 +490,22 @@ class _SVGPStep(torch.autograd.Function):
                 def put(X, at):
                     G64[at:at + X.shape[0]] = X
             gV, gsums = torch.empty_like(V_), torch.empty_like(sums_)
-            with torch.enable_grad():
-                K_leaf = K_.detach().requires_grad_(True)
-                Kinv_g, ldK_g, _ = mm_shared(K_leaf, jitter)
             gK = torch.zeros_like(K_)
             gKinv = -G_S[own].sum(0, keepdim=True)          # this rank's channels' share of dKinv (all of it when not sharded)
-            gldK = torch.zeros_like(ldK_g)
+            gldK = torch.zeros((), dtype=torch.float64, device=dev)
             for l0 in range(own.start, own.stop, lc):
                 sl = slice(l0, min(own.stop, l0 + lc))
-                with torch.enable_grad():
-                    lv = [t.detach().requires_grad_(True) for t in (A_[sl], V_[sl], sums_[:, sl].contiguous(), K_, Kinv_g, ldK_g)]
-                    mc = mm_channels(*lv, jitter, c, b_total)
-                g = torch.autograd.grad([mc["S"], mc["w"], mc["recon"], mc["kl"], mc["ce"]], lv,
-                                        grad_outputs=[G_S[sl], G_w[sl], g_recon[sl], g_kl[sl], g_ce[sl]], allow_unused=True)
-                del mc, lv
-                put(g[0] + g[0].transpose(-1, -2), l0)
-                gV[sl] = g[1]
-                gsums[:, sl] = g[2] if g[2] is not None else 0.0
-                gK += g[3]
-                gKinv += g[4]
-                gldK += g[5]
+                _, sv = mm_channels_fwd(A_[sl], V_[sl], sums_[:, sl].contiguous(), K_, Kinv, ldK_, jitter, c, b_total)
+                g = mm_channels_bwd(sv, K_, Kinv, G_S[sl], G_w[sl], g_recon[sl], g_kl[sl], g_ce[sl])
+                del sv
+                put(g["gA"] + g["gA"].transpose(-1, -2), l0)
+                gV[sl] = g["gV"]
+                gsums[:, sl] = g["gsums"]
+                gK += g["gK"]
+                gKinv += g["gKinv"]
+                gldK += g["gldK"]
                 del g
-            (gK_sh,) = torch.autograd.grad([Kinv_g, ldK_g], [K_leaf], grad_outputs=[gKinv, gldK])
-            gK += gK_sh
+            gK += mm_shared_bwd(Kinv, gKinv, gldK)
             del G_S, gKinv
             if sharded:
                 # the other ranks' dA_l + dA_l^T (operand planes / float64), dv_l and row-sum adjoints; dK_mm summed
@@ -463,7 +553,7 @@ class _SVGPStep(torch.autograd.Function):
         dZa, dZb, dhyp_m = be.kernel_bwd(spec, Fz, Fz, hyp, gKf, need_x=True, need_z=True)
         dFz = dFz + dZa.double() + dZb
         dhyp = dhyp + dhyp_m
-        ctx.mm = ctx.leaves = None
+        ctx.mm_saved = ctx.mm_in = None
         dx, dz, dh, dy, dn = ctx.in_dtypes
         return (dFx.to(dx) if need_x else None, dFz.to(dz), dhyp.to(dh), G_y.to(dy), G_noise.to(dn), None)
 

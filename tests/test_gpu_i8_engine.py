@@ -79,12 +79,15 @@ def test_split_i8(cuda_backend, R, C, S):
     assert (P.planes[:, :, C:] == 0).all()
 
 
-@pytest.mark.parametrize("pair", [True, False])
-@pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1)])
-def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, monkeypatch):
+@pytest.mark.parametrize("pair,split", [(True, True), (True, False), (False, False)])
+@pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1), (3000, 1024, 1)])
+def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
     """pair: the CTA-pair kernel (tcgen05.mma.cta_group::2; the weighted operand is the B side: rows b) / the single-CTA
-    kernel (weighted operand = A side: rows a).  Both must equal the digit-exact emulation of their own operand placement."""
+    kernel (weighted operand = A side: rows a).  Both must equal the digit-exact emulation of their own operand placement.
+    split (default): the diagonal blocks (2 t + 1, 2 t + 1), whose pair tile would lie half above the diagonal, run on the
+    single-CTA kernel after the pair kernel."""
     monkeypatch.setenv("SVGP_I8_PAIR", "1" if pair else "0")
+    monkeypatch.setenv("SVGP_I8_SYRK_SPLIT", "1" if split else "0")
     be = cuda_backend
     _, kop = _kop(be, N, M, L)
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -104,13 +107,19 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, monkeypatch):
         qa = (torch.tensor(2130706432.0, device="cuda") * torch.tensor(0.99999, device="cuda")) / prod.abs().amax(0)
         V = torch.round(prod * qa[None, :]).to(torch.int64)
         v = _balanced_digits4(V)
-        acc = [torch.zeros(M, M, dtype=F64, device="cuda") for _ in range(4)]
-        for t in range(4):
-            for u in range(4):
-                if t + u <= 3:
-                    acc[t + u] += (kd[u].t() @ v[t]) if pair else (v[t].t() @ kd[u])      # exact: |sum| < 2^53
-        i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
-        ref[l] = i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if pair else qa.double()[:, None])
+        def emulate(weighted_is_b):
+            acc = [torch.zeros(M, M, dtype=F64, device="cuda") for _ in range(4)]
+            for t in range(4):
+                for u in range(4):
+                    if t + u <= 3:
+                        acc[t + u] += (kd[u].t() @ v[t]) if weighted_is_b else (v[t].t() @ kd[u])      # exact: |sum| < 2^53
+            i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
+            return i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if weighted_is_b else qa.double()[:, None])
+        ref[l] = emulate(pair)
+        if pair and split:
+            single = emulate(False)
+            for b in range(1, (M + 127) // 128, 2):
+                ref[l][128 * b:128 * b + 128, 128 * b:128 * b + 128] = single[128 * b:128 * b + 128, 128 * b:128 * b + 128]
     ref = torch.tril(ref) + torch.tril(ref, -1).transpose(-1, -2)
     assert rel_err(A, ref) < 1e-12
     # and against the plain float64 contraction of the float64 kernel values: fp32 kernel arithmetic is what is left
@@ -118,8 +127,14 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, monkeypatch):
     assert rel_err(A, full) < 1e-6
 
 
+@pytest.mark.parametrize("pair,wide", [(True, True), (True, False), (False, True), (False, False)])
 @pytest.mark.parametrize("N,M,L,ndot", [(4096, 256, 4, 2), (3000, 384, 3, 3), (2048, 1024, 2, 0)])
-def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot):
+def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
+    """pair: CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) / single CTAs; wide: six MMAs per k-step (four of them N = 256
+    over two neighbouring digit planes and two neighbouring accumulators) / the ten N = 128 MMAs.  Same ten digit-plane
+    products in every variant, so all four must equal the same digit-exact emulation."""
+    monkeypatch.setenv("SVGP_I8_PAIR", "1" if pair else "0")
+    monkeypatch.setenv("SVGP_I8_WIDE", "1" if wide else "0")
     be = cuda_backend
     _, kop = _kop(be, N, M, L)
     g = torch.Generator(device="cuda").manual_seed(3)

@@ -12,6 +12,7 @@ from oracle import svgp_literal as lit
 import svgp_vae_b200 as pkg
 from svgp_vae_b200 import configs, ops
 
+F64 = torch.float64
 TOL = 2e-5          # the stand-in backend rounds K_nm, p, ... to fp32 exactly like the CUDA path
 
 
@@ -357,3 +358,40 @@ def test_sprites_M500_inducing_gradient_is_ill_conditioned_in_the_reference_itse
         else:
             assert rel_err(ab, a) < 1e-5 and rel_err(b, a) < TOL
     assert rel_err(r1["p_m"], r0["p_m"]) < TOL and rel_err(r1["p_v"], r0["p_v"]) < TOL
+
+
+def test_handwritten_mm_stage_adjoint_matches_autograd(oracle_backend):
+    """step.mm_channels_fwd / mm_channels_bwd / mm_shared_bwd (what the batched step runs: no graph, hand-written adjoint of
+    SVGPVAE_model.py:318-319, 328-331, 339-341, 264-279) against torch autograd through the readable definition
+    step.mm_stage, on random SPD inputs: values and all four gradients to 1e-10."""
+    from svgp_vae_b200 import step
+    torch.manual_seed(3)
+    L, M, N = 3, 24, 200
+    jitter, c, b_total = 1e-3, 7.5, float(N)
+    Z = torch.randn(M, 3, dtype=F64)
+    K = torch.exp(-0.5 * torch.cdist(Z, Z) ** 2).requires_grad_(True)
+    Kn = torch.randn(N, M, dtype=F64) * 0.3
+    p = torch.rand(N, L, dtype=F64) + 0.1
+    A = torch.einsum("nl,na,nb->lab", p, Kn, Kn).requires_grad_(True)
+    V = torch.randn(L, M, dtype=F64).requires_grad_(True)
+    sums = torch.randn(3, L, dtype=F64).requires_grad_(True)
+    mm = step.mm_stage(A, V, sums, K, jitter, c, b_total)
+    G_S, G_w = torch.randn(L, M, M, dtype=F64), torch.randn(L, M, dtype=F64)
+    G_S = G_S + G_S.transpose(-1, -2)
+    G_Kinv = torch.randn(1, M, M, dtype=F64)
+    gr, gk, gc = torch.randn(L, dtype=F64), torch.randn(L, dtype=F64), torch.randn(L, dtype=F64)
+    ref = torch.autograd.grad([mm["S"], mm["w"], mm["Kinv"], mm["recon"], mm["kl"], mm["ce"]], [A, V, sums, K],
+                              grad_outputs=[G_S, G_w, G_Kinv, gr, gk, gc])
+    with torch.no_grad():
+        Kd = K.detach()
+        Kinv, ldK, LinvK = step.mm_shared(Kd, jitter)
+        out, sv = step.mm_channels_fwd(A.detach(), V.detach(), sums.detach(), Kd, Kinv, ldK, jitter, c, b_total)
+        for k in ("S", "w", "Linv", "recon", "kl", "ce", "mu_hat", "A_hat"):
+            assert rel_err(out[k], mm[k].detach()) < 1e-12, k
+        g = step.mm_channels_bwd(sv, Kd, Kinv, G_S, G_w, gr, gk, gc)
+        gK = g["gK"] + step.mm_shared_bwd(Kinv, g["gKinv"] + G_Kinv, g["gldK"])
+    sym = lambda X: X + X.transpose(-1, -2)
+    assert rel_err(sym(g["gA"]), sym(ref[0])) < 1e-10              # pass D consumes dA + dA^T, the kernel adjoint dK + dK^T
+    assert rel_err(g["gV"], ref[1]) < 1e-10
+    assert rel_err(g["gsums"], ref[2]) < 1e-12
+    assert rel_err(sym(gK), sym(ref[3])) < 1e-10
