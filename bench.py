@@ -103,6 +103,17 @@ def workload_name(args, world):
     return "SWEEP N=%d per GPU x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3])" % (args.n, world, args.m, args.l)
 
 
+def workload_config(args, world):
+    """The `config` object of the JSON line: identical for both arms (it describes the workload, not an implementation)."""
+    strong = getattr(args, "strong", False)
+    n_gpu = args.n // world if strong else args.n
+    name = workload_name(args, world) if not strong else (
+        "SWEEP N=%d TOTAL split over %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3], strong scaling)" % (args.n, world, args.m, args.l))
+    return {"workload": name,
+            "l2": "inputs_exceed_l2 (K_nm alone is N x M x 4 B = %.1f GB per GPU, re-streamed by every pass of the step)" % (4.0 * n_gpu * args.m / 1e9),
+            "parallelism": "datapoints sharded over %d GPU(s)" % world}
+
+
 def cpu_reference_timer(max_rows, M, L):
     """-> full(rows): seconds of one fwd + bwd of the streamlined float64 restatement on `rows` rows of the workload."""
     from oracle import svgp_streamlined as st
@@ -194,7 +205,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = torch.get_num_threads()
-    n_total = args.n * args.gpus
+    n_total = args.n if args.strong else args.n * args.gpus
     sizes = [8192, 2048, 4096]
     full = cpu_reference_timer(max(sizes), args.m, args.l)
     t_start = time.perf_counter()
@@ -221,7 +232,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "datapoints/s", "n_gpus": args.gpus, "steps": len(samples),
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "extrapolated": True,
-            "config": {"workload": workload_name(args, world)},
+            "config": workload_config(args, world),
             "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "datapoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -414,10 +425,9 @@ def run_gpu(args):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "int8 digit planes on tcgen05 kind::i8 with exact int32 TMEM accumulation (SYRK, scaled GEMM: fp32-accurate operands, "
                      "no accumulation rounding) + 3 x FP16 split (row quads) + f64 MxM stage", "data": "synthetic",
-            "config": {"workload": workload_name(args, world) if not args.strong else
-                       "SWEEP N=%d TOTAL split over %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3], strong scaling)" % (n_total, world, M, L),
-                       "l2": "inputs_exceed_l2 (K_nm operand planes: fp16 hi/lo + 2 x 4 int8 digit planes = %.1f GB per GPU)" % (12.0 * N * M / 1e9),
-                       "parallelism": "N-sharded x%d, all-reduce of A_l/v_l and their adjoints, channel-sharded f64 MxM stage" % world},
+            "config": workload_config(args, world),
+            "impl_notes": {"operands": "K_nm operand planes: fp16 hi/lo + 2 x 4 int8 digit planes = %.1f GB per GPU" % (12.0 * N * M / 1e9),
+                           "parallelism": "N-sharded x%d, all-reduce of A_l/v_l and their adjoints, channel-sharded f64 MxM stage" % world},
             "roofline": {"bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s (bf16-equivalent)",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "note": "achieved = e x algorithmic FLOPs of the kernel's launch / its CUDA-event duration inside the step; e = MMAs issued "

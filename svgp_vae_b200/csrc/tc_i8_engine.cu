@@ -90,18 +90,25 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 
 // One k-block of MMAs: digit planes A_0..A_3 (slots 0-3 of the stage at `st`) against B_0..B_3 (slots 4-7), the ten pairs
 // t + u <= 3 into the accumulator of their order.  first = first k-block of the chain (the accumulators start from zero).
+// The B planes lie behind each other in the stage, so two neighbouring planes are ONE 256-row operand and (the accumulators
+// of consecutive orders being neighbours in TMEM) A_t x [B_u ; B_u+1] serves two pairs with one fetch of the A plane: six
+// MMAs instead of ten for the same ten products (see scaled_i8_kernel).
 __device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_base, bool first) {
-  uint64_t a[4], b[4];
+  constexpr uint32_t IDESC_W = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * I8_T) >> 3) << 17) | ((uint32_t)(I8_T >> 4) << 24);
+  uint64_t a[4];
 #pragma unroll
-  for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + t * I8_PLANE); b[t] = i8_desc(st + (4 + t) * I8_PLANE); }
+  for (int t = 0; t < 4; ++t) a[t] = i8_desc(st + t * I8_PLANE);
+  const uint64_t b01 = i8_desc(st + 4 * I8_PLANE), b23 = i8_desc(st + 6 * I8_PLANE);
 #pragma unroll
   for (int ks = 0; ks < I8_KB / 32; ++ks) {
     const uint64_t adv = (uint64_t)((ks * 32) >> 4);
     const uint32_t f = (first && ks == 0) ? 0u : 1u;
-#pragma unroll
-    for (int o = 0; o < 4; ++o)
-#pragma unroll
-      for (int t = 0; t <= o; ++t) umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, t == 0 ? f : 1u);
+    umma_i8_idesc(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);       // acc0 (+)= A0 B0, acc1 (+)= A0 B1
+    umma_i8_idesc(tmem_base + 2 * I8_T, a[0] + adv, b23 + adv, IDESC_W, f);       // acc2 (+)= A0 B2, acc3 (+)= A0 B3
+    umma_i8_idesc(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);      // acc1 += A1 B0, acc2 += A1 B1
+    umma_i8_idesc(tmem_base + 2 * I8_T, a[2] + adv, b01 + adv, IDESC_W, 1u);      // acc2 += A2 B0, acc3 += A2 B1
+    umma_i8(tmem_base + 3 * I8_T, a[1] + adv, b23 + adv, 1u);                     // acc3 += A1 B2
+    umma_i8(tmem_base + 3 * I8_T, a[3] + adv, b01 + adv, 1u);                     // acc3 += A3 B0
   }
 }
 
@@ -214,7 +221,7 @@ __host__ __device__ __forceinline__ float syrk_vq(float u) { return u > 0.f ? 21
 // sharp and never exceeded.  One thread per inducing point a, LG channels per pass (their running maxima in registers),
 // the |weights| of a 128-datapoint block staged in shared memory ([datapoint][channel]: 4 channels per 16-byte read).
 template <int LG>
-__global__ void __launch_bounds__(128) syrk_vmax_kernel(const int8_t* __restrict__ Kc, int64_t N, int64_t M, int64_t nblk,
+__global__ void __launch_bounds__(128, 4) syrk_vmax_kernel(const int8_t* __restrict__ Kc, int64_t N, int64_t M, int64_t nblk,
                                                         const float* __restrict__ Wt, int64_t ldwt, int64_t L, float* __restrict__ vmax) {
   __shared__ __align__(16) float ws[128][LG];
   const int64_t m = (int64_t)blockIdx.x * 128 + threadIdx.x;
@@ -1038,12 +1045,13 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   int rc = encode_i8(&map, kop->Kc, 4, dims, strides);
   if (rc) return rc;
   {
-    // grid of the weighted operand (see the transform): one pass over the K^T planes per 32 channels
+    // grid of the weighted operand (see the transform): one pass over the K^T planes per 64 channels
     if (cudaMemsetAsync(vmax, 0, L * M * sizeof(float), st) != cudaSuccess) return check_launch("svgp_syrk(i8 vmax memset)");
     int64_t gy = nblk < 64 ? nblk : 64;
     while (gy * 2 <= nblk && ceil_div(M, 128) * gy * 2 <= 148 * 8) gy *= 2;
     dim3 grid((unsigned)ceil_div(M, 128), (unsigned)gy);
-    syrk_vmax_kernel<32><<<grid, 128, 0, st>>>((const int8_t*)kop->Kc, N, M, nblk, Wt, ldwt, L, vmax);
+    if (L > 32) syrk_vmax_kernel<64><<<grid, 128, 0, st>>>((const int8_t*)kop->Kc, N, M, nblk, Wt, ldwt, L, vmax);
+    else syrk_vmax_kernel<32><<<grid, 128, 0, st>>>((const int8_t*)kop->Kc, N, M, nblk, Wt, ldwt, L, vmax);
     rc = check_launch("svgp_syrk(i8 vmax)");
     if (rc) return rc;
   }

@@ -9,8 +9,8 @@ two methods it calls per channel (approximate_posterior_params :303-343, variati
            -> all-reduce over the N-shards -> replicated float64 M x M stage (K3)
   pass B   per-row predictive moments p_m = K_nm w_l, p_v = kappa - h + |R_l^-1 k_i|^2 (K4)
   [decoder / caller]
-  pass C   adjoints of p_m, p_v: weighted SYRK + skinny GEMM -> all-reduce -> adjoint of the
-           M x M stage (torch autograd over ops.bmm64 / spd_inverse_logdet / spd_logdet)
+  pass C   adjoints of p_m, p_v: weighted SYRK + skinny GEMM -> all-reduce -> hand-written adjoint of the
+           M x M stage (mm_channels_bwd / mm_shared_bwd: batched float64 products, no autograd graph)
   pass D   dK_nm = sum_s diag(w_s) K_nm G_s over the 2L stacked matrices [dA+dA^T ; S - Kinv] and the
            row-dots k_i^T dA_l k_i from the same tcgen05 products (weights and dots live in the epilogue),
            then K1's adjoint into features / inducing points / hypers.
@@ -252,13 +252,13 @@ def mm_shared_bwd(Kinv_b, gKinv, gldK):
     return (gldK * Kinv_b - be.bmm64(be.bmm64(Kinv_b, Gs), Kinv_b)).squeeze(0)
 
 
-# autograd state of mm_channels: about this many (M, M) float64 matrices per channel stay alive between its
-# forward and backward (A, Sigma, S, KS, A_hat, its Cholesky factor, Kinv A_hat, Wm, products saved twice ...)
-_MM_LIVE_MATRICES = 16
+# state of the stage: about this many (M, M) float64 matrices per channel are alive at the peak of its backward (saved: A, S,
+# A_hat, its Cholesky factor, Kinv A_hat, Wm; temporaries of mm_channels_bwd: dS, dA_hat and two products, dSigma, dA)
+_MM_LIVE_MATRICES = 12
 
 
 def mm_chunk_channels(L, M, device, override=None):
-    """Channels per chunk of the M x M stage.  One chunk (= the whole stage, fastest) whenever its autograd state
+    """Channels per chunk of the M x M stage.  One chunk (= the whole stage, fastest) whenever its saved state
     fits the budget; otherwise the stage runs chunk by chunk -- forward without a graph, re-materialised chunk by
     chunk in the backward -- so that L x M x M float64 state is bounded (configs[4]: M = 4096, L = 128 is 17 GB per
     (L, M, M) tensor)."""

@@ -80,7 +80,7 @@ def test_split_i8(cuda_backend, R, C, S):
 
 
 @pytest.mark.parametrize("pair,split", [(True, True), (True, False), (False, False)])
-@pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1), (3000, 1024, 1)])
+@pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1), (3000, 1024, 1), (2500, 256, 40)])
 def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
     """pair: the CTA-pair kernel (tcgen05.mma.cta_group::2; the weighted operand is the B side: rows b) / the single-CTA
     kernel (weighted operand = A side: rows a).  Both must equal the digit-exact emulation of their own operand placement.

@@ -281,10 +281,10 @@ def test_mm_stage_memory_plan_and_channel_ownership():
     channels a rank owns when the stage is sharded (section 6)."""
     from svgp_vae_b200 import step
     dev = torch.device("cpu")
-    assert step.mm_chunk_channels(64, 1024, dev) == 64                      # 8.6 GB of state: one chunk
-    assert step.mm_chunk_channels(64, 2048, dev) == 64                      # 34 GB: still one chunk
-    lc = step.mm_chunk_channels(128, 4096, dev)                             # configs[4]: 275 GB of state -> chunks
-    assert 1 <= lc < 128 and 16 * 8.0 * 4096 * 4096 * lc <= 48e9
+    assert step.mm_chunk_channels(64, 1024, dev) == 64                      # 6.4 GB of state: one chunk
+    assert step.mm_chunk_channels(64, 2048, dev) == 64                      # 26 GB: still one chunk
+    lc = step.mm_chunk_channels(128, 4096, dev)                             # configs[4]: 206 GB of state -> chunks
+    assert 1 <= lc < 128 and step._MM_LIVE_MATRICES * 8.0 * 4096 * 4096 * lc <= 48e9
     n = -(-128 // lc)
     assert -(-128 // n) == lc                                               # chunks are balanced
     assert step.mm_chunk_channels(16, 4096, dev) == 16                      # an 8-way shard of configs[4] fits one chunk

@@ -234,7 +234,10 @@ class SimBackend(OracleBackend):
         Kc = self._kfixed(kop, m, 0)
         Kv = Kc.value()
         for l in range(W.shape[1]):
-            V = (W[:, l:l + 1].float() * Kv.float()).double()          # fp32 product in the transform
+            if os.environ.get("SIM_SYRK_EXACT_PRODUCT", "0") == "1":     # 64-bit integer product in the transform (one rounding, onto the grid)
+                V = W[:, l:l + 1].double() * Kv
+            else:
+                V = (W[:, l:l + 1].float() * Kv.float()).double()      # fp32 product in the transform
             Vf = m.fixed(V, 0, "a")
             r = sliced_matmul(Vf, Kc, m.cut, lambda a, b: a.t() @ b)
             out.append(r * Vf.scale.t() * Kc.scale)

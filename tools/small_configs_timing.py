@@ -71,6 +71,28 @@ def main():
         tot.backward()
     ms = timeit(ball, reps=10)
     print(json.dumps({"config": "ball batch=35 tmax=30 m=15", "path": "per-object calls fwd+bwd", "ms": ms, "videos_per_s": 35 / ms * 1e3}), flush=True)
+    # the same SVGP part through the product glue (ball_svgp_terms), eager and captured as CUDA graphs (GraphedBallStep)
+    mu0, var0 = cfg["y"].cuda().float(), cfg["noise"].cuda().float()
+
+    def ball_glue(fn):
+        def run():
+            m, v = mu0.clone().requires_grad_(True), var0.clone().requires_grad_(True)
+            pm, pv, kl = fn(m, v)
+            (kl.sum() + pm.sum() + pv.sum()).backward()
+        return run
+
+    def eager(m, v):
+        t = pkg.ball_svgp_terms(sx, sy, m, v)
+        return t["full_p_mu"], t["full_p_var"], t["KL_term"]
+    try:
+        ms = timeit(ball_glue(eager), reps=10)
+        print(json.dumps({"config": "ball batch=35 tmax=30 m=15", "path": "ball_svgp_terms fwd+bwd (eager)", "ms": ms, "videos_per_s": 35 / ms * 1e3}), flush=True)
+        step = pkg.GraphedBallStep(sx, sy, mu0.shape[0], mu0.shape[1])
+        ms = timeit(ball_glue(step), reps=100)
+        step.check()
+        print(json.dumps({"config": "ball batch=35 tmax=30 m=15", "path": "GraphedBallStep fwd+bwd (CUDA graphs)", "ms": ms, "videos_per_s": 35 / ms * 1e3}), flush=True)
+    except Exception as e:  # noqa: BLE001
+        print(json.dumps({"config": "ball", "path": "GraphedBallStep", "error": repr(e)[:300]}), flush=True)
 
 
 if __name__ == "__main__":
