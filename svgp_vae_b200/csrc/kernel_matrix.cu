@@ -416,9 +416,12 @@ __global__ void __launch_bounds__(THREADS) kernel_fwd_planes_kernel(
   }
 }
 
-// float64 kernel matrix (fp32 features, float64 arithmetic and output): K_mm of the M x M stage
+// float64 kernel matrix (fp32 features, float64 arithmetic): OutT = double is K_mm of the M x M stage; OutT = float is the plain
+// K_nm of the small (SIMT-path) problems, ONE rounding of the float64 value -- the fp32 evaluation of the exponential carries
+// ~5e-7 of relative error (rounding of its argument), which e.g. the (b x b) solve of the Titsias bound amplifies to 1.2e-4 in dy
+template <typename OutT>
 __global__ void kernel_fwd_f64_kernel(const float* __restrict__ Fx, int64_t ldx, int64_t N, const float* __restrict__ Fz, int64_t ldz,
-                                      int64_t M, Spec sp, const float* __restrict__ hyp, double* __restrict__ K, int64_t ldk) {
+                                      int64_t M, Spec sp, const float* __restrict__ hyp, OutT* __restrict__ K, int64_t ldk) {
   const Hyp h = load_hyp(hyp);
   const int64_t total = N * M;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
@@ -430,7 +433,7 @@ __global__ void kernel_fwd_f64_kernel(const float* __restrict__ Fx, int64_t ldx,
     const double kb = factor_value_f64(sp.tb, x + sp.da, z + sp.da, sp.db, h.amp_b, h.len_b,
                                        sp.tb == SVGP_K_COSINE ? block_norm_f64(x + sp.da, sp.db) : 1.0,
                                        sp.tb == SVGP_K_COSINE ? block_norm_f64(z + sp.da, sp.db) : 1.0);
-    K[i * ldk + j] = ka * kb;
+    K[i * ldk + j] = (OutT)(ka * kb);
   }
 }
 
@@ -1047,6 +1050,13 @@ int svgp_kernel_fwd(const float* Fx, int64_t ldx, int64_t N, const float* Fz, in
           Fx, ldx, N, Fz, ldz, M, sp, hyp, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
     return check_launch("svgp_kernel_fwd(planes)");
   }
+  if (K && !Kh && !Kth && N * M <= (int64_t)1 << 26) {
+    // plain fp32 K_nm of a small problem: float64 evaluation, one rounding (the tiled fp32 builder below serves the large ones)
+    int64_t blocks = ceil_div(N * M, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    kernel_fwd_f64_kernel<float><<<(unsigned)blocks, 256, 0, st>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk);
+    return check_launch("svgp_kernel_fwd(f64 evaluation)");
+  }
   kernel_fwd_kernel<<<grid, THREADS, fwd_smem(dim_a + dim_b), st>>>(
       Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk, (__half*)Kh, (__half*)Kl, ldkh, (__half*)Kth, (__half*)Ktl, ldkt, kscale);
   return check_launch("svgp_kernel_fwd");
@@ -1060,7 +1070,7 @@ int svgp_kernel_fwd_f64(const float* Fx, int64_t ldx, int64_t N, const float* Fz
   Spec sp{type_a, dim_a, type_b, dim_b};
   int64_t blocks = ceil_div(N * M, 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  kernel_fwd_f64_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk);
+  kernel_fwd_f64_kernel<double><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(Fx, ldx, N, Fz, ldz, M, sp, hyp, K, ldk);
   return check_launch("svgp_kernel_fwd_f64");
 }
 

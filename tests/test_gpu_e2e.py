@@ -205,11 +205,9 @@ def test_against_reference_source_golden(cuda_backend, name, kind, maker, clip):
     for gname, g in zip(names, g1):
         ref_g = T("grad_" + gname)
         if ref_g.abs().max() > 0:
-            # The two kernel hyper-parameter gradients are scalars left over from a ~7000-fold cancellation between the
-            # K_nm, K_mm and kappa contributions (the posterior is nearly invariant to the amplitude): with K_nm and
-            # dK_nm held in fp32 (the reference runs this config in float64) they carry up to ~1e-4 relative error
-            # themselves, so they get 3e-4; every tensor-valued gradient is held to 1e-4.
-            assert rel_err(g, ref_g) < (3e-4 if gname in ("amplitude", "length") else TOL), gname
+            # every gradient at 1e-4, the two kernel hyper-parameter scalars (left over from a ~7000-fold cancellation between
+            # the K_nm, K_mm and kappa contributions) included: measured 7e-7 .. 3.3e-5 (tests/probes/small_grad_errors.py)
+            assert rel_err(g, ref_g) < TOL, gname
     auxc = cfg["aux"].cuda()
     K = s.kernel_matrix(auxc, s.inducing_index_points, x_inducing=False)
     assert rel_err(K, T("K_nm")) < 1e-6
@@ -284,7 +282,10 @@ def test_titsias_branch_against_reference_source(cuda_backend):
     assert abs(float(r1["inside_elbo_recon"]) - sc[0]) < TOL * abs(sc[0]) and abs(float(r1["KL_term"]) - sc[3]) < TOL * abs(sc[3])
     assert rel_err(r1["p_m"], T("mnist_titsias/p_m")) < TOL and rel_err(r1["p_v"], T("mnist_titsias/p_v")) < TOL
     for g, n in zip(g1, ["y", "noise", "Z", "table"]):
-        assert rel_err(g, T("mnist_titsias/grad_" + n)) < 3 * TOL, n
+        # dnoise, dZ, dtable at 1e-4 (measured 4.2e-5, 2.0e-5, 5.3e-6).  dy = -cov^-1 y of the (b x b) system diag(noise) + K_nm Kinv K_mn
+        # sees the fp32 storage of K_nm amplified by cond(cov) ~ 1e3 (the reference runs this configuration in float64):
+        # measured 1.2e-4, held to 1.5e-4
+        assert rel_err(g, T("mnist_titsias/grad_" + n)) < (1.5 * TOL if n == "y" else TOL), n
     cfgb = configs.ball_inputs()
     sb = pkg.SVGP(name="x", **dict(cfgb["ctor"], titsias=True)).cuda()
     xc = cfgb["x"].cuda()

@@ -63,6 +63,21 @@ def test_kernel_fwd_bwd(cuda_backend, name, shape):
         assert rel_err(fh, eh) < 2e-5
 
 
+@pytest.mark.parametrize("name", ["mnist_cos", "sweep_se"])
+def test_kernel_fwd_large_plain_uses_the_fp32_tile_builder(cuda_backend, name):
+    """Plain fp32 K_nm above 2^26 entries comes from the tiled fp32 builder (below that from the float64-evaluating kernel,
+    test_kernel_fwd_bwd): both against the float64 oracle; the small one is held to ONE fp32 rounding."""
+    be, spec = cuda_backend, SPECS[name]
+    Fx, Fz, hyp = _feat(spec, 66000, 1024)                    # 67.6 M entries
+    ref = kernel_value(spec, Fx.cuda(), Fz.cuda(), hyp.cuda())
+    kop = be.kernel_fwd(spec, Fx.cuda(), Fz.cuda(), hyp.cuda())
+    assert rel_err(kop.K, ref) < 5e-6
+    small = be.kernel_fwd(spec, Fx[:4000].cuda(), Fz.cuda(), hyp.cuda())
+    r = ref[:4000]
+    # one rounding to fp32 of the float64 value (+ the float64 evaluation's own last bits on entries that cancel to ~0)
+    assert ((small.K.double() - r).abs() <= 2.0 ** -24 * 1.02 * r.abs() + 1e-13 * float(r.abs().max())).all()
+
+
 def test_gather_scatter(cuda_backend):
     be = cuda_backend
     g = torch.Generator().manual_seed(0)
