@@ -282,10 +282,10 @@ def test_titsias_branch_against_reference_source(cuda_backend):
     assert abs(float(r1["inside_elbo_recon"]) - sc[0]) < TOL * abs(sc[0]) and abs(float(r1["KL_term"]) - sc[3]) < TOL * abs(sc[3])
     assert rel_err(r1["p_m"], T("mnist_titsias/p_m")) < TOL and rel_err(r1["p_v"], T("mnist_titsias/p_v")) < TOL
     for g, n in zip(g1, ["y", "noise", "Z", "table"]):
-        # dnoise, dZ, dtable at 1e-4 (measured 4.2e-5, 2.0e-5, 5.3e-6).  dy = -cov^-1 y of the (b x b) system diag(noise) + K_nm Kinv K_mn
-        # sees the fp32 storage of K_nm amplified by cond(cov) ~ 1e3 (the reference runs this configuration in float64):
-        # measured 1.2e-4, held to 1.5e-4
-        assert rel_err(g, T("mnist_titsias/grad_" + n)) < (1.5 * TOL if n == "y" else TOL), n
+        # all four at 1e-4: measured 3.2e-5, 2.6e-5, 6.1e-6, 5.4e-6 (tests/probes/small_grad_errors.py).  dy = -cov^-1 y of the (b x b)
+        # system diag(noise) + K_nm Kinv K_mn amplifies errors of K_nm by cond(cov) ~ 1e3: 1.2e-4 while the small K_nm was evaluated
+        # in fp32 (5e-7 relative), 3.2e-5 with the float64 evaluation rounded once (kernel_matrix.cu, kernel_fwd_f64_kernel<float>)
+        assert rel_err(g, T("mnist_titsias/grad_" + n)) < TOL, n
     cfgb = configs.ball_inputs()
     sb = pkg.SVGP(name="x", **dict(cfgb["ctor"], titsias=True)).cuda()
     xc = cfgb["x"].cuda()
