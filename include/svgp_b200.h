@@ -61,7 +61,8 @@ int svgp_device_ok(void);          /* 1 if the current device is compute capabil
  * Fx (N x d) / Fz (M x d) are dense fp32 feature rows [block A | block B], d = dim_a+dim_b.
  * hyp = device float[4] = {amplitude_a, length_a, amplitude_b, length_b} (unused entries 1).
  * Outputs (each group may be NULL):
- *   K   (N x M fp32, ld = ldk)                         plain matrix for the SIMT consumers
+ *   K   (N x M fp32, ld = ldk)                         plain matrix for the SIMT consumers; requested alone and with
+ *                                                      N M <= 2^26 it is the float64 evaluation rounded once to fp32
  *   Kh, Kl   (N x M fp16 planes, ld = ldkh elements)   operand planes of the tcgen05 consumers:
  *   Kth, Ktl (transposed planes, datapoint-blocked:    value * scale = fp16 hi + fp16 lo (22 bits),
  *            element (m, n) at [n / 64] * ldkt + m * 64 + n % 64, ldkt >= 64 M; ceil(N / 64) blocks, the

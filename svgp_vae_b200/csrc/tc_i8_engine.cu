@@ -16,10 +16,13 @@
 // 24-bit operands or 9 pairs are NOT enough at M = 2048).  kind::i8 runs at twice the MAC rate of kind::f16
 // (profiles/r02_i8_mma_probe.jsonl: 8192 MAC / clk / SM), so 10 integer MMAs cost 5 fp16 MMAs against 3 before.
 //
-// Tile: 128 x 128 outputs, k-blocks of 64 reduction elements (one 64-byte swizzle row per operand row and digit plane),
-// three shared-memory stages of 8 planes x 8 KB; the four accumulators fill TMEM (4 x 128 columns), so the epilogue of
-// one chain does not overlap the MMAs of the next -- the SYRK chains are a whole window of datapoints long (irrelevant),
-// the scaled GEMM pays ~15 % at M = 1024 (less as M grows).
+// Tile: 128 x 128 outputs per CTA (256 x 128 per CTA pair with cta_group::2), k-blocks of 64 reduction elements (one 64-byte
+// swizzle row per operand row and digit plane), three or four shared-memory stages; the four accumulators fill TMEM
+// (4 x 128 columns), so the epilogue of one chain does not overlap the MMAs of the next -- the SYRK chains are a whole
+// window of datapoints long (irrelevant), the scaled GEMM pays ~11 % at M = 1024 (less as M grows).  Both kernels are
+// bound by shared-memory operand fetches (the MMA issuer never waits, profiles/r02_ncu_*_fullsize.csv): the "wide" form
+// issues the ten products of a k-step as six MMAs (two neighbouring B planes = one N = 256 operand, two neighbouring
+// accumulators = its destination) and so fetches an A plane 6 instead of 10 times.
 #include "tc_ptx.cuh"
 
 namespace svgp {
