@@ -236,13 +236,6 @@ int svgp_gemm_f64(int transA, int transB, int64_t Mr, int64_t Nc, int64_t Kd, do
                   int64_t strideB, double beta, double* C, int64_t ldc, int64_t strideC, int64_t batch,
                   void* stream);
 
-/* C[b] = alpha op(A[b]) op(B[b]) for square products whose result is symmetric by construction (K S K :341, Kinv A_hat Kinv
- * :286-294 as a trace, S G S in the adjoint of tf.linalg.inv): only the tiles touching the lower triangle are computed and
- * mirrored -- half the work of svgp_gemm_f64, an exactly symmetric result.  A, B: M x Kd / Kd x M after op().            */
-int svgp_gemm_f64_sym(int transA, int transB, int64_t M, int64_t Kd, double alpha, const double* A, int64_t lda,
-                      int64_t strideA, const double* B, int64_t ldb, int64_t strideB, double* C, int64_t ldc,
-                      int64_t strideC, int64_t batch, void* stream);
-
 /* ---------------------------------------------------------------------------------------
  * K4  fused row terms
  * ------------------------------------------------------------------------------------- */

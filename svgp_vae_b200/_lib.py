@@ -64,8 +64,6 @@ SIGNATURES = {
     "svgp_ltl_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P],
     "svgp_gemm_f64": [c_int, c_int, c_int64, c_int64, c_int64, c_double, _P, c_int64, c_int64, _P, c_int64,
                       c_int64, c_double, _P, c_int64, c_int64, c_int64, _P],
-    "svgp_gemm_f64_sym": [c_int, c_int, c_int64, c_int64, c_double, _P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int64,
-                          c_int64, _P],
     "svgp_rowstats_fwd": [_P, _P, _P, c_int64, c_int64, _P, _P, _P, _P],
     "svgp_predictive_fwd": [_P, _P, _P, _P, c_int64, c_int64, c_int, c_float, c_float, _P, _P, _P],
     "svgp_rowterms_bwd_pre": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, _P, _P, _P, _P, _P, _P],

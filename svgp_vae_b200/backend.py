@@ -491,21 +491,6 @@ class CudaBackend:
         self.launches += 1
         return C
 
-    def bmm64_sym(self, A, B, transA=False, transB=False):
-        """op(A[b]) op(B[b]) for square products that are symmetric by construction: lower-triangle tiles + mirror."""
-        A, B = _f64c(A), _f64c(B)
-        nb = max(A.shape[0], B.shape[0])
-        M = A.shape[2] if transA else A.shape[1]
-        Kd = A.shape[1] if transA else A.shape[2]
-        assert Kd == (B.shape[2] if transB else B.shape[1]) and M == (B.shape[1] if transB else B.shape[2]), (A.shape, B.shape)
-        C = torch.empty((nb, M, M), device=A.device, dtype=torch.float64)
-        sA = 0 if (A.shape[0] == 1 and nb > 1) else A.shape[1] * A.shape[2]
-        sB = 0 if (B.shape[0] == 1 and nb > 1) else B.shape[1] * B.shape[2]
-        _call("svgp_gemm_f64_sym", int(transA), int(transB), M, Kd, 1.0, _ptr(A), A.shape[2], sA, _ptr(B), B.shape[2], sB,
-              _ptr(C), M, M * M, nb, _stream())
-        self.launches += 2
-        return C
-
     # ---- K4 row terms ----------------------------------------------------------------------
     def rowstats(self, y, noise, kappa):
         y, noise, kappa = _f32c(y), _f32c(noise), _f32c(kappa)

@@ -466,21 +466,6 @@ int svgp_ltl_f64(const double* T, double* S, int64_t M, int64_t ld, int64_t stri
   return check_launch("svgp_ltl_f64");
 }
 
-// square product whose RESULT is symmetric by construction (K S K, Kinv A Kinv, S G S ...): only the tiles touching the lower
-// triangle are computed, the upper triangle is the mirror image -- half the DMMA work, and exactly symmetric
-int svgp_gemm_f64_sym(int transA, int transB, int64_t M, int64_t Kd, double alpha, const double* A, int64_t lda, int64_t strideA,
-                      const double* B, int64_t ldb, int64_t strideB, double* C, int64_t ldc, int64_t strideC, int64_t batch,
-                      void* stream) {
-  SVGP_REQUIRE(A && B && C && M >= 0 && Kd >= 0 && batch >= 0 && batch <= 65535 && ldc >= M, "bad argument");
-  if (M == 0 || batch == 0) return SVGP_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc = gemm_f64(transA, transB, M, M, Kd, alpha, A, lda, strideA, B, ldb, strideB, 0.0, C, ldc, strideC, batch, 1, st);
-  if (rc) return rc;
-  dim3 g((unsigned)(ceil_div(M * M, 256) < 1024 ? ceil_div(M * M, 256) : 1024), (unsigned)batch);
-  mirror_lower_f64_kernel<<<g, 256, 0, st>>>(C, M, ldc, strideC);
-  return check_launch("svgp_gemm_f64_sym");
-}
-
 int svgp_chol_f64(double* A, int64_t M, int64_t ld, int64_t stride, int64_t batch, int* status, double* ws, void* stream) {
   SVGP_REQUIRE(A && ws && M >= 1 && ld >= M && batch >= 1 && batch <= 65535, "bad argument");
   cudaStream_t st = (cudaStream_t)stream;

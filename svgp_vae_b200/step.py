@@ -175,7 +175,7 @@ def mm_channels_fwd(A, V, sums, K, Kinv_b, ldK, jitter, c, b_total):
     mu_hat = mv(Kb, w)
     a = mv(Kinv_b, mu_hat)
     KS = be.bmm64(Kb, S)
-    A_hat = be.bmm64_sym(KS, Kb)                              # K S K: symmetric by construction (lower tiles + mirror)
+    A_hat = be.bmm64(KS, Kb)
     del KS
     LfA, status = be.chol((A_hat + jitter * eye).contiguous())
     ops._check_status(status, "mm_channels_fwd(A_hat)")
@@ -183,7 +183,7 @@ def mm_channels_fwd(A, V, sums, K, Kinv_b, ldK, jitter, c, b_total):
     T = be.bmm64(Kinv_b, A_hat)                               # Kinv A_hat
     tr_KinvAhat = torch.diagonal(T, dim1=-2, dim2=-1).sum(-1)
     kl = 0.5 * (ldK - ld_Ahat - M + tr_KinvAhat + (mu_hat * a).sum(-1))
-    Wm = be.bmm64_sym(T, Kinv_b)                              # Kinv A_hat Kinv
+    Wm = be.bmm64(T, Kinv_b)                                  # Kinv A_hat Kinv
     s_pk, s_pyy, s_log = sums[0], sums[1], sums[2]
     s_ph = (Kinv_b * A).sum((-1, -2))
     s_t = (Wm * A).sum((-1, -2))
@@ -226,7 +226,7 @@ def mm_channels_bwd(sv, K, Kinv_b, G_S, G_w, g_recon, g_kl, g_ce):
     # adjoint of A_hat
     AhatInv = be.ltl(be.trinv(sv["LfA"]))
     KinvA = be.bmm64(Kinv_b, A)
-    Ahat_bar = -0.5 * k3 * AhatInv + 0.5 * k3 * Kinv_b - 0.5 * r3 * be.bmm64_sym(KinvA, Kinv_b)
+    Ahat_bar = -0.5 * k3 * AhatInv + 0.5 * k3 * Kinv_b - 0.5 * r3 * be.bmm64(KinvA, Kinv_b)
     del AhatInv, KinvA
     # adjoint of Kinv (this chunk's share)
     Y = be.bmm64(A, T)
@@ -235,9 +235,9 @@ def mm_channels_bwd(sv, K, Kinv_b, G_S, G_w, g_recon, g_kl, g_ce):
     # through A_hat = K S K
     Pm = be.bmm64(Ahat_bar, Kb)
     Q = be.bmm64(Pm, S)
-    S_bar = G_S - 0.5 * e3 * A + c * outer(w_bar, V) + be.bmm64_sym(Kb, Pm)            # K Ahat_bar K
+    S_bar = G_S - 0.5 * e3 * A + c * outer(w_bar, V) + be.bmm64(Kb, Pm)
     del Pm
-    Sig_bar = -be.bmm64_sym(be.bmm64(S, (0.5 * (S_bar + S_bar.transpose(-1, -2))).contiguous()), S)
+    Sig_bar = -be.bmm64(be.bmm64(S, (0.5 * (S_bar + S_bar.transpose(-1, -2))).contiguous()), S)
     del S_bar
     gK = (Q + Q.transpose(-1, -2) + outer(mu_bar, w) + Sig_bar).sum(0)
     del Q
@@ -249,7 +249,7 @@ def mm_shared_bwd(Kinv_b, gKinv, gldK):
     """dK through Kinv = (K + jI)^-1 and ldK = logdet(K + jI) (adjoint of mm_shared)."""
     be = get_backend()
     Gs = (0.5 * (gKinv + gKinv.transpose(-1, -2))).contiguous()
-    return (gldK * Kinv_b - be.bmm64_sym(be.bmm64(Kinv_b, Gs), Kinv_b)).squeeze(0)
+    return (gldK * Kinv_b - be.bmm64(be.bmm64(Kinv_b, Gs), Kinv_b)).squeeze(0)
 
 
 # state of the stage: about this many (M, M) float64 matrices per channel are alive at the peak of its backward (saved: A, S,

@@ -141,10 +141,6 @@ class OracleBackend:
         B = B.transpose(-1, -2) if transB else B
         return (A @ B).contiguous()
 
-    def bmm64_sym(self, A, B, transA=False, transB=False):
-        C = self.bmm64(A, B, transA, transB)
-        return torch.tril(C) + torch.tril(C, -1).transpose(-1, -2)          # lower triangle mirrored, like the library
-
     # K4 row terms
     def rowstats(self, y, noise, kappa):
         p = torch.where(noise == 0, torch.zeros_like(noise), 1.0 / torch.where(noise == 0, torch.ones_like(noise), noise))
