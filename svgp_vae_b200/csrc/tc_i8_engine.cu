@@ -84,6 +84,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, int (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld8_nowait(uint32_t taddr, int (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {     // generic mode: selector bit 3 = replicate sign
   uint32_t d;
@@ -735,6 +740,21 @@ struct ScaledI8Params {
   int debug;                    // experiments (SVGP_I8_DEBUG, wrong results): bit 0 = the epilogue releases TMEM without reading it
 };
 
+// Recombination of 8 columns of the four order accumulators (one fp32 rounding each: |acc_o| < 2^24 for M <= 1024, beyond that
+// the rounding of an order's sum is 2^-24 relative), scale, weighted running sum and -- DOT -- the row's k-dot.
+template <bool DOT>
+__device__ __forceinline__ void scaled8_chunk(const int (&a)[4][8], const float (&g)[8], float wgt, float* run, const float* kv, float& dsum) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float tv = fmaf(__int2float_rn(a[2][j]), 256.f, __int2float_rn(a[3][j]));
+    tv = fmaf(__int2float_rn(a[1][j]), 65536.f, tv);
+    tv = fmaf(__int2float_rn(a[0][j]), 16777216.f, tv);
+    tv *= g[j];
+    run[j] = fmaf(wgt, tv, run[j]);
+    if (DOT) dsum = fmaf(tv, kv[j], dsum);
+  }
+}
+
 constexpr int SCALED8_THREADS = 384;     // warp 0 TMA, warp 1 MMA (pair: the peer's warp 1 forwards its "stage full"), warps 4-11 epilogue
 constexpr int SCALED8_EPI_WARP0 = 4;
 
@@ -955,36 +975,55 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         const bool want_dot = has_dots && s < P.ndot;                      // warp-uniform
         float dsum = 0.f;
         const float* gs = P.gscale + s * P.Mc;
+        const int mcm1 = (int)P.Mc - 1;
+        const bool gvec = ((P.Mc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.gscale) & 15) == 0);
         mbar_wait(tfull, tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 64);
+        // Chunks of 8 columns (4 orders x 8 int32 per thread), double-buffered: the loads of chunk c + 1 are in flight while
+        // chunk c is recombined, and TMEM is handed back to the MMA issuer as soon as the LAST chunk sits in registers -- its
+        // arithmetic then overlaps the first MMAs of the next matrix (TMEM is full, so nothing else of this epilogue can).
+        int buf[2][4][8];
+        if (!(P.debug & 1)) {
 #pragma unroll
-        for (int c16 = 0; c16 < 4; ++c16) {
-          const int64_t c0 = cw0 + c16 * 16;
-          if (c0 < P.Mc && !(P.debug & 1)) {                               // warp-uniform
-            int a0[16], a1[16], a2[16], a3[16];
-            tmem_ld16_nowait(taddr + 0 * I8_T + c16 * 16, a0);
-            tmem_ld16_nowait(taddr + 1 * I8_T + c16 * 16, a1);
-            tmem_ld16_nowait(taddr + 2 * I8_T + c16 * 16, a2);
-            tmem_ld16_nowait(taddr + 3 * I8_T + c16 * 16, a3);
+          for (int o = 0; o < 4; ++o) tmem_ld8_nowait(taddr + o * I8_T, buf[0][o]);
+        }
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          if (!(P.debug & 1)) {
             tmem_ld_wait();
+            if (c8 < 7) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float g = (c0 + j < P.Mc) ? __ldg(gs + c0 + j) : 0.f;
-              // |acc_o| < 2^24 for M <= 1024 (exact conversions); beyond that the fp32 rounding of an order's sum is 2^-24 relative
-              float tv = fmaf(__int2float_rn(a2[j]), 256.f, __int2float_rn(a3[j]));
-              tv = fmaf(__int2float_rn(a1[j]), 65536.f, tv);
-              tv = fmaf(__int2float_rn(a0[j]), 16777216.f, tv);
-              tv *= g;
-              run[c16 * 16 + j] = fmaf(wgt, tv, run[c16 * 16 + j]);
-              if (want_dot) dsum = fmaf(tv, kv[c16 * 16 + j], dsum);
+              for (int o = 0; o < 4; ++o) tmem_ld8_nowait(taddr + o * I8_T + (c8 + 1) * 8, buf[(c8 + 1) & 1][o]);
             }
           }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR && crank != 0) mbar_arrive_remote(tempty, 0); else mbar_arrive(tempty);
+          if (c8 == 7) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR && crank != 0) mbar_arrive_remote(tempty, 0); else mbar_arrive(tempty);
+            }
+          }
+          const int c0 = (int)cw0 + c8 * 8;
+          if (c0 <= mcm1 && !(P.debug & 1)) {                              // warp-uniform
+            // the epilogue is issue-bound (2 warps per scheduler x 64 columns per matrix): four variants of the same arithmetic
+            // keep the per-column instruction count down -- scales by two 16-byte loads when the chunk is whole and aligned,
+            // no dot product (and no select) for the matrices that do not ask for one
+            if (c0 + 8 <= mcm1 + 1 && gvec) {
+              const float4 g0 = __ldg(reinterpret_cast<const float4*>(gs + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gs + c0 + 4));
+              const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+              if (want_dot) scaled8_chunk<true>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              else scaled8_chunk<false>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+            } else {
+              // ragged last tile / unaligned scales: columns past Mc read a clamped scale (their sums are never stored, their K
+              // entries are zero)
+              float g[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) g[j] = __ldg(gs + (c0 + j < mcm1 ? c0 + j : mcm1));
+              if (want_dot) scaled8_chunk<true>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              else scaled8_chunk<false>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+            }
+          }
         }
         tphase ^= 1;
         if (want_dot && live) atomicAdd(&P.dots[i * P.lddots + s], dsum * rs * rs * 16777216.f);

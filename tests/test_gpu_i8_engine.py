@@ -128,7 +128,7 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
 
 
 @pytest.mark.parametrize("pair,wide", [(True, True), (True, False), (False, True), (False, False)])
-@pytest.mark.parametrize("N,M,L,ndot", [(4096, 256, 4, 2), (3000, 384, 3, 3), (2048, 1024, 2, 0), (2304, 4096, 2, 1)])
+@pytest.mark.parametrize("N,M,L,ndot", [(4096, 256, 4, 2), (3000, 384, 3, 3), (2048, 1024, 2, 0), (2304, 4096, 2, 1), (2304, 330, 3, 2)])
 def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
     """pair: CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) / single CTAs; wide: six MMAs per k-step (four of them N = 256
     over two neighbouring digit planes and two neighbouring accumulators) / the ten N = 128 MMAs.  Same ten digit-plane
