@@ -240,7 +240,14 @@ class SimBackend(OracleBackend):
                 V = (W[:, l:l + 1].float() * Kv.float()).double()      # fp32 product in the transform
             Vf = m.fixed(V, 0, "a")
             r = sliced_matmul(Vf, Kc, m.cut, lambda a, b: a.t() @ b)
-            out.append(r * Vf.scale.t() * Kc.scale)
+            r = r * Vf.scale.t() * Kc.scale                              # V^T K: weighted operand = row index
+            sym = os.environ.get("SIM_SYRK_SYM", "")                     # how the kernel turns it into a symmetric matrix
+            if sym == "mirror":                                          # lower triangle of K^T V (weighted = column index), mirrored: the GPU kernel
+                rt = r.t()
+                r = torch.tril(rt) + torch.tril(rt, -1).t()
+            elif sym == "avg":                                           # both triangles computed, averaged
+                r = 0.5 * (r + r.t())
+            out.append(r)
         return torch.stack(out)
 
     def gemm_tn(self, kop, X):
