@@ -220,6 +220,7 @@ struct SyrkI8Params {
   int nwin, ntile;
   int64_t n_items;
   int split;                // pair kernel: leave the tiles tb = 2 ta + 1 out; single-CTA kernel: ONLY the blocks (2 t + 1, 2 t + 1)
+  int full;                 // pair kernel: every tile and every entry of K^T (w o K) (symmetrised afterwards by averaging, not mirroring)
 };
 
 // quantisation factor of the weighted operand of row a: |float(Kint) * wn * q| <= 127 2^24 (two fp32 roundings of headroom)
@@ -475,15 +476,17 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
 // Of the tile tb = 2 ta + 1 only the lower CTA's diagonal 128 x 128 block touches the triangle: with `split` those tiles are left
 // out here and their diagonal blocks (2 ta + 1, 2 ta + 1) go to the single-CTA kernel instead (10 % fewer MMAs at M = 1024).
 struct SyrkPairTiles {              // tiles (ta: 256 rows, tb: 128 columns) touching the lower triangle: tb <= 2 ta + 1
-  __host__ __device__ static int count(int64_t M, int split) {
+  __host__ __device__ static int count(int64_t M, int split, int full = 0) {
     const int T2 = (int)((M + 255) / 256), Tb = (int)((M + 127) / 128);
+    if (full) return T2 * Tb;
     int c = 0;
     for (int ta = 0; ta < T2; ++ta) c += (2 * ta + 2 - split < Tb ? 2 * ta + 2 - split : Tb);
     return c;
   }
   __host__ __device__ static int odd_blocks(int64_t M) { return (int)((M + 127) / 128) / 2; }      // blocks (2 t + 1, 2 t + 1)
-  __device__ static void decode(int idx, int64_t M, int split, int& ta_out, int& tb_out) {
+  __device__ static void decode(int idx, int64_t M, int split, int full, int& ta_out, int& tb_out) {
     const int T2 = (int)((M + 255) / 256), Tb = (int)((M + 127) / 128);
+    if (full) { ta_out = idx / Tb; tb_out = idx - ta_out * Tb; return; }
     int c = 0;
     for (int ta = 0; ta < T2; ++ta) {
       const int n = (2 * ta + 2 - split < Tb ? 2 * ta + 2 - split : Tb);
@@ -538,7 +541,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int64_t per_win = (int64_t)P.ntile * P.L;
     const int64_t win = item / per_win, rem = item - win * per_win;
     it.l = rem % P.L;
-    SyrkPairTiles::decode((int)(rem / P.L), P.M, P.split, it.ta, it.tb);
+    SyrkPairTiles::decode((int)(rem / P.L), P.M, P.split, P.full, it.ta, it.tb);
     it.n0 = win * P.win_rows;
     it.n1 = it.n0 + P.win_rows < P.N ? it.n0 + P.win_rows : P.N;
     it.nkb = (int)((it.n1 - it.n0 + I8_KB - 1) / I8_KB);
@@ -684,7 +687,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll 1
       for (int c16 = 0; c16 < I8_T / 16; ++c16) {
         const int64_t c0 = (int64_t)it.tb * I8_T + c16 * 16;
-        if (c0 > rmax_w || c0 >= P.M) break;                              // warp-uniform
+        if ((c0 > rmax_w && !P.full) || c0 >= P.M) break;                 // warp-uniform
         int a0[16], a1[16], a2[16], a3[16];
         tmem_ld16_nowait(taddr + 0 * I8_T + c16 * 16, a0);
         tmem_ld16_nowait(taddr + 1 * I8_T + c16 * 16, a1);
@@ -695,7 +698,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int64_t c = c0 + j;
-          if (r < P.M && c <= r) {
+          if (r < P.M && (c <= r || P.full) && c < P.M) {
             const float qc = syrk_vq(__ldg(P.vmax + it.l * P.M + c));
             if (qc > 0.f) {
               const long long i64 = ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
@@ -1077,7 +1080,16 @@ int64_t i8_syrk_window(int64_t N, int64_t M, int64_t L) {
   return w < 128 ? 128 : w;
 }
 
-int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, float* vmax, int64_t L, double* A, cudaStream_t st) {
+// both triangles + averaging instead of lower triangle + mirror (pair kernel only)
+bool i8_syrk_full(int64_t M) {
+  const char* e = getenv("SVGP_I8_SYRK_FULL");
+  if (e) return atoi(e) != 0;
+  return M > 2048;
+}
+
+int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, float* vmax, int64_t L, double* A, cudaStream_t st,
+               int* used_full) {
+  if (used_full) *used_full = 0;
   if (!kop->Kc || !kop->cscale) { set_error("tc_syrk_i8: int8 transposed planes missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (((uintptr_t)Wt & 15) || (ldwt % 128)) { set_error("tc_syrk_i8: weights need whole zero-padded 128-datapoint blocks"); return SVGP_ERR_ARG; }
   const int64_t N = kop->N, M = kop->M, nblk = (N + 127) / 128;
@@ -1125,9 +1137,13 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
     rc = encode_i8(&map64, kop->Kc, 4, dims, strides, I8_T / 2);
     if (rc) return rc;
     // SVGP_I8_SYRK_SPLIT=0: all tiles on the pair kernel (the diagonal blocks of the tiles tb = 2 ta + 1 then cost a whole tile)
+    // "full": both triangles, averaged afterwards (tc_syrk_i8_prep_run) -- twice the MMAs, for the sizes where the mirrored
+    // lower triangle costs parity (M > 2048; SVGP_I8_SYRK_FULL=0/1 overrides)
     const char* es = getenv("SVGP_I8_SYRK_SPLIT");
-    P.split = !(es && atoi(es) == 0) && SyrkPairTiles::odd_blocks(M) > 0 ? 1 : 0;
-    P.ntile = SyrkPairTiles::count(M, P.split);
+    P.full = i8_syrk_full(M) ? 1 : 0;
+    if (used_full) *used_full = P.full;
+    P.split = !P.full && !(es && atoi(es) == 0) && SyrkPairTiles::odd_blocks(M) > 0 ? 1 : 0;
+    P.ntile = SyrkPairTiles::count(M, P.split, P.full);
     P.n_items = (int64_t)P.nwin * P.ntile * L;
     const int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
     if (clusters > 0) {
@@ -1260,6 +1276,21 @@ __global__ void i8_wprep_kernel(const float* __restrict__ W, int64_t ldw, int64_
 
 int launch_mirror_lower(double* A, int64_t M, int64_t L, cudaStream_t st);      // tc_engine.cu
 
+// A_l <- (A_l + A_l^T) / 2 in place: the "full" SYRK computes every entry of K^T (w o K), whose quantisation noise K^T E keeps
+// its factor structure under averaging (a mirrored lower triangle does not: DESIGN.md section 7)
+__global__ void symmetrise_avg_kernel(double* __restrict__ A, int64_t M, int64_t L) {
+  const int64_t total = L * M * M;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t l = idx / (M * M), rem = idx - l * M * M, r = rem / M, c = rem - r * M;
+    if (c < r) {
+      const int64_t j = (l * M + c) * M + r;
+      const double v = 0.5 * (A[idx] + A[j]);
+      A[idx] = v;
+      A[j] = v;
+    }
+  }
+}
+
 int64_t i8_syrk_ws_floats(int64_t N, int64_t M, int64_t L) { return L * ((N + 127) / 128 * 128) + L + L * M; }
 
 // W (N x L) -> workspace [Wt (L x ldwt) | wmax (L)], then the SYRK
@@ -1275,8 +1306,15 @@ int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_
   i8_wprep_kernel<<<grid, 256, 0, st>>>(W, ldw, N, L, mx, Wt, ldwt);
   int rc = check_launch("svgp_syrk(i8 prep)");
   if (rc) return rc;
-  rc = tc_syrk_i8(kop, Wt, ldwt, mx, mx + L, L, A, st);
+  int full = 0;
+  rc = tc_syrk_i8(kop, Wt, ldwt, mx, mx + L, L, A, st, &full);
   if (rc) return rc;
+  if (full) {                                             // (the single-CTA fallback kernel has no full mode: it mirrors)
+    int64_t blocks = ceil_div(L * kop->M * kop->M, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    symmetrise_avg_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, kop->M, L);
+    return check_launch("svgp_syrk(i8 symmetrise)");
+  }
   return launch_mirror_lower(A, kop->M, L, st);          // the tiles cover the lower triangle only
 }
 

@@ -79,7 +79,7 @@ def test_split_i8(cuda_backend, R, C, S):
     assert (P.planes[:, :, C:] == 0).all()
 
 
-@pytest.mark.parametrize("pair,split", [(True, True), (True, False), (False, False)])
+@pytest.mark.parametrize("pair,split", [(True, True), (True, False), (False, False), (True, "full")])
 @pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1), (3000, 1024, 1), (2500, 256, 40), (9000, 4096, 1)])
 def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
     """pair: the CTA-pair kernel (tcgen05.mma.cta_group::2; the weighted operand is the B side: rows b) / the single-CTA
@@ -88,6 +88,8 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
     single-CTA kernel after the pair kernel."""
     monkeypatch.setenv("SVGP_I8_PAIR", "1" if pair else "0")
     monkeypatch.setenv("SVGP_I8_SYRK_SPLIT", "1" if split else "0")
+    full = split == "full"          # both triangles of K^T (w o K) on the pair kernel, averaged (default for M > 2048) instead of lower + mirror
+    monkeypatch.setenv("SVGP_I8_SYRK_FULL", "1" if full else "0")
     be = cuda_backend
     _, kop = _kop(be, N, M, L)
     g = torch.Generator(device="cuda").manual_seed(2)
@@ -116,12 +118,15 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
             i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
             return i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if weighted_is_b else qa.double()[:, None])
         ref[l] = emulate(pair)
-        if pair and split:
+        if full:
+            ref[l] = 0.5 * (ref[l] + ref[l].t())
+        elif pair and split:
             single = emulate(False)
             for b in range(1, (M + 127) // 128, 2):
                 ref[l][128 * b:128 * b + 128, 128 * b:128 * b + 128] = single[128 * b:128 * b + 128, 128 * b:128 * b + 128]
-    ref = torch.tril(ref) + torch.tril(ref, -1).transpose(-1, -2)
-    assert rel_err(A, ref) < 1e-12
+    if not full:
+        ref = torch.tril(ref) + torch.tril(ref, -1).transpose(-1, -2)
+    assert rel_err(A, ref) < 1e-12 and float((A - A.transpose(-1, -2)).abs().max()) == 0.0
     # and against the plain float64 contraction of the float64 kernel values: fp32 kernel arithmetic is what is left
     full = torch.einsum('il,ia,ib->lab', W.double(), kop.K64, kop.K64)
     assert rel_err(A, full) < 1e-6
