@@ -100,7 +100,8 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------------
 def workload_name(args, world):
     """The one workload string both arms print (the driver compares the `config` of the two lines)."""
-    return "SWEEP N=%d per GPU x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (configs[3])" % (args.n, world, args.m, args.l)
+    which = "configs[4] shapes" if (args.m, args.l) == (4096, 128) else "configs[3]"
+    return "SWEEP N=%d per GPU x %d GPU(s), M=%d, L=%d, product-SE d=4+4, jitter 1e-2 (%s)" % (args.n, world, args.m, args.l, which)
 
 
 def workload_config(args, world):

@@ -109,3 +109,26 @@ def test_step_against_float64_oracle_on_the_gpu(cuda_backend, n, m, l):
     print(o)
     for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "KL_term", "dy", "dnoise", "dhyp", "dZ"):
         assert o[k] < 1e-4, (k, o)
+
+
+def _m4096():
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "probes"))
+    import parity_fullsize
+    return parity_fullsize.run(16384, 4096, 2)
+
+
+def test_step_at_configs4_inducing_count_against_the_oracle(cuda_backend):
+    """configs[4]'s M = 4096 (the one shape of that M the float64 oracle can check on one GPU): with the full SYRK (both
+    triangles of K_nm^T (w o K_nm), averaged -- the default above M = 2048) every value and every tensor-valued gradient
+    is within 1e-4.  The mirrored lower triangle of the sweep sizes left the inducing-point gradient at 1.9e-4 here."""
+    o = _m4096()
+    print(o)
+    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "KL_term", "dy", "dnoise", "dZ"):
+        assert o[k] < 1e-4, (k, o)
+
+
+@pytest.mark.xfail(reason="M = 4096: the two kernel hyper-parameter scalars sit at 7e-4 (dK_nm of the scaled GEMM; DESIGN.md section 7)", strict=False)
+def test_hyper_gradients_at_configs4_inducing_count(cuda_backend):
+    assert _m4096()["dhyp"] < 1e-4
