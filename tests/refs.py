@@ -68,6 +68,29 @@ def oracle_objective(o, params, aux, y, noise, clip_pv=False):
     return res, J, grads
 
 
+def streamlined_objective(o, params, aux, y, noise, clip_pv=False):
+    """oracle_objective through the COLLAPSED float64 restatement (oracle/svgp_streamlined.py: no (b, m, m) tensor, all
+    channels at once; agrees with the literal one to 1e-12, tests/test_oracle.py) on the literal object's own kernel
+    matrices -- for the shapes where the literal per-channel loop takes minutes (SPRITES M = 500 at L = 64)."""
+    from oracle import svgp_streamlined as st
+    y = y.detach().to(F64).cpu().clone().requires_grad_(True)
+    noise = noise.detach().to(F64).cpu().clone().requires_grad_(True)
+    for t in params:
+        t.requires_grad_(True)
+    x = aux.detach().to(F64).cpu()
+    Z = o.inducing_index_points
+    K_nm = o.kernel_matrix(x, Z, x_inducing=False, y_inducing=True)
+    K_mm = o.kernel_matrix(Z, Z)
+    kappa = o.kernel_matrix(x, x, x_inducing=False, y_inducing=False, diag_only=True)
+    t = st.streamlined_terms(K_nm, K_mm, kappa, y, noise, o.N_train, o.jitter, clip_pv=clip_pv)
+    res = dict(t)
+    res.update(st.glue_from_terms(t, float(x.shape[0]), o.N_train))
+    gm, gv = upstream(tuple(y.shape))
+    J = res["KL_term"] + (gm * res["p_m"]).sum() + (gv * res["p_v"]).sum()
+    grads = torch.autograd.grad(J, [y, noise] + list(params), allow_unused=True)
+    return res, J, grads
+
+
 def product_objective(s, params, aux, y, noise, clip_pv=False, **kw):
     y = y.detach().clone().requires_grad_(True)
     noise = noise.detach().clone().requires_grad_(True)
