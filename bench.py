@@ -395,7 +395,10 @@ def run_gpu(args):
         # path issues 10 kind::i8 MMAs (digit-plane pairs) per MAC at twice the kind::f16 rate (profiles/r02_i8_mma_probe.jsonl)
         # = 5 bf16-equivalents; the fp16 path issues 3.  scaled_gemm = 2L full N x M x M products; syrk = lower triangle of
         # L products; rowquad (triangular factor) = half of L full products
-        kern_alg = {"svgp_scaled_gemm_i8": (2.0 * N * M * M * (2 * L), 5.0), "svgp_scaled_gemm": (2.0 * N * M * M * (2 * L), 3.0),
+        # (three-leading-digit products, step.py: the adjoint SYRK and the S - Kinv half of pass D issue 8 instead of 10 pairs
+        # up to M = 2048 -> e = 4 for them, 4.5 for the pass-D launch as a whole)
+        d3 = be.use_i8 and M <= 2048 and os.environ.get("SVGP_I8_D3", "1") != "0"
+        kern_alg = {"svgp_scaled_gemm_i8": (2.0 * N * M * M * (2 * L), 4.5 if d3 else 5.0), "svgp_scaled_gemm": (2.0 * N * M * M * (2 * L), 3.0),
                     "svgp_syrk": (1.0 * N * M * M * L, 5.0 if be.use_i8 else 3.0), "svgp_rowquad": (1.0 * N * M * M * L, 3.0)}
         top_flops, top_e = kern_alg.get(top_name, (float("nan"), float("nan")))
         # DRAM bytes of one launch of that kernel from the committed ncu capture of this exact workload (else null)
@@ -409,7 +412,7 @@ def run_gpu(args):
         achieved = top_e * top_flops / (top_ms * 1e-3) / 1e12
         # what the tensor kernels of this implementation really issue per step, in bf16-equivalent FLOPs: 2 SYRKs (N M^2 L each,
         # x5) + 1 triangular row quad (N M^2 L, x3) + the 2L-matrix product of pass D (2 N M^2 2L, x5)
-        launched = (2 * 5.0 + 3.0 + 4 * 5.0) * L * N * M * M if be.use_i8 else 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M
+        launched = (5.0 + (4.0 if d3 else 5.0) + 3.0 + 4 * (4.5 if d3 else 5.0)) * L * N * M * M if be.use_i8 else 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M
         # K1 (the kernel-matrix builder) is the HBM-bound kernel of the path: fp16 hi/lo row planes + 4 + 4 int8 digit planes
         k1_name = "svgp_kernel_fwd_i8" if "svgp_kernel_fwd_i8" in prof else "svgp_kernel_fwd"
         k1_ms = prof.get(k1_name, {}).get("max_ms")
@@ -432,7 +435,7 @@ def run_gpu(args):
             "roofline": {"bound": "tensor", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "TFLOP/s (bf16-equivalent)",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "note": "achieved = e x algorithmic FLOPs of the kernel's launch / its CUDA-event duration inside the step; e = MMAs issued "
-                                 "per algorithmic MAC in bf16-equivalents: 10 kind::i8 digit-plane MMAs at twice the bf16 rate = 5 (integer path), "
+                                 "per algorithmic MAC in bf16-equivalents: 10 kind::i8 digit-plane MMAs at twice the bf16 rate = 5 (integer path; 8 pairs = 4 for the matrices multiplied with three leading digits), "
                                  "3 (fp16 split path); peak = %s; fp16 cuBLAS 8192^3 timed in this run: %.1f TFLOP/s" % (peak_src, f16_run),
                          "kernel_ms": top_ms, "kernel_algorithmic_tflops": top_flops / (top_ms * 1e-3) / 1e12, "e": top_e,
                          "step_algorithmic_tflops": f_alg / t_s / 1e12,

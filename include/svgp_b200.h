@@ -48,6 +48,8 @@ extern "C" {
 #define SVGP_IMPL_TC 2   /* tcgen05 / TMEM / TMA, fp32-emulating 3 x FP16 split operands          */
 #define SVGP_IMPL_TC_I8 3 /* tcgen05 kind::i8 on base-256 digit planes: exact int32 accumulation (svgp_syrk only;
                              the scaled GEMM has its own entry point svgp_scaled_gemm_i8)            */
+#define SVGP_IMPL_TC_I8_D3 4 /* the same with the three leading digits of both operands (8 instead of 10 digit-plane
+                                pairs): enough for the ADJOINT SYRK dS_l = sum_i dq_il k_i k_i^T, not for the forward one  */
 
 int svgp_version(void);
 const char* svgp_last_error(void); /* host string, thread-local */
@@ -206,10 +208,11 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
  * transposed (row c of G_l multiplies k_i into output column c); K_nm as kop->Kr / rscale.  Mc = rows of each G_l
  * (M for the dK_nm product; any value for a skinny product such as K_nm Wm^T with L = 1, W = NULL).  Exact integer accumulation
  * of the 10 digit-plane pairs of order <= 3, one fp32 rounding when an accumulator tile leaves TMEM, fp32 running sums over
- * the L matrices.                                                                                                    */
+ * the L matrices.  nfull: the first nfull matrices use all 10 pairs, the rest the 8 pairs of the three leading digits of both
+ * operands (the S_l - Kinv family of pass D tolerates that, the dA_l + dA_l^T family does not; pass L for full precision).   */
 int svgp_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_planes, int64_t ldg,
                         const float* G_scale, int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate,
-                        float* dots, int64_t lddots, int64_t ndot, void* stream);
+                        float* dots, int64_t lddots, int64_t ndot, int64_t nfull, void* stream);
 
 /* out (N x M) (+)= W (N x L) @ V (L x M), all fp32 -- rank-L part of dK_nm (p_m, mean terms)  */
 int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t lda, const float* B,

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsvgp_b200.so")
 
 SVGP_K_NONE, SVGP_K_SE, SVGP_K_EXPSIN, SVGP_K_LINEAR, SVGP_K_COSINE = 0, 1, 2, 3, 4
-IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8 = 0, 1, 2, 3
+IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8, IMPL_TC_I8_D3 = 0, 1, 2, 3, 4
 
 
 class KopStruct(ctypes.Structure):
@@ -58,7 +58,7 @@ SIGNATURES = {
                            _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P],
     "svgp_split_i8": [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, _P, _P],
     "svgp_scaled_gemm_i8": [POINTER(KopStruct), _P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64,
-                            c_int64, _P],
+                            c_int64, c_int64, _P],
     "svgp_chol_f64": [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P],
     "svgp_trinv_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P],
     "svgp_ltl_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P],

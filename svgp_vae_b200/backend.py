@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8, KopStruct
+from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8, IMPL_TC_I8_D3, KopStruct
 
 
 class Kop:
@@ -333,8 +333,10 @@ class CudaBackend:
         P.planes[:, at * R:(at + b) * R] = tmp
         self.launches += 2
 
-    def scaled_gemm_i8(self, kop, W, G, out=None, ndot=0):
-        """scaled_gemm on the integer tensor-core path; G: PlanesI8 of L stacked (Mc, M) matrices (4 digit planes)."""
+    def scaled_gemm_i8(self, kop, W, G, out=None, ndot=0, nfull=None):
+        """scaled_gemm on the integer tensor-core path; G: PlanesI8 of L stacked (Mc, M) matrices (4 digit planes).
+        ``nfull``: the matrices from this index on are multiplied with the three leading digits of both operands only
+        (8 instead of 10 digit-plane pairs; default: all matrices at full precision)."""
         assert kop.i8 and isinstance(G, PlanesI8) and G.planes.shape[0] == 4 and G.C == kop.M
         L, Mc = G.B, G.R
         if W is not None:
@@ -346,7 +348,8 @@ class CudaBackend:
         dots = torch.zeros((kop.N, ndot), device=kop.device, dtype=torch.float32) if ndot else None
         s = kop.struct()
         _call("svgp_scaled_gemm_i8", ctypes.byref(s), _ptr(W), W.stride(0) if W is not None else 0, _ptr(G.planes), G.planes.stride(1),
-              _ptr(G.scale), L, Mc, _ptr(out), out.stride(0), int(accumulate), _ptr(dots), ndot, ndot, _stream())
+              _ptr(G.scale), L, Mc, _ptr(out), out.stride(0), int(accumulate), _ptr(dots), ndot, ndot,
+              L if nfull is None else int(nfull), _stream())
         self.launches += 1
         return (out, dots) if ndot else out
 
@@ -355,13 +358,14 @@ class CudaBackend:
         L = W.shape[1]
         A = torch.zeros((L, kop.M, kop.M), device=W.device, dtype=torch.float64)
         use_tc = kop.tc and impl != IMPL_SIMT
-        use_i8 = use_tc and kop.i8 and impl in (IMPL_AUTO, IMPL_TC_I8)
+        use_i8 = use_tc and kop.i8 and impl in (IMPL_AUTO, IMPL_TC_I8, IMPL_TC_I8_D3)
+        i8_impl = IMPL_TC_I8_D3 if impl == IMPL_TC_I8_D3 else IMPL_TC_I8     # D3: the adjoint SYRK (eight digit-plane pairs)
         ws = None
         if use_tc:
             ws = torch.empty(int(_lib.load().svgp_syrk_ws_floats(kop.N, kop.M, L)), device=W.device, dtype=torch.float32)
         s = kop.struct()
         _call("svgp_syrk", ctypes.byref(s), _ptr(W), W.stride(0), L, _ptr(A),
-              IMPL_TC_I8 if use_i8 else (IMPL_TC if use_tc else IMPL_SIMT), chunk_rows, _ptr(ws), _stream())
+              i8_impl if use_i8 else (IMPL_TC if use_tc else IMPL_SIMT), chunk_rows, _ptr(ws), _stream())
         self.launches += 4 if use_tc else 1
         return A
 

@@ -101,7 +101,7 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 // The B planes lie behind each other in the stage, so two neighbouring planes are ONE 256-row operand and (the accumulators
 // of consecutive orders being neighbours in TMEM) A_t x [B_u ; B_u+1] serves two pairs with one fetch of the A plane: six
 // MMAs instead of ten for the same ten products (see scaled_i8_kernel).
-__device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_base, bool first) {
+__device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_base, bool first, bool digits3) {
   constexpr uint32_t IDESC_W = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((2 * I8_T) >> 3) << 17) | ((uint32_t)(I8_T >> 4) << 24);
   uint64_t a[4];
 #pragma unroll
@@ -111,6 +111,14 @@ __device__ __forceinline__ void issue_kblock(uint32_t st, uint32_t tmem_base, bo
   for (int ks = 0; ks < I8_KB / 32; ++ks) {
     const uint64_t adv = (uint64_t)((ks * 32) >> 4);
     const uint32_t f = (first && ks == 0) ? 0u : 1u;
+    if (digits3) {                                                                // eight pairs: no A3, no B3
+      umma_i8_idesc(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);     // acc0 (+)= A0 B0, acc1 (+)= A0 B1
+      umma_i8(tmem_base + 2 * I8_T, a[0] + adv, b23 + adv, f);                    // acc2 (+)= A0 B2
+      umma_i8(tmem_base + 3 * I8_T, a[1] + adv, b23 + adv, f);                    // acc3 (+)= A1 B2
+      umma_i8_idesc(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);    // acc1 += A1 B0, acc2 += A1 B1
+      umma_i8_idesc(tmem_base + 2 * I8_T, a[2] + adv, b01 + adv, IDESC_W, 1u);    // acc2 += A2 B0, acc3 += A2 B1
+      continue;
+    }
     umma_i8_idesc(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);       // acc0 (+)= A0 B0, acc1 (+)= A0 B1
     umma_i8_idesc(tmem_base + 2 * I8_T, a[0] + adv, b23 + adv, IDESC_W, f);       // acc2 (+)= A0 B2, acc3 (+)= A0 B3
     umma_i8_idesc(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);      // acc1 += A1 B0, acc2 += A1 B1
@@ -221,6 +229,7 @@ struct SyrkI8Params {
   int64_t n_items;
   int split;                // pair kernel: leave the tiles tb = 2 ta + 1 out; single-CTA kernel: ONLY the blocks (2 t + 1, 2 t + 1)
   int full;                 // pair kernel: every tile and every entry of K^T (w o K) (symmetrised afterwards by averaging, not mirroring)
+  int digits3;              // the eight pairs of the three leading digits only (t, u <= 2, t + u <= 3): the ADJOINT SYRK tolerates it
 };
 
 // quantisation factor of the weighted operand of row a: |float(Kint) * wn * q| <= 127 2^24 (two fp32 roundings of headroom)
@@ -346,7 +355,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
         mbar_wait(S.ready(stage), phase);
         tc_fence_after();
         if (lane == 0) {
-          issue_kblock(S.stage(stage), tmem_base, kb == 0);
+          issue_kblock(S.stage(stage), tmem_base, kb == 0, P.digits3 != 0);
           umma_commit(S.empty(stage));
           if (kb == it.nkb - 1) umma_commit(S.tmem_full());
         }
@@ -595,7 +604,11 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 #pragma unroll
             for (int o = 0; o < 4; ++o)
 #pragma unroll
-              for (int t = 0; t <= o; ++t) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, t == 0 ? f : 1u);
+              for (int t = 0; t <= o; ++t) {
+                if (P.digits3 && (t == 3 || o - t == 3)) continue;         // three leading digits per operand: eight pairs
+                // (order 3 then starts at t = 1: that MMA carries the "first" flag)
+                umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, (t == 0 || (P.digits3 && o == 3 && t == 1)) ? f : 1u);
+              }
           }
           umma_commit_cg2(empty(stage));
           if (kb == it.nkb - 1) umma_commit_cg2(tfull);
@@ -740,6 +753,7 @@ struct ScaledI8Params {
   int64_t ldkr;
   int nct;                      // column tiles
   int64_t n_items;
+  int64_t nfull;                // matrices s < nfull: all ten digit-plane pairs; s >= nfull: the eight pairs of the three leading digits
   int debug;                    // experiments (SVGP_I8_DEBUG, wrong results): bit 0 = the epilogue releases TMEM without reading it
 };
 
@@ -836,19 +850,22 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             for (int kb = 0; kb < nkb; ++kb) {
               mbar_wait(empty(stage), phase ^ 1);
               const uint32_t st = base + stage * STAGE;
-              mbar_expect_tx(full(stage), STAGE);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) tma_load_3d(st + t * I8_PLANE, &mapK, full(stage), kb * I8_KB, row0, t);
+              // three leading digits only (s >= nfull): plane 3 of neither operand is read -- and, on the wide pair layout,
+              // neither slot Q (planes 2 | 3) nor slot T (plane 0 halves, the partner of A_3): 36 instead of 56 KB per stage
+              const bool d3 = s >= P.nfull;
+              const int na = d3 ? 3 : 4;
+              if (PAIR && WIDE) mbar_expect_tx(full(stage), na * I8_PLANE + (d3 ? I8_PLANE + I8_PLANE / 2 : 3 * I8_PLANE));
+              else mbar_expect_tx(full(stage), na * I8_PLANE + na * BPL);
+              for (int t = 0; t < na; ++t) tma_load_3d(st + t * I8_PLANE, &mapK, full(stage), kb * I8_KB, row0, t);
               if (PAIR && WIDE) {
                 const uint32_t sb = st + 4 * I8_PLANE;
                 const int32_t g0 = (int32_t)(s * P.Mc);
                 tma_load_3d(sb, &mapG, full(stage), kb * I8_KB, g0 + colt, (int32_t)crank);                       // P: plane 0 | 1
-                tma_load_3d(sb + I8_PLANE, &mapG, full(stage), kb * I8_KB, g0 + colt, 2 + (int32_t)crank);        // Q: plane 2 | 3
+                if (!d3) tma_load_3d(sb + I8_PLANE, &mapG, full(stage), kb * I8_KB, g0 + colt, 2 + (int32_t)crank);   // Q: plane 2 | 3
                 tma_load_3d(sb + 2 * I8_PLANE, &mapG64, full(stage), kb * I8_KB, g0 + col0, 2);                   // R: my half of plane 2
-                tma_load_3d(sb + 2 * I8_PLANE + I8_PLANE / 2, &mapG64, full(stage), kb * I8_KB, g0 + col0, 0);    // T: my half of plane 0
+                if (!d3) tma_load_3d(sb + 2 * I8_PLANE + I8_PLANE / 2, &mapG64, full(stage), kb * I8_KB, g0 + col0, 0);   // T: my half of plane 0
               } else {
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < na; ++u)
                   tma_load_3d(st + 4 * I8_PLANE + u * BPL, PAIR ? &mapG64 : &mapG, full(stage), kb * I8_KB, (int32_t)(s * P.Mc) + col0, u);
               }
               if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -882,7 +899,22 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                 for (int ks = 0; ks < I8_KB / 32; ++ks) {
                   const uint64_t adv = (uint64_t)((ks * 32) >> 4);
                   const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
-                  if (PAIR) {
+                  if (s >= P.nfull) {
+                    // three leading digits: A0 x [B0;B1], A0 x B2, A1 x B2, A1 x [B0;B1], A2 x [B0;B1] -- eight products, 512 MMA-cycles
+                    if (PAIR) {
+                      umma_i8_cg2(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);     // acc0 (+)= A0 B0, acc1 (+)= A0 B1
+                      umma_i8_cg2(tmem_base + 2 * I8_T, a[0] + adv, b2 + adv, IDESC, f);        // acc2 (+)= A0 B2
+                      umma_i8_cg2(tmem_base + 3 * I8_T, a[1] + adv, b2 + adv, IDESC, f);        // acc3 (+)= A1 B2
+                      umma_i8_cg2(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);    // acc1 += A1 B0, acc2 += A1 B1
+                      umma_i8_cg2(tmem_base + 2 * I8_T, a[2] + adv, b01 + adv, IDESC_W, 1u);    // acc2 += A2 B0, acc3 += A2 B1
+                    } else {
+                      umma_i8_idesc(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);
+                      umma_i8_idesc(tmem_base + 2 * I8_T, a[0] + adv, b2 + adv, IDESC, f);
+                      umma_i8_idesc(tmem_base + 3 * I8_T, a[1] + adv, b2 + adv, IDESC, f);
+                      umma_i8_idesc(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);
+                      umma_i8_idesc(tmem_base + 2 * I8_T, a[2] + adv, b01 + adv, IDESC_W, 1u);
+                    }
+                  } else if (PAIR) {
                     umma_i8_cg2(tmem_base + 0 * I8_T, a[0] + adv, b01 + adv, IDESC_W, f);       // acc0 (+)= A0 B0, acc1 (+)= A0 B1
                     umma_i8_cg2(tmem_base + 2 * I8_T, a[0] + adv, b23 + adv, IDESC_W, f);       // acc2 (+)= A0 B2, acc3 (+)= A0 B3
                     umma_i8_cg2(tmem_base + 1 * I8_T, a[1] + adv, b01 + adv, IDESC_W, 1u);      // acc1 += A1 B0, acc2 += A1 B1
@@ -907,8 +939,11 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
                   for (int o = 0; o < 4; ++o)
 #pragma unroll
                     for (int t = 0; t <= o; ++t) {
-                      if (PAIR) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, t == 0 ? f : 1u);
-                      else umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, t == 0 ? f : 1u);
+                      const bool d3 = s >= P.nfull;
+                      if (d3 && (t == 3 || o - t == 3)) continue;
+                      const uint32_t fl = (t == 0 || (d3 && o == 3 && t == 1)) ? f : 1u;
+                      if (PAIR) umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, fl);
+                      else umma_i8(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, fl);
                     }
                 }
               }
@@ -1088,7 +1123,7 @@ bool i8_syrk_full(int64_t M) {
 }
 
 int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* wmax, float* vmax, int64_t L, double* A, cudaStream_t st,
-               int* used_full) {
+               int* used_full, int digits3) {
   if (used_full) *used_full = 0;
   if (!kop->Kc || !kop->cscale) { set_error("tc_syrk_i8: int8 transposed planes missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (((uintptr_t)Wt & 15) || (ldwt % 128)) { set_error("tc_syrk_i8: weights need whole zero-padded 128-datapoint blocks"); return SVGP_ERR_ARG; }
@@ -1113,6 +1148,7 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   P.N = N; P.M = M; P.L = L; P.Wt = Wt; P.ldwt = ldwt; P.wmax = wmax; P.vmax = vmax; P.cscale = kop->cscale; P.A = A;
   P.win_rows = i8_syrk_window(N, M, L);
   P.nwin = (int)ceil_div(N, P.win_rows);
+  { const char* e3 = getenv("SVGP_I8_D3"); P.digits3 = (digits3 && !(e3 && atoi(e3) == 0)) ? 1 : 0; }   // SVGP_I8_D3=0: all ten pairs everywhere
   // CTA pairs (256 x 128 tiles, tcgen05.mma.cta_group::2) unless SVGP_I8_PAIR=0 or no co-resident clusters are available
   static int pair_clusters = -1;
   const char* ep = getenv("SVGP_I8_PAIR");
@@ -1172,7 +1208,8 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
 }
 
 int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* Gp, int64_t ldg, const float* gscale, int64_t L,
-                      int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, cudaStream_t st) {
+                      int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, int64_t nfull,
+                      cudaStream_t st) {
   if (!kop->Kr || !kop->rscale) { set_error("tc_scaled_gemm_i8: int8 planes of K_nm missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (dots && Mc != kop->M) { set_error("tc_scaled_gemm_i8: the k-dots need square M x M matrices"); return SVGP_ERR_ARG; }
   const int64_t N = kop->N, M = kop->M;
@@ -1196,6 +1233,7 @@ int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const vo
   P.out = out; P.ldo = ldo; P.accumulate = accumulate; P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
   P.Kr = (const int8_t*)kop->Kr; P.ldkr = kop->ldkr;
   P.nct = (int)ceil_div(Mc, I8_T);
+  { const char* e3 = getenv("SVGP_I8_D3"); P.nfull = (e3 && atoi(e3) == 0) ? L : nfull; }      // SVGP_I8_D3=0: all ten pairs everywhere
   { const char* e = getenv("SVGP_I8_DEBUG"); P.debug = e ? atoi(e) : 0; }
   // CTA pairs (tcgen05.mma.cta_group::2) when there are at least as many 256-row items as clusters; SVGP_I8_PAIR=0 forces
   // the single-CTA kernel, SVGP_I8_WIDE=0 the ten N = 128 MMAs per k-step instead of the six wide ones
@@ -1294,7 +1332,7 @@ __global__ void symmetrise_avg_kernel(double* __restrict__ A, int64_t M, int64_t
 int64_t i8_syrk_ws_floats(int64_t N, int64_t M, int64_t L) { return L * ((N + 127) / 128 * 128) + L + L * M; }
 
 // W (N x L) -> workspace [Wt (L x ldwt) | wmax (L)], then the SYRK
-int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st) {
+int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st, int digits3) {
   const int64_t N = kop->N, ldwt = (N + 127) / 128 * 128;
   float* Wt = ws;
   float* mx = ws + L * ldwt;
@@ -1307,7 +1345,7 @@ int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_
   int rc = check_launch("svgp_syrk(i8 prep)");
   if (rc) return rc;
   int full = 0;
-  rc = tc_syrk_i8(kop, Wt, ldwt, mx, mx + L, L, A, st, &full);
+  rc = tc_syrk_i8(kop, Wt, ldwt, mx, mx + L, L, A, st, &full, digits3);
   if (rc) return rc;
   if (full) {                                             // (the single-CTA fallback kernel has no full mode: it mirrors)
     int64_t blocks = ceil_div(L * kop->M * kop->M, 256);

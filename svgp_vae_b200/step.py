@@ -24,6 +24,7 @@ import math
 import torch
 
 from . import ops
+from ._lib import IMPL_AUTO, IMPL_TC_I8_D3
 from .backend import Planes, PlanesI8, get_backend
 
 LOG_2PI = 1.8378770664093453      # utils.py:498
@@ -416,7 +417,11 @@ class _SVGPStep(torch.autograd.Function):
         # collapsed CE sum), the stacked row weights [p | 2 dq1] and [p y | g_pm] of pass D, sum_l dq1 = d/d kappa_i (= -d/d h_i)
         clip_args = (mask, pv, kappa, h, q1raw, g_ce.float().contiguous()) if clip else None
         G_q1, Wstack, PYstack, G_p_clip, G_kappa = be.rowterms_bwd_pre(g_pv if g_pv is not None else None, g_pm, p, y, clip_args)
-        G_S = be.syrk(kop, G_q1, chunk_rows=cfg.get("chunk_rows", 0))
+        # the adjoint SYRK and the S_l - Kinv family of pass D tolerate the three leading digits of both operands (8 of the 10
+        # digit-plane pairs) up to M = 2048: they enter the parameter gradients only, not the values (at
+        # M = 4096, where dZ sits at the tolerance, the operand-format model shows 7.5e-5 -> 8.2e-5: all ten pairs there)
+        d3 = getattr(kop, "i8", False) and M <= 2048
+        G_S = be.syrk(kop, G_q1, impl=IMPL_TC_I8_D3 if d3 else IMPL_AUTO, chunk_rows=cfg.get("chunk_rows", 0))
         G_w = be.gemm_tn(kop, g_pm)
         for t in (G_S, G_w):
             _allreduce(t, group)
@@ -527,7 +532,8 @@ class _SVGPStep(torch.autograd.Function):
                 put(S[l0:l0 + lc] - Kinv, L + l0)
             Gstack = GA if use_i8 else (Planes(hi, lo, inv) if kop.tc else G64)
         if isinstance(Gstack, PlanesI8):
-            G_K, kGk = be.scaled_gemm_i8(kop, Wstack, Gstack, ndot=L)
+            # the S_l - Kinv family (second half of the stack) with the three leading digits: 8 instead of 10 pairs
+            G_K, kGk = be.scaled_gemm_i8(kop, Wstack, Gstack, ndot=L, nfull=L if d3 else 2 * L)
         else:
             G_K, kGk = be.scaled_gemm(kop, Wstack, Gstack, ndot=L)
         del Wstack, Gstack

@@ -10,6 +10,7 @@ import torch
 from conftest import rel_err
 from oracle_backend import kernel_value
 from svgp_vae_b200 import configs
+from svgp_vae_b200._lib import IMPL_TC_I8, IMPL_TC_I8_D3
 
 pytestmark = pytest.mark.gpu
 F64 = torch.float64
@@ -82,6 +83,18 @@ def test_split_i8(cuda_backend, R, C, S):
 @pytest.mark.parametrize("pair,split", [(True, True), (True, False), (False, False), (True, "full")])
 @pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (20000, 128, 1), (3000, 1024, 1), (2500, 256, 40), (9000, 4096, 1)])
 def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
+    _check_syrk_i8(cuda_backend, N, M, L, pair, split, False, monkeypatch)
+
+
+@pytest.mark.parametrize("pair,split", [(True, True), (False, False), (True, "full")])
+@pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (9000, 4096, 1)])
+def test_syrk_i8_three_leading_digits(cuda_backend, N, M, L, pair, split, monkeypatch):
+    """SVGP_IMPL_TC_I8_D3 (the adjoint SYRK of the step): the eight digit-plane pairs with t, u <= 2 -- still exact against the
+    emulation of the same eight pairs, and within fp32 operand accuracy of the float64 contraction."""
+    _check_syrk_i8(cuda_backend, N, M, L, pair, split, True, monkeypatch)
+
+
+def _check_syrk_i8(cuda_backend, N, M, L, pair, split, d3, monkeypatch):
     """pair: the CTA-pair kernel (tcgen05.mma.cta_group::2; the weighted operand is the B side: rows b) / the single-CTA
     kernel (weighted operand = A side: rows a).  Both must equal the digit-exact emulation of their own operand placement.
     split (default): the diagonal blocks (2 t + 1, 2 t + 1), whose pair tile would lie half above the diagonal, run on the
@@ -94,7 +107,7 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
     _, kop = _kop(be, N, M, L)
     g = torch.Generator(device="cuda").manual_seed(2)
     W = torch.randn(N, L, generator=g, device="cuda") * torch.exp(torch.randn(N, L, generator=g, device="cuda"))
-    A = be.syrk(kop, W.contiguous())
+    A = be.syrk(kop, W.contiguous(), impl=IMPL_TC_I8_D3 if d3 else IMPL_TC_I8)
     # emulation from the same planes: weighted operand = rn(float(Kint) * (w / wmax) * q_a) as a 32-bit integer, q_a from
     # the largest |float(Kint) * (w / wmax)| of row a
     k = _digits(kop.Kc)                                                   # (nblk, M, 128) each
@@ -113,7 +126,7 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
             acc = [torch.zeros(M, M, dtype=F64, device="cuda") for _ in range(4)]
             for t in range(4):
                 for u in range(4):
-                    if t + u <= 3:
+                    if t + u <= 3 and not (d3 and max(t, u) == 3):
                         acc[t + u] += (kd[u].t() @ v[t]) if weighted_is_b else (v[t].t() @ kd[u])      # exact: |sum| < 2^53
             i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
             return i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if weighted_is_b else qa.double()[:, None])
@@ -129,12 +142,24 @@ def test_syrk_i8_is_exact(cuda_backend, N, M, L, pair, split, monkeypatch):
     assert rel_err(A, ref) < 1e-12 and float((A - A.transpose(-1, -2)).abs().max()) == 0.0
     # and against the plain float64 contraction of the float64 kernel values: fp32 kernel arithmetic is what is left
     full = torch.einsum('il,ia,ib->lab', W.double(), kop.K64, kop.K64)
-    assert rel_err(A, full) < 1e-6
+    assert rel_err(A, full) < (2e-6 if d3 else 1e-6)
 
 
 @pytest.mark.parametrize("pair,wide", [(True, True), (True, False), (False, True), (False, False)])
 @pytest.mark.parametrize("N,M,L,ndot", [(4096, 256, 4, 2), (3000, 384, 3, 3), (2048, 1024, 2, 0), (2304, 4096, 2, 1), (2304, 330, 3, 2)])
 def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
+    _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, L, monkeypatch)
+
+
+@pytest.mark.parametrize("pair,wide", [(True, True), (True, False), (False, True), (False, False)])
+@pytest.mark.parametrize("N,M,L,ndot,nfull", [(4096, 256, 4, 2, 2), (3000, 384, 3, 3, 1), (2304, 4096, 2, 1, 1), (2304, 330, 3, 0, 0)])
+def test_scaled_gemm_i8_three_leading_digits(cuda_backend, N, M, L, ndot, nfull, pair, wide, monkeypatch):
+    """nfull < L: the matrices s >= nfull (the S_l - Kinv family of pass D) are multiplied with the eight digit-plane pairs
+    t, u <= 2 only; the planes that are not needed are not fetched either.  Exact against the emulation of the same pairs."""
+    _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch)
+
+
+def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch):
     """pair: CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) / single CTAs; wide: six MMAs per k-step (four of them N = 256
     over two neighbouring digit planes and two neighbouring accumulators) / the ten N = 128 MMAs.  Same ten digit-plane
     products in every variant, so all four must equal the same digit-exact emulation."""
@@ -148,7 +173,7 @@ def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
     G = d[:, :, None] * (R + R.transpose(-1, -2)) * d[:, None, :]
     W = torch.randn(N, L, generator=g, device="cuda")
     P = be.planes_i8(G, nslices=4)
-    res = be.scaled_gemm_i8(kop, W.contiguous(), P, ndot=ndot)
+    res = be.scaled_gemm_i8(kop, W.contiguous(), P, ndot=ndot, nfull=nfull)
     out, dots = res if ndot else (res, None)
     # emulation: kept digit-plane pairs, exact
     kd = [x[:, :M] for x in _digits(kop.Kr)]
@@ -161,7 +186,7 @@ def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
         T = torch.zeros(N, M, dtype=F64, device="cuda")
         for t in range(4):
             for u in range(4):
-                if t + u <= 3:
+                if t + u <= 3 and not (s >= nfull and max(t, u) == 3):
                     T += (kd[t] @ gd[u][s].t()) * 256.0 ** (3 - t - u)
         T = T * gs[s][None, :]                                            # plane units of the kernel's `tv`
         ref += W[:, s:s + 1].double() * rs[:, None] * 16777216.0 * T
@@ -175,7 +200,7 @@ def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
     assert rel_err(out, full) < 1e-5
     # accumulate flag
     base = torch.ones_like(out)
-    out2 = be.scaled_gemm_i8(kop, W.contiguous(), P, out=base.clone())
+    out2 = be.scaled_gemm_i8(kop, W.contiguous(), P, out=base.clone(), nfull=nfull)
     assert rel_err(out2 - 1.0, ref) < 5e-6
 
 

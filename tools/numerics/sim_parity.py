@@ -55,6 +55,8 @@ class Fixed:
         if drop <= 0:
             return self.Xi
         g = 2.0 ** drop
+        if os.environ.get("SIM_DIGITS") == "twos":       # the device's digits: d in [-128, 127] (residue 128 -> -128 + carry), mean -0.5
+            return torch.floor(self.Xi / g + 0.5) * g
         return torch.round(self.Xi / g) * g
 
     def digit(self, t):
@@ -301,8 +303,30 @@ class SimBackend(OracleBackend):
             m = self.m.of("scaledA" if s < ndot else "scaledS")
             if m is self.m:
                 m = self.m.of("scaled")
-            T = self._kg(kop, G64[s], m).float()                       # one rounding to fp32 out of the accumulators
-            r += W[:, s:s + 1].float() * T                              # fp32 running sum in the epilogue registers
+            if os.environ.get("SIM_EPI") and getattr(kop, "sim", False) and m.kind == "i8" and m.cut == 3:
+                # the kernel's own epilogue arithmetic (scaled8_chunk): four int32 order accumulators, each converted to fp32,
+                # a three-fma recombination, the column scale, an fma into the running sum
+                Gf = m.fixed(G64[s], 0, "b")
+                Kr = self._kfixed(kop, m, 1)
+                acc = [sum(Kr.digit(t) @ Gf.digit(o - t) for t in range(o + 1)) for o in range(4)]
+                unit = [2.0 ** -(8 * (3 - o)) for o in range(4)]          # digit(t) carries its weight: strip it -> plain integers
+                top = 2.0 ** (Kr.bits + 1 - 8) * 2.0 ** (Gf.bits + 1 - 8)
+                a = [(acc[o] / (top * 2.0 ** (-8 * o))) for o in range(4)]
+                af = [x.float().double() for x in a]
+                mode = os.environ["SIM_EPI"]
+                if mode == "int64":                                      # exact integer recombination, ONE rounding
+                    tv = (((a[0] * 256 + a[1]) * 256 + a[2]) * 256 + a[3]).float().double()
+                else:
+                    tv = (af[2] * 256.0 + af[3]).float().double()
+                    tv = (af[1] * 65536.0 + tv).float().double()
+                    tv = (af[0] * 16777216.0 + tv).float().double()
+                tv = (tv * Gf.scale.float().double()).float().double()
+                wgt = (W[:, s:s + 1].double() * Kr.scale * top * 2.0 ** -24).float().double()
+                r = (wgt * tv + r.double()).float()
+                T = (tv * (Kr.scale * top * 2.0 ** -24)).float()
+            else:
+                T = self._kg(kop, G64[s], m).float()                       # one rounding to fp32 out of the accumulators
+                r += W[:, s:s + 1].float() * T                              # fp32 running sum in the epilogue registers
             if s < ndot:
                 dots.append((T * self._kval(kop, m).float()).sum(-1, dtype=torch.float32))
         if out is not None:
