@@ -209,10 +209,20 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
  * (M for the dK_nm product; any value for a skinny product such as K_nm Wm^T with L = 1, W = NULL).  Exact integer accumulation
  * of the 10 digit-plane pairs of order <= 3, one fp32 rounding when an accumulator tile leaves TMEM, fp32 running sums over
  * the L matrices.  nfull: the first nfull matrices use all 10 pairs, the rest the 8 pairs of the three leading digits of both
- * operands (the S_l - Kinv family of pass D tolerates that, the dA_l + dA_l^T family does not; pass L for full precision).   */
+ * operands (the S_l - Kinv family of pass D tolerates that, the dA_l + dA_l^T family does not; pass L for full precision).
+ * K_bias (2 x N) / G_bias (2 x L * Mc): svgp_i8_pair_bias of kop->Kr and of G_planes, or both NULL.  With them the expectation
+ * of the digit-plane pairs that are not multiplied enters every entry before it is rounded: the digits of the format have mean
+ * -1/2, which leaves a deviation of ~1e-9 of an entry but of ONE sign over the whole N x M product -- visible only in sums over
+ * all of it that cancel 1e5-fold (the kernel hyper-parameter gradients at M = 4096).                                          */
 int svgp_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_planes, int64_t ldg,
                         const float* G_scale, int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate,
-                        float* dots, int64_t lddots, int64_t ndot, int64_t nfull, void* stream);
+                        float* dots, int64_t lddots, int64_t ndot, int64_t nfull, const float* K_bias, const float* G_bias,
+                        void* stream);
+
+/* Expected value of the dropped digit-plane pairs, one operand's share, from the digit sums of its four int8 planes
+ * (planes[s][r][c], pitch ld bytes, planes nrows * ld bytes apart; pad columns zero): bias[0][r] = -(S_1 + S_2 + S_3)[r] / 512
+ * for products with ten pairs, bias[1][r] = bias[0][r] - S_0[r] / 2 for products with eight (three leading digits).           */
+int svgp_i8_pair_bias(const void* planes, int64_t nrows, int64_t ld, float* bias, void* stream);
 
 /* out (N x M) (+)= W (N x L) @ V (L x M), all fp32 -- rank-L part of dK_nm (p_m, mean terms)  */
 int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t lda, const float* B,

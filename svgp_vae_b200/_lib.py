@@ -58,7 +58,8 @@ SIGNATURES = {
                            _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P, _P],
     "svgp_split_i8": [_P, c_int64, c_int64, c_int64, c_int, _P, c_int64, _P, _P],
     "svgp_scaled_gemm_i8": [POINTER(KopStruct), _P, c_int64, _P, c_int64, _P, c_int64, c_int64, _P, c_int64, c_int, _P, c_int64,
-                            c_int64, c_int64, _P],
+                            c_int64, c_int64, _P, _P, _P],
+    "svgp_i8_pair_bias": [_P, c_int64, c_int64, _P, _P],
     "svgp_chol_f64": [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P],
     "svgp_trinv_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P, _P],
     "svgp_ltl_f64": [_P, _P, c_int64, c_int64, c_int64, c_int64, _P],

@@ -31,6 +31,7 @@ class Kop:
         # int8 digit planes of the exact integer tensor-core products (svgp_kernel_fwd_i8): Kr (4, N, ldkr) row-scaled,
         # Kc (4, ceil(N / 128), M, 128) column-scaled and datapoint-blocked, with their scales
         self.Kr = self.rscale = self.Kc = self.cscale = None
+        self.Kr_bias = None              # svgp_i8_pair_bias of Kr, formed on first use
 
     @property
     def tc(self):
@@ -153,6 +154,10 @@ class CudaBackend:
         self.launches = 0          # kernels launched through this backend (bench reports it)
         self.tc_min_rows = max(2048, int(os.environ.get("SVGP_TC_MIN_ROWS", "2048")))    # the library needs N >= 2048 (tc_shape_ok)
         self.use_i8 = os.environ.get("SVGP_TC_I8", "1") != "0"
+        # expected value of the dropped digit-plane pairs added inside the integer scaled GEMM: from M = 2048 up by default (the
+        # coherent 1e-9 per entry it removes costs the hyper-parameter gradients 2e-5 at M = 2048 and 7e-4 at M = 4096, nothing
+        # measurable at M = 1024, and the two extra adds per column cost pass D 2.5 % there); SVGP_I8_DEBIAS=1 / 0: always / never
+        self.i8_debias = {"0": 1 << 62, "1": 0}.get(os.environ.get("SVGP_I8_DEBIAS", ""), 2048)
 
     def start_profile(self):
         global _PROFILE
@@ -333,10 +338,21 @@ class CudaBackend:
         P.planes[:, at * R:(at + b) * R] = tmp
         self.launches += 2
 
-    def scaled_gemm_i8(self, kop, W, G, out=None, ndot=0, nfull=None):
+    def pair_bias_i8(self, planes):
+        """(4, R, ld) int8 digit planes -> (2, R) fp32: this operand's share of the expected value of the digit-plane pairs the
+        integer products drop (svgp_i8_pair_bias; row 0: ten pairs kept, row 1: eight)."""
+        S, R, ld = planes.shape
+        assert S == 4 and planes.is_contiguous()
+        bias = torch.empty((2, R), device=planes.device, dtype=torch.float32)
+        _call("svgp_i8_pair_bias", _ptr(planes), R, ld, _ptr(bias), _stream())
+        self.launches += 1
+        return bias
+
+    def scaled_gemm_i8(self, kop, W, G, out=None, ndot=0, nfull=None, debias=None):
         """scaled_gemm on the integer tensor-core path; G: PlanesI8 of L stacked (Mc, M) matrices (4 digit planes).
         ``nfull``: the matrices from this index on are multiplied with the three leading digits of both operands only
-        (8 instead of 10 digit-plane pairs; default: all matrices at full precision)."""
+        (8 instead of 10 digit-plane pairs; default: all matrices at full precision).  ``debias``: add the expected value of
+        the dropped pairs to every entry before it is rounded (default: on; the digits have mean -1/2, see svgp_b200.h)."""
         assert kop.i8 and isinstance(G, PlanesI8) and G.planes.shape[0] == 4 and G.C == kop.M
         L, Mc = G.B, G.R
         if W is not None:
@@ -347,9 +363,14 @@ class CudaBackend:
             out = torch.empty((kop.N, Mc), device=kop.device, dtype=torch.float32)
         dots = torch.zeros((kop.N, ndot), device=kop.device, dtype=torch.float32) if ndot else None
         s = kop.struct()
+        kb = gb = None
+        if (kop.M >= self.i8_debias) if debias is None else debias:
+            if getattr(kop, "Kr_bias", None) is None:
+                kop.Kr_bias = self.pair_bias_i8(kop.Kr)                  # once per kernel matrix
+            kb, gb = kop.Kr_bias, self.pair_bias_i8(G.planes)
         _call("svgp_scaled_gemm_i8", ctypes.byref(s), _ptr(W), W.stride(0) if W is not None else 0, _ptr(G.planes), G.planes.stride(1),
               _ptr(G.scale), L, Mc, _ptr(out), out.stride(0), int(accumulate), _ptr(dots), ndot, ndot,
-              L if nfull is None else int(nfull), _stream())
+              L if nfull is None else int(nfull), _ptr(kb), _ptr(gb), _stream())
         self.launches += 1
         return (out, dots) if ndot else out
 

@@ -77,6 +77,42 @@ __global__ void split_i8_kernel(const double* __restrict__ x, int64_t nrows, int
   }
 }
 
+// ---- expectation of the digit-plane pairs a product does NOT multiply -----------------------------------------------------
+// The lower digits of the format lie in [-128, 127] and are uniformly distributed: mean -1/2, not 0.  A dropped pair
+// sum_k a_t[k] b_u[k] (t + u >= 4, and (0, 3) / (3, 0) with three leading digits) therefore has the expectation
+// -(sum_k a_t + sum_k b_u) / 2 - n / 4 (both lower digits) resp. -sum_k a_0 / 2 (a leading digit against a lower one), far below one
+// fp32 rounding of the entry but of one sign for every entry of the product.  This kernel forms one operand's share from its
+// digit sums, in units of the order-3 accumulator:  bias[0][r] = -(S_1 + S_2 + S_3) / 512  (the three order-4 pairs, ten pairs
+// kept),  bias[1][r] = bias[0][r] - S_0 / 2  (eight pairs kept).  The constant -3 n / 1024 is the consumer's.
+// One warp per row; the digits of four columns are summed by one dp4a.
+__global__ void pair_bias_kernel(const int8_t* __restrict__ planes, int64_t nrows, int64_t ld, float* __restrict__ bias) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarp = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t plane = nrows * ld;
+  for (int64_t r = warp; r < nrows; r += nwarp) {
+    int s0 = 0, s123 = 0;
+    for (int64_t c = lane * 16; c < ld; c += 32 * 16) {
+      const int8_t* bp = planes + r * ld + c;
+      const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(bp));
+      s0 = __dp4a((int)d0.x, 0x01010101, s0); s0 = __dp4a((int)d0.y, 0x01010101, s0);
+      s0 = __dp4a((int)d0.z, 0x01010101, s0); s0 = __dp4a((int)d0.w, 0x01010101, s0);
+#pragma unroll
+      for (int t = 1; t < 4; ++t) {
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(bp + t * plane));
+        s123 = __dp4a((int)d.x, 0x01010101, s123); s123 = __dp4a((int)d.y, 0x01010101, s123);
+        s123 = __dp4a((int)d.z, 0x01010101, s123); s123 = __dp4a((int)d.w, 0x01010101, s123);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s123 += __shfl_xor_sync(0xffffffffu, s123, o); }
+    if (lane == 0) {
+      const float b = -(float)s123 / 512.f;
+      bias[r] = b;
+      bias[nrows + r] = b - 0.5f * (float)s0;
+    }
+  }
+}
+
 }  // namespace svgp
 
 using namespace svgp;
@@ -99,6 +135,16 @@ int svgp_split_i8(const double* x, int64_t nrows, int64_t cols, int64_t ldx, int
   else
     split_i8_kernel<3><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, nrows, cols, ldx, (int8_t*)planes, ldp, scale);
   return check_launch("svgp_split_i8");
+}
+
+int svgp_i8_pair_bias(const void* planes, int64_t nrows, int64_t ld, float* bias, void* stream) {
+  SVGP_REQUIRE(planes && bias && nrows >= 0, "null argument");
+  SVGP_REQUIRE(ld % 16 == 0 && ld > 0 && ((uintptr_t)planes & 15) == 0, "plane pitch must be a multiple of 16 bytes");
+  if (nrows == 0) return SVGP_OK;
+  int64_t blocks = ceil_div(nrows, 8);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  pair_bias_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const int8_t*)planes, nrows, ld, bias);
+  return check_launch("svgp_i8_pair_bias");
 }
 
 }  // extern "C"

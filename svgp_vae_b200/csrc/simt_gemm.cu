@@ -330,7 +330,7 @@ int64_t i8_syrk_ws_floats(int64_t N, int64_t M, int64_t L);
 int tc_syrk_i8_prep_run(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, double* A, float* ws, cudaStream_t st, int digits3);
 int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* Gp, int64_t ldg, const float* gscale, int64_t L,
                       int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, int64_t nfull,
-                      cudaStream_t st);
+                      const float* kcorr, const float* gcorr, cudaStream_t st);
 
 static inline int64_t pad8(int64_t n) { return (n + 7) / 8 * 8; }
 static inline KAccess kaccess(const svgp_kop* kop) {
@@ -479,14 +479,15 @@ int svgp_scaled_gemm(const svgp_kop* kop, const float* W, int64_t ldw, const voi
 
 int svgp_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* G_planes, int64_t ldg, const float* G_scale,
                         int64_t L, int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot,
-                        int64_t nfull, void* stream) {
+                        int64_t nfull, const float* K_bias, const float* G_bias, void* stream) {
   SVGP_REQUIRE(kop && G_planes && G_scale && out && L >= 1 && Mc >= 1 && nfull >= 0, "null argument");
+  SVGP_REQUIRE((K_bias == nullptr) == (G_bias == nullptr), "K_bias and G_bias come together (svgp_i8_pair_bias of both operands)");
   SVGP_REQUIRE(!dots || (ndot >= 0 && ndot <= L && lddots >= ndot), "bad dots argument");
   SVGP_REQUIRE(kop->Kr && kop->rscale && kop->M >= 128 && kop->N >= 128, "integer path needs the int8 planes (svgp_kernel_fwd_i8) and M, N >= 128");
   SVGP_REQUIRE(ldg % 16 == 0 && ldg >= kop->M && ldo >= Mc, "bad pitch");
   if (kop->N == 0) return SVGP_OK;
   return tc_scaled_gemm_i8(kop, W, ldw, G_planes, ldg, G_scale, L, Mc, out, ldo, accumulate, dots, lddots, ndot, nfull < L ? nfull : L,
-                           (cudaStream_t)stream);
+                           K_bias, G_bias, (cudaStream_t)stream);
 }
 
 int svgp_gemm_f32(int64_t Mr, int64_t Nc, int64_t Kd, const float* A, int64_t lda, const float* B, int64_t ldb, float* C,

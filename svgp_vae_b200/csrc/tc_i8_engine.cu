@@ -754,16 +754,24 @@ struct ScaledI8Params {
   int nct;                      // column tiles
   int64_t n_items;
   int64_t nfull;                // matrices s < nfull: all ten digit-plane pairs; s >= nfull: the eight pairs of the three leading digits
+  const float* kcorr;           // [2][N] expectation of the dropped digit-plane pairs, K_nm's share (svgp_i8_pair_bias); null: no correction
+  const float* gcorr;           // [2][L * Mc] the same for row c of matrix s ([0]: ten pairs kept, [1]: eight)
   int debug;                    // experiments (SVGP_I8_DEBUG, wrong results): bit 0 = the epilogue releases TMEM without reading it
 };
 
 // Recombination of 8 columns of the four order accumulators (one fp32 rounding each: |acc_o| < 2^24 for M <= 1024, beyond that
 // the rounding of an order's sum is 2^-24 relative), scale, weighted running sum and -- DOT -- the row's k-dot.
-template <bool DOT>
-__device__ __forceinline__ void scaled8_chunk(const int (&a)[4][8], const float (&g)[8], float wgt, float* run, const float* kv, float& dsum) {
+// CORR: the expectation of the digit-plane pairs that were NOT multiplied is added to the order-3 accumulator before anything
+// is rounded (ck: this row's share, cg: the columns' share).  The device's base-256 digits lie in [-128, 127]: the lower ones
+// have mean -1/2, so a dropped pair (t, u) sums to M / 4 - ... per entry instead of zero -- 1e-9 of an entry, far below one fp32
+// rounding, but of ONE sign for all N x M entries of dK_nm, and the kernel hyper-parameter gradients are sums over all of them
+// that cancel 1e5-fold (dhyp at M = 4096: 7e-4 without).  Added before the roundings it survives them in the mean.
+template <bool DOT, bool CORR>
+__device__ __forceinline__ void scaled8_chunk(const int (&a)[4][8], const float (&g)[8], const float (&cg)[8], float ck, float wgt,
+                                              float* run, const float* kv, float& dsum) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float tv = fmaf(__int2float_rn(a[2][j]), 256.f, __int2float_rn(a[3][j]));
+    float tv = fmaf(__int2float_rn(a[2][j]), 256.f, CORR ? __int2float_rn(a[3][j]) + (cg[j] + ck) : __int2float_rn(a[3][j]));
     tv = fmaf(__int2float_rn(a[1][j]), 65536.f, tv);
     tv = fmaf(__int2float_rn(a[0][j]), 16777216.f, tv);
     tv *= g[j];
@@ -980,6 +988,9 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
       const int64_t cw0 = (item % P.nct) * I8_T + half * 64;               // first column of this warp
       const bool live = i < P.N;
       const float rs = live ? P.rscale[i] : 0.f;
+      const bool corr = P.kcorr != nullptr;
+      const float ck_full = (corr && live) ? __ldg(P.kcorr + i) - 3.f * (float)P.M / 1024.f : 0.f;     // three dropped order-4 pairs: 3 M / 4 / 256
+      const float ck_d3 = (corr && live) ? __ldg(P.kcorr + P.N + i) - 3.f * (float)P.M / 1024.f : 0.f;
       float run[64], kv[64];
 #pragma unroll
       for (int j = 0; j < 64; ++j) run[j] = 0.f;
@@ -1013,8 +1024,11 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
         const bool want_dot = has_dots && s < P.ndot;                      // warp-uniform
         float dsum = 0.f;
         const float* gs = P.gscale + s * P.Mc;
+        const float* gc = corr ? P.gcorr + (s >= P.nfull ? P.L * P.Mc : 0) + s * P.Mc : gs;
+        const float ck = s >= P.nfull ? ck_d3 : ck_full;
         const int mcm1 = (int)P.Mc - 1;
-        const bool gvec = ((P.Mc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.gscale) & 15) == 0);
+        const bool gvec = ((P.Mc & 3) == 0) && ((reinterpret_cast<uintptr_t>(P.gscale) & 15) == 0) &&
+                          (!corr || (((P.L * P.Mc) & 3) == 0 && (reinterpret_cast<uintptr_t>(P.gcorr) & 15) == 0));
         mbar_wait(tfull, tphase);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(half * 64);
@@ -1050,16 +1064,24 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             if (c0 + 8 <= mcm1 + 1 && gvec) {
               const float4 g0 = __ldg(reinterpret_cast<const float4*>(gs + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gs + c0 + 4));
               const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-              if (want_dot) scaled8_chunk<true>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
-              else scaled8_chunk<false>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              if (corr) {
+                const float4 c0v = __ldg(reinterpret_cast<const float4*>(gc + c0)), c1v = __ldg(reinterpret_cast<const float4*>(gc + c0 + 4));
+                const float cg[8] = {c0v.x, c0v.y, c0v.z, c0v.w, c1v.x, c1v.y, c1v.z, c1v.w};
+                if (want_dot) scaled8_chunk<true, true>(buf[c8 & 1], g, cg, ck, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+                else scaled8_chunk<false, true>(buf[c8 & 1], g, cg, ck, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              } else if (want_dot) scaled8_chunk<true, false>(buf[c8 & 1], g, g, 0.f, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              else scaled8_chunk<false, false>(buf[c8 & 1], g, g, 0.f, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
             } else {
               // ragged last tile / unaligned scales: columns past Mc read a clamped scale (their sums are never stored, their K
               // entries are zero)
-              float g[8];
+              float g[8], cg[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) g[j] = __ldg(gs + (c0 + j < mcm1 ? c0 + j : mcm1));
-              if (want_dot) scaled8_chunk<true>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
-              else scaled8_chunk<false>(buf[c8 & 1], g, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              for (int j = 0; j < 8; ++j) {
+                g[j] = __ldg(gs + (c0 + j < mcm1 ? c0 + j : mcm1));
+                cg[j] = corr ? __ldg(gc + (c0 + j < mcm1 ? c0 + j : mcm1)) : 0.f;
+              }
+              if (want_dot) scaled8_chunk<true, true>(buf[c8 & 1], g, cg, ck, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
+              else scaled8_chunk<false, true>(buf[c8 & 1], g, cg, ck, wgt, &run[c8 * 8], &kv[c8 * 8], dsum);
             }
           }
         }
@@ -1209,7 +1231,7 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
 
 int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const void* Gp, int64_t ldg, const float* gscale, int64_t L,
                       int64_t Mc, float* out, int64_t ldo, int accumulate, float* dots, int64_t lddots, int64_t ndot, int64_t nfull,
-                      cudaStream_t st) {
+                      const float* kcorr, const float* gcorr, cudaStream_t st) {
   if (!kop->Kr || !kop->rscale) { set_error("tc_scaled_gemm_i8: int8 planes of K_nm missing (svgp_kernel_fwd_i8)"); return SVGP_ERR_ARG; }
   if (dots && Mc != kop->M) { set_error("tc_scaled_gemm_i8: the k-dots need square M x M matrices"); return SVGP_ERR_ARG; }
   const int64_t N = kop->N, M = kop->M;
@@ -1232,6 +1254,7 @@ int tc_scaled_gemm_i8(const svgp_kop* kop, const float* W, int64_t ldw, const vo
   P.N = N; P.M = M; P.L = L; P.Mc = Mc; P.rscale = kop->rscale; P.gscale = gscale; P.W = W; P.ldw = ldw;
   P.out = out; P.ldo = ldo; P.accumulate = accumulate; P.dots = dots; P.lddots = lddots; P.ndot = dots ? ndot : 0;
   P.Kr = (const int8_t*)kop->Kr; P.ldkr = kop->ldkr;
+  P.kcorr = (kcorr && gcorr) ? kcorr : nullptr; P.gcorr = P.kcorr ? gcorr : nullptr;
   P.nct = (int)ceil_div(Mc, I8_T);
   { const char* e3 = getenv("SVGP_I8_D3"); P.nfull = (e3 && atoi(e3) == 0) ? L : nfull; }      // SVGP_I8_D3=0: all ten pairs everywhere
   { const char* e = getenv("SVGP_I8_DEBUG"); P.debug = e ? atoi(e) : 0; }

@@ -8,6 +8,8 @@ sub-blocks:
   * sub-block exactness   a 256 x 256 block of A_l and 4096 rows of p_m / q against float64 torch on the same K_nm
   * the whole step        finite outputs, KL >= 0 per channel, p_v > 0, and the shard-additive ELBO sums
 """
+import functools
+
 import pytest
 import torch
 
@@ -111,6 +113,7 @@ def test_step_against_float64_oracle_on_the_gpu(cuda_backend, n, m, l):
         assert o[k] < 1e-4, (k, o)
 
 
+@functools.lru_cache(maxsize=1)
 def _m4096():
     import os
     import sys
@@ -125,12 +128,14 @@ def test_step_at_configs4_inducing_count_against_the_oracle(cuda_backend):
     encoder outputs are within 1e-4."""
     o = _m4096()
     print(o)
-    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "KL_term", "dy", "dnoise"):
+    # dhyp: 4.2e-4 / 7e-4 on two sets of inputs until the expected value of the dropped digit-plane pairs entered the scaled
+    # GEMM's epilogue (svgp_i8_pair_bias: the format's digits have mean -1/2); 3.2e-5 with it
+    for k in ("p_m", "p_v", "recon_l", "kl_l", "ce_l", "KL_term", "dy", "dnoise", "dhyp"):
         assert o[k] < 1e-4, (k, o)
 
 
 @pytest.mark.xfail(reason="M = 4096: the inducing-point gradient sits AT the tolerance with the full SYRK (8.3e-5 / 1.25e-4 on two sets of "
-                          "inputs; 1.9e-4 with the mirrored one), the two kernel hyper-parameter scalars at 7e-4 (DESIGN.md section 7)", strict=False)
-def test_parameter_gradients_at_configs4_inducing_count(cuda_backend):
+                          "inputs; 1.9e-4 with the mirrored one): the fixed-point image of K_nm in the SYRK (DESIGN.md section 7)", strict=False)
+def test_inducing_point_gradient_at_configs4_inducing_count(cuda_backend):
     o = _m4096()
-    assert o["dZ"] < 1e-4 and o["dhyp"] < 1e-4, o
+    assert o["dZ"] < 1e-4, o

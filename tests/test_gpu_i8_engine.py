@@ -148,18 +148,19 @@ def _check_syrk_i8(cuda_backend, N, M, L, pair, split, d3, monkeypatch):
 @pytest.mark.parametrize("pair,wide", [(True, True), (True, False), (False, True), (False, False)])
 @pytest.mark.parametrize("N,M,L,ndot", [(4096, 256, 4, 2), (3000, 384, 3, 3), (2048, 1024, 2, 0), (2304, 4096, 2, 1), (2304, 330, 3, 2)])
 def test_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, monkeypatch):
-    _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, L, monkeypatch)
+    _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, L, monkeypatch, debias=True)
 
 
 @pytest.mark.parametrize("pair,wide", [(True, True), (True, False), (False, True), (False, False)])
-@pytest.mark.parametrize("N,M,L,ndot,nfull", [(4096, 256, 4, 2, 2), (3000, 384, 3, 3, 1), (2304, 4096, 2, 1, 1), (2304, 330, 3, 0, 0)])
-def test_scaled_gemm_i8_three_leading_digits(cuda_backend, N, M, L, ndot, nfull, pair, wide, monkeypatch):
+@pytest.mark.parametrize("N,M,L,ndot,nfull,debias", [(4096, 256, 4, 2, 2, False), (3000, 384, 3, 3, 1, True), (2304, 4096, 2, 1, 1, True),
+                                                     (2304, 330, 3, 0, 0, False)])
+def test_scaled_gemm_i8_three_leading_digits(cuda_backend, N, M, L, ndot, nfull, debias, pair, wide, monkeypatch):
     """nfull < L: the matrices s >= nfull (the S_l - Kinv family of pass D) are multiplied with the eight digit-plane pairs
     t, u <= 2 only; the planes that are not needed are not fetched either.  Exact against the emulation of the same pairs."""
-    _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch)
+    _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch, debias=debias)
 
 
-def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch):
+def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch, debias=debias):
     """pair: CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) / single CTAs; wide: six MMAs per k-step (four of them N = 256
     over two neighbouring digit planes and two neighbouring accumulators) / the ten N = 128 MMAs.  Same ten digit-plane
     products in every variant, so all four must equal the same digit-exact emulation."""
@@ -173,13 +174,14 @@ def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkey
     G = d[:, :, None] * (R + R.transpose(-1, -2)) * d[:, None, :]
     W = torch.randn(N, L, generator=g, device="cuda")
     P = be.planes_i8(G, nslices=4)
-    res = be.scaled_gemm_i8(kop, W.contiguous(), P, ndot=ndot, nfull=nfull)
+    res = be.scaled_gemm_i8(kop, W.contiguous(), P, ndot=ndot, nfull=nfull, debias=debias)
     out, dots = res if ndot else (res, None)
     # emulation: kept digit-plane pairs, exact
     kd = [x[:, :M] for x in _digits(kop.Kr)]
     gd = [x.reshape(L, M, -1)[:, :, :M] for x in _digits(P.planes)]
     rs, gs = kop.rscale.double(), P.scale.double().reshape(L, M)
     Kint = _ints(kop.Kr)[:, :M]
+    kb, gb = be.pair_bias_i8(kop.Kr).double(), be.pair_bias_i8(P.planes).double()
     ref = torch.zeros(N, M, dtype=F64, device="cuda")
     dref = torch.zeros(N, max(ndot, 1), dtype=F64, device="cuda")
     for s in range(L):
@@ -188,6 +190,9 @@ def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkey
             for u in range(4):
                 if t + u <= 3 and not (s >= nfull and max(t, u) == 3):
                     T += (kd[t] @ gd[u][s].t()) * 256.0 ** (3 - t - u)
+        # + the expected value of the dropped pairs (svgp_i8_pair_bias of both operands), as the kernel adds it before rounding
+        if debias:
+            T += kb[int(s >= nfull)][:, None] + gb[int(s >= nfull)][s * M:(s + 1) * M][None, :] - 3.0 * M / 1024.0
         T = T * gs[s][None, :]                                            # plane units of the kernel's `tv`
         ref += W[:, s:s + 1].double() * rs[:, None] * 16777216.0 * T
         if s < ndot:
@@ -200,7 +205,7 @@ def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkey
     assert rel_err(out, full) < 1e-5
     # accumulate flag
     base = torch.ones_like(out)
-    out2 = be.scaled_gemm_i8(kop, W.contiguous(), P, out=base.clone(), nfull=nfull)
+    out2 = be.scaled_gemm_i8(kop, W.contiguous(), P, out=base.clone(), nfull=nfull, debias=debias)
     assert rel_err(out2 - 1.0, ref) < 5e-6
 
 
@@ -213,3 +218,43 @@ def test_gemm_nn_i8(cuda_backend):
     out = be.gemm_nn(kop, Wm)
     assert out.shape == (N, L)
     assert rel_err(out, kop.K64 @ Wm.t()) < 2e-6
+
+
+def test_pair_bias_i8(cuda_backend):
+    be = cuda_backend
+    _, kop = _kop(be, 3000, 330, 2)
+    b = be.pair_bias_i8(kop.Kr).double()
+    d = _digits(kop.Kr)
+    s123 = (d[1] + d[2] + d[3]).sum(1)
+    assert torch.equal(b[0], (-s123 / 512.0).float().double())
+    assert rel_err(b[1], -s123 / 512.0 - 0.5 * d[0].sum(1)) < 1e-6
+
+
+@pytest.mark.parametrize("nfull", [1, 0])
+def test_scaled_gemm_i8_dropped_pairs_are_unbiased(cuda_backend, nfull):
+    """The digits of the format have mean -1/2, so the digit-plane pairs the product drops do NOT average to zero: without the
+    correction every entry is off by the same few units of the order-3 accumulator (1e-9 of a typical entry -- and the reason
+    the kernel hyper-parameter gradients missed 1e-4 at M = 4096).  Made visible with a G whose two leading digit planes are
+    empty (small products: fp32 resolves single units): mean deviation from the exact 16-pair product, in accumulator units."""
+    from svgp_vae_b200.backend import PlanesI8
+    be = cuda_backend
+    N, M, Mc = 2304, 4096, 256
+    _, kop = _kop(be, N, M, 1)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    planes = torch.zeros(4, Mc, M, dtype=torch.int8, device="cuda")
+    planes[2:] = torch.randint(-128, 128, (2, Mc, M), generator=g, device="cuda", dtype=torch.int8)
+    P = PlanesI8(planes, torch.ones(Mc, device="cuda"), 1, Mc, M)
+    Kint = _ints(kop.Kr)[:, :M]
+    exact = Kint @ (planes[2].double() * 256.0 + planes[3].double()).t() / 16777216.0          # accumulator units
+    unit = (kop.rscale.double() * 16777216.0)[:, None]
+    dev = {}
+    for debias in (False, True):
+        out = be.scaled_gemm_i8(kop, None, P, nfull=nfull, debias=debias)
+        dev[debias] = float((out.double() / unit - exact).mean())
+    # dropped with all ten pairs: (1, 3) and (2, 2) of the non-empty planes -- a digit of K against a digit of mean -1/2, i.e.
+    # -(S_1 + S_2)[i] / 2 / 256 (the digit sums of K's row: NOT -M / 2 each, the leading digit of a small entry is positive);
+    # with eight pairs also (0, 3): -S_0[i] / 2
+    d = _digits(kop.Kr)
+    expect = float(((d[1] + d[2]).sum(1) / 512.0 + (0.0 if nfull else 0.5 * d[0].sum(1))).mean())
+    assert abs(dev[False] - expect) < 0.05 * abs(expect) + 0.05
+    assert abs(dev[True]) < 0.01 * abs(expect) + 0.05

@@ -38,8 +38,14 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max())
 
 
+TWOS_OPS = set(x for x in os.environ.get("SIM_TWOS", "").split(",") if x)      # ops whose digits are the device's (biased) ones
+if os.environ.get("SIM_DIGITS") == "twos":
+    TWOS_OPS = {"syrk", "syrkg", "scaledA", "scaledS", "scaled", "nn", "quad"}
+
+
 class Fixed:
     """Fixed-point image of X: X ~= Xi * scale, |Xi| <= 127 * 2^(bits-7); scale constant along `axis` (the reduction axis)."""
+    twos = False           # set per simulated op (SIM_TWOS): balanced round-to-nearest digits otherwise
 
     def __init__(self, X, axis, bits, nslices):
         self.bits, self.ns = bits, nslices
@@ -55,7 +61,7 @@ class Fixed:
         if drop <= 0:
             return self.Xi
         g = 2.0 ** drop
-        if os.environ.get("SIM_DIGITS") == "twos":       # the device's digits: d in [-128, 127] (residue 128 -> -128 + carry), mean -0.5
+        if Fixed.twos:       # the device's digits: d in [-128, 127] (residue 128 -> -128 + carry), mean -0.5 for the lower ones
             return torch.floor(self.Xi / g + 0.5) * g
         return torch.round(self.Xi / g) * g
 
@@ -191,6 +197,7 @@ class SimBackend(OracleBackend):
     def syrk(self, kop, W, impl=0, chunk_rows=0):
         self.nsyrk += 1
         m = self.m.of("syrk" if self.nsyrk == 1 else "syrkg")
+        Fixed.twos = ("syrk" if self.nsyrk == 1 else "syrkg") in TWOS_OPS
         if not getattr(kop, "sim", False) or m.kind == "exact":
             return super().syrk(kop, W)
         if m.kind == "f16hl":
@@ -276,10 +283,12 @@ class SimBackend(OracleBackend):
         return r * Kr.scale * Gf.scale
 
     def gemm_nn(self, kop, Wm):
+        Fixed.twos = "nn" in TWOS_OPS
         return self._kg(kop, Wm.to(F64).t(), self.m.of("nn")).float()
 
     def rowquad(self, kop, S64, tri=False, impl=0, out=None):
         m = self.m.of("quad")
+        Fixed.twos = "quad" in TWOS_OPS
         qs = []
         for l in range(S64.shape[0]):
             if tri:
@@ -301,6 +310,7 @@ class SimBackend(OracleBackend):
         L2 = G64.shape[0]
         for s in range(L2):
             m = self.m.of("scaledA" if s < ndot else "scaledS")
+            Fixed.twos = ("scaledA" if s < ndot else "scaledS") in TWOS_OPS
             if m is self.m:
                 m = self.m.of("scaled")
             if os.environ.get("SIM_EPI") and getattr(kop, "sim", False) and m.kind == "i8" and m.cut == 3:
@@ -312,6 +322,13 @@ class SimBackend(OracleBackend):
                 unit = [2.0 ** -(8 * (3 - o)) for o in range(4)]          # digit(t) carries its weight: strip it -> plain integers
                 top = 2.0 ** (Kr.bits + 1 - 8) * 2.0 ** (Gf.bits + 1 - 8)
                 a = [(acc[o] / (top * 2.0 ** (-8 * o))) for o in range(4)]
+                if os.environ.get("SIM_CORR"):
+                    # expectation of the dropped order-4 pairs (1,3) (2,2) (3,1) of digits d = e - 1/2 (e symmetric): the device's
+                    # rank-1 correction  -(SK_123[i] + SG_123[a]) / 512 - 3 M / 1024  in units of the order-3 accumulator
+                    u = lambda F, t: F.digit(t) / 2.0 ** (F.bits + 1 - 8 * (t + 1))        # plain integer digits
+                    sk = sum(u(Kr, t).sum(1, keepdim=True) for t in (1, 2, 3))
+                    sg = sum(u(Gf, t).sum(0, keepdim=True) for t in (1, 2, 3))
+                    a[3] = a[3] - (sk + sg) / 512.0 - 3.0 * Kr.Xi.shape[1] / 1024.0
                 af = [x.float().double() for x in a]
                 mode = os.environ["SIM_EPI"]
                 if mode == "int64":                                      # exact integer recombination, ONE rounding
