@@ -506,13 +506,21 @@ struct SyrkPairTiles {              // tiles (ta: 256 rows, tb: 128 columns) tou
   }
 };
 
+// D3 (three leading digits, the adjoint SYRK): the fourth digit plane of the raw A operand is never multiplied and is not
+// loaded either (the transform still needs all four planes of ITS rows): 40 instead of 48 KB per stage, five stages instead of four.
+constexpr int I8_SMEM_PAIR_D3 = 5 * (3 * I8_PLANE + 4 * (I8_PLANE / 2)) + 1024 + 256;
+static_assert(I8_SMEM_PAIR_D3 <= 227 * 1024, "shared memory budget");
+
+template <bool D3>
 __global__ void __launch_bounds__(SYRK8_THREADS, 1)
 syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB64, const SyrkI8Params P) {
-  constexpr int STAGES = 4;
+  constexpr int STAGES = D3 ? 5 : 4;
+  constexpr int NA = D3 ? 3 : 4;                                    // digit planes of the raw operand in a stage
   constexpr int BPL = I8_PLANE / 2;                                 // one digit plane of this CTA's 64 weighted rows
-  constexpr int STAGE = 4 * I8_PLANE + 4 * BPL;                     // 48 KB
+  constexpr int STAGE = NA * I8_PLANE + 4 * BPL;                    // 48 KB (D3: 40 KB)
   constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(I8_T >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
-  static_assert(STAGES * STAGE + 1024 + 256 <= I8_SMEM, "shared memory budget");
+  static_assert(STAGES * STAGE + 1024 + 256 <= (D3 ? I8_SMEM_PAIR_D3 : I8_SMEM), "shared memory budget");
+  static_assert(8 * (5 * STAGES + 3) <= 256, "barriers live in the 256 bytes behind the stages");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = base + STAGES * STAGE;
@@ -572,10 +580,10 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           // this CTA's 64 rows of the weighted operand first (the transform warps work on them while the A planes land)
           mbar_expect_tx(fullB(stage), 4 * BPL);
 #pragma unroll
-          for (int s = 0; s < 4; ++s) tma_load_4d(st + 4 * I8_PLANE + s * BPL, &mapB64, fullB(stage), off, it.tb * I8_T + (int32_t)crank * 64, blk, s);
-          mbar_expect_tx(fullA(stage), 4 * I8_PLANE);
+          for (int s = 0; s < 4; ++s) tma_load_4d(st + NA * I8_PLANE + s * BPL, &mapB64, fullB(stage), off, it.tb * I8_T + (int32_t)crank * 64, blk, s);
+          mbar_expect_tx(fullA(stage), NA * I8_PLANE);
 #pragma unroll
-          for (int s = 0; s < 4; ++s) tma_load_4d(st + s * I8_PLANE, &mapA, fullA(stage), off, it.ta * 256 + (int32_t)crank * I8_T, blk, s);
+          for (int s = 0; s < NA; ++s) tma_load_4d(st + s * I8_PLANE, &mapA, fullA(stage), off, it.ta * 256 + (int32_t)crank * I8_T, blk, s);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -596,7 +604,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           const uint32_t st = base + stage * STAGE;
           uint64_t a[4], b[4];
 #pragma unroll
-          for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + t * I8_PLANE); b[t] = i8_desc(st + 4 * I8_PLANE + t * BPL); }
+          for (int t = 0; t < 4; ++t) { a[t] = i8_desc(st + (t < NA ? t : 0) * I8_PLANE); b[t] = i8_desc(st + NA * I8_PLANE + t * BPL); }
 #pragma unroll
           for (int ks = 0; ks < I8_KB / 32; ++ks) {
             const uint64_t adv = (uint64_t)((ks * 32) >> 4);
@@ -605,9 +613,9 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
             for (int o = 0; o < 4; ++o)
 #pragma unroll
               for (int t = 0; t <= o; ++t) {
-                if (P.digits3 && (t == 3 || o - t == 3)) continue;         // three leading digits per operand: eight pairs
+                if (D3 && (t == 3 || o - t == 3)) continue;                // three leading digits per operand: eight pairs
                 // (order 3 then starts at t = 1: that MMA carries the "first" flag)
-                umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, (t == 0 || (P.digits3 && o == 3 && t == 1)) ? f : 1u);
+                umma_i8_cg2(tmem_base + o * I8_T, a[t] + adv, b[o - t] + adv, IDESC, (t == 0 || (D3 && o == 3 && t == 1)) ? f : 1u);
               }
           }
           umma_commit_cg2(empty(stage));
@@ -654,7 +662,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           }
         }
         mbar_wait(fullB(stage), phase);
-        const uint32_t a = base + stage * STAGE + 4 * I8_PLANE + row * I8_KB + pchunk * 16;
+        const uint32_t a = base + stage * STAGE + NA * I8_PLANE + row * I8_KB + pchunk * 16;
         const uint4 k0 = lds128(a), k1 = lds128(a + BPL), k2 = lds128(a + 2 * BPL), k3 = lds128(a + 3 * BPL);
         const uint32_t k0w[4] = {k0.x, k0.y, k0.z, k0.w}, k1w[4] = {k1.x, k1.y, k1.z, k1.w};
         const uint32_t k2w[4] = {k2.x, k2.y, k2.z, k2.w}, k3w[4] = {k3.x, k3.y, k3.z, k3.w};
@@ -1172,7 +1180,10 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   P.nwin = (int)ceil_div(N, P.win_rows);
   { const char* e3 = getenv("SVGP_I8_D3"); P.digits3 = (digits3 && !(e3 && atoi(e3) == 0)) ? 1 : 0; }   // SVGP_I8_D3=0: all ten pairs everywhere
   // CTA pairs (256 x 128 tiles, tcgen05.mma.cta_group::2) unless SVGP_I8_PAIR=0 or no co-resident clusters are available
-  static int pair_clusters = -1;
+  static int pair_clusters_v[2] = {-1, -1};                            // per kernel variant (all ten pairs / three leading digits)
+  int& pair_clusters = pair_clusters_v[P.digits3];
+  auto pair_kernel = P.digits3 ? syrk_i8_pair_kernel<true> : syrk_i8_pair_kernel<false>;
+  const int pair_smem = P.digits3 ? I8_SMEM_PAIR_D3 : I8_SMEM;
   const char* ep = getenv("SVGP_I8_PAIR");
   const bool want_pair = !(ep && atoi(ep) == 0);
   cudaLaunchConfig_t cfg = {};
@@ -1184,10 +1195,11 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   cfg.stream = st;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (want_pair && pair_clusters < 0) {
-    if (cudaFuncSetAttribute(syrk_i8_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM) != cudaSuccess) return check_launch("svgp_syrk(i8 attr)");
+    if (cudaFuncSetAttribute(pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, pair_smem) != cudaSuccess) return check_launch("svgp_syrk(i8 attr)");
     cfg.gridDim = dim3(num_sms() / 2 * 2, 1, 1);
+    cfg.dynamicSmemBytes = pair_smem;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, syrk_i8_pair_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, pair_kernel, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = 0; }
     pair_clusters = n;
   }
   if (want_pair && pair_clusters > 0) {
@@ -1206,7 +1218,8 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
     const int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
     if (clusters > 0) {
       cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
-      if (cudaLaunchKernelEx(&cfg, syrk_i8_pair_kernel, map, map64, P) != cudaSuccess) return check_launch("svgp_syrk(i8 pair)");
+      cfg.dynamicSmemBytes = pair_smem;
+      if (cudaLaunchKernelEx(&cfg, pair_kernel, map, map64, P) != cudaSuccess) return check_launch("svgp_syrk(i8 pair)");
       rc = check_launch("svgp_syrk(i8 pair)");
       if (rc) return rc;
     }

@@ -160,7 +160,7 @@ def test_scaled_gemm_i8_three_leading_digits(cuda_backend, N, M, L, ndot, nfull,
     _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch, debias=debias)
 
 
-def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch, debias=debias):
+def _check_scaled_gemm_i8(cuda_backend, N, M, L, ndot, pair, wide, nfull, monkeypatch, debias=True):
     """pair: CTA pairs (tcgen05.mma.cta_group::2, 256 x 128 tiles) / single CTAs; wide: six MMAs per k-step (four of them N = 256
     over two neighbouring digit planes and two neighbouring accumulators) / the ten N = 128 MMAs.  Same ten digit-plane
     products in every variant, so all four must equal the same digit-exact emulation."""
