@@ -48,6 +48,9 @@ extern "C" {
 #define SVGP_IMPL_TC 2   /* tcgen05 / TMEM / TMA, fp32-emulating 3 x FP16 split operands          */
 #define SVGP_IMPL_TC_I8 3 /* tcgen05 kind::i8 on base-256 digit planes: exact int32 accumulation (svgp_syrk only;
                              the scaled GEMM has its own entry point svgp_scaled_gemm_i8)            */
+#define SVGP_IMPL_TC_I8_O4 5 /* the same with thirteen pairs: the three pairs of order 4 as well, as a second set of work items on the
+                                CTA-pair kernel (full form only: both triangles; otherwise as SVGP_IMPL_TC_I8).  The FORWARD SYRK
+                                at M > 2048, where the truncation after order 3 holds the inducing-point gradient at 1e-4          */
 #define SVGP_IMPL_TC_I8_D3 4 /* the same with the three leading digits of both operands (8 instead of 10 digit-plane
                                 pairs): enough for the ADJOINT SYRK dS_l = sum_i dq_il k_i k_i^T, not for the forward one  */
 

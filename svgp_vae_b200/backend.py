@@ -12,7 +12,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8, IMPL_TC_I8_D3, KopStruct
+from ._lib import IMPL_AUTO, IMPL_SIMT, IMPL_TC, IMPL_TC_I8, IMPL_TC_I8_D3, IMPL_TC_I8_O4, KopStruct
 
 
 class Kop:
@@ -379,8 +379,9 @@ class CudaBackend:
         L = W.shape[1]
         A = torch.zeros((L, kop.M, kop.M), device=W.device, dtype=torch.float64)
         use_tc = kop.tc and impl != IMPL_SIMT
-        use_i8 = use_tc and kop.i8 and impl in (IMPL_AUTO, IMPL_TC_I8, IMPL_TC_I8_D3)
-        i8_impl = IMPL_TC_I8_D3 if impl == IMPL_TC_I8_D3 else IMPL_TC_I8     # D3: the adjoint SYRK (eight digit-plane pairs)
+        use_i8 = use_tc and kop.i8 and impl in (IMPL_AUTO, IMPL_TC_I8, IMPL_TC_I8_D3, IMPL_TC_I8_O4)
+        # D3: the adjoint SYRK (eight digit-plane pairs); O4: the forward SYRK above M = 2048 (thirteen)
+        i8_impl = impl if impl in (IMPL_TC_I8_D3, IMPL_TC_I8_O4) else IMPL_TC_I8
         ws = None
         if use_tc:
             ws = torch.empty(int(_lib.load().svgp_syrk_ws_floats(kop.N, kop.M, L)), device=W.device, dtype=torch.float32)

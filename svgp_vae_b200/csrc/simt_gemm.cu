@@ -360,10 +360,10 @@ int svgp_syrk(const svgp_kop* kop, const float* W, int64_t ldw, int64_t L, doubl
   SVGP_REQUIRE(kop && W && A && L >= 1, "null argument");
   if (kop->N == 0 || kop->M == 0) return SVGP_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (impl == SVGP_IMPL_TC_I8 || impl == SVGP_IMPL_TC_I8_D3 || (impl == SVGP_IMPL_AUTO && kop->Kc && kop->cscale && tc_shape_ok(kop))) {
+  if (impl == SVGP_IMPL_TC_I8 || impl == SVGP_IMPL_TC_I8_D3 || impl == SVGP_IMPL_TC_I8_O4 || (impl == SVGP_IMPL_AUTO && kop->Kc && kop->cscale && tc_shape_ok(kop))) {
     SVGP_REQUIRE(ws != nullptr, "TC path needs the workspace (svgp_syrk_ws_floats)");
     SVGP_REQUIRE(kop->Kc && kop->cscale && kop->M >= 128 && kop->N >= 128, "integer path needs the int8 planes (svgp_kernel_fwd_i8) and M, N >= 128");
-    return tc_syrk_i8_prep_run(kop, W, ldw, L, A, ws, st, impl == SVGP_IMPL_TC_I8_D3 ? 1 : 0);
+    return tc_syrk_i8_prep_run(kop, W, ldw, L, A, ws, st, impl == SVGP_IMPL_TC_I8_D3 ? 1 : (impl == SVGP_IMPL_TC_I8_O4 ? 2 : 0));
   }
   if (use_tc(kop, impl)) {
     SVGP_REQUIRE(ws != nullptr, "TC path needs the workspace (svgp_syrk_ws_floats)");

@@ -230,6 +230,8 @@ struct SyrkI8Params {
   int split;                // pair kernel: leave the tiles tb = 2 ta + 1 out; single-CTA kernel: ONLY the blocks (2 t + 1, 2 t + 1)
   int full;                 // pair kernel: every tile and every entry of K^T (w o K) (symmetrised afterwards by averaging, not mirroring)
   int digits3;              // the eight pairs of the three leading digits only (t, u <= 2, t + u <= 3): the ADJOINT SYRK tolerates it
+  int order4;               // pair kernel: a second set of items adds the order-4 pairs (1,3) (2,2) (3,1) -- thirteen pairs in all
+  int64_t n_items_main;     // items of the ten-pair products (== n_items without order4)
 };
 
 // quantisation factor of the weighted operand of row a: |float(Kint) * wn * q| <= 127 2^24 (two fp32 roundings of headroom)
@@ -552,9 +554,16 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_ptr));
 
-  struct Item { int64_t l, n0, n1; int ta, tb, nkb; };
+  // Order-4 items (P.order4; M > 2048): the ten pairs t + u <= 3 leave 2^-32 of the operands' grids per product term; at
+  // M = 4096 that truncation of the FORWARD SYRK is what holds the inducing-point gradient at the tolerance (operand-format
+  // model: dZ 6.0e-5 -> 3.1e-5 with the three pairs of order 4, as good as an exact product; a fifth digit changes nothing).
+  // TMEM is full with four accumulators, so the three extra pairs run as items of their own -- same tiles, same pipeline, one
+  // accumulator, weight 2^-8 of the order-3 unit.
+  struct Item { int64_t l, n0, n1; int ta, tb, nkb; bool o4; };
   auto decode = [&](int64_t item) -> Item {
     Item it;
+    it.o4 = !D3 && item >= P.n_items_main;
+    if (it.o4) item -= P.n_items_main;
     const int64_t per_win = (int64_t)P.ntile * P.L;
     const int64_t win = item / per_win, rem = item - win * per_win;
     it.l = rem % P.L;
@@ -609,6 +618,12 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           for (int ks = 0; ks < I8_KB / 32; ++ks) {
             const uint64_t adv = (uint64_t)((ks * 32) >> 4);
             const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
+            if (it.o4) {                                                   // order 4 into the first accumulator
+              umma_i8_cg2(tmem_base, a[1] + adv, b[3] + adv, IDESC, f);
+              umma_i8_cg2(tmem_base, a[2] + adv, b[2] + adv, IDESC, 1u);
+              umma_i8_cg2(tmem_base, a[3] + adv, b[1] + adv, IDESC, 1u);
+              continue;
+            }
 #pragma unroll
             for (int o = 0; o < 4; ++o)
 #pragma unroll
@@ -701,7 +716,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const Item it = decode(item);
       const int64_t r = (int64_t)it.ta * 256 + crank * I8_T + qd * 32 + lane;        // output row a
       const int64_t rmax_w = (int64_t)it.ta * 256 + crank * I8_T + qd * 32 + 31;
-      const double rs = (r < P.M) ? 16777216.0 * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
+      const double rs = (r < P.M) ? (it.o4 ? 65536.0 : 16777216.0) * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
       mbar_wait(tfull, tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
@@ -722,7 +737,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (r < P.M && (c <= r || P.full) && c < P.M) {
             const float qc = syrk_vq(__ldg(P.vmax + it.l * P.M + c));
             if (qc > 0.f) {
-              const long long i64 = ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
+              const long long i64 = it.o4 ? (long long)a0[j] : ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
               atomicAdd(dst + j, (double)i64 * rs * ((double)__ldg(P.cscale + c) / (double)qc));
             }
           }
@@ -1178,7 +1193,9 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   P.N = N; P.M = M; P.L = L; P.Wt = Wt; P.ldwt = ldwt; P.wmax = wmax; P.vmax = vmax; P.cscale = kop->cscale; P.A = A;
   P.win_rows = i8_syrk_window(N, M, L);
   P.nwin = (int)ceil_div(N, P.win_rows);
-  { const char* e3 = getenv("SVGP_I8_D3"); P.digits3 = (digits3 && !(e3 && atoi(e3) == 0)) ? 1 : 0; }   // SVGP_I8_D3=0: all ten pairs everywhere
+  // digits3: 1 = the eight pairs of three leading digits (SVGP_I8_D3=0: all ten pairs everywhere), 2 = thirteen pairs (order 4 too)
+  { const char* e3 = getenv("SVGP_I8_D3"); P.digits3 = (digits3 == 1 && !(e3 && atoi(e3) == 0)) ? 1 : 0; }
+  const bool want_order4 = digits3 == 2;
   // CTA pairs (256 x 128 tiles, tcgen05.mma.cta_group::2) unless SVGP_I8_PAIR=0 or no co-resident clusters are available
   static int pair_clusters_v[2] = {-1, -1};                            // per kernel variant (all ten pairs / three leading digits)
   int& pair_clusters = pair_clusters_v[P.digits3];
@@ -1214,7 +1231,10 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
     if (used_full) *used_full = P.full;
     P.split = !P.full && !(es && atoi(es) == 0) && SyrkPairTiles::odd_blocks(M) > 0 ? 1 : 0;
     P.ntile = SyrkPairTiles::count(M, P.split, P.full);
-    P.n_items = (int64_t)P.nwin * P.ntile * L;
+    P.n_items = P.n_items_main = (int64_t)P.nwin * P.ntile * L;
+    // thirteen pairs: only without the diagonal split (its blocks run on the single-CTA kernel, which has no order-4 items)
+    { const char* e4 = getenv("SVGP_I8_SYRK_O4"); P.order4 = (want_order4 && !P.split && !(e4 && atoi(e4) == 0)) ? 1 : 0; }
+    if (P.order4) P.n_items = 2 * P.n_items_main;
     const int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
     if (clusters > 0) {
       cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);

@@ -24,7 +24,7 @@ import math
 import torch
 
 from . import ops
-from ._lib import IMPL_AUTO, IMPL_TC_I8_D3
+from ._lib import IMPL_AUTO, IMPL_TC_I8_D3, IMPL_TC_I8_O4
 from .backend import Planes, PlanesI8, get_backend
 
 LOG_2PI = 1.8378770664093453      # utils.py:498
@@ -296,7 +296,10 @@ class _SVGPStep(torch.autograd.Function):
         K64 = be.kernel_fwd_f64(spec, Fz32, Fz32, hyp32)
         kappa = be.kernel_diag_fwd(spec, Fx32, Fx32, hyp32)
         p, py, sums = be.rowstats(y32, n32, kappa)
-        A = be.syrk(kop, p, chunk_rows=cfg.get("chunk_rows", 0))
+        # above M = 2048 the forward SYRK multiplies the three digit-plane pairs of order 4 as well (thirteen pairs): what the ten
+        # leave out is what holds the inducing-point gradient at the tolerance there
+        o4 = getattr(kop, "i8", False) and M > 2048
+        A = be.syrk(kop, p, impl=IMPL_TC_I8_O4 if o4 else IMPL_AUTO, chunk_rows=cfg.get("chunk_rows", 0))
         V = be.gemm_tn(kop, py)
         b_total = float(N)
         if group is not None:

@@ -10,7 +10,7 @@ import torch
 from conftest import rel_err
 from oracle_backend import kernel_value
 from svgp_vae_b200 import configs
-from svgp_vae_b200._lib import IMPL_TC_I8, IMPL_TC_I8_D3
+from svgp_vae_b200._lib import IMPL_TC_I8, IMPL_TC_I8_D3, IMPL_TC_I8_O4
 
 pytestmark = pytest.mark.gpu
 F64 = torch.float64
@@ -94,6 +94,13 @@ def test_syrk_i8_three_leading_digits(cuda_backend, N, M, L, pair, split, monkey
     _check_syrk_i8(cuda_backend, N, M, L, pair, split, True, monkeypatch)
 
 
+@pytest.mark.parametrize("N,M,L", [(4096, 256, 3), (6000, 384, 2), (9000, 4096, 1)])
+def test_syrk_i8_thirteen_pairs(cuda_backend, N, M, L, monkeypatch):
+    """SVGP_IMPL_TC_I8_O4 (the forward SYRK of the step above M = 2048): the three pairs of order 4 as a second set of work items
+    on the pair kernel, full form."""
+    _check_syrk_i8(cuda_backend, N, M, L, True, "full", "o4", monkeypatch)
+
+
 def _check_syrk_i8(cuda_backend, N, M, L, pair, split, d3, monkeypatch):
     """pair: the CTA-pair kernel (tcgen05.mma.cta_group::2; the weighted operand is the B side: rows b) / the single-CTA
     kernel (weighted operand = A side: rows a).  Both must equal the digit-exact emulation of their own operand placement.
@@ -107,7 +114,8 @@ def _check_syrk_i8(cuda_backend, N, M, L, pair, split, d3, monkeypatch):
     _, kop = _kop(be, N, M, L)
     g = torch.Generator(device="cuda").manual_seed(2)
     W = torch.randn(N, L, generator=g, device="cuda") * torch.exp(torch.randn(N, L, generator=g, device="cuda"))
-    A = be.syrk(kop, W.contiguous(), impl=IMPL_TC_I8_D3 if d3 else IMPL_TC_I8)
+    o4, d3 = d3 == "o4", d3 is True
+    A = be.syrk(kop, W.contiguous(), impl=IMPL_TC_I8_O4 if o4 else (IMPL_TC_I8_D3 if d3 else IMPL_TC_I8))
     # emulation from the same planes: weighted operand = rn(float(Kint) * (w / wmax) * q_a) as a 32-bit integer, q_a from
     # the largest |float(Kint) * (w / wmax)| of row a
     k = _digits(kop.Kc)                                                   # (nblk, M, 128) each
@@ -129,6 +137,9 @@ def _check_syrk_i8(cuda_backend, N, M, L, pair, split, d3, monkeypatch):
                     if t + u <= 3 and not (d3 and max(t, u) == 3):
                         acc[t + u] += (kd[u].t() @ v[t]) if weighted_is_b else (v[t].t() @ kd[u])      # exact: |sum| < 2^53
             i64 = ((acc[0].to(torch.int64) * 256 + acc[1].to(torch.int64)) * 256 + acc[2].to(torch.int64)) * 256 + acc[3].to(torch.int64)
+            if o4:                                          # order 4: (1, 3) (2, 2) (3, 1), a 256th of the order-3 unit
+                acc4 = sum((kd[4 - t].t() @ v[t]) if weighted_is_b else (v[t].t() @ kd[4 - t]) for t in (1, 2, 3))
+                return (i64.double() + acc4 / 256.0) * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if weighted_is_b else qa.double()[:, None])
             return i64.double() * (16777216.0 * wmax.double()) * cs[:, None] * cs[None, :] / (qa.double()[None, :] if weighted_is_b else qa.double()[:, None])
         ref[l] = emulate(pair)
         if full:
