@@ -399,7 +399,7 @@ def run_gpu(args):
         # up to M = 2048 -> e = 4 for them, 4.5 for the pass-D launch as a whole)
         d3 = be.use_i8 and M <= 2048 and os.environ.get("SVGP_I8_D3", "1") != "0"
         kern_alg = {"svgp_scaled_gemm_i8": (2.0 * N * M * M * (2 * L), 4.5 if d3 else 5.0), "svgp_scaled_gemm": (2.0 * N * M * M * (2 * L), 3.0),
-                    "svgp_syrk": (1.0 * N * M * M * L, 5.0 if be.use_i8 else 3.0), "svgp_rowquad": (1.0 * N * M * M * L, 3.0)}
+                    "svgp_syrk": (1.0 * N * M * M * L, (13.0 if M > 2048 else 5.0) if be.use_i8 else 3.0), "svgp_rowquad": (1.0 * N * M * M * L, 3.0)}
         top_flops, top_e = kern_alg.get(top_name, (float("nan"), float("nan")))
         # DRAM bytes of one launch of that kernel from the committed ncu capture of this exact workload (else null)
         traffic = None
@@ -412,7 +412,9 @@ def run_gpu(args):
         achieved = top_e * top_flops / (top_ms * 1e-3) / 1e12
         # what the tensor kernels of this implementation really issue per step, in bf16-equivalent FLOPs: 2 SYRKs (N M^2 L each,
         # x5) + 1 triangular row quad (N M^2 L, x3) + the 2L-matrix product of pass D (2 N M^2 2L, x5)
-        launched = (5.0 + (4.0 if d3 else 5.0) + 3.0 + 4 * (4.5 if d3 else 5.0)) * L * N * M * M if be.use_i8 else 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M
+        # above M = 2048 both SYRKs compute both triangles (x 2) and the forward one multiplies thirteen pairs (6.5)
+        syrk_e = (2 * 6.5 + 2 * 5.0) if M > 2048 else (5.0 + (4.0 if d3 else 5.0))
+        launched = (syrk_e + 3.0 + 4 * (4.5 if d3 else 5.0)) * L * N * M * M if be.use_i8 else 3 * (3.0 * L + 2.0 * (2 * L)) * N * M * M
         # K1 (the kernel-matrix builder) is the HBM-bound kernel of the path: fp16 hi/lo row planes + 4 + 4 int8 digit planes
         k1_name = "svgp_kernel_fwd_i8" if "svgp_kernel_fwd_i8" in prof else "svgp_kernel_fwd"
         k1_ms = prof.get(k1_name, {}).get("max_ms")
