@@ -513,7 +513,7 @@ struct SyrkPairTiles {              // tiles (ta: 256 rows, tb: 128 columns) tou
 constexpr int I8_SMEM_PAIR_D3 = 5 * (3 * I8_PLANE + 4 * (I8_PLANE / 2)) + 1024 + 256;
 static_assert(I8_SMEM_PAIR_D3 <= 227 * 1024, "shared memory budget");
 
-template <bool D3>
+template <bool D3, bool O4>
 __global__ void __launch_bounds__(SYRK8_THREADS, 1)
 syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB64, const SyrkI8Params P) {
   constexpr int STAGES = D3 ? 5 : 4;
@@ -562,7 +562,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   struct Item { int64_t l, n0, n1; int ta, tb, nkb; bool o4; };
   auto decode = [&](int64_t item) -> Item {
     Item it;
-    it.o4 = !D3 && item >= P.n_items_main;
+    it.o4 = O4 && item >= P.n_items_main;          // (an instantiation of its own: the ten-pair kernel stays as it was)
     if (it.o4) item -= P.n_items_main;
     const int64_t per_win = (int64_t)P.ntile * P.L;
     const int64_t win = item / per_win, rem = item - win * per_win;
@@ -618,7 +618,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           for (int ks = 0; ks < I8_KB / 32; ++ks) {
             const uint64_t adv = (uint64_t)((ks * 32) >> 4);
             const uint32_t f = (kb == 0 && ks == 0) ? 0u : 1u;
-            if (it.o4) {                                                   // order 4 into the first accumulator
+            if (O4 && it.o4) {                                             // order 4 into the first accumulator
               umma_i8_cg2(tmem_base, a[1] + adv, b[3] + adv, IDESC, f);
               umma_i8_cg2(tmem_base, a[2] + adv, b[2] + adv, IDESC, 1u);
               umma_i8_cg2(tmem_base, a[3] + adv, b[1] + adv, IDESC, 1u);
@@ -716,7 +716,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
       const Item it = decode(item);
       const int64_t r = (int64_t)it.ta * 256 + crank * I8_T + qd * 32 + lane;        // output row a
       const int64_t rmax_w = (int64_t)it.ta * 256 + crank * I8_T + qd * 32 + 31;
-      const double rs = (r < P.M) ? (it.o4 ? 65536.0 : 16777216.0) * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
+      const double rs = (r < P.M) ? ((O4 && it.o4) ? 65536.0 : 16777216.0) * (double)P.wmax[it.l] * (double)P.cscale[r] : 0.0;
       mbar_wait(tfull, tphase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16);
@@ -737,7 +737,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
           if (r < P.M && (c <= r || P.full) && c < P.M) {
             const float qc = syrk_vq(__ldg(P.vmax + it.l * P.M + c));
             if (qc > 0.f) {
-              const long long i64 = it.o4 ? (long long)a0[j] : ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
+              const long long i64 = (O4 && it.o4) ? (long long)a0[j] : ((((long long)a0[j] * 256 + a1[j]) * 256 + a2[j]) * 256) + a3[j];
               atomicAdd(dst + j, (double)i64 * rs * ((double)__ldg(P.cscale + c) / (double)qc));
             }
           }
@@ -1197,9 +1197,18 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
   { const char* e3 = getenv("SVGP_I8_D3"); P.digits3 = (digits3 == 1 && !(e3 && atoi(e3) == 0)) ? 1 : 0; }
   const bool want_order4 = digits3 == 2;
   // CTA pairs (256 x 128 tiles, tcgen05.mma.cta_group::2) unless SVGP_I8_PAIR=0 or no co-resident clusters are available
-  static int pair_clusters_v[2] = {-1, -1};                            // per kernel variant (all ten pairs / three leading digits)
-  int& pair_clusters = pair_clusters_v[P.digits3];
-  auto pair_kernel = P.digits3 ? syrk_i8_pair_kernel<true> : syrk_i8_pair_kernel<false>;
+  // SVGP_I8_SYRK_SPLIT=0: all tiles on the pair kernel (the diagonal blocks of the tiles tb = 2 ta + 1 then cost a whole tile)
+  // "full": both triangles, averaged afterwards (tc_syrk_i8_prep_run) -- twice the MMAs, for the sizes where the mirrored
+  // lower triangle costs parity (M > 2048; SVGP_I8_SYRK_FULL=0/1 overrides)
+  const char* es = getenv("SVGP_I8_SYRK_SPLIT");
+  P.full = i8_syrk_full(M) ? 1 : 0;
+  P.split = !P.full && !(es && atoi(es) == 0) && SyrkPairTiles::odd_blocks(M) > 0 ? 1 : 0;
+  // thirteen pairs: only without the diagonal split (its blocks run on the single-CTA kernel, which has no order-4 items)
+  { const char* e4 = getenv("SVGP_I8_SYRK_O4"); P.order4 = (want_order4 && !P.split && !(e4 && atoi(e4) == 0)) ? 1 : 0; }
+  static int pair_clusters_v[3] = {-1, -1, -1};                        // per kernel variant: ten pairs / three leading digits / thirteen pairs
+  const int variant = P.digits3 ? 1 : (P.order4 ? 2 : 0);
+  int& pair_clusters = pair_clusters_v[variant];
+  auto pair_kernel = variant == 1 ? syrk_i8_pair_kernel<true, false> : (variant == 2 ? syrk_i8_pair_kernel<false, true> : syrk_i8_pair_kernel<false, false>);
   const int pair_smem = P.digits3 ? I8_SMEM_PAIR_D3 : I8_SMEM;
   const char* ep = getenv("SVGP_I8_PAIR");
   const bool want_pair = !(ep && atoi(ep) == 0);
@@ -1223,17 +1232,9 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
     CUtensorMap map64;
     rc = encode_i8(&map64, kop->Kc, 4, dims, strides, I8_T / 2);
     if (rc) return rc;
-    // SVGP_I8_SYRK_SPLIT=0: all tiles on the pair kernel (the diagonal blocks of the tiles tb = 2 ta + 1 then cost a whole tile)
-    // "full": both triangles, averaged afterwards (tc_syrk_i8_prep_run) -- twice the MMAs, for the sizes where the mirrored
-    // lower triangle costs parity (M > 2048; SVGP_I8_SYRK_FULL=0/1 overrides)
-    const char* es = getenv("SVGP_I8_SYRK_SPLIT");
-    P.full = i8_syrk_full(M) ? 1 : 0;
     if (used_full) *used_full = P.full;
-    P.split = !P.full && !(es && atoi(es) == 0) && SyrkPairTiles::odd_blocks(M) > 0 ? 1 : 0;
     P.ntile = SyrkPairTiles::count(M, P.split, P.full);
     P.n_items = P.n_items_main = (int64_t)P.nwin * P.ntile * L;
-    // thirteen pairs: only without the diagonal split (its blocks run on the single-CTA kernel, which has no order-4 items)
-    { const char* e4 = getenv("SVGP_I8_SYRK_O4"); P.order4 = (want_order4 && !P.split && !(e4 && atoi(e4) == 0)) ? 1 : 0; }
     if (P.order4) P.n_items = 2 * P.n_items_main;
     const int64_t clusters = P.n_items < pair_clusters ? P.n_items : pair_clusters;
     if (clusters > 0) {
@@ -1247,7 +1248,7 @@ int tc_syrk_i8(const svgp_kop* kop, const float* Wt, int64_t ldwt, const float* 
     P.ntile = SyrkPairTiles::odd_blocks(M);              // the diagonal blocks left out above, on single CTAs
   } else {
     const int64_t T = ceil_div(M, I8_T);
-    P.split = 0;
+    P.split = P.full = P.order4 = 0;                     // (the single-CTA kernel: lower triangle, ten pairs or eight)
     P.ntile = (int)(T * (T + 1) / 2);
   }
   P.n_items = (int64_t)P.nwin * P.ntile * L;
