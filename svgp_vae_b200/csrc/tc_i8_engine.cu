@@ -60,6 +60,19 @@ __device__ __forceinline__ void umma_i8_idesc(uint32_t d_tmem, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
+// one elected lane of a converged warp: unlike `lane == 0` the compiler knows that exactly one lane runs the guarded block, so the
+// 64-bit descriptors of the MMAs move to uniform registers without a per-lane "waterfall" loop around every tcgen05.mma
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {        // K-major, 64-byte swizzle rows, 8-row groups 512 B apart
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -356,7 +369,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
         mbar_wait(S.fullB(stage), phase);
         mbar_wait(S.ready(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           issue_kblock(S.stage(stage), tmem_base, kb == 0, P.digits3 != 0);
           umma_commit(S.empty(stage));
           if (kb == it.nkb - 1) umma_commit(S.tmem_full());
@@ -609,7 +622,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
         mbar_wait(ready(stage), phase);
         mbar_wait_cluster(pfull(stage), phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           const uint32_t st = base + stage * STAGE;
           uint64_t a[4], b[4];
 #pragma unroll
@@ -915,7 +928,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
             mbar_wait(full(stage), phase);
             if (PAIR) mbar_wait_cluster(pfull(stage), phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
               const uint32_t st = base + stage * STAGE;
               uint64_t a[4], b[4];
 #pragma unroll
