@@ -356,7 +356,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
 
   auto role_producer = [&]() {
     // =============================== TMA producer ===============================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode(item);
@@ -444,7 +444,7 @@ tc_kernel(const __grid_constant__ CUtensorMap mapA_hi, const __grid_constant__ C
           mbar_wait(full(stage), phase);
           if (HAS_XFORM) mbar_wait(ready(stage), phase);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint32_t sa = smem + stage * STAGE_BYTES;
             const uint64_t a_hi = make_smem_desc<RB>(sa), a_lo = make_smem_desc<RB>(sa + A_BYTES);
             const uint64_t b_hi = make_smem_desc<RB>(sa + 2 * A_BYTES), b_lo = make_smem_desc<RB>(sa + 2 * A_BYTES + B_BYTES);

@@ -60,19 +60,6 @@ __device__ __forceinline__ void umma_i8_idesc(uint32_t d_tmem, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-// one elected lane of a converged warp: unlike `lane == 0` the compiler knows that exactly one lane runs the guarded block, so the
-// 64-bit descriptors of the MMAs move to uniform registers without a per-lane "waterfall" loop around every tcgen05.mma
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n"
-      ".reg .pred P;\n"
-      "elect.sync _|P, 0xffffffff;\n"
-      "selp.u32 %0, 1, 0, P;\n"
-      "}\n"
-      : "=r"(pred));
-  return pred != 0;
-}
 __device__ __forceinline__ uint64_t i8_desc(uint32_t saddr) {        // K-major, 64-byte swizzle rows, 8-row groups 512 B apart
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
@@ -338,7 +325,7 @@ syrk_i8_kernel(const __grid_constant__ CUtensorMap mapKc, const SyrkI8Params P) 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode(item);
@@ -590,7 +577,7 @@ syrk_i8_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
 
   if (warp == 0) {
     // =============================== TMA producer ===============================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
       for (int64_t item = unit; item < P.n_items; item += nunits) {
         const Item it = decode(item);
@@ -884,7 +871,7 @@ scaled_i8_kernel(const __grid_constant__ CUtensorMap mapK, const __grid_constant
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0) {
       // =============================== TMA producer ===============================================
-      if (lane == 0) {
+      if (elect_one()) {
         int stage = 0; uint32_t phase = 0;
         for (int64_t item = unit; item < P.n_items; item += nunits) {
           const int32_t row0 = (int32_t)((item / P.nct) * ROWS + crank * I8_T);
