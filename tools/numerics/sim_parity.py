@@ -13,6 +13,17 @@ tensor-core operand format whose ACCUMULATION IS EXACT (integer MMA, int32 accum
 
 and reports per-tensor parity against the streamlined float64 oracle exactly like tests/probes/parity_probe.py.
 Usage: python tools/numerics/sim_parity.py N M L model [model ...]
+
+A model may override single ops: 'i8:0:4x4:3+syrk=...+syrkg=...+scaledA=...+scaledS=...+quad=...+nn=...' (syrk = the forward
+SYRK, syrkg = its adjoint, scaledA / scaledS = the dA + dA^T / S - Kinv halves of pass D); the cut may be a list of digit pairs
+('i8:0:4x4:00,01,02,10,11,12,20,21' = the eight pairs of three leading digits).  Environment switches:
+  SIM_DIGITS=twos      the device's digits (d in [-128, 127]: the lower ones have mean -1/2) instead of round-to-nearest balanced
+                       ones, everywhere; SIM_TWOS=op,op,... the same for single ops (this is what reproduced the GPU's 7e-4 of the
+                       hyper-parameter gradients at M = 4096: DESIGN.md section 7)
+  SIM_EPI=fma|int64    the scaled GEMM's own epilogue arithmetic (order accumulators -> fp32 by three fmas / one int64 conversion)
+  SIM_CORR=1           with SIM_EPI: the expected value of the dropped order-4 pairs added before rounding (svgp_i8_pair_bias)
+  SIM_SYRK_SYM=mirror|avg   how the SYRK result is symmetrised (lower triangle mirrored / both triangles averaged)
+  SIM_SYRK_EXACT_PRODUCT=1, SIM_KNOISE, SIM_KMMNOISE   earlier experiments (section 7)
 """
 import json
 import os
