@@ -27,6 +27,38 @@ def test_library_exports_every_declared_symbol():
     assert lib.svgp_last_error() is not None          # host-only call, no device needed
 
 
+def _prototypes():
+    """name -> list of C parameter types of every prototype in the header (comments stripped)."""
+    src = open(os.path.join(ROOT, "include", "svgp_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(svgp_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src):
+        params = params.strip()
+        plist = [] if params in ("", "void") else [re.sub(r"\s+", " ", q.strip()) for q in params.split(",")]
+        out[name] = [re.sub(r"\s*\w+$", "", q) if not q.endswith("*") else q for q in plist]      # drop the parameter name
+    return out
+
+
+def test_ctypes_signatures_match_the_header_prototypes():
+    """Every entry of _lib.SIGNATURES has the arity of its prototype and a pointer / 64-bit / int / double in the same places:
+    a ctypes call with a stale signature would pass garbage into a kernel launch instead of failing."""
+    import ctypes
+    kinds = {ctypes.c_void_p: "ptr", ctypes.c_int64: "i64", ctypes.c_int: "int", ctypes.c_double: "f64", ctypes.c_float: "f32"}
+
+    def kind_of_c(t):
+        if "*" in t:
+            return "ptr"
+        t = t.replace("const ", "").strip()
+        return {"int64_t": "i64", "int": "int", "double": "f64", "float": "f32"}[t]
+
+    protos = _prototypes()
+    assert set(protos) == set(_lib.SIGNATURES)
+    for name, args in _lib.SIGNATURES.items():
+        want = [kind_of_c(t) for t in protos[name]]
+        got = ["ptr" if (a not in kinds) else kinds[a] for a in args]           # POINTER(KopStruct) etc. count as pointers
+        assert got == want, (name, got, want)
+
+
 def test_product_fails_loudly_without_a_gpu():
     import torch
     if torch.cuda.is_available():
