@@ -395,3 +395,39 @@ def test_handwritten_mm_stage_adjoint_matches_autograd(oracle_backend):
     assert rel_err(g["gV"], ref[1]) < 1e-10
     assert rel_err(g["gsums"], ref[2]) < 1e-12
     assert rel_err(sym(gK), sym(ref[3])) < 1e-10
+
+
+def test_digit_format_bias_and_its_correction():
+    """The arithmetic behind svgp_i8_pair_bias (include/svgp_b200.h), on the CPU: the device's base-256 digits
+    ((V + 0x808080) ^ 0x808080: d in [-128, 127]) have mean -1/2 in the lower places, so the digit-plane pairs a product drops
+    (t + u >= 4) do not average to zero; -(S_123[i] + S_123[a]) / 512 - 3 n / 1024 from the digit SUMS of the two operands removes
+    their mean, also when one operand's small entries carry their sign in a "lower" digit (the rows of K_nm).  The second
+    operand's digits come in antithetic pairs of columns (d and -1 - d, both uniform on [-128, 127]), so the zero-mean part of the
+    dropped pairs cancels exactly and the check is deterministic."""
+    g = torch.Generator().manual_seed(7)
+    n, rows, cols = 2048, 64, 48
+
+    def digits(V):                                         # balanced digits of int64 |V| < 2^31, most significant first
+        out = []
+        for _ in range(3):
+            d = ((V + 128) % 256) - 128
+            out.append(d.double())
+            V = (V - d) // 256
+        return [V.double()] + out[::-1]
+
+    # K-like operand: non-negative, most entries tiny against the row maximum
+    K = (2.0 ** 31 * 0.99 * torch.exp(-8.0 * torch.rand(rows, n, generator=g, dtype=F64))).round().long()
+    kd = digits(K)
+    assert all(float(d.min()) >= -128 and float(d.max()) <= 127 for d in kd[1:])
+    assert float(kd[1].mean()) > 1.0                       # NOT -1/2: the leading digit of a small positive entry is positive
+    half = [torch.randint(-128, 128, (cols // 2, n), generator=g).double() for _ in range(4)]
+    gd = [torch.cat([h, -1.0 - h]) for h in half]          # uniform digits, mean exactly -1/2
+    dropped = sum((kd[t] @ gd[u].t()) * 256.0 ** (3 - t - u) for t in range(4) for u in range(4) if t + u >= 4)
+    s123 = lambda d: (d[1] + d[2] + d[3]).sum(1)
+    corr = -s123(kd)[:, None] / 512.0 - s123(gd)[None, :] / 512.0 - 3.0 * n / 1024.0
+    m = float(dropped.mean())
+    assert abs(m) > 3.0                                    # units of the order-3 accumulator: a bias, not noise
+    # what is left are the pairs of order 5 and 6 (1 / 256 of the above)
+    assert abs(float((dropped - corr).mean())) < 0.01 * abs(m)
+    # the constant n / 4 per dropped pair alone would NOT do for this operand: its digit sums are far from -n / 2
+    assert abs(m - 3.0 * n / 4.0 / 256.0) > 0.5 * abs(m)
